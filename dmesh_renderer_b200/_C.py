@@ -1,0 +1,265 @@
+"""`_C` shim: the four entry points of the reference's pybind module
+(/root/reference/ext.cpp:4-12, render.h:10-111) with the same names, positional
+signatures, return tuples, validation messages and edge-case behaviour
+(render.cu:29-412), implemented on top of the C ABI of libdmesh_b200.so.
+
+PyTorch is used only for device memory (output / state tensors are allocated
+through the caching allocator exactly like the reference's torch::full /
+resize_ lambdas, render.cu:18-24,87-100) and for the current stream.  All
+compute happens in the hand-written sm_100a kernels behind the C ABI; there is
+no fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+NUM_CHANNELS = 3  # cuda_rasterizer/config.h:4
+
+
+def _err(msg):
+    # AT_ERROR -> c10::Error -> RuntimeError on the Python side
+    raise RuntimeError(msg)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        # the reference's .data<float>() throws for any other dtype
+        raise RuntimeError("expected scalar type Float but found %s for %s" % (str(t.dtype).replace("torch.", ""), name))
+    return t.contiguous()
+
+
+def _i32(t, name):
+    if t.dtype != torch.int32:
+        raise RuntimeError("expected scalar type Int but found %s for %s" % (str(t.dtype).replace("torch.", ""), name))
+    return t.contiguous()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("dmesh_renderer_b200 is CUDA-only (sm_100a); got a %s tensor. There is no CPU fallback." % t.device)
+
+
+class _Pinned:
+    """One pinned int32 per device for the num_rendered read-back (the single
+    host<->device synchronisation of a forward call, as in
+    rasterizer_impl.cu:287-292)."""
+    _slots = {}
+
+    @classmethod
+    def get(cls, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in cls._slots:
+            cls._slots[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        return cls._slots[key]
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_common(verts, faces, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats, verts_depth, faces_intense, tri):
+    # messages follow render.cu:49-79 (tri) and 237-267 (tet)
+    if verts.dim() != 2 or verts.size(1) != 3:
+        _err("verts must have dimensions (num_points, 3)")
+    if faces.dim() != 2 or faces.size(1) != 3:
+        _err("faces must have dimensions (num_faces, 3)")
+    names = ("(B, 4, 4)" if tri else "(batch_size, 4, 4)")
+    for t, n in ((mv_mats, "mv_mats"), (proj_mats, "proj_mats"), (inv_mv_mats, "inv_mv_mats"), (inv_proj_mats, "inv_proj_mats")):
+        if t.dim() != 3 or t.size(1) != 4 or t.size(2) != 4:
+            _err("%s must have dimensions %s" % (n, names))
+    if verts_depth.dim() != 2 or verts_depth.size(1) != verts.size(0):
+        _err("verts_depth must have dimensions (B, num_points,)" if tri else "verts_depth must have dimensions (batch_size, num_verts)")
+    if faces_intense.dim() != 2 or faces_intense.size(1) != faces.size(0):
+        _err("faces_intense must have dimensions (B, num_faces,)" if tri else "faces_intense must have dimensions (batch_size, num_faces)")
+
+
+# ---------------------------------------------------------------------------
+# tri renderer
+# ---------------------------------------------------------------------------
+def render_tris(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                verts_depth, faces_intense, image_height, image_width):
+    """RasterizeTrianglesCUDA (render.cu:29-132).
+    Returns (num_rendered, color[B,3,H,W], depth[B,1,H,W], pointBuffer, faceBuffer, binningBuffer, imgBuffer)."""
+    if verts.dim() != 2 or verts.size(1) != 3:
+        _err("verts must have dimensions (num_points, 3)")
+    if faces.dim() != 2 or faces.size(1) != 3:
+        _err("faces must have dimensions (num_faces, 3)")
+    if verts_color.dim() != 2 or verts_color.size(0) != verts.size(0):
+        _err("vert color must have dimensions (num_points, N)")
+    if faces_opacity.dim() != 1 or faces_opacity.size(0) != faces.size(0):
+        _err("face opacity must have dimensions (num_faces,)")
+    _check_common(verts, faces, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats, verts_depth, faces_intense, True)
+    _require_cuda(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                  verts_depth, faces_intense)
+    lib = _lib.load()
+    B, P, F = mv_mats.size(0), verts.size(0), faces.size(0)
+    H, W = int(image_height), int(image_width)
+    dev = verts.device
+    if verts_color.size(1) != NUM_CHANNELS:
+        _err("vert color must have dimensions (num_points, 3)")
+
+    with torch.cuda.device(dev):
+        u8 = dict(dtype=torch.uint8, device=dev)
+        if P == 0:
+            # render.cu:88-89,105: zero images (not background), empty state
+            z = torch.zeros
+            return (0, z((B, NUM_CHANNELS, H, W), dtype=torch.float32, device=dev),
+                    z((B, 1, H, W), dtype=torch.float32, device=dev),
+                    torch.empty(0, **u8), torch.empty(0, **u8), torch.empty(0, **u8), torch.empty(0, **u8))
+
+        bg = _f32(background, "background")
+        verts_c, faces_c = _f32(verts, "verts"), _i32(faces, "faces")
+        vcol, fopa = _f32(verts_color, "verts_color"), _f32(faces_opacity, "faces_opacity")
+        mv, pj = _f32(mv_mats, "mv_mats"), _f32(proj_mats, "proj_mats")
+        imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
+        vdep, fint = _f32(verts_depth, "verts_depth"), _f32(faces_intense, "faces_intense")
+
+        sizes = (ctypes.c_size_t * 3)()
+        _lib.check(lib.dmr_tri_state_bytes(B, P, F, W, H, sizes))
+        point_buf = torch.empty(sizes[0], **u8)
+        face_buf = torch.empty(sizes[1], **u8)
+        img_buf = torch.empty(sizes[2], **u8)
+        out_color = torch.empty((B, NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        out_depth = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+
+        pinned = _Pinned.get(dev)
+        stream = _stream()
+        _lib.check(lib.dmr_tri_forward_bin(B, P, F, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa), _ptr(mv),
+                                           _ptr(pj), _ptr(vdep), _ptr(fint), _ptr(point_buf), _ptr(face_buf),
+                                           ctypes.c_void_p(pinned.data_ptr()), stream))
+        torch.cuda.current_stream().synchronize()   # the one sync: R sizes the binning buffer
+        R = int(pinned[0])
+        bin_buf = torch.empty(lib.dmr_binning_bytes(R) if R > 0 else 0, **u8)
+        _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(point_buf),
+                                              _ptr(face_buf), _ptr(bin_buf), _ptr(img_buf), _ptr(out_color),
+                                              _ptr(out_depth), stream))
+    return R, out_color, out_depth, point_buf, face_buf, bin_buf, img_buf
+
+
+def render_tris_backward(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
+                         inv_proj_mats, verts_depth, faces_intense, dL_dout_color, dL_dout_depth, R, pointBuffer,
+                         faceBuffer, binningBuffer, imageBuffer):
+    """RasterizeTrianglesBackwardCUDA (render.cu:134-208).
+    Returns (dL_dverts[P,3], dL_dvcolor[P,3], dL_dfopacity[F], dL_dvdepth[B,P], dL_dfintense[B,F])."""
+    lib = _lib.load()
+    B, P, F = mv_mats.size(0), verts.size(0), faces.size(0)
+    H, W = dL_dout_color.size(2), dL_dout_color.size(3)
+    dev = verts.device
+    with torch.cuda.device(dev):
+        z = dict(dtype=torch.float32, device=dev)
+        dL_dverts = torch.zeros((P, 3), **z)
+        dL_dvcolor = torch.zeros((P, NUM_CHANNELS), **z)
+        dL_dfopacity = torch.zeros((F,), **z)
+        dL_dvdepth = torch.zeros((B, P), **z)
+        dL_dfintense = torch.zeros((B, F), **z)
+        if F != 0 and P != 0 and R > 0:
+            _require_cuda(dL_dout_color, dL_dout_depth)
+            bg = _f32(background, "background")
+            imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
+            gc, gd = _f32(dL_dout_color, "dL_dout_color"), _f32(dL_dout_depth, "dL_dout_depth")
+            _lib.check(lib.dmr_tri_backward(B, P, F, W, H, int(R), _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(pointBuffer),
+                                            _ptr(faceBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd),
+                                            _ptr(dL_dverts), _ptr(dL_dvcolor), _ptr(dL_dfopacity), _ptr(dL_dvdepth),
+                                            _ptr(dL_dfintense), _stream()))
+    return dL_dverts, dL_dvcolor, dL_dfopacity, dL_dvdepth, dL_dfintense
+
+
+# ---------------------------------------------------------------------------
+# tet renderer
+# ---------------------------------------------------------------------------
+def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                verts_depth, faces_intense, tets, face_tets, tet_faces, image_height, image_width, ray_random_seed):
+    """RenderFTetsCUDA (render.cu:213-336).
+    Returns (color[B,3,H,W], depth[B,1,H,W], active_f32[B,H,W], pointBuffer, faceBuffer, binningBuffer, imgBuffer)."""
+    if verts.dim() != 2 or verts.size(1) != 3:
+        _err("verts must have dimensions (num_points, 3)")
+    if faces.dim() != 2 or faces.size(1) != 3:
+        _err("faces must have dimensions (num_faces, 3)")
+    if verts_color.dim() != 2 or verts_color.size(0) != verts.size(0) or verts_color.size(1) != 3:
+        _err("vert_color must have dimensions (num_verts, 3)")
+    if faces_opacity.dim() != 1 or faces_opacity.size(0) != faces.size(0):
+        _err("face_opacity must have dimensions (num_faces)")
+    _check_common(verts, faces, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats, verts_depth, faces_intense, False)
+    if tets.dim() != 2 or tets.size(1) != 4:
+        _err("tets must have dimensions (num_tets, 4)")
+    if face_tets.dim() != 2 or face_tets.size(0) != faces.size(0) or face_tets.size(1) != 2:
+        _err("face_tets must have dimensions (num_faces, 2)")
+    if tet_faces.dim() != 2 or tet_faces.size(0) != tets.size(0) or tet_faces.size(1) != 4:
+        _err("tet_faces must have dimensions (num_tets, 4)")
+    _require_cuda(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                  verts_depth, faces_intense, tets, face_tets, tet_faces)
+    lib = _lib.load()
+    B, P, F, T = mv_mats.size(0), verts.size(0), faces.size(0), tets.size(0)
+    H, W = int(image_height), int(image_width)
+    dev = verts.device
+    with torch.cuda.device(dev):
+        u8 = dict(dtype=torch.uint8, device=dev)
+        bg = _f32(background, "background")
+        verts_c, faces_c = _f32(verts, "verts"), _i32(faces, "faces")
+        vcol, fopa = _f32(verts_color, "verts_color"), _f32(faces_opacity, "faces_opacity")
+        mv, pj = _f32(mv_mats, "mv_mats"), _f32(proj_mats, "proj_mats")
+        imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
+        fint = _f32(faces_intense, "faces_intense")
+        _f32(verts_depth, "verts_depth")   # dtype check only: the tet renderer never reads it
+        tets_c, ft_c, tf_c = _i32(tets, "tets"), _i32(face_tets, "face_tets"), _i32(tet_faces, "tet_faces")
+
+        sizes = (ctypes.c_size_t * 3)()
+        _lib.check(lib.dmr_tet_state_bytes(B, P, F, T, W, H, sizes))
+        point_buf = torch.empty(sizes[0], **u8)
+        face_buf = torch.empty(sizes[1], **u8)
+        img_buf = torch.empty(sizes[2], **u8)
+        out_color = torch.empty((B, NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        out_depth = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        out_active = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+
+        pinned = _Pinned.get(dev)
+        stream = _stream()
+        _lib.check(lib.dmr_tet_forward_bin(B, P, F, T, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa),
+                                           _ptr(mv), _ptr(pj), _ptr(tets_c), _ptr(ft_c), _ptr(tf_c), _ptr(point_buf),
+                                           _ptr(face_buf), ctypes.c_void_p(pinned.data_ptr()), stream))
+        torch.cuda.current_stream().synchronize()
+        R = int(pinned[0])
+        bin_buf = torch.empty(lib.dmr_binning_bytes(R) if R > 0 else 0, **u8)
+        _lib.check(lib.dmr_tet_forward_render(B, P, F, T, W, H, R, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj),
+                                              _ptr(imv), _ptr(ipj), _ptr(fint), _ptr(point_buf), _ptr(face_buf),
+                                              _ptr(bin_buf), _ptr(img_buf), _ptr(out_color), _ptr(out_depth),
+                                              _ptr(out_active), stream))
+    return out_color, out_depth, out_active, point_buf, face_buf, bin_buf, img_buf
+
+
+def render_tets_backward(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
+                         inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, grad_color, grad_depth,
+                         pointBuffer, faceBuffer, binningBuffer, imageBuffer, ray_random_seed=None):
+    """RenderFTetsBackwardCUDA (render.cu:338-412).
+    Returns (dL_dverts_color[P,3], dL_dfaces_opacity[F]).  `ray_random_seed` is an
+    optional trailing argument beyond the reference's 20: the autograd wrapper passes
+    the forward's seed so that jittered rays (seed > 0) are re-read from the image
+    buffer; with the reference's 20 arguments pixel-centre rays are used."""
+    lib = _lib.load()
+    B, P, F, T = mv_mats.size(0), verts.size(0), faces.size(0), tets.size(0)
+    H, W = grad_color.size(2), grad_color.size(3)
+    dev = verts.device
+    if ray_random_seed is None:
+        ray_random_seed = 0
+    with torch.cuda.device(dev):
+        z = dict(dtype=torch.float32, device=dev)
+        dL_dverts_color = torch.zeros((P, 3), **z)
+        dL_dfaces_opacity = torch.zeros((F,), **z)
+        if B * H * W > 0 and F > 0 and T > 0:
+            bg = _f32(background, "background")
+            mv, pj = _f32(mv_mats, "mv_mats"), _f32(proj_mats, "proj_mats")
+            imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
+            fint = _f32(faces_intense, "faces_intense")
+            gc, gd = _f32(grad_color, "grad_color"), _f32(grad_depth, "grad_depth")
+            _lib.check(lib.dmr_tet_backward(B, P, F, T, W, H, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj),
+                                            _ptr(imv), _ptr(ipj), _ptr(fint), _ptr(pointBuffer), _ptr(faceBuffer),
+                                            _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(dL_dverts_color),
+                                            _ptr(dL_dfaces_opacity), _stream()))
+    return dL_dverts_color, dL_dfaces_opacity

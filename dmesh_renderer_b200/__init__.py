@@ -1,0 +1,179 @@
+"""dmesh_renderer_b200 -- B200-native drop-in for the `dmesh_renderer` package.
+
+Public surface = the reference's (/root/reference/dmesh_renderer/__init__.py):
+    TriRenderSettings, render_tri, TriRenderer          (:13-225)
+    TetRenderSettings, render_tet, TetRenderer          (:237-488)
+with identical argument order, dtype handling, return values and gradient
+positions.  `import dmesh_renderer_b200 as dmesh_renderer` is the whole
+migration.
+
+All compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
+libdmesh_b200.so (include/dmesh_b200.h) through the `_C` shim; PyTorch provides
+device memory, the current stream and autograd plumbing only.
+"""
+from typing import NamedTuple
+
+import torch as th
+
+from . import _C
+
+__all__ = ["TriRenderSettings", "render_tri", "TriRenderer", "TetRenderSettings", "render_tet", "TetRenderer"]
+
+
+# =============================================================================
+# TriRenderer: semi-transparent triangles, mean-depth ordered compositing.
+# =============================================================================
+class TriRenderSettings(NamedTuple):      # reference __init__.py:13-16
+    image_height: int
+    image_width: int
+    bg: th.Tensor
+
+
+def render_tri(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
+               render_settings: TriRenderSettings):
+    """reference __init__.py:18-43"""
+    return _RenderTri.apply(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
+                            render_settings)
+
+
+class _RenderTri(th.autograd.Function):
+    """reference __init__.py:45-170"""
+
+    @staticmethod
+    def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
+                render_settings):
+        inv_mv_mats = th.inverse(mv_mats)
+        inv_proj_mats = th.inverse(proj_mats)
+        args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
+                inv_proj_mats, verts_depth, faces_intense, render_settings.image_height, render_settings.image_width)
+        try:
+            # depth in [-1, 1]: -1 near, 1 far
+            num_rendered, color, depth, pointBuffer, faceBuffer, binningBuffer, imgBuffer = _C.render_tris(*args)
+        except Exception as ex:
+            print("\nAn error occured in forward.")
+            print(ex)
+            raise ex
+        ctx.render_settings = render_settings
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                              verts_depth, faces_intense, pointBuffer, faceBuffer, binningBuffer, imgBuffer)
+        return color, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_depth):
+        num_rendered = ctx.num_rendered
+        render_settings = ctx.render_settings
+        (verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats, verts_depth,
+         faces_intense, pointBuffer, faceBuffer, binningBuffer, imgBuffer) = ctx.saved_tensors
+        args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
+                inv_proj_mats, verts_depth, faces_intense, grad_out_color, grad_out_depth, num_rendered, pointBuffer,
+                faceBuffer, binningBuffer, imgBuffer)
+        try:
+            grad_verts, grad_verts_color, grad_faces_opacity, grad_verts_depth, grad_faces_intense = \
+                _C.render_tris_backward(*args)
+        except Exception as ex:
+            print("\nAn error occured in backward.\n")
+            raise ex
+        # gradient positions: reference __init__.py:156-168
+        return (grad_verts, None, grad_verts_color, grad_faces_opacity, None, None, grad_verts_depth,
+                grad_faces_intense, None)
+
+
+class TriRenderer(th.nn.Module):
+    """reference __init__.py:172-225"""
+
+    def __init__(self, render_settings: TriRenderSettings):
+        super().__init__()
+        self.render_settings = render_settings
+
+    def forward(self, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense):
+        """
+        verts [P,3] f32, faces [F,3] int, verts_color [P,3], faces_opacity [F]   (view independent)
+        mv_mats, proj_mats [B,4,4] in maths convention (transposed here, as the reference does)
+        verts_depth [B,P], faces_intense [B,F]                                   (per view)
+        returns color [B,3,H,W], depth [B,1,H,W]
+        """
+        return render_tri(verts, faces.to(dtype=th.int32), verts_color, faces_opacity, mv_mats.transpose(1, 2),
+                          proj_mats.transpose(1, 2), verts_depth, faces_intense, self.render_settings)
+
+
+# =============================================================================
+# TetRenderer: faces of a tetrahedral complex, exact depth order by ray marching
+# through tet adjacency; gradients to vertex colours and face opacities only.
+# =============================================================================
+class TetRenderSettings(NamedTuple):      # reference __init__.py:237-241
+    image_height: int
+    image_width: int
+    bg: th.Tensor
+    ray_random_seed: int
+
+
+def render_tet(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
+               face_tets, tet_faces, render_settings: TetRenderSettings):
+    """reference __init__.py:243-275"""
+    return _RenderTet.apply(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
+                            tets, face_tets, tet_faces, render_settings)
+
+
+class _RenderTet(th.autograd.Function):
+    """reference __init__.py:277-424"""
+
+    @staticmethod
+    def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
+                face_tets, tet_faces, render_settings):
+        inv_mv_mats = th.inverse(mv_mats)
+        inv_proj_mats = th.inverse(proj_mats)
+        args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
+                inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, render_settings.image_height,
+                render_settings.image_width, render_settings.ray_random_seed)
+        try:
+            color, depth, active, pointBuffer, faceBuffer, binningBuffer, imgBuffer = _C.render_tets(*args)
+        except Exception as ex:
+            print("\nAn error occured in forward.")
+            raise ex
+        active = (active > 0.5)
+        ctx.render_settings = render_settings
+        ctx.save_for_backward(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                              verts_depth, faces_intense, tets, face_tets, tet_faces, pointBuffer, faceBuffer,
+                              binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(active)
+        return color, depth, active
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_depth, grad_out_active):
+        render_settings = ctx.render_settings
+        (verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats, verts_depth,
+         faces_intense, tets, face_tets, tet_faces, pointBuffer, faceBuffer, binningBuffer, imgBuffer) = ctx.saved_tensors
+        args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
+                inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, grad_out_color, grad_out_depth,
+                pointBuffer, faceBuffer, binningBuffer, imgBuffer, render_settings.ray_random_seed)
+        try:
+            grad_verts_color, grad_faces_opacity = _C.render_tets_backward(*args)
+        except Exception as ex:
+            print("\nAn error occured in backward.\n")
+            raise ex
+        # gradient positions: reference __init__.py:407-422
+        return (None, None, grad_verts_color, grad_faces_opacity, None, None, None, None, None, None, None, None)
+
+
+class TetRenderer(th.nn.Module):
+    """reference __init__.py:426-488"""
+
+    def __init__(self, render_settings: TetRenderSettings):
+        super().__init__()
+        self.render_settings = render_settings
+
+    def forward(self, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
+                face_tets, tet_faces):
+        """
+        Gradients only for verts_color and faces_opacity.  verts_depth is accepted
+        but unused (depth comes from the re-projected hit point).
+        tets [T,4], face_tets [F,2] (-1 = boundary), tet_faces [T,4]
+        returns color [B,3,H,W], depth [B,1,H,W], active [B,H,W] bool
+        """
+        f32, i32 = th.float32, th.int32
+        return render_tet(verts.to(dtype=f32), faces.to(dtype=i32), verts_color.to(dtype=f32),
+                          faces_opacity.to(dtype=f32), mv_mats.to(dtype=f32).transpose(1, 2),
+                          proj_mats.to(dtype=f32).transpose(1, 2), verts_depth.to(dtype=f32),
+                          faces_intense.to(dtype=f32), tets.to(dtype=i32), face_tets.to(dtype=i32),
+                          tet_faces.to(dtype=i32), self.render_settings)

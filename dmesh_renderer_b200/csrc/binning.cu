@@ -1,0 +1,245 @@
+// binning.cu -- prefix sum, (tile|depth) key emission, tile ranges.
+//
+//   inclusive_scan_kernel   replaces cub::DeviceScan::InclusiveSum
+//                           (cuda_rasterizer/rasterizer_impl.cu:278-284,
+//                            cuda_renderer/renderer_impl.cu:296-302)
+//   duplicate_kernel        replaces duplicateWithKeys
+//                           (rasterizer_impl.cu:44-97, renderer_impl.cu:44-99)
+//   tile_ranges_kernel      replaces identifyTileRanges (rasterizer_impl.cu:102-124)
+//
+// All three are HBM-bound; see DESIGN.md for the algorithmic bytes.
+#include "common.cuh"
+
+namespace dmr {
+
+// ---------------------------------------------------------------------------
+// Single-pass inclusive scan (decoupled look-back), uint32.
+// state[0] = ticket counter, state[1] = grand total, state[32 + t] = tile
+// descriptor { flag:2 | value:30 }.  state must be zero on entry.
+// One read and one write of the data: 8 B per element.
+// ---------------------------------------------------------------------------
+#define SCAN_FLAG_AGG  (1u << 30)
+#define SCAN_FLAG_INCL (2u << 30)
+#define SCAN_VAL_MASK  ((1u << 30) - 1u)
+
+__global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
+    const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ state,
+    int32_t* __restrict__ total_mapped)
+{
+    __shared__ uint32_t s_warp[DMR_SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_excl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) s_tile = atomicAdd(&state[0], 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t base = (size_t)tile * DMR_SCAN_TILE + (size_t)tid * DMR_SCAN_ITEMS;
+
+    // blocked arrangement: 16 consecutive items per thread = 4 x 128-bit loads
+    uint32_t v[DMR_SCAN_ITEMS];
+    if (base + DMR_SCAN_ITEMS <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+#pragma unroll
+        for (int q = 0; q < DMR_SCAN_ITEMS / 4; q++) {
+            uint4 t = p[q];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < DMR_SCAN_ITEMS; i++) v[i] = (base + i < n) ? in[base + i] : 0u;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < DMR_SCAN_ITEMS; i++) { sum += v[i]; v[i] = sum; }
+
+    // warp inclusive scan of the thread sums
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t warp_off = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < DMR_SCAN_THREADS / 32; w++) {
+        uint32_t t = s_warp[w];
+        if (w < warp) warp_off += t;
+        tile_total += t;
+    }
+    uint32_t thread_excl = warp_off + incl - sum;
+
+    // publish + decoupled look-back (warp 0)
+    if (warp == 0) {
+        uint32_t* desc = state + 32;
+        if (lane == 0) st_volatile_u32(&desc[tile], (tile == 0 ? SCAN_FLAG_INCL : SCAN_FLAG_AGG) | tile_total);
+        uint32_t excl = 0;
+        if (tile > 0) {
+            long long t = (long long)tile - 1;
+            while (true) {
+                long long idx = t - lane;
+                uint32_t d = SCAN_FLAG_INCL;   // virtual predecessor of tile 0: inclusive 0
+                if (idx >= 0) {
+                    do { d = ld_volatile_u32(&desc[idx]); } while ((d >> 30) == 0);
+                }
+                unsigned incl_mask = __ballot_sync(0xffffffffu, (d >> 30) == 2u);
+                int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+                uint32_t c = (lane <= first) ? (d & SCAN_VAL_MASK) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (incl_mask) break;
+                t -= 32;
+            }
+            if (lane == 0) st_volatile_u32(&desc[tile], SCAN_FLAG_INCL | (excl + tile_total));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            size_t ntile = (n + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+            if ((size_t)tile == ntile - 1) {
+                state[1] = excl + tile_total;
+                if (total_mapped) *total_mapped = (int32_t)(excl + tile_total);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t add = s_excl + thread_excl;
+
+    if (base + DMR_SCAN_ITEMS <= n) {
+        uint4* p = reinterpret_cast<uint4*>(out + base);
+#pragma unroll
+        for (int q = 0; q < DMR_SCAN_ITEMS / 4; q++)
+            p[q] = make_uint4(v[4 * q] + add, v[4 * q + 1] + add, v[4 * q + 2] + add, v[4 * q + 3] + add);
+    } else {
+#pragma unroll
+        for (int i = 0; i < DMR_SCAN_ITEMS; i++)
+            if (base + i < n) out[base + i] = v[i] + add;
+    }
+}
+
+int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* state, int32_t* total_host,
+                       cudaStream_t stream)
+{
+    if (n == 0) {
+        if (total_host) *total_host = 0;
+        return 0;
+    }
+    size_t ntile = (n + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+    inclusive_scan_kernel<<<(unsigned)ntile, DMR_SCAN_THREADS, 0, stream>>>(in, out, n, state, nullptr);
+    DMR_LAUNCH_CHECK("inclusive_scan_kernel");
+    if (total_host)
+        DMR_CUDA(cudaMemcpyAsync(total_host, state + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Key emission.  The reference runs one thread per face with a serial loop
+// over its tile rectangle (strided 12-byte writes, load imbalance on large
+// triangles).  Here a block owns 256 consecutive faces and its 256 threads
+// walk the block's contiguous OUTPUT range, locating the owning face by
+// binary search in shared memory -> every key/value store is coalesced.
+// Emission order (face-major, then y, then x) and key layout are those of
+// rasterizer_impl.cu:84-96:  key = (tile + tiles*b) << 32 | depth_bits,
+// value = face id within the view.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) duplicate_kernel(
+    size_t BF, int F, int tiles_x, int tiles_per_view,
+    const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, const uint32_t* __restrict__ depth_key,
+    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    __shared__ uint32_t s_incl[256];
+    __shared__ uint2 s_rect[256];
+    __shared__ uint32_t s_depth[256];
+    const int tid = threadIdx.x;
+    const size_t f0 = (size_t)blockIdx.x * 256;
+    const size_t f = f0 + tid;
+    const uint32_t start = (f0 == 0) ? 0u : offsets[f0 - 1];
+    uint32_t my_incl = 0xffffffffu;
+    if (f < BF) {
+        my_incl = offsets[f];
+        s_rect[tid] = rect[f];
+        s_depth[tid] = depth_key[f];
+    }
+    s_incl[tid] = my_incl;
+    __syncthreads();
+    const int nface = (int)((BF - f0 < 256) ? (BF - f0) : 256);
+    const uint32_t end = s_incl[nface - 1];
+
+    for (uint32_t o = start + tid; o < end; o += 256) {
+        // smallest i with s_incl[i] > o
+        int lo = 0, hi = nface - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (s_incl[mid] > o) hi = mid; else lo = mid + 1;
+        }
+        const int i = lo;
+        const uint32_t excl = (i == 0) ? start : s_incl[i - 1];
+        const uint32_t k = o - excl;
+        const uint2 r = s_rect[i];
+        const uint32_t x0 = r.x & 0xffffu, x1 = r.x >> 16, y0 = r.y & 0xffffu;
+        const uint32_t w = x1 - x0;
+        const uint32_t ty = y0 + k / w, tx = x0 + k % w;
+        const size_t gf = f0 + i;
+        const uint32_t b = (uint32_t)(gf / (size_t)F);
+        const uint32_t face = (uint32_t)(gf - (size_t)b * F);
+        uint64_t key = (uint64_t)(ty * (uint32_t)tiles_x + tx) + (uint64_t)tiles_per_view * b;
+        key = (key << 32) | (uint64_t)s_depth[i];
+        keys[o] = key;
+        vals[o] = face;
+    }
+}
+
+int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32_t* offsets, const uint2* rect,
+                        const uint32_t* depth_key, uint64_t* keys, uint32_t* vals, size_t R, cudaStream_t stream)
+{
+    if (BF == 0 || R == 0) return 0;
+    unsigned nblk = (unsigned)((BF + 255) / 256);
+    duplicate_kernel<<<nblk, 256, 0, stream>>>(BF, F, tiles_x, tiles_x * tiles_y, offsets, rect, depth_key, keys, vals);
+    DMR_LAUNCH_CHECK("duplicate_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Tile ranges: boundaries of equal tile-id runs in the sorted key list.
+// ranges must be zero on entry (tiles without instances keep (0,0),
+// rasterizer_impl.cu:330).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, size_t L,
+                                                          uint2* __restrict__ ranges)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    uint32_t cur = (uint32_t)(keys[idx] >> 32);
+    if (idx == 0) {
+        ranges[cur].x = 0;
+    } else {
+        uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        if (cur != prev) {
+            ranges[prev].y = (uint32_t)idx;
+            ranges[cur].x = (uint32_t)idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+}
+
+int identify_tile_ranges(const uint64_t* keys_sorted, size_t R, uint2* ranges, cudaStream_t stream)
+{
+    if (R == 0) return 0;
+    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(keys_sorted, R, ranges);
+    DMR_LAUNCH_CHECK("tile_ranges_kernel");
+    return 0;
+}
+
+// Number of key bits above the depth word.  The reference's getHigherMsb
+// (rasterizer_impl.cu:25-40) is a bisection that returns the bit length of n
+// (and 1 for n == 0); the closed form below gives the same value for every n.
+uint32_t higher_msb(uint32_t n)
+{
+    uint32_t bits = 0;
+    while (n) { bits++; n >>= 1; }
+    return bits ? bits : 1u;
+}
+
+}  // namespace dmr

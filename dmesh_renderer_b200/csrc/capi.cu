@@ -1,0 +1,252 @@
+// capi.cu -- extern "C" boundary of libdmesh_b200.so (see include/dmesh_b200.h).
+// Host-side stage sequencing; replaces CudaRasterizer::Rasterizer::forward /
+// backward (cuda_rasterizer/rasterizer_impl.cu:175-383, 387-467) and
+// CudaRenderer::Renderer::forward / backward (cuda_renderer/renderer_impl.cu:193-498)
+// without their per-stage cudaDeviceSynchronize (auxiliary.h:425-432).
+#include "tri.cuh"
+#include "tet.cuh"
+#include "../../include/dmesh_b200.h"
+#include <cstdarg>
+#include <cstdio>
+
+namespace dmr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what)
+{
+    set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return DMR_ECUDA;
+}
+
+BinningLayout BinningLayout::make(size_t R)
+{
+    BinningLayout L;
+    size_t o = 0;
+    L.keys_unsorted = o; o = align_up(o + 8 * R, 256);
+    L.vals_unsorted = o; o = align_up(o + 4 * R, 256);
+    L.keys_sorted = o;   o = align_up(o + 8 * R, 256);
+    L.vals_sorted = o;   o = align_up(o + 4 * R, 256);
+    L.sort_temp = o;     o = align_up(o + sort_temp_bytes(R), 256);
+    L.total = o + 256;
+    return L;
+}
+
+static bool sizes_ok(long long B, long long P, long long F, long long W, long long H)
+{
+    if (B < 0 || P < 0 || F < 0 || W <= 0 || H <= 0) { set_error("negative or zero size"); return false; }
+    if (B * P >= (1LL << 31) || B * F >= (1LL << 31) || B * W * H >= (1LL << 31)) {
+        set_error("B*P, B*F and B*W*H must stay below 2^31");
+        return false;
+    }
+    if ((W + DMR_TILE - 1) / DMR_TILE >= 65536 || (H + DMR_TILE - 1) / DMR_TILE >= 65536) {
+        set_error("image too large for 16-bit tile coordinates");
+        return false;
+    }
+    return true;
+}
+
+template <typename T>
+static T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<unsigned char*>(base) + off); }
+template <typename T>
+static const T* at(const void* base, size_t off) { return reinterpret_cast<const T*>(static_cast<const unsigned char*>(base) + off); }
+
+}  // namespace dmr
+
+using namespace dmr;
+
+extern "C" {
+
+int dmr_abi_version(void) { return 1; }
+const char* dmr_last_error(void) { return g_err; }
+
+int dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3])
+{
+    if (!out) { set_error("out is null"); return DMR_EINVAL; }
+    if (!sizes_ok(B, P, F, W, H)) return DMR_ETOOLARGE;
+    out[0] = align_up(sizeof(float4) * (size_t)B * P, 256) + 256;
+    out[1] = TriFaceLayout::make((size_t)B * F).total;
+    out[2] = TriImageLayout::make(B, W, H).total;
+    return DMR_OK;
+}
+
+size_t dmr_binning_bytes(size_t R) { return BinningLayout::make(R).total; }
+
+size_t dmr_sort_temp_bytes(size_t n) { return sort_temp_bytes(n); }
+
+int dmr_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
+                   int end_bit, void* temp, dmr_stream_t stream)
+{
+    if (n && (!keys_in || !vals_in || !keys_out || !vals_out || !temp)) { set_error("null pointer"); return DMR_EINVAL; }
+    return sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, (cudaStream_t)stream);
+}
+
+int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, const int* faces,
+                        const float* verts_color, const float* faces_opacity, const float* mv_mats,
+                        const float* proj_mats, const float* verts_depth, const float* faces_intense,
+                        void* point_buffer, void* face_buffer, int32_t* num_rendered_host, dmr_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sizes_ok(B, P, F, W, H)) return DMR_ETOOLARGE;
+    if (!num_rendered_host) { set_error("num_rendered_host is null"); return DMR_EINVAL; }
+    if (B == 0 || P == 0 || F == 0) { *num_rendered_host = 0; return DMR_OK; }
+    if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats || !verts_depth ||
+        !faces_intense || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
+    const size_t BF = (size_t)B * F;
+    TriFaceLayout L = TriFaceLayout::make(BF);
+    float4* vimg = static_cast<float4*>(point_buffer);
+    size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.scan_state), 0, 4 * (ntile + 64), stream));
+    int rc;
+    if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, verts_depth, vimg, stream))) return rc;
+    if ((rc = tri_preprocess_faces(B, P, F, W, H, faces, vimg, verts, verts_color, faces_opacity, faces_intense,
+                                   at<uint32_t>(face_buffer, L.tiles_touched), at<uint32_t>(face_buffer, L.depth_key),
+                                   at<uint2>(face_buffer, L.rect), at<TriRecord>(face_buffer, L.records), stream)))
+        return rc;
+    if ((rc = inclusive_scan_u32(at<uint32_t>(face_buffer, L.tiles_touched), at<uint32_t>(face_buffer, L.offsets), BF,
+                                 at<uint32_t>(face_buffer, L.scan_state), num_rendered_host, stream)))
+        return rc;
+    return DMR_OK;
+}
+
+static int bin_sort_ranges(int B, int F, int W, int H, size_t R, const uint32_t* offsets, const uint2* rect,
+                           const uint32_t* depth_key, void* binning_buffer, uint2* ranges, cudaStream_t stream)
+{
+    const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
+    const size_t tiles = (size_t)B * tx * ty;
+    DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream));
+    if (R == 0) return DMR_OK;
+    BinningLayout L = BinningLayout::make(R);
+    uint64_t* ku = at<uint64_t>(binning_buffer, L.keys_unsorted);
+    uint32_t* vu = at<uint32_t>(binning_buffer, L.vals_unsorted);
+    uint64_t* ks = at<uint64_t>(binning_buffer, L.keys_sorted);
+    uint32_t* vs = at<uint32_t>(binning_buffer, L.vals_sorted);
+    int rc;
+    if ((rc = duplicate_with_keys((size_t)B * F, F, tx, ty, offsets, rect, depth_key, ku, vu, R, stream))) return rc;
+    const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);   // rasterizer_impl.cu:316-324
+    if ((rc = sort_pairs(ku, vu, ks, vs, R, end_bit, at<void>(binning_buffer, L.sort_temp), stream))) return rc;
+    if ((rc = identify_tile_ranges(ks, R, ranges, stream))) return rc;
+    return DMR_OK;
+}
+
+int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float* background,
+                           const float* inv_mv_mats, const float* inv_proj_mats, const void* point_buffer,
+                           void* face_buffer, void* binning_buffer, void* image_buffer, float* out_color,
+                           float* out_depth, dmr_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sizes_ok(B, P, F, W, H) || R < 0) return DMR_ETOOLARGE;
+    if (B == 0) return DMR_OK;
+    if (!background || !inv_mv_mats || !inv_proj_mats || !image_buffer || !out_color || !out_depth ||
+        (R > 0 && (!binning_buffer || !face_buffer))) { set_error("null pointer"); return DMR_EINVAL; }
+    (void)point_buffer;
+    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
+    TriImageLayout IL = TriImageLayout::make(B, W, H);
+    uint2* ranges = at<uint2>(image_buffer, IL.ranges);
+    int rc = bin_sort_ranges(B, F, W, H, (size_t)R, R ? at<uint32_t>(face_buffer, FL.offsets) : nullptr,
+                             R ? at<uint2>(face_buffer, FL.rect) : nullptr,
+                             R ? at<uint32_t>(face_buffer, FL.depth_key) : nullptr, binning_buffer, ranges, stream);
+    if (rc) return rc;
+    TriRenderParams p = {};
+    p.B = B; p.F = F; p.W = W; p.H = H; p.P = P;
+    p.ranges = ranges;
+    if (R) {
+        BinningLayout BL = BinningLayout::make((size_t)R);
+        p.face_list = at<uint32_t>(binning_buffer, BL.vals_sorted);
+        p.records = at<TriRecord>(face_buffer, FL.records);
+    }
+    p.bg = background; p.inv_mv = inv_mv_mats; p.inv_proj = inv_proj_mats;
+    p.final_T = at<float>(image_buffer, IL.final_T);
+    p.prev_T = at<float>(image_buffer, IL.prev_T);
+    p.n_contrib = at<uint32_t>(image_buffer, IL.n_contrib);
+    p.out_color = out_color; p.out_depth = out_depth;
+    return tri_render_forward(p, stream);
+}
+
+int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* background, const float* inv_mv_mats,
+                     const float* inv_proj_mats, const void* point_buffer, const void* face_buffer,
+                     const void* binning_buffer, const void* image_buffer, const float* dL_dcolor,
+                     const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity,
+                     float* dL_dvdepth, float* dL_dfintense, dmr_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!sizes_ok(B, P, F, W, H) || R < 0) return DMR_ETOOLARGE;
+    if (B == 0 || F == 0 || R == 0) return DMR_OK;   // nothing was composited: all gradients stay zero
+    if (!background || !inv_mv_mats || !inv_proj_mats || !face_buffer || !binning_buffer || !image_buffer ||
+        !dL_dcolor || !dL_ddepth || !dL_dverts || !dL_dvcolor || !dL_dfopacity || !dL_dvdepth || !dL_dfintense) {
+        set_error("null pointer");
+        return DMR_EINVAL;
+    }
+    (void)point_buffer;
+    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
+    TriImageLayout IL = TriImageLayout::make(B, W, H);
+    BinningLayout BL = BinningLayout::make((size_t)R);
+    TriRenderParams p = {};
+    p.B = B; p.F = F; p.W = W; p.H = H; p.P = P;
+    p.ranges = at<uint2>(image_buffer, IL.ranges);
+    p.face_list = at<uint32_t>(binning_buffer, BL.vals_sorted);
+    p.records = at<TriRecord>(face_buffer, FL.records);
+    p.bg = background; p.inv_mv = inv_mv_mats; p.inv_proj = inv_proj_mats;
+    p.final_T = const_cast<float*>(at<float>(image_buffer, IL.final_T));
+    p.prev_T = const_cast<float*>(at<float>(image_buffer, IL.prev_T));
+    p.n_contrib = const_cast<uint32_t*>(at<uint32_t>(image_buffer, IL.n_contrib));
+    p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
+    p.dL_dverts = dL_dverts; p.dL_dvcolor = dL_dvcolor; p.dL_dfopacity = dL_dfopacity;
+    p.dL_dvdepth = dL_dvdepth; p.dL_dfintense = dL_dfintense;
+    return tri_render_backward(p, stream);
+}
+
+int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, int H, size_t R, const void* buffer,
+                   const void** ptr, size_t* count)
+{
+    if (!buffer || !ptr || !count) { set_error("null pointer"); return DMR_EINVAL; }
+    (void)T;
+    const size_t BF = (size_t)B * F, BP = (size_t)B * P, BI = (size_t)B * W * H;
+    const size_t tiles = (size_t)B * ((W + DMR_TILE - 1) / DMR_TILE) * ((H + DMR_TILE - 1) / DMR_TILE);
+    size_t off = 0, n = 0;
+    if (kind == DMR_VIEW_VERTS_IMAGE) { off = 0; n = BP; }
+    else if (kind >= DMR_VIEW_KEYS_UNSORTED && kind <= DMR_VIEW_VALUES_SORTED) {
+        BinningLayout L = BinningLayout::make(R);
+        n = R;
+        off = kind == DMR_VIEW_KEYS_UNSORTED ? L.keys_unsorted : kind == DMR_VIEW_VALUES_UNSORTED ? L.vals_unsorted
+            : kind == DMR_VIEW_KEYS_SORTED ? L.keys_sorted : L.vals_sorted;
+    } else if (renderer == 0) {
+        TriFaceLayout FL = TriFaceLayout::make(BF);
+        TriImageLayout IL = TriImageLayout::make(B, W, H);
+        switch (kind) {
+        case DMR_VIEW_TILES_TOUCHED: off = FL.tiles_touched; n = BF; break;
+        case DMR_VIEW_FACE_OFFSETS:  off = FL.offsets; n = BF; break;
+        case DMR_VIEW_DEPTH_KEYS:    off = FL.depth_key; n = BF; break;
+        case DMR_VIEW_RANGES:        off = IL.ranges; n = tiles; break;
+        case DMR_VIEW_N_CONTRIB:     off = IL.n_contrib; n = BI; break;
+        case DMR_VIEW_FINAL_T:       off = IL.final_T; n = BI; break;
+        default: set_error("unknown view kind %d", kind); return DMR_EINVAL;
+        }
+    } else {
+        TetFaceLayout FL = TetFaceLayout::make(BF, (size_t)F, (size_t)T);
+        TetImageLayout IL = TetImageLayout::make(B, W, H);
+        switch (kind) {
+        case DMR_VIEW_TILES_TOUCHED: off = FL.tiles_touched; n = BF; break;
+        case DMR_VIEW_FACE_OFFSETS:  off = FL.offsets; n = BF; break;
+        case DMR_VIEW_DEPTH_KEYS:    off = FL.depth_key; n = BF; break;
+        case DMR_VIEW_RANGES:        off = IL.ranges; n = tiles; break;
+        case DMR_VIEW_N_CONTRIB:     off = IL.n_contrib; n = BI; break;
+        case DMR_VIEW_FINAL_T:       off = IL.final_log_T; n = BI; break;
+        case DMR_VIEW_FIRST_FACE:    off = IL.first_face; n = BI; break;
+        case DMR_VIEW_FIRST_TET:     off = IL.first_tet; n = BI; break;
+        default: set_error("unknown view kind %d", kind); return DMR_EINVAL;
+        }
+    }
+    *ptr = static_cast<const unsigned char*>(buffer) + off;
+    *count = n;
+    return DMR_OK;
+}
+
+}  // extern "C"

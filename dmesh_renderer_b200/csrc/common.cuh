@@ -1,0 +1,216 @@
+// common.cuh -- shared device helpers, workspace layouts and error plumbing of
+// libdmesh_b200.so (sm_100a only).
+//
+// Numerical contract: integer outputs of the binning stages
+// must be bit-identical to the reference, so every float expression that feeds
+// a float->int conversion keeps the reference's operation order (cited per
+// function) and is compiled with nvcc defaults (-fmad=true, IEEE div/sqrt, no
+// fast-math), exactly as the reference is built.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define DMR_TILE 16            // cuda_rasterizer/config.h:5-6 (BLOCK_X, BLOCK_Y)
+#define DMR_T_EPS 0.0001f      // cuda_rasterizer/auxiliary.h:8
+
+namespace dmr {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+#define DMR_CUDA(call)                                                     \
+    do {                                                                   \
+        cudaError_t e__ = (call);                                          \
+        if (e__ != cudaSuccess) return ::dmr::cuda_fail(e__, #call);       \
+    } while (0)
+#define DMR_LAUNCH_CHECK(name)                                             \
+    do {                                                                   \
+        cudaError_t e__ = cudaGetLastError();                              \
+        if (e__ != cudaSuccess) return ::dmr::cuda_fail(e__, name);        \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// small vector helpers.  dot/cross/transform keep the expression shape of the
+// reference (cuda_rasterizer/cuda_math.h:1524-1527, 1696-1699 and
+// auxiliary.h:71-90) so that nvcc contracts them into the same FMA chains.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b)
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+// column-major 4x4 * (p,1): auxiliary.h:71-90
+__device__ __forceinline__ float3 xform43(float3 p, const float* m)
+{
+    return f3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+              m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+              m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float4 xform44(float3 p, const float* m)
+{
+    return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+                       m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+                       m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+
+// auxiliary.h:245-253
+__device__ __forceinline__ float clamp_w(float w)
+{
+    const float eps = 1e-4;
+    if (w >= 0 && w < eps) return eps;
+    else if (w < 0 && w > -eps) return -eps;
+    return w;
+}
+// auxiliary.h:33-41 -- evaluated in DOUBLE then rounded (App. A.3)
+__device__ __forceinline__ float ndc2pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+__device__ __forceinline__ float pix2ndc(float v, int S) { return ((v * 2.0 + 1.0) / S) - 1.0; }
+
+// Pixel ray, tri flavour: cuda_rasterizer/forward.cu:199-230.
+// tet flavour (len = max(len,1e-4)): cuda_renderer/forward.cu:129-144.
+template <bool TET>
+__device__ __forceinline__ void pixel_ray(const float* inv_mv, const float* inv_proj, float pixfx, float pixfy,
+                                          int W, int H, float3& ro, float3& rd)
+{
+    ro = f3(inv_mv[12], inv_mv[13], inv_mv[14]);
+    float nx = pix2ndc(pixfx, W);
+    float ny = pix2ndc(pixfy, H);
+    float4 pv = xform44(f3(nx, ny, -1.0f), inv_proj);
+    float4 pw = xform44(f3(pv.x, pv.y, pv.z), inv_mv);
+    rd = f3(pw.x, pw.y, pw.z) - ro;
+    float len;
+    if (TET) {
+        len = sqrtf(dot3(rd, rd));
+        len = fmaxf(len, 0.0001f);
+    } else {
+        len = sqrtf(dot3(rd, rd)) + 0.0000001f;
+    }
+    rd = rd / len;
+}
+
+// ---------------------------------------------------------------------------
+// raw memory helpers
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Per-(view,face) setup record of the tri renderer: everything the per-tile
+// render kernels need, gathered ONCE per face in the face-preprocess kernel so
+// that staging an instance is one contiguous 144-byte copy instead of the
+// reference's ~10 scattered sectors behind two levels of indirection
+// (cuda_rasterizer/forward.cu:358-400).
+//
+// Edge functions: in_tri() (cuda_rasterizer/auxiliary.h:179-243) evaluates
+//     s_k = cx_k*(py - y_k) - cy_k*(px - x_k) - bias_k      (32-bit, wrapping)
+// with px = 16*x+8, py = 16*y+8 for the pixel centre.  All operations are ring
+// operations mod 2^32, so the affine form
+//     s_k = ea[k]*x + eb[k]*y + ec[k]                        (mod 2^32)
+// with ea = -16*cy, eb = 16*cx, ec = 8*cx - 8*cy + cy*x_k - cx*y_k - bias is
+// bit-identical, including the reference's overflow behaviour.  A degenerate
+// triangle (area == 0) is encoded as ea=eb=ec=0 (never covered).
+// ---------------------------------------------------------------------------
+struct __align__(16) TriRecord {
+    // q0..q2: hot part (coverage test)
+    uint32_t ea0, eb0, ec0; float opacity;
+    uint32_t ea1, eb1, ec1; float intense;
+    uint32_t ea2, eb2, ec2; uint32_t flags;   // bit0: edge values cannot overflow on screen
+    // q3..q8: shading part
+    float v0[3], v1[3], v2[3];                // world positions
+    float c0[3], c1[3], c2[3];                // vertex colours
+    float d0, d1, d2;                         // per-view vertex depths
+    int   i0, i1, i2;                         // vertex ids (gradient scatter)
+};
+static_assert(sizeof(TriRecord) == 144, "TriRecord must be 9 x 16 bytes");
+#define DMR_REC_WORDS 36
+#define DMR_REC_SAFE 1u
+
+// ---------------------------------------------------------------------------
+// workspace layouts (all offsets 256-byte aligned)
+// ---------------------------------------------------------------------------
+#define DMR_SCAN_THREADS 256
+#define DMR_SCAN_ITEMS 16
+#define DMR_SCAN_TILE (DMR_SCAN_THREADS * DMR_SCAN_ITEMS)
+
+struct TriFaceLayout {
+    size_t tiles_touched, offsets, depth_key, rect, scan_state, records, total;
+    __host__ static TriFaceLayout make(size_t BF)
+    {
+        TriFaceLayout L;
+        size_t o = 0;
+        L.tiles_touched = o; o = align_up(o + 4 * BF, 256);
+        L.offsets = o;       o = align_up(o + 4 * BF, 256);
+        L.depth_key = o;     o = align_up(o + 4 * BF, 256);
+        L.rect = o;          o = align_up(o + 8 * BF, 256);
+        size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+        L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);   // [0]=ticket, [1]=total, [32..]=descriptors
+        L.records = o;       o = align_up(o + sizeof(TriRecord) * BF, 256);
+        L.total = o + 256;
+        return L;
+    }
+};
+
+struct TriImageLayout {
+    size_t final_T, prev_T, n_contrib, ranges, total;
+    __host__ static TriImageLayout make(size_t B, size_t W, size_t H)
+    {
+        TriImageLayout L;
+        size_t BI = B * W * H;
+        size_t tiles = B * ((W + DMR_TILE - 1) / DMR_TILE) * ((H + DMR_TILE - 1) / DMR_TILE);
+        size_t o = 0;
+        L.final_T = o;   o = align_up(o + 4 * BI, 256);
+        L.prev_T = o;    o = align_up(o + 4 * BI, 256);
+        L.n_contrib = o; o = align_up(o + 4 * BI, 256);
+        L.ranges = o;    o = align_up(o + 8 * tiles, 256);
+        L.total = o + 256;
+        return L;
+    }
+};
+
+// binning buffer: A = unsorted (duplicate output), B = sorted, then sort temp
+struct BinningLayout {
+    size_t keys_unsorted, vals_unsorted, keys_sorted, vals_sorted, sort_temp, total;
+    __host__ static BinningLayout make(size_t R);
+};
+
+// ---------------------------------------------------------------------------
+// stage launchers (host)
+// ---------------------------------------------------------------------------
+size_t sort_temp_bytes(size_t n);
+int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
+               int end_bit, void* temp, cudaStream_t stream);
+
+int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* state /* zeroed, ntile+64 words */,
+                       int32_t* total_host /* pinned, may be null */, cudaStream_t stream);
+
+int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32_t* offsets, const uint2* rect,
+                        const uint32_t* depth_key, uint64_t* keys, uint32_t* vals, size_t R, cudaStream_t stream);
+
+int identify_tile_ranges(const uint64_t* keys_sorted, size_t R, uint2* ranges /* zeroed */, cudaStream_t stream);
+
+uint32_t higher_msb(uint32_t n);
+
+}  // namespace dmr

@@ -1,0 +1,223 @@
+// preprocess.cu -- per-vertex projection and per-(view,face) setup.
+//
+//   preprocess_points_kernel   replaces preprocessPointCUDA
+//                              (cuda_rasterizer/forward.cu:17-47, identical copy
+//                              cuda_renderer/forward.cu:21-52)
+//   tri_preprocess_faces_kernel replaces preprocessFaceCUDA
+//                              (cuda_rasterizer/forward.cu:76-149) and hoists the
+//                              per-face part of in_tri (auxiliary.h:179-243) and
+//                              the per-instance gathers of renderCUDA
+//                              (forward.cu:358-400) into one 144-byte record.
+//
+// Both are HBM-bound streaming kernels: one thread per element, 128-bit
+// loads/stores, records transposed through shared memory so that the global
+// write of a block's 256 records is one contiguous 36 KB burst.
+#include "tri.cuh"
+
+namespace dmr {
+
+// ---------------------------------------------------------------------------
+// points: out[b*P+p] = { pix.x, pix.y, ndc.z, verts_depth[b,p] }
+// algorithmic bytes per (b,p): 12 (xyz) + 4 (depth) read, 16 written.
+// The reference also stores ndc.xy (never read downstream).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_points_kernel(
+    int B, int P, int W, int H,
+    const float* __restrict__ verts, const float* __restrict__ mv_mats, const float* __restrict__ proj_mats,
+    const float* __restrict__ verts_depth,   // may be null (tet path: unused lane)
+    float4* __restrict__ vimg)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (idx >= (size_t)P) return;
+    const float* mv = mv_mats + 16 * b;
+    const float* pj = proj_mats + 16 * b;
+
+    float3 p = f3(verts[3 * idx + 0], verts[3 * idx + 1], verts[3 * idx + 2]);
+    float3 pv = xform43(p, mv);
+    float4 pp = xform44(pv, pj);
+    float pw = 1.0 / clamp_w(pp.w);                 // forward.cu:38 (double literal, float result)
+    float3 ndc = f3(pp.x * pw, pp.y * pw, pp.z * pw);
+
+    float4 o;
+    o.x = ndc2pix(ndc.x, W);
+    o.y = ndc2pix(ndc.y, H);
+    o.z = ndc.z;
+    o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : 0.0f;
+    vimg[(size_t)b * P + idx] = o;
+}
+
+int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
+                      const float* verts_depth, float4* vimg, cudaStream_t stream)
+{
+    if (B <= 0 || P <= 0) return 0;
+    dim3 grid((P + 255) / 256, B);
+    preprocess_points_kernel<<<grid, 256, 0, stream>>>(B, P, W, H, verts, mv, proj, verts_depth, vimg);
+    DMR_LAUNCH_CHECK("preprocess_points_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Tile rectangle of a triangle: getRectFromTri (auxiliary.h:55-69).
+// Float -> int is cvt.rzi (saturating, NaN -> 0) as in the reference.  A
+// rectangle whose max is not above its min in either axis covers 0 tiles.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tile_rect(float2 p0, float2 p1, float2 p2, int gx, int gy, int& x0, int& y0, int& x1,
+                                          int& y1)
+{
+    float mnx = fminf(fminf(p0.x, p1.x), p2.x), mny = fminf(fminf(p0.y, p1.y), p2.y);
+    float mxx = fmaxf(fmaxf(p0.x, p1.x), p2.x), mxy = fmaxf(fmaxf(p0.y, p1.y), p2.y);
+    x0 = min(gx, max(0, (int)(mnx / DMR_TILE)));
+    y0 = min(gy, max(0, (int)(mny / DMR_TILE)));
+    x1 = min(gx, max(0, (int)((unsigned)(int)(mxx / DMR_TILE) + 1u)));
+    y1 = min(gy, max(0, (int)((unsigned)(int)(mxy / DMR_TILE) + 1u)));
+}
+
+// ---------------------------------------------------------------------------
+// Edge-function setup: the per-face half of in_tri (auxiliary.h:191-240).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void edge_setup(float2 p1, float2 p2, float2 p3, int W, int H, uint32_t* ea, uint32_t* eb,
+                                           uint32_t* ec, uint32_t& flags)
+{
+    const float subpixel = 16.0f;
+    int x1 = (int)(p1.x * subpixel), y1 = (int)(p1.y * subpixel);
+    int x2 = (int)(p2.x * subpixel), y2 = (int)(p2.y * subpixel);
+    int x3 = (int)(p3.x * subpixel), y3 = (int)(p3.y * subpixel);
+    // wrapping 32-bit arithmetic throughout (the reference's int math wraps in hardware)
+    uint32_t ux1 = x1, uy1 = y1, ux2 = x2, uy2 = y2, ux3 = x3, uy3 = y3;
+    int area = (int)((ux2 - ux1) * (uy3 - uy1) - (ux3 - ux1) * (uy2 - uy1));
+    flags = 0;
+    if (area == 0) {
+        for (int k = 0; k < 3; k++) { ea[k] = 0; eb[k] = 0; ec[k] = 0; }
+        flags = DMR_REC_SAFE;
+        return;
+    }
+    if (area < 0) {   // make CCW: swap vertices 2 and 3
+        uint32_t t = ux2; ux2 = ux3; ux3 = t;
+        t = uy2; uy2 = uy3; uy3 = t;
+    }
+    uint32_t vx[3] = { ux1, ux2, ux3 }, vy[3] = { uy1, uy2, uy3 };
+    bool safe = true;
+    // exact (64-bit) check that no intermediate of the pixel test can overflow
+    {
+        long long lx1 = (int)ux1, ly1 = (int)uy1, lx2 = (int)ux2, ly2 = (int)uy2, lx3 = (int)ux3, ly3 = (int)uy3;
+        long long a64 = (lx2 - lx1) * (ly3 - ly1) - (lx3 - lx1) * (ly2 - ly1);
+        const long long lim = 0x3fffffffLL;
+        if (llabs(lx1) > lim || llabs(ly1) > lim || llabs(lx2) > lim || llabs(ly2) > lim || llabs(lx3) > lim ||
+            llabs(ly3) > lim || llabs(a64) > 0x7fffffffLL)
+            safe = false;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int kn = (k + 1) % 3;
+        uint32_t cx = vx[k] - vx[kn], cy = vy[k] - vy[kn];
+        int scx = (int)cx, scy = (int)cy;
+        uint32_t bias = (scy > 0 || (scy == 0 && scx > 0)) ? 1u : 0u;
+        ea[k] = (uint32_t)0 - 16u * cy;
+        eb[k] = 16u * cx;
+        ec[k] = 8u * cx - 8u * cy + cy * vx[k] - cx * vy[k] - bias;
+        if (safe) {
+            long long lcx = (long long)(int)vx[k] - (long long)(int)vx[kn];
+            long long lcy = (long long)(int)vy[k] - (long long)(int)vy[kn];
+            long long A = -16 * lcy, Bc = 16 * lcx;
+            long long C = 8 * lcx - 8 * lcy + lcy * (long long)(int)vx[k] - lcx * (long long)(int)vy[k] - (long long)bias;
+            long long bound = llabs(A) * (long long)W + llabs(Bc) * (long long)H + llabs(C);
+            if (llabs(lcx) > 0x7ffffffLL || llabs(lcy) > 0x7ffffffLL || bound > 0x7fffffffLL) safe = false;
+        }
+    }
+    flags = safe ? DMR_REC_SAFE : 0u;
+}
+
+// ---------------------------------------------------------------------------
+// faces (tri): tiles_touched, tile rect, depth key, 144-byte record.
+// algorithmic bytes per (b,f): read 12 (idx) + 3*16 (vimg) + 3*12 (pos) +
+// 3*12 (colour) + 4 + 4, write 4 + 4 + 8 + 144.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
+    int B, int P, int F, int W, int H, int gx, int gy,
+    const int* __restrict__ faces, const float4* __restrict__ vimg,
+    const float* __restrict__ verts, const float* __restrict__ verts_color,
+    const float* __restrict__ faces_opacity, const float* __restrict__ faces_intense,
+    uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
+    TriRecord* __restrict__ records)
+{
+    __shared__ uint4 s_rec[256 * 9];
+    const int tid = threadIdx.x;
+    const size_t f0 = (size_t)blockIdx.x * 256;
+    const int b = blockIdx.y;
+    const size_t f = f0 + tid;
+    const bool valid = f < (size_t)F;
+
+    if (valid) {
+        int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+        const float4* vb = vimg + (size_t)b * P;
+        float4 a0 = vb[i0], a1 = vb[i1], a2 = vb[i2];
+
+        // forward.cu:101-121
+        float max_z = a0.z, min_z = a0.z, depth = 0;
+        depth += a0.z;
+        max_z = fmaxf(max_z, a1.z); min_z = fminf(min_z, a1.z); depth += a1.z;
+        max_z = fmaxf(max_z, a2.z); min_z = fminf(min_z, a2.z); depth += a2.z;
+        depth = depth / 3.0f;
+
+        uint32_t touched = 0;
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        float2 p0 = make_float2(a0.x, a0.y), p1 = make_float2(a1.x, a1.y), p2 = make_float2(a2.x, a2.y);
+        if (!(max_z < -1.0f || min_z > 1.0f)) {    // forward.cu:124
+            tile_rect(p0, p1, p2, gx, gy, x0, y0, x1, y1);
+            if (x1 > x0 && y1 > y0) touched = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
+        }
+        // forward.cu:146-148
+        float dk = (depth + 1.0f) * 0.5f;
+        if (dk < 0.0f) dk = 0.0f;
+        if (dk > 1.0f) dk = 1.0f;
+
+        size_t bf = (size_t)b * F + f;
+        tiles_touched[bf] = touched;
+        depth_key[bf] = __float_as_uint(dk);
+        rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+
+        uint32_t ea[3], eb[3], ec[3], flags;
+        edge_setup(p0, p1, p2, W, H, ea, eb, ec, flags);
+
+        uint4* r = s_rec + tid * 9;
+        r[0] = make_uint4(ea[0], eb[0], ec[0], __float_as_uint(faces_opacity[f]));
+        r[1] = make_uint4(ea[1], eb[1], ec[1], __float_as_uint(faces_intense[bf]));
+        r[2] = make_uint4(ea[2], eb[2], ec[2], flags);
+        const float* q0 = verts + 3 * (size_t)i0; const float* q1 = verts + 3 * (size_t)i1; const float* q2 = verts + 3 * (size_t)i2;
+        const float* k0 = verts_color + 3 * (size_t)i0; const float* k1 = verts_color + 3 * (size_t)i1; const float* k2 = verts_color + 3 * (size_t)i2;
+        float w[24];
+        w[0] = q0[0]; w[1] = q0[1]; w[2] = q0[2]; w[3] = q1[0]; w[4] = q1[1]; w[5] = q1[2];
+        w[6] = q2[0]; w[7] = q2[1]; w[8] = q2[2];
+        w[9] = k0[0]; w[10] = k0[1]; w[11] = k0[2]; w[12] = k1[0]; w[13] = k1[1]; w[14] = k1[2];
+        w[15] = k2[0]; w[16] = k2[1]; w[17] = k2[2];
+        w[18] = a0.w; w[19] = a1.w; w[20] = a2.w;
+        w[21] = __int_as_float(i0); w[22] = __int_as_float(i1); w[23] = __int_as_float(i2);
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            r[3 + q] = make_uint4(__float_as_uint(w[4 * q]), __float_as_uint(w[4 * q + 1]), __float_as_uint(w[4 * q + 2]),
+                                  __float_as_uint(w[4 * q + 3]));
+    }
+    __syncthreads();
+    // coalesced write-out of the block's records
+    size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
+    uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
+    for (size_t i = tid; i < nvalid * 9; i += 256) dst[i] = s_rec[i];
+}
+
+int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
+                         const float* verts_color, const float* faces_opacity, const float* faces_intense,
+                         uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TriRecord* records,
+                         cudaStream_t stream)
+{
+    if (B <= 0 || F <= 0) return 0;
+    int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
+    dim3 grid((F + 255) / 256, B);
+    tri_preprocess_faces_kernel<<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
+                                                         faces_opacity, faces_intense, tiles_touched, depth_key, rect,
+                                                         records);
+    DMR_LAUNCH_CHECK("tri_preprocess_faces_kernel");
+    return 0;
+}
+
+}  // namespace dmr

@@ -1,0 +1,330 @@
+// radix_sort.cu -- hand-written onesweep LSD radix sort of (u64 key, u32 value)
+// pairs on bits [0, end_bit).  Replaces cub::DeviceRadixSort::SortPairs
+// (cuda_rasterizer/rasterizer_impl.cu:319-324, cuda_renderer/renderer_impl.cu:335-340).
+// The result is fully specified (stable ascending order on the selected bits),
+// so it is bit-identical to CUB's.
+//
+// Structure (per sort):
+//   1. hist_kernel     one read of the keys -> all per-pass 256-bin histograms
+//   2. plan_kernel     exclusive scan of each histogram; passes whose digit is
+//                      constant over all keys are skipped (identity permutation);
+//                      ping-pong buffers are assigned so that the LAST executed
+//                      pass writes the caller's output arrays
+//   3. onesweep_kernel one launch per pass: tile-local stable ranking with
+//                      warp match, decoupled look-back across tiles for the
+//                      per-digit global prefix, scatter through shared memory so
+//                      global stores are coalesced per digit run.
+// Algorithmic bytes: 8 B/key (histogram) + 24 B/key per executed pass.
+#include "common.cuh"
+
+namespace dmr {
+
+#define RS_THREADS 256
+#define RS_KPT 16
+#define RS_TILE (RS_THREADS * RS_KPT)
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_MAX_PASS 8
+
+#define RS_FLAG_AGG  (1u << 30)
+#define RS_FLAG_INCL (2u << 30)
+#define RS_VAL_MASK  ((1u << 30) - 1u)
+
+// control block living in the temp buffer (zeroed before every sort)
+struct SortCtl {
+    uint32_t ticket[RS_MAX_PASS];
+    uint32_t exec[RS_MAX_PASS];
+    uint32_t src[RS_MAX_PASS];   // 0 = input, 1 = output, 2 = temp
+    uint32_t dst[RS_MAX_PASS];
+};
+
+struct SortTempLayout {
+    size_t keys_tmp, vals_tmp, zero_begin, hist, ctl, desc, total;
+    size_t ntile;
+    __host__ static SortTempLayout make(size_t n)
+    {
+        SortTempLayout L;
+        L.ntile = (n + RS_TILE - 1) / RS_TILE;
+        size_t o = 0;
+        L.keys_tmp = o; o = align_up(o + 8 * n, 256);
+        L.vals_tmp = o; o = align_up(o + 4 * n, 256);
+        L.zero_begin = o;
+        L.hist = o;     o = align_up(o + 4 * 256 * RS_MAX_PASS, 256);
+        L.ctl = o;      o = align_up(o + sizeof(SortCtl), 256);
+        L.desc = o;     o = align_up(o + 4 * 256 * L.ntile * RS_MAX_PASS, 256);
+        L.total = o + 256;
+        return L;
+    }
+};
+
+size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n).total; }
+
+// ---------------------------------------------------------------------------
+// 1. histograms of all passes in one sweep
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rs_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int npass, int end_bit,
+                                                      uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t s_hist[RS_MAX_PASS * 256];
+    for (int i = threadIdx.x; i < npass * 256; i += 256) s_hist[i] = 0;
+    __syncthreads();
+
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (size_t base = (size_t)blockIdx.x * 256; base < n; base += stride) {
+        size_t i = base + threadIdx.x;
+        bool valid = i < n;
+        uint64_t k = valid ? keys[i] : 0;
+        unsigned act = __ballot_sync(0xffffffffu, valid);
+        for (int p = 0; p < npass; p++) {
+            int shift = 8 * p;
+            uint32_t mask = (end_bit - shift >= 8) ? 0xffu : ((1u << (end_bit - shift)) - 1u);
+            uint32_t d = (uint32_t)(k >> shift) & mask;
+            // constant digits (e.g. the top depth byte, the batch bits) would be a
+            // 32-way same-address shared atomic: aggregate them in the warp.
+            uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act) - 1);
+            bool uni = __all_sync(0xffffffffu, !valid || d == d0);
+            if (uni) {
+                if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1) && act) atomicAdd(&s_hist[p * 256 + d0], __popc(act));
+            } else if (valid) {
+                atomicAdd(&s_hist[p * 256 + d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += 256) {
+        uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 2. plan: exclusive scans + pass skipping + buffer assignment (1 block)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rs_plan_kernel(uint32_t* __restrict__ hist, SortCtl* __restrict__ ctl, size_t n,
+                                                      int npass)
+{
+    __shared__ uint32_t s_scan[256];
+    __shared__ uint32_t s_skip[RS_MAX_PASS];
+    const int tid = threadIdx.x;
+    for (int p = 0; p < npass; p++) {
+        uint32_t c = hist[p * 256 + tid];
+        if (tid == 0) s_skip[p] = 0;
+        __syncthreads();
+        if ((size_t)c == n) s_skip[p] = 1;   // every key has the same digit -> identity pass
+        s_scan[tid] = c;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            uint32_t t = (tid >= d) ? s_scan[tid - d] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        hist[p * 256 + tid] = s_scan[tid] - c;   // exclusive
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int nexec = 0;
+        for (int p = 0; p < npass; p++) nexec += s_skip[p] ? 0 : 1;
+        if (nexec == 0) { s_skip[0] = 0; nexec = 1; }   // always move input -> output
+        int k = 0;
+        uint32_t cur = 0;   // where the data currently lives
+        for (int p = 0; p < npass; p++) {
+            if (s_skip[p]) { ctl->exec[p] = 0; continue; }
+            uint32_t dst = ((nexec - 1 - k) % 2 == 0) ? 1u : 2u;
+            ctl->exec[p] = 1;
+            ctl->src[p] = cur;
+            ctl->dst[p] = dst;
+            cur = dst;
+            k++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 3. one onesweep pass
+// ---------------------------------------------------------------------------
+struct RsBuffers {
+    const uint64_t* kin; const uint32_t* vin;
+    uint64_t* kout; uint32_t* vout;
+    uint64_t* ktmp; uint32_t* vtmp;
+};
+
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(RsBuffers buf, size_t n, int pass, int end_bit,
+                                                                  const uint32_t* __restrict__ hist_excl,
+                                                                  SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
+{
+    if (!ctl->exec[pass]) return;
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_smem);                       // RS_TILE
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + 8 * RS_TILE);         // RS_TILE
+    uint32_t* s_whist = s_vals + RS_TILE;                                          // RS_WARPS * 256
+    uint32_t* s_dbase = s_whist + RS_WARPS * 256;                                  // 256: local exclusive digit base
+    int32_t*  s_gbase = reinterpret_cast<int32_t*>(s_dbase + 256);                 // 256: global pos - local pos (wrapping)
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s = ctl->src[pass], d_sel = ctl->dst[pass];
+    const uint64_t* kin = (s == 0) ? buf.kin : (s == 1 ? buf.kout : buf.ktmp);
+    const uint32_t* vin = (s == 0) ? buf.vin : (s == 1 ? buf.vout : buf.vtmp);
+    uint64_t* kout = (d_sel == 1) ? buf.kout : buf.ktmp;
+    uint32_t* vout = (d_sel == 1) ? buf.vout : buf.vtmp;
+
+    if (tid == 0) s_tile = atomicAdd(&ctl->ticket[pass], 1u);
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) s_whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const size_t tile_base = (size_t)tile * RS_TILE;
+    const uint32_t nvalid = (uint32_t)((n - tile_base < RS_TILE) ? (n - tile_base) : RS_TILE);
+
+    const int shift = 8 * pass;
+    const uint32_t dmask = (end_bit - shift >= 8) ? 0xffu : ((1u << (end_bit - shift)) - 1u);
+
+    // warp-striped load: item i of lane l sits at warp_base + i*32 + l, so that
+    // (i, lane) order == global order (stability)
+    const uint32_t wbase = warp * (32 * RS_KPT);
+    uint64_t key[RS_KPT];
+    uint32_t val[RS_KPT];
+#pragma unroll
+    for (int i = 0; i < RS_KPT; i++) {
+        uint32_t loc = wbase + i * 32 + lane;
+        bool ok = loc < nvalid;
+        key[i] = ok ? kin[tile_base + loc] : ~0ull;
+        val[i] = ok ? vin[tile_base + loc] : 0u;
+    }
+
+    // stable rank inside the warp, digit by digit occurrence
+    uint32_t rank[RS_KPT];
+    uint32_t* wh = s_whist + warp * 256;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < RS_KPT; i++) {
+        uint32_t loc = wbase + i * 32 + lane;
+        uint32_t d = (loc < nvalid) ? ((uint32_t)(key[i] >> shift) & dmask) : 256u + 0u;   // padding: own class
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t before = __popc(peers & lt_mask);
+        uint32_t old = 0;
+        if (d < 256u && lane == leader) { old = wh[d]; wh[d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = old + before;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread t owns digit t: exclusive scan over warps, tile count
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+        uint32_t t = s_whist[w * 256 + tid];
+        s_whist[w * 256 + tid] = count;
+        count += t;
+    }
+    // publish the tile aggregate as early as possible
+    uint32_t* my_desc = desc + ((size_t)pass * gridDim.x + tile) * 256 + tid;
+    st_volatile_u32(my_desc, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | count);
+
+    // exclusive scan over digits (local base inside the tile)
+    {
+        uint32_t incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __shared__ uint32_t s_wsum[RS_WARPS];
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += s_wsum[w];
+        s_dbase[tid] = woff + incl - count;
+    }
+
+    // decoupled look-back for digit `tid`
+    uint32_t excl = 0;
+    if (tile > 0) {
+        long long t = (long long)tile - 1;
+        while (t >= 0) {
+            const uint32_t* p = desc + ((size_t)pass * gridDim.x + t) * 256 + tid;
+            uint32_t v;
+            do { v = ld_volatile_u32(p); } while ((v >> 30) == 0);
+            excl += v & RS_VAL_MASK;
+            if ((v >> 30) == 2u) break;
+            t--;
+        }
+        st_volatile_u32(my_desc, RS_FLAG_INCL | (excl + count));
+    }
+    s_gbase[tid] = (int32_t)(hist_excl[pass * 256 + tid] + excl - s_dbase[tid]);
+    __syncthreads();
+
+    // scatter into shared memory in digit order
+#pragma unroll
+    for (int i = 0; i < RS_KPT; i++) {
+        uint32_t loc = wbase + i * 32 + lane;
+        if (loc < nvalid) {
+            uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
+            uint32_t pos = s_dbase[d] + wh[d] + rank[i];
+            s_keys[pos] = key[i];
+            s_vals[pos] = val[i];
+        }
+    }
+    __syncthreads();
+
+    // coalesced write-out
+    for (uint32_t p = tid; p < nvalid; p += RS_THREADS) {
+        uint64_t k = s_keys[p];
+        uint32_t d = (uint32_t)(k >> shift) & dmask;
+        size_t g = (size_t)(uint32_t)(s_gbase[d] + (int32_t)p);
+        kout[g] = k;
+        vout[g] = s_vals[p];
+    }
+}
+
+static const size_t RS_SMEM_BYTES = 8 * RS_TILE + 4 * RS_TILE + 4 * RS_WARPS * 256 + 4 * 256 + 4 * 256;
+
+int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
+               int end_bit, void* temp, cudaStream_t stream)
+{
+    if (n == 0) return 0;
+    if (end_bit < 1 || end_bit > 64) { set_error("sort_pairs: end_bit %d out of range", end_bit); return 1; }
+    if (n >= (1ull << 30)) { set_error("sort_pairs: n=%zu exceeds 2^30", n); return 3; }
+    const int npass = (end_bit + 7) / 8;
+    SortTempLayout L = SortTempLayout::make(n);
+    unsigned char* t = static_cast<unsigned char*>(temp);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(t + L.hist);
+    SortCtl* ctl = reinterpret_cast<SortCtl*>(t + L.ctl);
+    uint32_t* desc = reinterpret_cast<uint32_t*>(t + L.desc);
+    size_t zero_bytes = (L.desc - L.zero_begin) + 4 * 256 * L.ntile * (size_t)npass;
+    DMR_CUDA(cudaMemsetAsync(t + L.zero_begin, 0, zero_bytes, stream));
+
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    size_t hblocks = (n + 255) / 256;
+    size_t hmax = (size_t)sm_count * 8;
+    if (hblocks > hmax) hblocks = hmax;
+    rs_hist_kernel<<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
+    DMR_LAUNCH_CHECK("rs_hist_kernel");
+    rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
+    DMR_LAUNCH_CHECK("rs_plan_kernel");
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMR_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+        attr_set = true;
+    }
+    RsBuffers buf;
+    buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
+    buf.ktmp = reinterpret_cast<uint64_t*>(t + L.keys_tmp);
+    buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
+    for (int p = 0; p < npass; p++) {
+        rs_onesweep_kernel<<<(unsigned)L.ntile, RS_THREADS, RS_SMEM_BYTES, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
+        DMR_LAUNCH_CHECK("rs_onesweep_kernel");
+    }
+    return 0;
+}
+
+}  // namespace dmr

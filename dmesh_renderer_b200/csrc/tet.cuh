@@ -1,0 +1,118 @@
+// tet.cuh -- records, workspace layouts and launch interface of the tet renderer.
+#pragma once
+#include "common.cuh"
+
+namespace dmr {
+
+// Per-(view,face) record staged by the first-intersection kernel
+// (replaces the gathers of cuda_renderer/forward.cu:368-381): 48 bytes.
+struct __align__(16) TetFaceRec {
+    float p0[3], p1[3], p2[3];   // world positions in faces[] order
+    float min_depth, max_depth;  // clamped (z+1)/2, cuda_renderer/forward.cu:253-259
+    uint32_t pad;
+};
+static_assert(sizeof(TetFaceRec) == 48, "TetFaceRec must be 3 x 16 bytes");
+
+// View-independent per-tet adjacency record used by the ray march.  The
+// reference re-gathers, at every step, tet_faces -> faces -> verts (3 dependent
+// levels), the tet's 4 vertices four times over and face_tets
+// (cuda_renderer/forward.cu:672-768, ~670 B per step).  One 224-byte record per
+// tet turns that into a single dependent load.
+struct TetSide {
+    int face;                    // tet_faces[4*t + k]
+    int next_tet;                // first entry of face_tets[face] that is neither t nor -1, else -1
+    float p0[3], p1[3], p2[3];   // face vertices in faces[] order
+    float n[3];                  // outward unit normal of `face` w.r.t. this tet (auxiliary.h:345-394)
+};
+struct __align__(16) TetRec { TetSide side[4]; };
+static_assert(sizeof(TetRec) == 224, "TetRec must be 14 x 16 bytes");
+
+// View-independent per-face shading record: 64 bytes.
+struct __align__(16) TetShade {
+    float c0[3], c1[3], c2[3];   // vertex colours
+    float opacity;
+    int i0, i1, i2;              // vertex ids (gradient scatter)
+    int t0, t1;                  // face_tets[2f], face_tets[2f+1]
+    uint32_t pad;
+};
+static_assert(sizeof(TetShade) == 64, "TetShade must be 4 x 16 bytes");
+
+struct TetFaceLayout {
+    size_t tiles_touched, offsets, depth_key, rect, scan_state, face_rec, tet_rec, shade, total;
+    __host__ static TetFaceLayout make(size_t BF, size_t F, size_t T)
+    {
+        TetFaceLayout L;
+        size_t o = 0;
+        L.tiles_touched = o; o = align_up(o + 4 * BF, 256);
+        L.offsets = o;       o = align_up(o + 4 * BF, 256);
+        L.depth_key = o;     o = align_up(o + 4 * BF, 256);
+        L.rect = o;          o = align_up(o + 8 * BF, 256);
+        size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+        L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);
+        L.face_rec = o;      o = align_up(o + sizeof(TetFaceRec) * BF, 256);
+        L.tet_rec = o;       o = align_up(o + sizeof(TetRec) * T, 256);
+        L.shade = o;         o = align_up(o + sizeof(TetShade) * F, 256);
+        L.total = o + 256;
+        return L;
+    }
+};
+
+struct TetImageLayout {
+    size_t n_contrib, ranges, final_log_T, prev_log_T, first_face, first_tet, last_face, last_tet, active, jitter, total;
+    __host__ static TetImageLayout make(size_t B, size_t W, size_t H)
+    {
+        TetImageLayout L;
+        size_t BI = B * W * H;
+        size_t tiles = B * ((W + DMR_TILE - 1) / DMR_TILE) * ((H + DMR_TILE - 1) / DMR_TILE);
+        size_t o = 0;
+        L.n_contrib = o;   o = align_up(o + 4 * BI, 256);
+        L.ranges = o;      o = align_up(o + 8 * tiles, 256);
+        L.final_log_T = o; o = align_up(o + 4 * BI, 256);
+        L.prev_log_T = o;  o = align_up(o + 4 * BI, 256);
+        L.first_face = o;  o = align_up(o + 4 * BI, 256);
+        L.first_tet = o;   o = align_up(o + 4 * BI, 256);
+        L.last_face = o;   o = align_up(o + 4 * BI, 256);
+        L.last_tet = o;    o = align_up(o + 4 * BI, 256);
+        L.active = o;      o = align_up(o + BI, 256);
+        L.jitter = o;      o = align_up(o + 8 * BI, 256);   // float2 pixel coordinate, written only when seed > 0
+        L.total = o + 256;
+        return L;
+    }
+};
+
+struct TetParams {
+    int B, P, F, T, W, H;
+    // scene
+    const float* verts; const int* faces; const int* tets; const int* face_tets; const int* tet_faces;
+    const float* mv; const float* proj; const float* inv_mv; const float* inv_proj;
+    const float* faces_intense;   // [B,F]
+    const float* bg;
+    // records
+    const TetFaceRec* face_rec;   // [B*F]
+    const TetRec* tet_rec;        // [T]
+    const TetShade* shade;        // [F]
+    // binning
+    const uint2* ranges; const uint32_t* face_list;
+    // per-pixel state
+    const float2* jitter;         // null when ray_random_seed <= 0
+    int* first_face; int* first_tet; int* last_face; int* last_tet;
+    float* final_log_T; float* prev_log_T; uint32_t* n_contrib; uint8_t* active;
+    // outputs
+    float* out_color; float* out_depth; float* out_active;
+    // backward
+    const float* dL_dcolor; const float* dL_ddepth;
+    float* dL_dverts_color; float* dL_dfaces_opacity;
+};
+
+int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
+                         uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
+                         cudaStream_t stream);
+int tet_build_records(int P, int F, int T, const float* verts, const int* faces, const float* verts_color,
+                      const float* faces_opacity, const int* tets, const int* face_tets, const int* tet_faces,
+                      TetRec* tet_rec, TetShade* shade, cudaStream_t stream);
+int tet_jitter(int B, int W, int H, int seed, float2* jitter, cudaStream_t stream);
+int tet_first_intersect(const TetParams& p, cudaStream_t stream);
+int tet_march_forward(const TetParams& p, cudaStream_t stream);
+int tet_march_backward(const TetParams& p, cudaStream_t stream);
+
+}  // namespace dmr

@@ -1,0 +1,219 @@
+/*
+ * dmesh_b200.h -- C ABI of libdmesh_b200.so
+ *
+ * B200-native (sm_100a) replacement for the hot path of SonSang/dmesh_renderer:
+ * the tile-based differentiable rasterizer, tri renderer (cuda_rasterizer/) and
+ * tet renderer (cuda_renderer/).  Plain pointers and sizes only; no torch types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * the reference repository).  The Python `_C` shim
+ * (dmesh_renderer_b200/_C.py) binds exactly these symbols and re-creates the
+ * four pybind functions of ext.cpp:4-12 on top of them.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`
+ *   - all work is enqueued on `stream` (a cudaStream_t); the library never
+ *     synchronises the device except where stated, never allocates device
+ *     memory, and keeps no global state (re-entrant per stream)
+ *   - return value: 0 on success, non-zero DMR_E* code otherwise; the message
+ *     is available through dmr_last_error() (thread-local)
+ *   - matrices are the 16 floats of the reference's column-major convention
+ *     (cuda_rasterizer/auxiliary.h:71-90): x' = m[0]x + m[4]y + m[8]z + m[12]
+ *   - tile size is fixed at 16x16 (cuda_rasterizer/config.h:4-6)
+ */
+#ifndef DMESH_B200_H_
+#define DMESH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMR_OK            0
+#define DMR_EINVAL        1   /* bad argument (null pointer, negative size ...)   */
+#define DMR_ECUDA         2   /* a CUDA runtime call or kernel launch failed      */
+#define DMR_ETOOLARGE     3   /* a size exceeds the 32-bit index budget of a stage */
+
+typedef void* dmr_stream_t;   /* cudaStream_t */
+
+/* Library identification. */
+int         dmr_abi_version(void);
+const char* dmr_last_error(void);
+
+/* ------------------------------------------------------------------------ */
+/* Sizes of the opaque state buffers.                                        */
+/* Replaces required<VertState|FaceState|ImageState>() and the resize        */
+/* lambdas: cuda_rasterizer/rasterizer_impl.h:61-67, render.cu:18-24,        */
+/* rasterizer_impl.cu:200-221 (tri); cuda_renderer/renderer_impl.cu:225-238. */
+/* out[0]=point buffer, out[1]=face buffer, out[2]=image buffer (bytes).     */
+/* ------------------------------------------------------------------------ */
+int    dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3]);
+int    dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[3]);
+/* Replaces required<BinningState>(R): rasterizer_impl.cu:297-299.           */
+size_t dmr_binning_bytes(size_t R);
+
+/* ------------------------------------------------------------------------ */
+/* Tri renderer, forward, phase 1: preprocess + per-face records + scan.     */
+/* Replaces stages T1-T4 of CudaRasterizer::Rasterizer::forward              */
+/* (cuda_rasterizer/rasterizer_impl.cu:226-292): preprocessPointCUDA         */
+/* (forward.cu:17-47), preprocessFaceCUDA (forward.cu:76-149),               */
+/* cub::DeviceScan::InclusiveSum and the 4-byte D2H of num_rendered.         */
+/* `num_rendered_host` must be pinned host memory; the value is valid after  */
+/* the caller synchronises `stream` (this call does not synchronise).        */
+/* ------------------------------------------------------------------------ */
+int dmr_tri_forward_bin(
+    int B, int P, int F, int W, int H,
+    const float* verts,          /* [P,3]   */
+    const int*   faces,          /* [F,3]   */
+    const float* verts_color,    /* [P,3]   */
+    const float* faces_opacity,  /* [F]     */
+    const float* mv_mats,        /* [B,16]  */
+    const float* proj_mats,      /* [B,16]  */
+    const float* verts_depth,    /* [B,P]   */
+    const float* faces_intense,  /* [B,F]   */
+    void* point_buffer, void* face_buffer,
+    int32_t* num_rendered_host,
+    dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Tri renderer, forward, phase 2: binning + sort + tile ranges + render.    */
+/* Replaces stages T5-T10 (rasterizer_impl.cu:297-380): duplicateWithKeys    */
+/* (rasterizer_impl.cu:44-97), cub::DeviceRadixSort::SortPairs (319-324),    */
+/* the ranges memset + identifyTileRanges (102-124, 330-337),                */
+/* generateRaysCUDA (forward.cu:184-231) and renderCUDA (forward.cu:257-489).*/
+/* out_color [B,3,H,W], out_depth [B,1,H,W] are fully written.               */
+/* ------------------------------------------------------------------------ */
+int dmr_tri_forward_render(
+    int B, int P, int F, int W, int H, int R,
+    const float* background,     /* [3] device */
+    const float* inv_mv_mats,    /* [B,16] */
+    const float* inv_proj_mats,  /* [B,16] */
+    const void* point_buffer, void* face_buffer,
+    void* binning_buffer, void* image_buffer,
+    float* out_color, float* out_depth,
+    dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Tri renderer, backward.                                                   */
+/* Replaces CudaRasterizer::Rasterizer::backward                              */
+/* (rasterizer_impl.cu:387-467) -> TRI_BACKWARD::renderCUDA                   */
+/* (cuda_rasterizer/backward.cu:9-421).  The five gradient buffers must be   */
+/* zero-initialised by the caller (the reference does torch::zeros,          */
+/* render.cu:166-171); gradients are accumulated into them.                  */
+/* ------------------------------------------------------------------------ */
+int dmr_tri_backward(
+    int B, int P, int F, int W, int H, int R,
+    const float* background,
+    const float* inv_mv_mats, const float* inv_proj_mats,
+    const void* point_buffer, const void* face_buffer,
+    const void* binning_buffer, const void* image_buffer,
+    const float* dL_dcolor,      /* [B,3,H,W] */
+    const float* dL_ddepth,      /* [B,1,H,W] */
+    float* dL_dverts,            /* [P,3]  summed over views */
+    float* dL_dvcolor,           /* [P,3]  summed over views */
+    float* dL_dfopacity,         /* [F]    summed over views */
+    float* dL_dvdepth,           /* [B,P]  */
+    float* dL_dfintense,         /* [B,F]  */
+    dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Tet renderer, forward, phase 1.  Replaces E1, E4, E5 of                   */
+/* CudaRenderer::Renderer::forward (cuda_renderer/renderer_impl.cu:241-310): */
+/* preprocessPointCUDA (cuda_renderer/forward.cu:21-52), preprocessFaceCUDA  */
+/* (178-260), InclusiveSum + D2H; and builds the per-tet adjacency records   */
+/* that replace the per-step gathers of cuda_renderer/forward.cu:672-768.    */
+/* ------------------------------------------------------------------------ */
+int dmr_tet_forward_bin(
+    int B, int P, int F, int T, int W, int H,
+    const float* verts, const int* faces,
+    const float* verts_color, const float* faces_opacity,
+    const float* mv_mats, const float* proj_mats,
+    const int* tets,             /* [T,4] */
+    const int* face_tets,        /* [F,2], -1 = none */
+    const int* tet_faces,        /* [T,4] */
+    void* point_buffer, void* face_buffer,
+    int32_t* num_rendered_host,
+    dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Tet renderer, forward, phase 2.  Replaces E2/E3, E6-E10                   */
+/* (renderer_impl.cu:254-262, 312-409): generateRaysCUDA                     */
+/* (cuda_renderer/forward.cu:82-145, incl. the cuRAND XORWOW jitter when     */
+/* ray_random_seed > 0), duplicateWithKeys on min_depth                      */
+/* (renderer_impl.cu:44-99,318-329), SortPairs, identifyTileRanges,          */
+/* firstIntersectCUDA (forward.cu:298-445) and the ray-marching renderCUDA   */
+/* (forward.cu:485-815).  out_active [B,H,W] is 1.0f / 0.0f.                 */
+/* ------------------------------------------------------------------------ */
+int dmr_tet_forward_render(
+    int B, int P, int F, int T, int W, int H, int R,
+    int ray_random_seed,
+    const float* background,
+    const float* mv_mats, const float* proj_mats,
+    const float* inv_mv_mats, const float* inv_proj_mats,
+    const float* faces_intense,  /* [B,F] */
+    const void* point_buffer, void* face_buffer,
+    void* binning_buffer, void* image_buffer,
+    float* out_color, float* out_depth, float* out_active,
+    dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Tet renderer, backward.  Replaces CudaRenderer::Renderer::backward        */
+/* (renderer_impl.cu:413-498) -> TET_BACKWARD::renderCUDA                    */
+/* (cuda_renderer/backward.cu:86-487).  Gradient buffers zeroed by caller.   */
+/* ------------------------------------------------------------------------ */
+int dmr_tet_backward(
+    int B, int P, int F, int T, int W, int H,
+    int ray_random_seed,         /* same value as in the forward call */
+    const float* background,
+    const float* mv_mats, const float* proj_mats,
+    const float* inv_mv_mats, const float* inv_proj_mats,
+    const float* faces_intense,
+    const void* point_buffer, const void* face_buffer,
+    const void* image_buffer,
+    const float* dL_dcolor, const float* dL_ddepth,
+    float* dL_dverts_color,      /* [P,3] */
+    float* dL_dfaces_opacity,    /* [F]   */
+    dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
+/* Read-only views into the state buffers for the bit-exact parity checks    */
+/* (the reference exposes the same quantities through the fromChunk layouts, */
+/* rasterizer_impl.cu:127-171).  Returns a device pointer and element count. */
+/* ------------------------------------------------------------------------ */
+enum dmr_view_kind {
+    DMR_VIEW_VERTS_IMAGE    = 0,  /* float4[B*P] {img.x,img.y,ndc.z,depth}   point buffer */
+    DMR_VIEW_TILES_TOUCHED  = 1,  /* uint32[B*F]                              face buffer  */
+    DMR_VIEW_FACE_OFFSETS   = 2,  /* uint32[B*F] inclusive scan               face buffer  */
+    DMR_VIEW_DEPTH_KEYS     = 3,  /* uint32[B*F] float bits of the sort depth face buffer  */
+    DMR_VIEW_KEYS_UNSORTED  = 4,  /* uint64[R]                                binning      */
+    DMR_VIEW_VALUES_UNSORTED= 5,  /* uint32[R]                                binning      */
+    DMR_VIEW_KEYS_SORTED    = 6,  /* uint64[R]                                binning      */
+    DMR_VIEW_VALUES_SORTED  = 7,  /* uint32[R]                                binning      */
+    DMR_VIEW_RANGES         = 8,  /* uint2[B*tiles]                           image buffer */
+    DMR_VIEW_N_CONTRIB      = 9,  /* uint32[B*W*H]                            image buffer */
+    DMR_VIEW_FINAL_T        = 10, /* float[B*W*H] (tet: final log T)          image buffer */
+    DMR_VIEW_FIRST_FACE     = 11, /* int32[B*W*H] (tet only)                  image buffer */
+    DMR_VIEW_FIRST_TET      = 12  /* int32[B*W*H] (tet only)                  image buffer */
+};
+int dmr_debug_view(int renderer /*0=tri,1=tet*/, int kind,
+                   int B, int P, int F, int T, int W, int H, size_t R,
+                   const void* buffer, const void** ptr, size_t* count);
+
+/* ------------------------------------------------------------------------ */
+/* Stand-alone stable LSD radix sort of (uint64 key, uint32 value) pairs on  */
+/* bits [0, end_bit) -- the hand-written onesweep that replaces              */
+/* cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:319-324).  Exposed    */
+/* for unit tests and the sort micro-benchmark.  `temp` must hold            */
+/* dmr_sort_temp_bytes(n) bytes.  Inputs are not modified.                   */
+/* ------------------------------------------------------------------------ */
+size_t dmr_sort_temp_bytes(size_t n);
+int    dmr_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in,
+                      uint64_t* keys_out, uint32_t* vals_out,
+                      size_t n, int end_bit, void* temp, dmr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMESH_B200_H_ */

@@ -1,0 +1,131 @@
+"""GPU parity: CUDA tri path (through the public API -> _C shim -> C ABI) against
+the UNMODIFIED reference extension (oracle/_ref) on identical seeded scenes.
+
+Tolerances (BASELINE.json north_star):
+  * integer / indexing work (tiles_touched, offsets, R, sorted keys + values,
+    tile ranges, n_contrib): bit-exact
+  * forward images: <= 1e-5 max-abs
+  * gradients: <= 1e-4 relative L2 (atomic reordering allowed)
+"""
+import numpy as np
+import pytest
+import torch
+
+import ref_harness
+from dmesh_renderer_b200 import TriRenderer, TriRenderSettings, _C, debug, scenes
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def need_ref():
+    if ref_harness.ref_module() is None:
+        pytest.skip("oracle/_ref not built")
+
+
+def ours_forward(s):
+    mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
+    imv, ipj = torch.inverse(mv), torch.inverse(pj)
+    out = _C.render_tris(s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth,
+                         s.faces_intense, s.H, s.W)
+    return out, (mv, pj, imv, ipj)
+
+
+@pytest.mark.parametrize("name", ["tiny_tri", "small_tri", "C1", "C2"])
+def test_tri_intermediates_and_images(name):
+    need_ref()
+    s = scenes.to_device(scenes.config(name), "cuda")
+    B, P, F = s.mv_mats.shape[0], s.verts.shape[0], s.faces.shape[0]
+    ref = ref_harness.ref_tri_forward(s)
+    ri = ref_harness.ref_tri_intermediates(s, ref)
+    (R, color, depth, pb, fb, bb, ib), _ = ours_forward(s)
+
+    dims = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=R)
+    vimg = debug.view("tri", "verts_image", pb, **dims)
+    np.testing.assert_array_equal(vimg[:, :2].view(np.uint32), ri["verts_image"].view(np.uint32))
+    np.testing.assert_array_equal(vimg[:, 2].view(np.uint32), ri["ndc_z"].view(np.uint32))
+    tt = debug.view("tri", "tiles_touched", fb, **dims)
+    np.testing.assert_array_equal(tt, ri["tiles_touched"])
+    np.testing.assert_array_equal(debug.view("tri", "offsets", fb, **dims), ri["offsets"])
+    assert R == ref["R"]
+    dk = debug.view("tri", "depth_keys", fb, **dims)
+    live = tt > 0      # culled faces leave depths[] unwritten in the reference
+    np.testing.assert_array_equal(dk[live], ri["depths"].view(np.uint32)[live])
+    np.testing.assert_array_equal(debug.view("tri", "keys_unsorted", bb, **dims), ri["keys_unsorted"])
+    np.testing.assert_array_equal(debug.view("tri", "values_unsorted", bb, **dims), ri["values_unsorted"])
+    np.testing.assert_array_equal(debug.view("tri", "keys_sorted", bb, **dims), ri["keys_sorted"])
+    np.testing.assert_array_equal(debug.view("tri", "values_sorted", bb, **dims), ri["values_sorted"])
+    np.testing.assert_array_equal(debug.view("tri", "ranges", ib, **dims), ri["ranges"])
+    np.testing.assert_array_equal(debug.view("tri", "n_contrib", ib, **dims), ri["n_contrib"])
+    np.testing.assert_array_equal(debug.view("tri", "final_T", ib, **dims).view(np.uint32), ri["final_T"].view(np.uint32))
+
+    assert (color - ref["color"]).abs().max().item() <= IMG_TOL
+    assert (depth - ref["depth"]).abs().max().item() <= IMG_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny_tri", "small_tri", "C1", "C2"])
+def test_tri_gradients(name):
+    need_ref()
+    s = scenes.to_device(scenes.config(name), "cuda")
+    gc, gd = [t.cuda() for t in scenes.cotangents(s)]
+    ref = ref_harness.ref_tri_forward(s)
+    rg = ref_harness.ref_tri_backward(s, ref, gc, gd)
+
+    leaves = [s.verts.clone().requires_grad_(), s.verts_color.clone().requires_grad_(),
+              s.faces_opacity.clone().requires_grad_(), s.verts_depth.clone().requires_grad_(),
+              s.faces_intense.clone().requires_grad_()]
+    renderer = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
+    color, depth = renderer(leaves[0], s.faces, leaves[1], leaves[2], s.mv_mats, s.proj_mats, leaves[3], leaves[4])
+    torch.autograd.backward([color, depth], [gc, gd])
+    names = ["verts", "verts_color", "faces_opacity", "verts_depth", "faces_intense"]
+    for n, leaf, r in zip(names, leaves, rg):
+        e = rel_l2(leaf.grad, r)
+        assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
+
+
+def test_tri_empty_and_edge_cases():
+    dev = "cuda"
+    s = scenes.to_device(scenes.config("tiny_tri"), dev)
+    mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
+    imv, ipj = torch.inverse(mv), torch.inverse(pj)
+    B = mv.shape[0]
+    # P == 0: zero images, empty buffers (render.cu:88-89,105)
+    e = torch.zeros
+    out = _C.render_tris(s.bg, e(0, 3, device=dev), e(0, 3, dtype=torch.int32, device=dev), e(0, 3, device=dev),
+                         e(0, device=dev), mv, pj, imv, ipj, e(B, 0, device=dev), e(B, 0, device=dev), s.H, s.W)
+    assert out[0] == 0 and out[1].abs().max().item() == 0 and out[3].numel() == 0
+    # everything behind the camera: background image, R == 0, zero gradients
+    verts = s.verts.clone()
+    verts[:, :] = s.verts * 0.01 + torch.tensor([3.0, 2.0, 10.0], device=dev) * 3
+    R, color, depth, pb, fb, bb, ib = _C.render_tris(s.bg, verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj,
+                                                     s.verts_depth, s.faces_intense, s.H, s.W)
+    assert R == 0
+    assert torch.equal(color, torch.ones_like(color)) and torch.equal(depth, torch.ones_like(depth))
+    g = _C.render_tris_backward(s.bg, verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth,
+                                s.faces_intense, torch.ones_like(color), torch.ones_like(depth), R, pb, fb, bb, ib)
+    assert all(t.abs().max().item() == 0 for t in g)
+    # validation errors carry the reference's messages (render.cu:49-79)
+    with pytest.raises(RuntimeError, match="verts must have dimensions"):
+        _C.render_tris(s.bg, s.verts[:, :2], s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth,
+                       s.faces_intense, s.H, s.W)
+    with pytest.raises(RuntimeError, match="faces_intense must have dimensions"):
+        _C.render_tris(s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth,
+                       s.faces_intense[:, :5], s.H, s.W)
+
+
+def test_tri_non_multiple_of_16_image():
+    need_ref()
+    s = scenes.random_tri_scene("odd", 21, 2000, 0.1, 100, 75, B=2)
+    s = scenes.to_device(s, "cuda")
+    ref = ref_harness.ref_tri_forward(s)
+    (R, color, depth, *_), _ = ours_forward(s)
+    assert R == ref["R"]
+    assert (color - ref["color"]).abs().max().item() <= IMG_TOL
+    assert (depth - ref["depth"]).abs().max().item() <= IMG_TOL
