@@ -1,18 +1,175 @@
-// capi_tet.cu -- tet renderer entry points (placeholder until tet_kernels.cu lands)
+// capi_tet.cu -- extern "C" entry points of the tet renderer (include/dmesh_b200.h).
+// Stage sequencing of CudaRenderer::Renderer::forward / backward
+// (cuda_renderer/renderer_impl.cu:193-410, 413-498) without the per-stage
+// device synchronisation.
 #include "tet.cuh"
 #include "../../include/dmesh_b200.h"
+
 using namespace dmr;
-extern "C" {
-int dmr_tet_state_bytes(int, int, int, int, int, int, size_t*) { set_error("tet renderer not built"); return DMR_EINVAL; }
-int dmr_tet_forward_bin(int, int, int, int, int, int, const float*, const int*, const float*, const float*, const float*,
-                        const float*, const int*, const int*, const int*, void*, void*, int32_t*, dmr_stream_t)
-{ set_error("tet renderer not built"); return DMR_EINVAL; }
-int dmr_tet_forward_render(int, int, int, int, int, int, int, int, const float*, const float*, const float*, const float*,
-                           const float*, const float*, const void*, void*, void*, void*, float*, float*, float*,
-                           dmr_stream_t)
-{ set_error("tet renderer not built"); return DMR_EINVAL; }
-int dmr_tet_backward(int, int, int, int, int, int, int, const float*, const float*, const float*, const float*,
-                     const float*, const float*, const void*, const void*, const void*, const float*, const float*,
-                     float*, float*, dmr_stream_t)
-{ set_error("tet renderer not built"); return DMR_EINVAL; }
+
+namespace {
+
+template <typename T>
+T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<unsigned char*>(base) + off); }
+template <typename T>
+const T* at(const void* base, size_t off) { return reinterpret_cast<const T*>(static_cast<const unsigned char*>(base) + off); }
+
+bool tet_sizes_ok(long long B, long long P, long long F, long long T, long long W, long long H)
+{
+    if (B < 0 || P < 0 || F < 0 || T < 0 || W <= 0 || H <= 0) { set_error("negative or zero size"); return false; }
+    if (B * P >= (1LL << 31) || B * F >= (1LL << 31) || B * W * H >= (1LL << 31) || T >= (1LL << 31)) {
+        set_error("B*P, B*F, T and B*W*H must stay below 2^31");
+        return false;
+    }
+    if ((W + DMR_TILE - 1) / DMR_TILE >= 65536 || (H + DMR_TILE - 1) / DMR_TILE >= 65536) {
+        set_error("image too large for 16-bit tile coordinates");
+        return false;
+    }
+    return true;
 }
+
+}  // namespace
+
+extern "C" {
+
+int dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[3])
+{
+    if (!out) { set_error("out is null"); return DMR_EINVAL; }
+    if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
+    out[0] = align_up(sizeof(float4) * (size_t)B * P, 256) + 256;
+    out[1] = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T).total;
+    out[2] = TetImageLayout::make(B, W, H).total;
+    return DMR_OK;
+}
+
+int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* verts, const int* faces,
+                        const float* verts_color, const float* faces_opacity, const float* mv_mats,
+                        const float* proj_mats, const int* tets, const int* face_tets, const int* tet_faces,
+                        void* point_buffer, void* face_buffer, int32_t* num_rendered_host, dmr_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
+    if (!num_rendered_host) { set_error("num_rendered_host is null"); return DMR_EINVAL; }
+    if (B == 0 || P == 0 || F == 0) { *num_rendered_host = 0; return DMR_OK; }
+    if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats || !face_tets ||
+        (T > 0 && (!tets || !tet_faces)) || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
+    const size_t BF = (size_t)B * F;
+    TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F, (size_t)T);
+    float4* vimg = static_cast<float4*>(point_buffer);
+    size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.scan_state), 0, 4 * (ntile + 64), stream));
+    int rc;
+    if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, nullptr, vimg, stream))) return rc;
+    if ((rc = tet_preprocess_faces(B, P, F, W, H, faces, vimg, verts, at<uint32_t>(face_buffer, L.tiles_touched),
+                                   at<uint32_t>(face_buffer, L.depth_key), at<uint2>(face_buffer, L.rect),
+                                   at<TetFaceRec>(face_buffer, L.face_rec), stream)))
+        return rc;
+    if ((rc = inclusive_scan_u32(at<uint32_t>(face_buffer, L.tiles_touched), at<uint32_t>(face_buffer, L.offsets), BF,
+                                 at<uint32_t>(face_buffer, L.scan_state), num_rendered_host, stream)))
+        return rc;
+    // view-independent march records; independent of the scan, enqueued behind it
+    if ((rc = tet_build_records(P, F, T, verts, faces, verts_color, faces_opacity, tets, face_tets, tet_faces,
+                                at<TetRec>(face_buffer, L.tet_rec), at<TetShade>(face_buffer, L.shade), stream)))
+        return rc;
+    return DMR_OK;
+}
+
+static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, int seed, const float* bg,
+                        const float* mv, const float* proj, const float* inv_mv, const float* inv_proj,
+                        const float* faces_intense, const void* face_buffer, const void* image_buffer)
+{
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T);
+    TetImageLayout IL = TetImageLayout::make(B, W, H);
+    p = TetParams{};
+    p.B = B; p.P = P; p.F = F; p.T = T; p.W = W; p.H = H;
+    p.mv = mv; p.proj = proj; p.inv_mv = inv_mv; p.inv_proj = inv_proj;
+    p.faces_intense = faces_intense; p.bg = bg;
+    p.face_rec = at<TetFaceRec>(face_buffer, FL.face_rec);
+    p.tet_rec = at<TetRec>(face_buffer, FL.tet_rec);
+    p.shade = at<TetShade>(face_buffer, FL.shade);
+    p.ranges = at<uint2>(image_buffer, IL.ranges);
+    p.jitter = seed > 0 ? at<float2>(image_buffer, IL.jitter) : nullptr;
+    void* ib = const_cast<void*>(image_buffer);
+    p.first_face = at<int>(ib, IL.first_face);
+    p.first_tet = at<int>(ib, IL.first_tet);
+    p.last_face = at<int>(ib, IL.last_face);
+    p.last_tet = at<int>(ib, IL.last_tet);
+    p.final_log_T = at<float>(ib, IL.final_log_T);
+    p.prev_log_T = at<float>(ib, IL.prev_log_T);
+    p.n_contrib = at<uint32_t>(ib, IL.n_contrib);
+    p.active = at<uint8_t>(ib, IL.active);
+}
+
+int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int ray_random_seed,
+                           const float* background, const float* mv_mats, const float* proj_mats,
+                           const float* inv_mv_mats, const float* inv_proj_mats, const float* faces_intense,
+                           const void* point_buffer, void* face_buffer, void* binning_buffer, void* image_buffer,
+                           float* out_color, float* out_depth, float* out_active, dmr_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!tet_sizes_ok(B, P, F, T, W, H) || R < 0) return DMR_ETOOLARGE;
+    if (B == 0) return DMR_OK;
+    if (!background || !mv_mats || !proj_mats || !inv_mv_mats || !inv_proj_mats || !face_buffer || !image_buffer ||
+        !out_color || !out_depth || !out_active || (F > 0 && !faces_intense) || (R > 0 && !binning_buffer)) {
+        set_error("null pointer");
+        return DMR_EINVAL;
+    }
+    (void)point_buffer;
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T);
+    TetImageLayout IL = TetImageLayout::make(B, W, H);
+    const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
+    const size_t tiles = (size_t)B * tx * ty;
+    uint2* ranges = at<uint2>(image_buffer, IL.ranges);
+    int rc;
+    DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream));
+    TetParams p;
+    fill_params(p, B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                faces_intense, face_buffer, image_buffer);
+    if (ray_random_seed > 0)
+        if ((rc = tet_jitter(B, W, H, ray_random_seed, at<float2>(image_buffer, IL.jitter), stream))) return rc;
+    if (R > 0) {
+        BinningLayout BL = BinningLayout::make((size_t)R);
+        uint64_t* ku = at<uint64_t>(binning_buffer, BL.keys_unsorted);
+        uint32_t* vu = at<uint32_t>(binning_buffer, BL.vals_unsorted);
+        uint64_t* ks = at<uint64_t>(binning_buffer, BL.keys_sorted);
+        uint32_t* vs = at<uint32_t>(binning_buffer, BL.vals_sorted);
+        if ((rc = duplicate_with_keys((size_t)B * F, F, tx, ty, at<uint32_t>(face_buffer, FL.offsets),
+                                      at<uint2>(face_buffer, FL.rect), at<uint32_t>(face_buffer, FL.depth_key), ku, vu,
+                                      (size_t)R, stream)))
+            return rc;
+        const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);   // renderer_impl.cu:332-340
+        if ((rc = sort_pairs(ku, vu, ks, vs, (size_t)R, end_bit, at<void>(binning_buffer, BL.sort_temp), stream)))
+            return rc;
+        if ((rc = identify_tile_ranges(ks, (size_t)R, ranges, stream))) return rc;
+        p.face_list = vs;
+    }
+    p.out_color = out_color; p.out_depth = out_depth; p.out_active = out_active;
+    if ((rc = tet_first_intersect(p, stream))) return rc;
+    if ((rc = tet_march_forward(p, stream))) return rc;
+    return DMR_OK;
+}
+
+int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_seed, const float* background,
+                     const float* mv_mats, const float* proj_mats, const float* inv_mv_mats,
+                     const float* inv_proj_mats, const float* faces_intense, const void* point_buffer,
+                     const void* face_buffer, const void* image_buffer, const float* dL_dcolor, const float* dL_ddepth,
+                     float* dL_dverts_color, float* dL_dfaces_opacity, dmr_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
+    if (B == 0 || F == 0 || T == 0) return DMR_OK;
+    if (!background || !mv_mats || !proj_mats || !inv_mv_mats || !inv_proj_mats || !faces_intense || !face_buffer ||
+        !image_buffer || !dL_dcolor || !dL_ddepth || !dL_dverts_color || !dL_dfaces_opacity) {
+        set_error("null pointer");
+        return DMR_EINVAL;
+    }
+    (void)point_buffer;
+    TetParams p;
+    fill_params(p, B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
+                faces_intense, face_buffer, image_buffer);
+    p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
+    p.dL_dverts_color = dL_dverts_color; p.dL_dfaces_opacity = dL_dfaces_opacity;
+    return tet_march_backward(p, stream);
+}
+
+}  // extern "C"

@@ -13,6 +13,7 @@
 // loads/stores, records transposed through shared memory so that the global
 // write of a block's 256 records is one contiguous 36 KB burst.
 #include "tri.cuh"
+#include "tet.cuh"
 
 namespace dmr {
 
@@ -217,6 +218,74 @@ int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
                                                          faces_opacity, faces_intense, tiles_touched, depth_key, rect,
                                                          records);
     DMR_LAUNCH_CHECK("tri_preprocess_faces_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// faces (tet): replaces TET preprocessFaceCUDA (cuda_renderer/forward.cu:178-260).
+// Sort depth is the clamped MIN depth (renderer_impl.cu:325); the record carries
+// the world-space triangle plus min/max depth for firstIntersect.
+// algorithmic bytes per (b,f): read 12 + 3*16 + 3*12, write 4 + 4 + 8 + 48.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
+    int B, int P, int F, int gx, int gy,
+    const int* __restrict__ faces, const float4* __restrict__ vimg, const float* __restrict__ verts,
+    uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
+    TetFaceRec* __restrict__ records)
+{
+    __shared__ uint4 s_rec[256 * 3];
+    const int tid = threadIdx.x;
+    const size_t f0 = (size_t)blockIdx.x * 256;
+    const int b = blockIdx.y;
+    const size_t f = f0 + tid;
+    if (f < (size_t)F) {
+        int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+        const float4* vb = vimg + (size_t)b * P;
+        float4 a0 = vb[i0], a1 = vb[i1], a2 = vb[i2];
+        float max_z = a0.z, min_z = a0.z;
+        max_z = fmaxf(max_z, a1.z); min_z = fminf(min_z, a1.z);
+        max_z = fmaxf(max_z, a2.z); min_z = fminf(min_z, a2.z);
+
+        uint32_t touched = 0;
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        if (!(max_z < -1.0f || min_z > 1.0f)) {
+            tile_rect(make_float2(a0.x, a0.y), make_float2(a1.x, a1.y), make_float2(a2.x, a2.y), gx, gy, x0, y0, x1, y1);
+            if (x1 > x0 && y1 > y0) touched = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
+        }
+        float mn = (min_z + 1.0f) * 0.5f;
+        if (mn < 0.0f) mn = 0.0f;
+        if (mn > 1.0f) mn = 1.0f;
+        float mx = (max_z + 1.0f) * 0.5f;
+        if (mx < 0.0f) mx = 0.0f;
+        if (mx > 1.0f) mx = 1.0f;
+
+        size_t bf = (size_t)b * F + f;
+        tiles_touched[bf] = touched;
+        depth_key[bf] = __float_as_uint(mn);
+        rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+
+        const float* q0 = verts + 3 * (size_t)i0; const float* q1 = verts + 3 * (size_t)i1; const float* q2 = verts + 3 * (size_t)i2;
+        uint4* r = s_rec + tid * 3;
+        r[0] = make_uint4(__float_as_uint(q0[0]), __float_as_uint(q0[1]), __float_as_uint(q0[2]), __float_as_uint(q1[0]));
+        r[1] = make_uint4(__float_as_uint(q1[1]), __float_as_uint(q1[2]), __float_as_uint(q2[0]), __float_as_uint(q2[1]));
+        r[2] = make_uint4(__float_as_uint(q2[2]), __float_as_uint(mn), __float_as_uint(mx), 0u);
+    }
+    __syncthreads();
+    size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
+    uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
+    for (size_t i = tid; i < nvalid * 3; i += 256) dst[i] = s_rec[i];
+}
+
+int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
+                         uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
+                         cudaStream_t stream)
+{
+    if (B <= 0 || F <= 0) return 0;
+    int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
+    dim3 grid((F + 255) / 256, B);
+    tet_preprocess_faces_kernel<<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched, depth_key,
+                                                         rect, rec);
+    DMR_LAUNCH_CHECK("tet_preprocess_faces_kernel");
     return 0;
 }
 

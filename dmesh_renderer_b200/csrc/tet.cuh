@@ -18,13 +18,11 @@ static_assert(sizeof(TetFaceRec) == 48, "TetFaceRec must be 3 x 16 bytes");
 // levels), the tet's 4 vertices four times over and face_tets
 // (cuda_renderer/forward.cu:672-768, ~670 B per step).  One 224-byte record per
 // tet turns that into a single dependent load.
-struct TetSide {
-    int face;                    // tet_faces[4*t + k]
-    int next_tet;                // first entry of face_tets[face] that is neither t nor -1, else -1
-    float p0[3], p1[3], p2[3];   // face vertices in faces[] order
-    float n[3];                  // outward unit normal of `face` w.r.t. this tet (auxiliary.h:345-394)
+struct __align__(16) TetRec {
+    int face[4];          // tet_faces[4*t + k]
+    int next_tet[4];      // first entry of face_tets[face[k]] that is neither t nor -1, else -1
+    float geo[4][12];     // per side: p0, p1, p2 (faces[] order), outward unit normal w.r.t. this tet
 };
-struct __align__(16) TetRec { TetSide side[4]; };
 static_assert(sizeof(TetRec) == 224, "TetRec must be 14 x 16 bytes");
 
 // View-independent per-face shading record: 64 bytes.
@@ -82,8 +80,6 @@ struct TetImageLayout {
 
 struct TetParams {
     int B, P, F, T, W, H;
-    // scene
-    const float* verts; const int* faces; const int* tets; const int* face_tets; const int* tet_faces;
     const float* mv; const float* proj; const float* inv_mv; const float* inv_proj;
     const float* faces_intense;   // [B,F]
     const float* bg;
@@ -104,6 +100,8 @@ struct TetParams {
     float* dL_dverts_color; float* dL_dfaces_opacity;
 };
 
+int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
+                      const float* verts_depth, float4* vimg, cudaStream_t stream);
 int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
                          cudaStream_t stream);

@@ -1,0 +1,542 @@
+// tet_kernels.cu -- tet renderer: adjacency records, first intersection, ray march.
+//
+//   tet_build_*_kernel          hoist tet_face_outward_normal (cuda_renderer/auxiliary.h:345-394),
+//                               get_face_vert / get_face_vert_color (402-456) and the
+//                               face_tets neighbour search (forward.cu:761-767) out of the march
+//   tet_jitter_kernel           setup_curand_kernel + jitter of generateRaysCUDA (forward.cu:82-88,120-123)
+//   tet_first_intersect_kernel  replaces firstIntersectCUDA (forward.cu:298-445)
+//   tet_march_fwd_kernel        replaces TET_FORWARD::renderCUDA (forward.cu:485-815)
+//   tet_march_bwd_kernel        replaces TET_BACKWARD::renderCUDA (backward.cu:86-487)
+//
+// Forward images must match the reference to 1e-5, which requires IDENTICAL
+// branch decisions along every ray (hit tests, normal signs); all such
+// expressions keep the reference's operation order.
+#include "tet.cuh"
+#include <curand_kernel.h>
+
+namespace dmr {
+
+// ---------------------------------------------------------------------------
+// geometry helpers
+// ---------------------------------------------------------------------------
+
+// Moeller-Trumbore with inside test: cuda_renderer/auxiliary.h:265-296.
+// tuv is left untouched when denom == 0 (as in the reference).
+__device__ __forceinline__ bool ray_tri_hit(float3 ro, float3 rd, float3 p0, float3 p1, float3 p2, float3& tuv)
+{
+    float3 T = ro - p0;
+    float3 E1 = p1 - p0;
+    float3 E2 = p2 - p0;
+    float3 Pv = cross3(rd, E2);
+    float3 Q = cross3(T, E1);
+    float denom = dot3(Pv, E1);
+    if (denom == 0.0f) return false;
+    float inv_denom = 1.0f / denom;
+    tuv.x = dot3(Q, E2) * inv_denom;
+    tuv.y = dot3(Pv, T) * inv_denom;
+    tuv.z = dot3(Q, rd) * inv_denom;
+    return (tuv.x >= 0.0f && tuv.y >= 0.0f && tuv.z >= 0.0f && tuv.y + tuv.z <= 1.0f);
+}
+
+__device__ __forceinline__ float3 ld3(const float* p) { return f3(p[0], p[1], p[2]); }
+
+// cuda_renderer/auxiliary.h:345-394
+__device__ __forceinline__ float3 outward_normal(float3 p0, float3 p1, float3 p2, float3 q0, float3 q1, float3 q2,
+                                                 float3 q3)
+{
+    float3 d1 = p1 - p0;
+    float3 d2 = p2 - p0;
+    float3 n = cross3(d1, d2);
+    float n_norm = sqrtf(dot3(n, n));
+    n_norm = fmaxf(n_norm, 0.0001f);
+    n = n / n_norm;
+    float3 centre = (q0 + q1 + q2 + q3) * 0.25f;
+    float3 d = centre - p0;
+    float dp = dot3(n, d);
+    if (dp > 0.0f) n = -n;
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// record builders (view independent, once per forward call)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tet_build_tetrec_kernel(
+    int T, const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ tets,
+    const int* __restrict__ face_tets, const int* __restrict__ tet_faces, TetRec* __restrict__ out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int4 tv = reinterpret_cast<const int4*>(tets)[t];
+    const int4 tf = reinterpret_cast<const int4*>(tet_faces)[t];
+    float3 q0 = ld3(verts + 3 * (size_t)tv.x), q1 = ld3(verts + 3 * (size_t)tv.y);
+    float3 q2 = ld3(verts + 3 * (size_t)tv.z), q3 = ld3(verts + 3 * (size_t)tv.w);
+    const int fid[4] = { tf.x, tf.y, tf.z, tf.w };
+    int nxt[4];
+    uint4* o = reinterpret_cast<uint4*>(out + t);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int f = fid[k];
+        const int a = faces[3 * (size_t)f], b = faces[3 * (size_t)f + 1], c = faces[3 * (size_t)f + 2];
+        float3 p0 = ld3(verts + 3 * (size_t)a), p1 = ld3(verts + 3 * (size_t)b), p2 = ld3(verts + 3 * (size_t)c);
+        float3 n = outward_normal(p0, p1, p2, q0, q1, q2, q3);
+        // forward.cu:761-767
+        int nt = -1;
+        for (int i = 0; i < 2; i++) {
+            int cand = face_tets[2 * (size_t)f + i];
+            if (cand == t || cand == -1) continue;
+            nt = cand;
+            break;
+        }
+        nxt[k] = nt;
+        o[2 + 3 * k + 0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), __float_as_uint(p1.x));
+        o[2 + 3 * k + 1] = make_uint4(__float_as_uint(p1.y), __float_as_uint(p1.z), __float_as_uint(p2.x), __float_as_uint(p2.y));
+        o[2 + 3 * k + 2] = make_uint4(__float_as_uint(p2.z), __float_as_uint(n.x), __float_as_uint(n.y), __float_as_uint(n.z));
+    }
+    o[0] = make_uint4(fid[0], fid[1], fid[2], fid[3]);
+    o[1] = make_uint4(nxt[0], nxt[1], nxt[2], nxt[3]);
+}
+
+__global__ void __launch_bounds__(256) tet_build_shade_kernel(
+    int F, const int* __restrict__ faces, const float* __restrict__ verts_color, const float* __restrict__ faces_opacity,
+    const int* __restrict__ face_tets, TetShade* __restrict__ out)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int a = faces[3 * (size_t)f], b = faces[3 * (size_t)f + 1], c = faces[3 * (size_t)f + 2];
+    float3 c0 = ld3(verts_color + 3 * (size_t)a), c1 = ld3(verts_color + 3 * (size_t)b), c2 = ld3(verts_color + 3 * (size_t)c);
+    uint4* o = reinterpret_cast<uint4*>(out + f);
+    o[0] = make_uint4(__float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c0.z), __float_as_uint(c1.x));
+    o[1] = make_uint4(__float_as_uint(c1.y), __float_as_uint(c1.z), __float_as_uint(c2.x), __float_as_uint(c2.y));
+    o[2] = make_uint4(__float_as_uint(c2.z), __float_as_uint(faces_opacity[f]), a, b);
+    o[3] = make_uint4(c, face_tets[2 * (size_t)f], face_tets[2 * (size_t)f + 1], 0);
+}
+
+int tet_build_records(int P, int F, int T, const float* verts, const int* faces, const float* verts_color,
+                      const float* faces_opacity, const int* tets, const int* face_tets, const int* tet_faces,
+                      TetRec* tet_rec, TetShade* shade, cudaStream_t stream)
+{
+    (void)P;
+    if (T > 0) {
+        tet_build_tetrec_kernel<<<(T + 255) / 256, 256, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
+        DMR_LAUNCH_CHECK("tet_build_tetrec_kernel");
+    }
+    if (F > 0) {
+        tet_build_shade_kernel<<<(F + 255) / 256, 256, 0, stream>>>(F, faces, verts_color, faces_opacity, face_tets, shade);
+        DMR_LAUNCH_CHECK("tet_build_shade_kernel");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// jittered pixel coordinates (ray_random_seed > 0): XORWOW, sequence = pixel index
+// forward.cu:82-88, 120-123.  Stored (8 B/px) so that first-intersect, march and
+// backward see the same ray without re-running curand_init three times.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tet_jitter_kernel(int BI, int W, int H, int seed, float2* __restrict__ jitter)
+{
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= BI) return;
+    curandState st;
+    curand_init(seed, idx, 0, &st);
+    int pixel_id = idx % (W * H);
+    int pixel_x = pixel_id % W, pixel_y = pixel_id / W;
+    float2 o;
+    o.x = pixel_x - 0.5f + (0.5f * curand_uniform(&st));
+    o.y = pixel_y - 0.5f + (0.5f * curand_uniform(&st));
+    jitter[idx] = o;
+}
+
+int tet_jitter(int B, int W, int H, int seed, float2* jitter, cudaStream_t stream)
+{
+    int BI = B * W * H;
+    if (BI <= 0) return 0;
+    tet_jitter_kernel<<<(BI + 255) / 256, 256, 0, stream>>>(BI, W, H, seed, jitter);
+    DMR_LAUNCH_CHECK("tet_jitter_kernel");
+    return 0;
+}
+
+__device__ __forceinline__ void tet_pixel_ray(const TetParams& p, int b, uint32_t px, uint32_t py, size_t bpix,
+                                              float3& ro, float3& rd)
+{
+    float fx = px + 0.5f, fy = py + 0.5f;
+    if (p.jitter) { float2 j = p.jitter[bpix]; fx = j.x; fy = j.y; }
+    pixel_ray<true>(p.inv_mv + 16 * b, p.inv_proj + 16 * b, fx, fy, p.W, p.H, ro, rd);
+}
+
+// ---------------------------------------------------------------------------
+// first intersection: per tile, faces sorted by min depth
+// ---------------------------------------------------------------------------
+#define FI_RB 256
+
+__global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
+{
+    __shared__ uint4 s_rec[FI_RB * 3];
+    __shared__ int s_face[FI_RB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+    const uint32_t px = blockIdx.x * DMR_TILE + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * DMR_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
+    const size_t bpix = (size_t)b * p.W * p.H + (size_t)py * p.W + px;
+    bool done = !inside;
+
+    float3 ro = f3(0, 0, 0), rd = f3(0, 0, 1);
+    if (inside) tet_pixel_ray(p, b, px, py, bpix, ro, rd);
+
+    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + blockIdx.y * tiles_x + blockIdx.x];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + FI_RB - 1) / FI_RB;
+
+    float min_T = -1.0f, min_T_max_depth = -1.0f;
+    int first_face = -1;
+
+    for (int r = 0; r < rounds; r++) {
+        if (__syncthreads_count(done) == 256) break;
+        {
+            uint32_t pos = range.x + (uint32_t)r * FI_RB + tid;
+            if (pos < range.y) {
+                uint32_t face = p.face_list[pos];
+                s_face[tid] = (int)face;
+                const uint4* src = reinterpret_cast<const uint4*>(p.face_rec + (size_t)b * p.F + face);
+                s_rec[tid * 3 + 0] = src[0];
+                s_rec[tid * 3 + 1] = src[1];
+                s_rec[tid * 3 + 2] = src[2];
+            }
+        }
+        __syncthreads();
+        const int cnt = min(FI_RB, total - r * FI_RB);
+        for (int j = 0; !done && j < cnt; j++) {
+            const float* w = reinterpret_cast<const float*>(s_rec + j * 3);
+            // forward.cu:388-391
+            if (min_T >= 0.0f && w[9] > min_T_max_depth) { done = true; continue; }
+            float3 tuv;
+            bool hit = ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
+            if (!hit) continue;
+            float cur = tuv.x;
+            if (min_T < 0.0f || cur < min_T) {
+                min_T = cur;
+                min_T_max_depth = w[10];
+                first_face = s_face[j];
+            }
+        }
+    }
+
+    if (!inside) return;
+    // forward.cu:419-444: the adjacent tet whose outward normal opposes the ray
+    int first_tet = -1;
+    if (first_face >= 0) {
+        const TetShade* sh = p.shade + first_face;
+        const int cand[2] = { sh->t0, sh->t1 };
+        for (int i = 0; i < 2; i++) {
+            int tet_id = cand[i];
+            if (tet_id < 0) continue;
+            const TetRec* tr = p.tet_rec + tet_id;
+            float3 n = f3(0, 0, 0);
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (!found && tr->face[k] == first_face) { n = f3(tr->geo[k][9], tr->geo[k][10], tr->geo[k][11]); found = true; }
+            if (!found) continue;   // inconsistent adjacency tables
+            if (dot3(n, rd) < 0.0f) first_tet = tet_id;
+        }
+    }
+    p.first_face[bpix] = first_face;
+    p.first_tet[bpix] = first_tet;
+}
+
+int tet_first_intersect(const TetParams& p, cudaStream_t stream)
+{
+    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    tet_first_intersect_kernel<<<grid, 256, 0, stream>>>(p);
+    DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// forward march
+// ---------------------------------------------------------------------------
+struct TetStep {   // result of looking for the exit (or entry) face of a tet
+    int face, tet;
+    float rt, iu, iv;
+    bool ok;
+};
+
+// Among the sides of `tet` other than `curr_face`, the unique one hit by the ray whose
+// outward normal has the requested sign against the ray: forward.cu:672-768 (EXIT: normal
+// along the ray) and backward.cu:382-477 (ENTRY: normal against the ray).
+template <bool EXIT>
+__device__ __forceinline__ TetStep tet_step(const TetRec* __restrict__ tr, int curr_face, float3 ro, float3 rd)
+{
+    TetStep s;
+    s.ok = true;
+    s.face = -1; s.tet = -1; s.rt = 0; s.iu = 0; s.iv = 0;
+    const int4 fid = *reinterpret_cast<const int4*>(tr->face);
+    const int4 nxt = *reinterpret_cast<const int4*>(tr->next_tet);
+    const int f[4] = { fid.x, fid.y, fid.z, fid.w };
+    const int nt[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
+    int cnt = 0, hits = 0;
+    bool have_curr = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4* g4 = reinterpret_cast<const float4*>(tr->geo[k]);
+        const float4 g0 = g4[0], g1 = g4[1], g2 = g4[2];
+        const float3 n = f3(g2.y, g2.z, g2.w);
+        const float dn = dot3(n, rd);
+        if (f[k] == curr_face) {
+            // the face we stand on must face the other way (error case 2)
+            if (!have_curr) { if (EXIT ? (dn >= 0.0f) : (dn <= 0.0f)) s.ok = false; }
+            have_curr = true;
+            continue;
+        }
+        cnt++;
+        float3 tuv;
+        bool hit = ray_tri_hit(ro, rd, f3(g0.x, g0.y, g0.z), f3(g0.w, g1.x, g1.y), f3(g1.z, g1.w, g2.x), tuv);
+        if (hit && (EXIT ? (dn > 0.0f) : (dn < 0.0f))) {
+            s.face = f[k]; s.tet = nt[k];
+            s.rt = tuv.x; s.iu = tuv.y; s.iv = tuv.z;
+            hits++;
+        }
+    }
+    if (cnt != 3) s.ok = false;      // error case 1
+    if (hits != 1) s.ok = false;     // error case 3
+    return s;
+}
+
+__global__ void __launch_bounds__(256) tet_march_fwd_kernel(TetParams p)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const uint32_t px = blockIdx.x * DMR_TILE + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * DMR_TILE + (warp >> 1) * 4 + (lane >> 3);
+    if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
+    const size_t HW = (size_t)p.W * p.H;
+    const size_t pix = (size_t)py * p.W + px;
+    const size_t bpix = (size_t)b * HW + pix;
+
+    float3 ro, rd;
+    tet_pixel_ray(p, b, px, py, bpix, ro, rd);
+    const float* mv = p.mv + 16 * b;
+    const float* pj = p.proj + 16 * b;
+
+    const int first_face = p.first_face[bpix], first_tet = p.first_tet[bpix];
+    bool done = false;
+    float rt = 0.0f, iu = 0.0f, iv = 0.0f;
+    if (first_face == -1 || first_tet == -1) done = true;
+    else {
+        const float* w = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F + first_face);
+        float3 tuv = f3(0, 0, 0);
+        ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
+        rt = tuv.x; iu = tuv.y; iv = tuv.z;
+    }
+
+    float3 C = f3(0, 0, 0);
+    float D = 0.0f, log_T = 0.0f, prev_log_T = 0.0f;
+    int last_face = -1, last_tet = -1;
+    bool active = false;
+    uint32_t n_contrib = 0;
+    int curr_face = first_face, curr_tet = first_tet;
+
+    while (!done) {
+        // 1. composite the current face (forward.cu:600-653)
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
+        const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2];
+        const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
+        const float opacity = s2.y;
+        const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
+        float3 col = (c0 + (c1 - c0) * iu + (c2 - c0) * iv);
+        col = col * intense;
+        float tmp_T = expf(log_T);
+        C = C + tmp_T * opacity * col;
+        float3 pt = ro + (rd * rt);
+        float4 pn = xform44(xform43(pt, mv), pj);
+        float pw = 1.0f / clamp_w(pn.w);
+        float pd = pn.z * pw;
+        D += tmp_T * opacity * pd;
+
+        prev_log_T = log_T;
+        if (opacity < 1.0f) log_T += logf(1.0f - opacity);
+        else log_T = logf(DMR_T_EPS * 0.1f);
+        if (expf(log_T) < DMR_T_EPS) { done = true; active = true; }
+
+        n_contrib++;
+        last_face = curr_face;
+        last_tet = curr_tet;
+
+        // 2. next face (forward.cu:662-775)
+        if (curr_tet == -1) { active = true; done = true; }
+        if (!done) {
+            TetStep s = tet_step<true>(p.tet_rec + curr_tet, curr_face, ro, rd);
+            if (!s.ok) { done = true; }   // numerical failure: pixel stays inactive
+            curr_face = s.face; curr_tet = s.tet;
+            rt = s.rt; iu = s.iu; iv = s.iv;
+        }
+    }
+
+    p.final_log_T[bpix] = log_T;
+    p.prev_log_T[bpix] = prev_log_T;
+    p.last_face[bpix] = last_face;
+    p.last_tet[bpix] = last_tet;
+    p.n_contrib[bpix] = n_contrib;
+    p.active[bpix] = active ? 1 : 0;
+    if (active) {
+        float fT = expf(log_T);
+        p.out_color[(size_t)b * 3 * HW + 0 * HW + pix] = C.x + fT * p.bg[0];
+        p.out_color[(size_t)b * 3 * HW + 1 * HW + pix] = C.y + fT * p.bg[1];
+        p.out_color[(size_t)b * 3 * HW + 2 * HW + pix] = C.z + fT * p.bg[2];
+        p.out_depth[bpix] = D + fT * 1.0f;
+        p.out_active[bpix] = 1.0f;
+    } else {
+        p.out_color[(size_t)b * 3 * HW + 0 * HW + pix] = p.bg[0];
+        p.out_color[(size_t)b * 3 * HW + 1 * HW + pix] = p.bg[1];
+        p.out_color[(size_t)b * 3 * HW + 2 * HW + pix] = p.bg[2];
+        p.out_depth[bpix] = 1.0f;
+        p.out_active[bpix] = 0.0f;
+    }
+}
+
+int tet_march_forward(const TetParams& p, cudaStream_t stream)
+{
+    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    tet_march_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+    DMR_LAUNCH_CHECK("tet_march_fwd_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// backward march
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tet_march_bwd_kernel(TetParams p)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z;
+    const uint32_t px = blockIdx.x * DMR_TILE + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * DMR_TILE + (warp >> 1) * 4 + (lane >> 3);
+    if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
+    const size_t HW = (size_t)p.W * p.H;
+    const size_t pix = (size_t)py * p.W + px;
+    const size_t bpix = (size_t)b * HW + pix;
+
+    if (!p.active[bpix]) return;                    // backward.cu:160-163
+    const int last_face = p.last_face[bpix];
+    if (last_face == -1) return;                    // backward.cu:190-193
+    const int last_tet = p.last_tet[bpix];
+    const int first_face = p.first_face[bpix];
+
+    const float fin_prev_log_T = p.prev_log_T[bpix];
+    const float fin_log_T = p.final_log_T[bpix];
+    const float final_prev_T = expf(fin_prev_log_T);
+    const float final_T = expf(fin_log_T);
+    float prev_log_T = fin_prev_log_T;
+
+    const float g0 = p.dL_dcolor[(size_t)b * 3 * HW + 0 * HW + pix];
+    const float g1 = p.dL_dcolor[(size_t)b * 3 * HW + 1 * HW + pix];
+    const float g2 = p.dL_dcolor[(size_t)b * 3 * HW + 2 * HW + pix];
+    const float gd = p.dL_ddepth[bpix];
+    const float dLc[3] = { g0, g1, g2 };
+
+    float3 ro, rd;
+    tet_pixel_ray(p, b, px, py, bpix, ro, rd);
+    const float* mv = p.mv + 16 * b;
+    const float* pj = p.proj + 16 * b;
+
+    float rt, iu, iv;
+    {
+        const float* w = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F + last_face);
+        float3 tuv = f3(0, 0, 0);
+        ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
+        rt = tuv.x; iu = tuv.y; iv = tuv.z;
+    }
+    int curr_face = last_face, curr_tet = last_tet;
+    // the tet on the near side of the last face: backward.cu:224-232
+    {
+        const TetShade* sh = p.shade + curr_face;
+        const int cand[2] = { sh->t0, sh->t1 };
+        for (int i = 0; i < 2; i++) {
+            if (cand[i] == curr_tet) continue;
+            curr_tet = cand[i];
+            break;
+        }
+    }
+
+    // backward.cu:324-329
+    float bg_dot = 0; bg_dot += p.bg[0] * g0; bg_dot += p.bg[1] * g1; bg_dot += p.bg[2] * g2;
+    float bd_dot = 0; bd_dot += 1.0 * gd;
+
+    float last_alpha = 0.0f, last_depth = 0.0f, accum_recd = 0.0f;
+    float last_color[3] = { 0, 0, 0 }, accum_rec[3] = { 0, 0, 0 };
+    bool first_iter = true, done = false;
+
+    while (!done) {
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
+        const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2], s3 = sh4[3];
+        const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
+        const float opacity = s2.y;
+        const int vi0 = __float_as_int(s2.z), vi1 = __float_as_int(s2.w), vi2 = __float_as_int(s3.x);
+        const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
+
+        // backward.cu:252-270
+        float i0 = 1.0f - iu - iv, i1 = iu, i2 = iv;
+        float3 col = (i0 * c0) + (i1 * c1) + (i2 * c2);
+        col = col * intense;
+        float3 pt = ro + (rd * rt);
+        float4 pn = xform44(xform43(pt, mv), pj);
+        float pw = 1.0f / clamp_w(pn.w);
+        float pd = pn.z * pw;
+
+        if (!first_iter) prev_log_T = prev_log_T - logf(1.0f - opacity);
+        first_iter = false;
+        float prev_T = expf(prev_log_T);
+
+        // backward.cu:288-339
+        float dL_dcol[3];
+        float dL_dopa = 0.0f;
+        const float tc[3] = { col.x, col.y, col.z };
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float c = tc[ch];
+            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+            last_color[ch] = c;
+            dL_dcol[ch] = dLc[ch] * opacity * prev_T;
+            dL_dopa += (c - accum_rec[ch]) * dLc[ch];
+        }
+        accum_recd = last_alpha * last_depth + (1.f - last_alpha) * accum_recd;
+        last_depth = pd;
+        dL_dopa += (pd - accum_recd) * gd;
+        dL_dopa *= prev_T;
+        last_alpha = opacity;
+        if (opacity == 1.0f) {
+            dL_dopa += (-final_prev_T) * bg_dot;
+            dL_dopa += (-final_prev_T) * bd_dot;
+        } else {
+            dL_dopa += (-final_T / (1.f - opacity)) * bg_dot;
+            dL_dopa += (-final_T / (1.f - opacity)) * bd_dot;
+        }
+
+        // backward.cu:341-360
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            atomicAdd(&p.dL_dverts_color[3 * (size_t)vi0 + ch], i0 * dL_dcol[ch] * intense);
+            atomicAdd(&p.dL_dverts_color[3 * (size_t)vi1 + ch], i1 * dL_dcol[ch] * intense);
+            atomicAdd(&p.dL_dverts_color[3 * (size_t)vi2 + ch], i2 * dL_dcol[ch] * intense);
+        }
+        atomicAdd(&p.dL_dfaces_opacity[curr_face], dL_dopa);
+
+        if (curr_face == first_face) break;          // backward.cu:363-366
+        if (curr_tet == -1) break;                   // backward.cu:373-376
+        TetStep s = tet_step<false>(p.tet_rec + curr_tet, curr_face, ro, rd);
+        if (!s.ok) done = true;
+        curr_face = s.face; curr_tet = s.tet;
+        rt = s.rt; iu = s.iu; iv = s.iv;
+    }
+}
+
+int tet_march_backward(const TetParams& p, cudaStream_t stream)
+{
+    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    tet_march_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    DMR_LAUNCH_CHECK("tet_march_bwd_kernel");
+    return 0;
+}
+
+}  // namespace dmr

@@ -27,8 +27,6 @@ struct TriRenderParams {
     float* dL_dfintense;
 };
 
-int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
-                      const float* verts_depth, float4* vimg, cudaStream_t stream);
 int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          const float* verts_color, const float* faces_opacity, const float* faces_intense,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TriRecord* records,
