@@ -71,9 +71,14 @@ def build(force=False, verbose=True):
         "-DTORCH_EXTENSION_NAME=" + MODNAME,
         "-DTORCH_API_INCLUDE_EXTENSION_H",
         "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
-        "-std=c++17", "-O3",
-        # nvcc defaults otherwise (fmad=true, IEEE div/sqrt, no fast-math) as
-        # in the reference's own build.
+        "-std=c++17",
+        # nvcc defaults, exactly like the reference's own setup.py build (SURVEY
+        # App. A.10): device code -O3 / fmad=true / IEEE div+sqrt / no fast-math,
+        # HOST code unoptimised.  The latter matters: Renderer::forward
+        # (cuda_renderer/renderer_impl.cu:193,410) is declared int and has no
+        # return statement; with host -O2/-O3 gcc 13 treats the end of the
+        # function as unreachable and falls through into the CHECK_CUDA throw
+        # ("RuntimeError: no error").  At nvcc's default host -O0 it is benign.
         "-gencode", "arch=compute_100,code=sm_100",
         "-include", "cstdint",
         "--expt-relaxed-constexpr",
@@ -94,7 +99,7 @@ def build(force=False, verbose=True):
         if r.returncode != 0:
             raise RuntimeError("reference build failed: %s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
         if verbose:
-            print("[build_ref] compiled", cmd[-len(common) - len(inc) - 2 - 1] if False else cmd[3 if cmd[2] != "-x" else 5])
+            print("[build_ref] compiled", [c for c in cmd if c.endswith((".cu", ".cpp"))][0])
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         list(ex.map(run, cmds))
