@@ -30,6 +30,10 @@ SIGNATURES = {
     "dmr_tet_forward_render": (c_int, [c_int] * 8 + [c_void_p] * 13 + [c_void_p]),
     "dmr_tet_backward": (c_int, [c_int] * 7 + [c_void_p] * 13 + [c_void_p]),
     "dmr_debug_view": (c_int, [c_int] * 8 + [c_size_t, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t)]),
+    "dmr_profile_enable": (c_int, [c_int]),
+    "dmr_profile_stage_count": (c_int, []),
+    "dmr_profile_stage_name": (ctypes.c_char_p, [c_int]),
+    "dmr_profile_read": (c_int, [ctypes.POINTER(ctypes.c_float)]),
     "dmr_sort_temp_bytes": (c_size_t, [c_size_t]),
     "dmr_sort_pairs": (c_int, [c_void_p] * 4 + [c_size_t, c_int, c_void_p, c_void_p]),
 }

@@ -127,8 +127,11 @@ int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* st
         return 0;
     }
     size_t ntile = (n + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+    {
+    ProfScope prof(ST_SCAN, stream);
     inclusive_scan_kernel<<<(unsigned)ntile, DMR_SCAN_THREADS, 0, stream>>>(in, out, n, state, nullptr);
     DMR_LAUNCH_CHECK("inclusive_scan_kernel");
+    }
     if (total_host)
         DMR_CUDA(cudaMemcpyAsync(total_host, state + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     return 0;
@@ -196,6 +199,7 @@ int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32
 {
     if (BF == 0 || R == 0) return 0;
     unsigned nblk = (unsigned)((BF + 255) / 256);
+    ProfScope prof(ST_DUPLICATE, stream);
     duplicate_kernel<<<nblk, 256, 0, stream>>>(BF, F, tiles_x, tiles_x * tiles_y, offsets, rect, depth_key, keys, vals);
     DMR_LAUNCH_CHECK("duplicate_kernel");
     return 0;
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __rest
 int identify_tile_ranges(const uint64_t* keys_sorted, size_t R, uint2* ranges, cudaStream_t stream)
 {
     if (R == 0) return 0;
+    ProfScope prof(ST_RANGES, stream);
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(keys_sorted, R, ranges);
     DMR_LAUNCH_CHECK("tile_ranges_kernel");
     return 0;

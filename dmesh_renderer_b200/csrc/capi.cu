@@ -26,6 +26,34 @@ int cuda_fail(cudaError_t e, const char* what)
     return DMR_ECUDA;
 }
 
+// ---- stage timing ------------------------------------------------------------
+static const char* const g_stage_names[ST_COUNT] = {
+    "preprocess_points", "preprocess_faces", "scan", "duplicate_with_keys", "sort_histogram", "sort_plan",
+    "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "sort_pass4", "sort_pass5", "sort_pass6", "sort_pass7",
+    "tile_ranges", "tri_render_forward", "tri_render_backward", "tet_build_records", "tet_jitter",
+    "tet_first_intersect", "tet_march_forward", "tet_march_backward" };
+struct Prof {
+    bool on = false, created = false;
+    cudaEvent_t ev[ST_COUNT][2];
+    bool used[ST_COUNT];
+};
+static Prof g_prof;
+void prof_begin(int stage, cudaStream_t s)
+{
+    if (!g_prof.on) return;
+    if (!g_prof.created) {
+        for (int i = 0; i < ST_COUNT; i++) { cudaEventCreate(&g_prof.ev[i][0]); cudaEventCreate(&g_prof.ev[i][1]); g_prof.used[i] = false; }
+        g_prof.created = true;
+    }
+    cudaEventRecord(g_prof.ev[stage][0], s);
+}
+void prof_end(int stage, cudaStream_t s)
+{
+    if (!g_prof.on) return;
+    cudaEventRecord(g_prof.ev[stage][1], s);
+    g_prof.used[stage] = true;
+}
+
 BinningLayout BinningLayout::make(size_t R)
 {
     BinningLayout L;
@@ -66,6 +94,31 @@ extern "C" {
 
 int dmr_abi_version(void) { return 1; }
 const char* dmr_last_error(void) { return g_err; }
+
+int dmr_profile_enable(int on)
+{
+    g_prof.on = on != 0;
+    if (g_prof.created) for (int i = 0; i < ST_COUNT; i++) g_prof.used[i] = false;
+    return DMR_OK;
+}
+int dmr_profile_stage_count(void) { return ST_COUNT; }
+const char* dmr_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? g_stage_names[i] : ""; }
+int dmr_profile_read(float* ms_out)
+{
+    if (!ms_out) { set_error("ms_out is null"); return DMR_EINVAL; }
+    for (int i = 0; i < ST_COUNT; i++) {
+        ms_out[i] = -1.0f;
+        if (!g_prof.created || !g_prof.used[i]) continue;
+        cudaError_t e = cudaEventSynchronize(g_prof.ev[i][1]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+        float ms = 0;
+        e = cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
+        ms_out[i] = ms;
+        g_prof.used[i] = false;
+    }
+    return DMR_OK;
+}
 
 int dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3])
 {

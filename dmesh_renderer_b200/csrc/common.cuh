@@ -34,6 +34,23 @@ int  cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 // ---------------------------------------------------------------------------
+// per-stage timing hook (dmr_profile_*): CUDA events recorded on the launching
+// stream around every kernel when enabled; no synchronisation, off by default.
+// ---------------------------------------------------------------------------
+enum Stage {
+    ST_POINTS = 0, ST_FACES, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PLAN,
+    ST_SORT_PASS0, ST_SORT_PASS1, ST_SORT_PASS2, ST_SORT_PASS3, ST_SORT_PASS4, ST_SORT_PASS5, ST_SORT_PASS6, ST_SORT_PASS7,
+    ST_RANGES, ST_TRI_FWD, ST_TRI_BWD, ST_TET_RECORDS, ST_TET_JITTER, ST_TET_FIRST, ST_TET_FWD, ST_TET_BWD, ST_COUNT
+};
+void prof_begin(int stage, cudaStream_t s);
+void prof_end(int stage, cudaStream_t s);
+struct ProfScope {
+    int st; cudaStream_t s;
+    ProfScope(int stage, cudaStream_t stream) : st(stage), s(stream) { prof_begin(st, s); }
+    ~ProfScope() { prof_end(st, s); }
+};
+
+// ---------------------------------------------------------------------------
 // small vector helpers.  dot/cross/transform keep the expression shape of the
 // reference (cuda_rasterizer/cuda_math.h:1524-1527, 1696-1699 and
 // auxiliary.h:71-90) so that nvcc contracts them into the same FMA chains.

@@ -53,6 +53,7 @@ int preprocess_points(int B, int P, int W, int H, const float* verts, const floa
 {
     if (B <= 0 || P <= 0) return 0;
     dim3 grid((P + 255) / 256, B);
+    ProfScope prof(ST_POINTS, stream);
     preprocess_points_kernel<<<grid, 256, 0, stream>>>(B, P, W, H, verts, mv, proj, verts_depth, vimg);
     DMR_LAUNCH_CHECK("preprocess_points_kernel");
     return 0;
@@ -214,6 +215,7 @@ int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
     if (B <= 0 || F <= 0) return 0;
     int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
     dim3 grid((F + 255) / 256, B);
+    ProfScope prof(ST_FACES, stream);
     tri_preprocess_faces_kernel<<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
                                                          faces_opacity, faces_intense, tiles_touched, depth_key, rect,
                                                          records);
@@ -283,6 +285,7 @@ int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
     if (B <= 0 || F <= 0) return 0;
     int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
     dim3 grid((F + 255) / 256, B);
+    ProfScope prof(ST_FACES, stream);
     tet_preprocess_faces_kernel<<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched, depth_key,
                                                          rect, rec);
     DMR_LAUNCH_CHECK("tet_preprocess_faces_kernel");

@@ -306,10 +306,16 @@ int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_
     size_t hblocks = (n + 255) / 256;
     size_t hmax = (size_t)sm_count * 8;
     if (hblocks > hmax) hblocks = hmax;
-    rs_hist_kernel<<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
-    DMR_LAUNCH_CHECK("rs_hist_kernel");
-    rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
-    DMR_LAUNCH_CHECK("rs_plan_kernel");
+    {
+        ProfScope prof(ST_SORT_HIST, stream);
+        rs_hist_kernel<<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
+        DMR_LAUNCH_CHECK("rs_hist_kernel");
+    }
+    {
+        ProfScope prof(ST_SORT_PLAN, stream);
+        rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
+        DMR_LAUNCH_CHECK("rs_plan_kernel");
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -321,6 +327,7 @@ int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_
     buf.ktmp = reinterpret_cast<uint64_t*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
     for (int p = 0; p < npass; p++) {
+        ProfScope prof(ST_SORT_PASS0 + p, stream);
         rs_onesweep_kernel<<<(unsigned)L.ntile, RS_THREADS, RS_SMEM_BYTES, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
         DMR_LAUNCH_CHECK("rs_onesweep_kernel");
     }

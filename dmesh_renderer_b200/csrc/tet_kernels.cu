@@ -116,6 +116,7 @@ int tet_build_records(int P, int F, int T, const float* verts, const int* faces,
                       TetRec* tet_rec, TetShade* shade, cudaStream_t stream)
 {
     (void)P;
+    ProfScope prof(ST_TET_RECORDS, stream);
     if (T > 0) {
         tet_build_tetrec_kernel<<<(T + 255) / 256, 256, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
         DMR_LAUNCH_CHECK("tet_build_tetrec_kernel");
@@ -150,6 +151,7 @@ int tet_jitter(int B, int W, int H, int seed, float2* jitter, cudaStream_t strea
 {
     int BI = B * W * H;
     if (BI <= 0) return 0;
+    ProfScope prof(ST_TET_JITTER, stream);
     tet_jitter_kernel<<<(BI + 255) / 256, 256, 0, stream>>>(BI, W, H, seed, jitter);
     DMR_LAUNCH_CHECK("tet_jitter_kernel");
     return 0;
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
 int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 {
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    ProfScope prof(ST_TET_FIRST, stream);
     tet_first_intersect_kernel<<<grid, 256, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
     return 0;
@@ -398,6 +401,7 @@ __global__ void __launch_bounds__(256) tet_march_fwd_kernel(TetParams p)
 int tet_march_forward(const TetParams& p, cudaStream_t stream)
 {
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    ProfScope prof(ST_TET_FWD, stream);
     tet_march_fwd_kernel<<<grid, 256, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_march_fwd_kernel");
     return 0;
@@ -534,6 +538,7 @@ __global__ void __launch_bounds__(256) tet_march_bwd_kernel(TetParams p)
 int tet_march_backward(const TetParams& p, cudaStream_t stream)
 {
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    ProfScope prof(ST_TET_BWD, stream);
     tet_march_bwd_kernel<<<grid, 256, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_march_bwd_kernel");
     return 0;

@@ -430,6 +430,7 @@ int tri_render_forward(const TriRenderParams& p, cudaStream_t stream)
 {
     if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    ProfScope prof(ST_TRI_FWD, stream);
     tri_render_fwd_kernel<<<grid, 256, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tri_render_fwd_kernel");
     return 0;
@@ -439,6 +440,7 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
 {
     if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    ProfScope prof(ST_TRI_BWD, stream);
     tri_render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tri_render_bwd_kernel");
     return 0;

@@ -213,6 +213,21 @@ int    dmr_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in,
                       uint64_t* keys_out, uint32_t* vals_out,
                       size_t n, int end_bit, void* temp, dmr_stream_t stream);
 
+/* ------------------------------------------------------------------------ */
+/* Per-stage device timing.  No reference counterpart: the reference has no   */
+/* tracing at all and serialises every stage with       */
+/* cudaDeviceSynchronize (cuda_rasterizer/auxiliary.h:425-432).  When enabled */
+/* a pair of CUDA events is recorded on the launching stream around every     */
+/* kernel (no synchronisation); dmr_profile_read() waits for the events of    */
+/* the most recent call and returns the elapsed milliseconds per stage        */
+/* (-1 = stage not run since the last read).  Used by bench.py for the        */
+/* roofline of the dominant kernel.  Not thread-safe; one stream at a time.   */
+/* ------------------------------------------------------------------------ */
+int         dmr_profile_enable(int on);
+int         dmr_profile_stage_count(void);
+const char* dmr_profile_stage_name(int stage);
+int         dmr_profile_read(float* ms_out /* [dmr_profile_stage_count()] */);
+
 #ifdef __cplusplus
 }
 #endif

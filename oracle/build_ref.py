@@ -49,14 +49,14 @@ def so_path():
     return os.path.join(OUT, MODNAME + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, relink=False):
     """Compile the reference extension.  Returns the .so path, or None when
     /root/reference is absent (GPU box: the prebuilt file is used)."""
     target = so_path()
-    if os.path.exists(target) and not force:
-        return target
     if not os.path.isdir(REF):
-        return None
+        return target if os.path.exists(target) else None
+    if os.path.exists(target) and not force and not relink:
+        return target
     import torch  # noqa: F401  (header locations only)
     from torch.utils import cpp_extension as ce
 
@@ -78,7 +78,11 @@ def build(force=False, verbose=True):
         # (cuda_renderer/renderer_impl.cu:193,410) is declared int and has no
         # return statement; with host -O2/-O3 gcc 13 treats the end of the
         # function as unreachable and falls through into the CHECK_CUDA throw
-        # ("RuntimeError: no error").  At nvcc's default host -O0 it is benign.
+        # ("RuntimeError: no error").  At nvcc's default host -O0, gcc 13 turns the
+        # same spot into a trap (-funreachable-traps is on by default at -O0) and
+        # the process dies with SIGILL; -fno-unreachable-traps restores the
+        # benign fall-off-the-end behaviour older compilers gave the reference.
+        "-Xcompiler", "-fno-unreachable-traps",
         "-gencode", "arch=compute_100,code=sm_100",
         "-include", "cstdint",
         "--expt-relaxed-constexpr",
@@ -92,7 +96,8 @@ def build(force=False, verbose=True):
         objs.append(o)
         src = os.path.join(REF, s)
         extra = ["-x", "cu"] if s.endswith(".cpp") else []
-        cmds.append(["nvcc", "-c", *extra, src, "-o", o, *common, *inc])
+        if force or not os.path.exists(o):
+            cmds.append(["nvcc", "-c", *extra, src, "-o", o, *common, *inc])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -132,5 +137,5 @@ def load():
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv)
+    p = build(force="--force" in sys.argv, relink="--relink" in sys.argv)
     print(p)
