@@ -38,8 +38,11 @@ struct Prof {
     bool used[ST_COUNT];
 };
 static Prof g_prof;
+static unsigned long long g_launches = 0;   // kernels launched by this library (bench.py: gpu_launches)
+void count_launch(int n) { g_launches += (unsigned long long)n; }
 void prof_begin(int stage, cudaStream_t s)
 {
+    g_launches++;
     if (!g_prof.on) return;
     if (!g_prof.created) {
         for (int i = 0; i < ST_COUNT; i++) { cudaEventCreate(&g_prof.ev[i][0]); cudaEventCreate(&g_prof.ev[i][1]); g_prof.used[i] = false; }
@@ -94,6 +97,8 @@ extern "C" {
 
 int dmr_abi_version(void) { return 1; }
 const char* dmr_last_error(void) { return g_err; }
+
+unsigned long long dmr_launch_count(void) { return g_launches; }
 
 int dmr_profile_enable(int on)
 {

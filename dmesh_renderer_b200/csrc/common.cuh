@@ -42,7 +42,8 @@ enum Stage {
     ST_SORT_PASS0, ST_SORT_PASS1, ST_SORT_PASS2, ST_SORT_PASS3, ST_SORT_PASS4, ST_SORT_PASS5, ST_SORT_PASS6, ST_SORT_PASS7,
     ST_RANGES, ST_TRI_FWD, ST_TRI_BWD, ST_TET_RECORDS, ST_TET_JITTER, ST_TET_FIRST, ST_TET_FWD, ST_TET_BWD, ST_COUNT
 };
-void prof_begin(int stage, cudaStream_t s);
+void count_launch(int n);
+void prof_begin(int stage, cudaStream_t s);   // also counts one kernel launch
 void prof_end(int stage, cudaStream_t s);
 struct ProfScope {
     int st; cudaStream_t s;

@@ -117,6 +117,7 @@ int tet_build_records(int P, int F, int T, const float* verts, const int* faces,
 {
     (void)P;
     ProfScope prof(ST_TET_RECORDS, stream);
+    if (T > 0 && F > 0) count_launch(1);   // two kernels under one scope
     if (T > 0) {
         tet_build_tetrec_kernel<<<(T + 255) / 256, 256, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
         DMR_LAUNCH_CHECK("tet_build_tetrec_kernel");

@@ -223,6 +223,8 @@ int    dmr_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in,
 /* (-1 = stage not run since the last read).  Used by bench.py for the        */
 /* roofline of the dominant kernel.  Not thread-safe; one stream at a time.   */
 /* ------------------------------------------------------------------------ */
+/* Number of kernels this library has launched so far in the process. */
+unsigned long long dmr_launch_count(void);
 int         dmr_profile_enable(int on);
 int         dmr_profile_stage_count(void);
 const char* dmr_profile_stage_name(int stage);

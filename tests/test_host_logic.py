@@ -1,0 +1,88 @@
+"""CPU: host-side logic of the drop-in boundary -- validation messages of the `_C` shim
+(reference render.cu:49-79, 237-277), the CUDA-only guard (no CPU fallback), camera sharding,
+seeded scene generation."""
+import pytest
+import torch
+
+from dmesh_renderer_b200 import (TetRenderer, TetRenderSettings, TriRenderer, TriRenderSettings, _C, scenes)
+from dmesh_renderer_b200.multiview import shard_views
+
+
+def tri_args(s):
+    mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
+    return [s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, torch.inverse(mv), torch.inverse(pj),
+            s.verts_depth, s.faces_intense, s.H, s.W]
+
+
+@pytest.mark.parametrize("idx,bad,msg", [
+    (1, lambda t: t[:, :2], "verts must have dimensions"),
+    (2, lambda t: t[:, :2], "faces must have dimensions"),
+    (3, lambda t: t[:5], "vert color must have dimensions"),
+    (4, lambda t: t[:5], "face opacity must have dimensions"),
+    (5, lambda t: t[:, :3], "mv_mats must have dimensions"),
+    (6, lambda t: t[0], "proj_mats must have dimensions"),
+    (7, lambda t: t[:, :, :2], "inv_mv_mats must have dimensions"),
+    (9, lambda t: t[:, :7], "verts_depth must have dimensions"),
+    (10, lambda t: t[:, :7], "faces_intense must have dimensions"),
+])
+def test_tri_validation_messages(idx, bad, msg):
+    a = tri_args(scenes.config("tiny_tri"))
+    a[idx] = bad(a[idx])
+    with pytest.raises(RuntimeError, match=msg):
+        _C.render_tris(*a)
+
+
+def test_tet_validation_messages():
+    s = scenes.config("tiny_tet")
+    mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
+    a = [s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, torch.inverse(mv), torch.inverse(pj),
+         s.verts_depth, s.faces_intense, s.tets, s.face_tets, s.tet_faces, s.H, s.W, 0]
+    for idx, bad, msg in [(11, lambda t: t[:, :3], "tets must have dimensions"),
+                          (12, lambda t: t[:4], "face_tets must have dimensions"),
+                          (13, lambda t: t[:4], "tet_faces must have dimensions"),
+                          (3, lambda t: t[:, :2], "vert_color must have dimensions")]:
+        b = list(a)
+        b[idx] = bad(b[idx])
+        with pytest.raises(RuntimeError, match=msg):
+            _C.render_tets(*b)
+
+
+def test_no_cpu_fallback():
+    a = tri_args(scenes.config("tiny_tri"))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        _C.render_tris(*a)
+    s = scenes.config("tiny_tri")
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        TriRenderer(TriRenderSettings(s.H, s.W, s.bg))(s.verts, s.faces, s.verts_color, s.faces_opacity, s.mv_mats,
+                                                       s.proj_mats, s.verts_depth, s.faces_intense)
+
+
+def test_api_surface_matches_reference_names():
+    import dmesh_renderer_b200 as m
+    for n in ["TriRenderSettings", "render_tri", "TriRenderer", "TetRenderSettings", "render_tet", "TetRenderer"]:
+        assert hasattr(m, n)
+    assert TriRenderSettings._fields == ("image_height", "image_width", "bg")
+    assert TetRenderSettings._fields == ("image_height", "image_width", "bg", "ray_random_seed")
+    for n in ["render_tris", "render_tris_backward", "render_tets", "render_tets_backward"]:
+        assert callable(getattr(_C, n))
+    assert isinstance(TetRenderer(TetRenderSettings(8, 8, torch.ones(3), 0)), torch.nn.Module)
+
+
+def test_shard_views_partitions_all_cameras():
+    for n, ws in [(64, 1), (64, 2), (64, 8), (7, 4), (3, 8)]:
+        got = [v for r in range(ws) for v in shard_views(n, r, ws)]
+        assert got == list(range(n))
+        sizes = [len(shard_views(n, r, ws)) for r in range(ws)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_scenes_are_deterministic_and_sized():
+    a, b = scenes.config("tiny_tri"), scenes.config("tiny_tri")
+    assert torch.equal(a.verts, b.verts) and torch.equal(a.faces_intense, b.faces_intense)
+    s = scenes.config("C1")
+    assert s.faces.shape == (10_000, 3) and s.verts.shape == (30_000, 3) and (s.H, s.W) == (256, 256)
+    t = scenes.config("tiny_tet")
+    T, F = t.tets.shape[0], t.faces.shape[0]
+    assert T == 6 * 4 ** 3 and t.tet_faces.shape == (T, 4) and t.face_tets.shape == (F, 2)
+    # every interior face has two tets, every boundary face one
+    assert int((t.face_tets[:, 1] < 0).sum()) == 6 * 2 * 4 * 4
