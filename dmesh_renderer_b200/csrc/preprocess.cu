@@ -18,7 +18,7 @@
 namespace dmr {
 
 // ---------------------------------------------------------------------------
-// points: out[b*P+p] = { pix.x, pix.y, ndc.z, verts_depth[b,p] }
+// points: out[b*P+p] = { pix.x, pix.y, ndc.z, verts_depth[b,p] }  (tet: 4th lane = clip w)
 // algorithmic bytes per (b,p): 12 (xyz) + 4 (depth) read, 16 written.
 // The reference also stores ndc.xy (never read downstream).
 // ---------------------------------------------------------------------------
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) preprocess_points_kernel(
     o.x = ndc2pix(ndc.x, W);
     o.y = ndc2pix(ndc.y, H);
     o.z = ndc.z;
-    o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : 0.0f;
+    o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : pp.w;   // tet path: clip-space w (bbox validity)
     vimg[(size_t)b * P + idx] = o;
 }
 
@@ -227,7 +227,7 @@ int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
 // faces (tet): replaces TET preprocessFaceCUDA (cuda_renderer/forward.cu:178-260).
 // Sort depth is the clamped MIN depth (renderer_impl.cu:325); the record carries
 // the world-space triangle plus min/max depth for firstIntersect.
-// algorithmic bytes per (b,f): read 12 + 3*16 + 3*12, write 4 + 4 + 8 + 48.
+// algorithmic bytes per (b,f): read 12 + 3*16 + 3*12, write 4 + 4 + 8 + 64.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
     int B, int P, int F, int gx, int gy,
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
     uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
     TetFaceRec* __restrict__ records)
 {
-    __shared__ uint4 s_rec[256 * 3];
+    __shared__ uint4 s_rec[256 * 4];
     const int tid = threadIdx.x;
     const size_t f0 = (size_t)blockIdx.x * 256;
     const int b = blockIdx.y;
@@ -244,6 +244,23 @@ __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
         int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
         const float4* vb = vimg + (size_t)b * P;
         float4 a0 = vb[i0], a1 = vb[i1], a2 = vb[i2];
+        // conservative pixel bounds of the projected triangle (valid only if all w are safely positive)
+        uint32_t bbx = 0xffff0000u, bby = 0xffff0000u;
+        if (a0.w > 1e-4f && a1.w > 1e-4f && a2.w > 1e-4f) {
+            float lx = fminf(fminf(a0.x, a1.x), a2.x), hx = fmaxf(fmaxf(a0.x, a1.x), a2.x);
+            float ly = fminf(fminf(a0.y, a1.y), a2.y), hy = fmaxf(fmaxf(a0.y, a1.y), a2.y);
+            // ray through pixel x passes at x+0.5 (or, jittered, in (x-0.5, x]); keep x when that can lie in
+            // [lx-1, hx+1]  <=>  x in [ceil(lx-1.5), floor(hx+1.5)]
+            int x0 = max(0, min(65535, (int)fmaxf(fminf(ceilf(lx - 1.5f), 70000.0f), -1.0f)));
+            int x1 = max(-1, min(65535, (int)fmaxf(fminf(floorf(hx + 1.5f), 70000.0f), -2.0f)));
+            int y0 = max(0, min(65535, (int)fmaxf(fminf(ceilf(ly - 1.5f), 70000.0f), -1.0f)));
+            int y1 = max(-1, min(65535, (int)fmaxf(fminf(floorf(hy + 1.5f), 70000.0f), -2.0f)));
+            if (x1 < x0 || y1 < y0) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }   // empty on screen
+            if (lx == lx && hx == hx && ly == ly && hy == hy) {           // NaN coordinates keep the full range
+                bbx = (uint32_t)x0 | ((uint32_t)x1 << 16);
+                bby = (uint32_t)y0 | ((uint32_t)y1 << 16);
+            }
+        }
         float max_z = a0.z, min_z = a0.z;
         max_z = fmaxf(max_z, a1.z); min_z = fminf(min_z, a1.z);
         max_z = fmaxf(max_z, a2.z); min_z = fminf(min_z, a2.z);
@@ -267,15 +284,16 @@ __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
         rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
 
         const float* q0 = verts + 3 * (size_t)i0; const float* q1 = verts + 3 * (size_t)i1; const float* q2 = verts + 3 * (size_t)i2;
-        uint4* r = s_rec + tid * 3;
+        uint4* r = s_rec + tid * 4;
         r[0] = make_uint4(__float_as_uint(q0[0]), __float_as_uint(q0[1]), __float_as_uint(q0[2]), __float_as_uint(q1[0]));
         r[1] = make_uint4(__float_as_uint(q1[1]), __float_as_uint(q1[2]), __float_as_uint(q2[0]), __float_as_uint(q2[1]));
-        r[2] = make_uint4(__float_as_uint(q2[2]), __float_as_uint(mn), __float_as_uint(mx), 0u);
+        r[2] = make_uint4(__float_as_uint(q2[2]), __float_as_uint(mn), __float_as_uint(mx), bbx);
+        r[3] = make_uint4(bby, 0u, 0u, 0u);
     }
     __syncthreads();
     size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
     uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
-    for (size_t i = tid; i < nvalid * 3; i += 256) dst[i] = s_rec[i];
+    for (size_t i = tid; i < nvalid * 4; i += 256) dst[i] = s_rec[i];
 }
 
 int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,

@@ -19,8 +19,8 @@
 
 namespace dmr {
 
-#define RS_THREADS 256
-#define RS_KPT 16
+#define RS_THREADS 512
+#define RS_KPT 8
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASS 8
@@ -59,38 +59,51 @@ struct SortTempLayout {
 size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n).total; }
 
 // ---------------------------------------------------------------------------
-// 1. histograms of all passes in one sweep
+// 1. histograms of all passes in one sweep.  8 keys per thread are loaded
+// before any is consumed (memory-level parallelism); a digit that is equal for
+// all 256 keys of a warp batch (the top depth byte, the batch bits, usually the
+// upper tile bits) costs one shared atomic instead of 256.
 // ---------------------------------------------------------------------------
+#define RSH_KPT 8
 __global__ void __launch_bounds__(256) rs_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int npass, int end_bit,
                                                       uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t s_hist[RS_MAX_PASS * 256];
-    for (int i = threadIdx.x; i < npass * 256; i += 256) s_hist[i] = 0;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < npass * 256; i += 256) s_hist[i] = 0;
     __syncthreads();
 
-    const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t base = (size_t)blockIdx.x * 256; base < n; base += stride) {
-        size_t i = base + threadIdx.x;
-        bool valid = i < n;
-        uint64_t k = valid ? keys[i] : 0;
-        unsigned act = __ballot_sync(0xffffffffu, valid);
+    const size_t chunk = 256 * RSH_KPT;
+    for (size_t base = (size_t)blockIdx.x * chunk; base < n; base += (size_t)gridDim.x * chunk) {
+        uint64_t k[RSH_KPT];
+        const bool full = base + chunk <= n;
+#pragma unroll
+        for (int i = 0; i < RSH_KPT; i++) {
+            size_t idx = base + (size_t)i * 256 + tid;
+            k[i] = (full || idx < n) ? keys[idx] : 0;
+        }
         for (int p = 0; p < npass; p++) {
-            int shift = 8 * p;
-            uint32_t mask = (end_bit - shift >= 8) ? 0xffu : ((1u << (end_bit - shift)) - 1u);
-            uint32_t d = (uint32_t)(k >> shift) & mask;
-            // constant digits (e.g. the top depth byte, the batch bits) would be a
-            // 32-way same-address shared atomic: aggregate them in the warp.
-            uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act) - 1);
-            bool uni = __all_sync(0xffffffffu, !valid || d == d0);
-            if (uni) {
-                if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1) && act) atomicAdd(&s_hist[p * 256 + d0], __popc(act));
-            } else if (valid) {
-                atomicAdd(&s_hist[p * 256 + d], 1u);
+            const int shift = 8 * p;
+            const uint32_t mask = (end_bit - shift >= 8) ? 0xffu : ((1u << (end_bit - shift)) - 1u);
+            uint32_t d[RSH_KPT];
+            bool same = full;
+#pragma unroll
+            for (int i = 0; i < RSH_KPT; i++) {
+                d[i] = (uint32_t)(k[i] >> shift) & mask;
+                same = same && d[i] == d[0];
+            }
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d[0], 0);
+            if (__all_sync(0xffffffffu, same && d[0] == d0)) {
+                if (lane == 0) atomicAdd(&s_hist[p * 256 + d0], 32u * RSH_KPT);
+            } else {
+#pragma unroll
+                for (int i = 0; i < RSH_KPT; i++)
+                    if (full || base + (size_t)i * 256 + tid < n) atomicAdd(&s_hist[p * 256 + d[i]], 1u);
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npass * 256; i += 256) {
+    for (int i = tid; i < npass * 256; i += 256) {
         uint32_t c = s_hist[i];
         if (c) atomicAdd(&hist[i], c);
     }
@@ -148,9 +161,9 @@ struct RsBuffers {
     uint64_t* ktmp; uint32_t* vtmp;
 };
 
-__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(RsBuffers buf, size_t n, int pass, int end_bit,
-                                                                  const uint32_t* __restrict__ hist_excl,
-                                                                  SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
+__global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(RsBuffers buf, size_t n, int pass, int end_bit,
+                                                                     const uint32_t* __restrict__ hist_excl,
+                                                                     SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
 {
     if (!ctl->exec[pass]) return;
     extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -160,6 +173,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(RsBuffers buf, 
     uint32_t* s_dbase = s_whist + RS_WARPS * 256;                                  // 256: local exclusive digit base
     int32_t*  s_gbase = reinterpret_cast<int32_t*>(s_dbase + 256);                 // 256: global pos - local pos (wrapping)
     __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_wsum[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s = ctl->src[pass], d_sel = ctl->dst[pass];
@@ -188,7 +202,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(RsBuffers buf, 
         uint32_t loc = wbase + i * 32 + lane;
         bool ok = loc < nvalid;
         key[i] = ok ? kin[tile_base + loc] : ~0ull;
-        val[i] = ok ? vin[tile_base + loc] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_KPT; i++) {
+        uint32_t loc = wbase + i * 32 + lane;
+        val[i] = (loc < nvalid) ? vin[tile_base + loc] : 0u;
     }
 
     // stable rank inside the warp, digit by digit occurrence
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(RsBuffers buf, 
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
         uint32_t loc = wbase + i * 32 + lane;
-        uint32_t d = (loc < nvalid) ? ((uint32_t)(key[i] >> shift) & dmask) : 256u + 0u;   // padding: own class
+        uint32_t d = (loc < nvalid) ? ((uint32_t)(key[i] >> shift) & dmask) : 256u;   // padding: own class
         unsigned peers = __match_any_sync(0xffffffffu, d);
         int leader = __ffs(peers) - 1;
         uint32_t before = __popc(peers & lt_mask);
@@ -210,50 +228,53 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(RsBuffers buf, 
     }
     __syncthreads();
 
-    // thread t owns digit t: exclusive scan over warps, tile count
+    // thread t < 256 owns digit t: exclusive scan over warps, tile count, publish, look-back
     uint32_t count = 0;
+    uint32_t* my_desc = nullptr;
+    if (tid < 256) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) {
-        uint32_t t = s_whist[w * 256 + tid];
-        s_whist[w * 256 + tid] = count;
-        count += t;
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t t = s_whist[w * 256 + tid];
+            s_whist[w * 256 + tid] = count;
+            count += t;
+        }
+        // publish the tile aggregate as early as possible
+        my_desc = desc + ((size_t)pass * gridDim.x + tile) * 256 + tid;
+        st_volatile_u32(my_desc, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | count);
     }
-    // publish the tile aggregate as early as possible
-    uint32_t* my_desc = desc + ((size_t)pass * gridDim.x + tile) * 256 + tid;
-    st_volatile_u32(my_desc, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | count);
-
     // exclusive scan over digits (local base inside the tile)
-    {
-        uint32_t incl = count;
+    uint32_t incl = count;
+    if (tid < 256) {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        __shared__ uint32_t s_wsum[RS_WARPS];
         if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (tid < 256) {
         uint32_t woff = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += s_wsum[w];
+        for (int w = 0; w < 8; w++) if (w < warp) woff += s_wsum[w];
         s_dbase[tid] = woff + incl - count;
-    }
 
-    // decoupled look-back for digit `tid`
-    uint32_t excl = 0;
-    if (tile > 0) {
-        long long t = (long long)tile - 1;
-        while (t >= 0) {
-            const uint32_t* p = desc + ((size_t)pass * gridDim.x + t) * 256 + tid;
-            uint32_t v;
-            do { v = ld_volatile_u32(p); } while ((v >> 30) == 0);
-            excl += v & RS_VAL_MASK;
-            if ((v >> 30) == 2u) break;
-            t--;
+        // decoupled look-back for digit `tid`
+        uint32_t excl = 0;
+        if (tile > 0) {
+            long long t = (long long)tile - 1;
+            while (t >= 0) {
+                const uint32_t* pd = desc + ((size_t)pass * gridDim.x + t) * 256 + tid;
+                uint32_t v;
+                do { v = ld_volatile_u32(pd); } while ((v >> 30) == 0);
+                excl += v & RS_VAL_MASK;
+                if ((v >> 30) == 2u) break;
+                t--;
+            }
+            st_volatile_u32(my_desc, RS_FLAG_INCL | (excl + count));
         }
-        st_volatile_u32(my_desc, RS_FLAG_INCL | (excl + count));
+        s_gbase[tid] = (int32_t)(hist_excl[pass * 256 + tid] + excl - s_dbase[tid]);
     }
-    s_gbase[tid] = (int32_t)(hist_excl[pass * 256 + tid] + excl - s_dbase[tid]);
     __syncthreads();
 
     // scatter into shared memory in digit order
@@ -303,8 +324,8 @@ int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
     }
-    size_t hblocks = (n + 255) / 256;
-    size_t hmax = (size_t)sm_count * 8;
+    size_t hblocks = (n + 256 * RSH_KPT - 1) / (256 * RSH_KPT);
+    size_t hmax = (size_t)sm_count * 8;   // 8 resident CTAs per SM
     if (hblocks > hmax) hblocks = hmax;
     {
         ProfScope prof(ST_SORT_HIST, stream);

@@ -5,13 +5,18 @@
 namespace dmr {
 
 // Per-(view,face) record staged by the first-intersection kernel
-// (replaces the gathers of cuda_renderer/forward.cu:368-381): 48 bytes.
+// (replaces the gathers of cuda_renderer/forward.cu:368-381): 64 bytes.
+// bbox = conservative screen-space pixel bounds (projected vertices +-1 px) used to skip
+// faces no pixel of a warp's block / no pixel at all can hit; 0..65535 (= no culling) when
+// a vertex is not safely in front of the camera (w <= 1e-4), where the projected
+// vertices do not bound the visible part of the triangle.
 struct __align__(16) TetFaceRec {
     float p0[3], p1[3], p2[3];   // world positions in faces[] order
     float min_depth, max_depth;  // clamped (z+1)/2, cuda_renderer/forward.cu:253-259
-    uint32_t pad;
+    uint32_t bbox_x, bbox_y;     // lo | hi << 16, inclusive pixel bounds
+    uint32_t pad[3];
 };
-static_assert(sizeof(TetFaceRec) == 48, "TetFaceRec must be 3 x 16 bytes");
+static_assert(sizeof(TetFaceRec) == 64, "TetFaceRec must be 4 x 16 bytes");
 
 // View-independent per-tet adjacency record used by the ray march.  The
 // reference re-gathers, at every step, tet_faces -> faces -> verts (3 dependent

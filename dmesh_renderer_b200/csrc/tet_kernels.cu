@@ -171,15 +171,21 @@ __device__ __forceinline__ void tet_pixel_ray(const TetParams& p, int b, uint32_
 // ---------------------------------------------------------------------------
 #define FI_RB 256
 
+// Hierarchical search: per group of 32 staged faces each lane tests one face's screen bbox against
+// the warp's 8x4 pixel block; survivors are walked in list order, and a pixel runs the (expensive)
+// ray/triangle test only when it lies inside the face's bbox.  Faces are sorted by min depth, so
+// deferring the reference's early-out check (forward.cu:388-391) to the next processed face cannot
+// change the result: every later face has a min depth at least as large.
 __global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
 {
-    __shared__ uint4 s_rec[FI_RB * 3];
+    __shared__ uint4 s_rec[FI_RB * 4];
     __shared__ int s_face[FI_RB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
-    const uint32_t px = blockIdx.x * DMR_TILE + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * DMR_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t bx0 = blockIdx.x * DMR_TILE + (warp & 1) * 8, by0 = blockIdx.y * DMR_TILE + (warp >> 1) * 4;
+    const uint32_t px = bx0 + (lane & 7);
+    const uint32_t py = by0 + (lane >> 3);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
     const size_t bpix = (size_t)b * p.W * p.H + (size_t)py * p.W + px;
     bool done = !inside;
@@ -202,25 +208,42 @@ __global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
                 uint32_t face = p.face_list[pos];
                 s_face[tid] = (int)face;
                 const uint4* src = reinterpret_cast<const uint4*>(p.face_rec + (size_t)b * p.F + face);
-                s_rec[tid * 3 + 0] = src[0];
-                s_rec[tid * 3 + 1] = src[1];
-                s_rec[tid * 3 + 2] = src[2];
+                s_rec[tid * 4 + 0] = src[0];
+                s_rec[tid * 4 + 1] = src[1];
+                s_rec[tid * 4 + 2] = src[2];
+                s_rec[tid * 4 + 3] = src[3];
             }
         }
         __syncthreads();
         const int cnt = min(FI_RB, total - r * FI_RB);
-        for (int j = 0; !done && j < cnt; j++) {
-            const float* w = reinterpret_cast<const float*>(s_rec + j * 3);
-            // forward.cu:388-391
-            if (min_T >= 0.0f && w[9] > min_T_max_depth) { done = true; continue; }
-            float3 tuv;
-            bool hit = ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
-            if (!hit) continue;
-            float cur = tuv.x;
-            if (min_T < 0.0f || cur < min_T) {
-                min_T = cur;
-                min_T_max_depth = w[10];
-                first_face = s_face[j];
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            const int jl = c0 + lane;
+            bool keep = false;
+            if (jl < cnt) {
+                const uint32_t bx = s_rec[jl * 4 + 2].w, by = s_rec[jl * 4 + 3].x;
+                keep = (bx & 0xffffu) <= bx0 + 7 && (bx >> 16) >= bx0 && (by & 0xffffu) <= by0 + 3 && (by >> 16) >= by0;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int j = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (done) continue;
+                const uint4 q2 = s_rec[j * 4 + 2];
+                // forward.cu:388-391
+                if (min_T >= 0.0f && __uint_as_float(q2.y) > min_T_max_depth) { done = true; continue; }
+                const uint32_t by = s_rec[j * 4 + 3].x;
+                if (px < (q2.w & 0xffffu) || px > (q2.w >> 16) || py < (by & 0xffffu) || py > (by >> 16)) continue;
+                const float* w = reinterpret_cast<const float*>(s_rec + j * 4);
+                float3 tuv;
+                bool hit = ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
+                if (!hit) continue;
+                float cur = tuv.x;
+                if (min_T < 0.0f || cur < min_T) {
+                    min_T = cur;
+                    min_T_max_depth = w[10];
+                    first_face = s_face[j];
+                }
             }
         }
     }
