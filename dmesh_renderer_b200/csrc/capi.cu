@@ -30,7 +30,7 @@ int cuda_fail(cudaError_t e, const char* what)
 static const char* const g_stage_names[ST_COUNT] = {
     "preprocess_points", "preprocess_faces", "scan", "duplicate_with_keys", "sort_histogram", "sort_plan",
     "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "sort_pass4", "sort_pass5", "sort_pass6", "sort_pass7",
-    "tile_ranges", "tri_render_forward", "tri_render_backward", "tet_build_records", "tet_jitter",
+    "tile_ranges", "tri_render_forward", "tri_render_backward", "tri_grad_finish", "tet_build_records", "tet_jitter",
     "tet_first_intersect", "tet_march_forward", "tet_march_backward" };
 struct Prof {
     bool on = false, created = false;
@@ -258,6 +258,9 @@ int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* back
     p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
     p.dL_dverts = dL_dverts; p.dL_dvcolor = dL_dvcolor; p.dL_dfopacity = dL_dfopacity;
     p.dL_dvdepth = dL_dvdepth; p.dL_dfintense = dL_dfintense;
+    // backward scratch lives in the face buffer (opaque state owned by autograd ctx)
+    p.grad_stats = const_cast<float*>(at<float>(face_buffer, FL.grad_stats));
+    DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (size_t)96 * B * F, stream));
     return tri_render_backward(p, stream);
 }
 

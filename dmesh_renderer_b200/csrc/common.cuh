@@ -40,7 +40,7 @@ int  cuda_fail(cudaError_t e, const char* what);
 enum Stage {
     ST_POINTS = 0, ST_FACES, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PLAN,
     ST_SORT_PASS0, ST_SORT_PASS1, ST_SORT_PASS2, ST_SORT_PASS3, ST_SORT_PASS4, ST_SORT_PASS5, ST_SORT_PASS6, ST_SORT_PASS7,
-    ST_RANGES, ST_TRI_FWD, ST_TRI_BWD, ST_TET_RECORDS, ST_TET_JITTER, ST_TET_FIRST, ST_TET_FWD, ST_TET_BWD, ST_COUNT
+    ST_RANGES, ST_TRI_FWD, ST_TRI_BWD, ST_TRI_BWD_FINISH, ST_TET_RECORDS, ST_TET_JITTER, ST_TET_FIRST, ST_TET_FWD, ST_TET_BWD, ST_COUNT
 };
 void count_launch(int n);
 void prof_begin(int stage, cudaStream_t s);   // also counts one kernel launch
@@ -174,7 +174,7 @@ static_assert(sizeof(TriRecord) == 144, "TriRecord must be 9 x 16 bytes");
 #define DMR_SCAN_TILE (DMR_SCAN_THREADS * DMR_SCAN_ITEMS)
 
 struct TriFaceLayout {
-    size_t tiles_touched, offsets, depth_key, rect, scan_state, records, total;
+    size_t tiles_touched, offsets, depth_key, rect, scan_state, records, grad_stats, total;
     __host__ static TriFaceLayout make(size_t BF)
     {
         TriFaceLayout L;
@@ -186,6 +186,7 @@ struct TriFaceLayout {
         size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
         L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);   // [0]=ticket, [1]=total, [32..]=descriptors
         L.records = o;       o = align_up(o + sizeof(TriRecord) * BF, 256);
+        L.grad_stats = o;    o = align_up(o + 96 * BF, 256);   // backward scratch: 24 floats per (view, face)
         L.total = o + 256;
         return L;
     }

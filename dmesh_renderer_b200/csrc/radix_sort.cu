@@ -24,6 +24,7 @@ namespace dmr {
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASS 8
+#define RS_LB 8          // look-back descriptors fetched per step
 
 #define RS_FLAG_AGG  (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
@@ -260,16 +261,27 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(RsBuffers bu
         s_dbase[tid] = woff + incl - count;
 
         // decoupled look-back for digit `tid`
+        // The walk back over predecessors that have only published their aggregate is a chain of
+        // dependent L2 round trips when done one descriptor at a time (and ~300 tiles are in flight):
+        // fetch RS_LB descriptors per step so the latencies overlap, then consume them in order.
         uint32_t excl = 0;
         if (tile > 0) {
+            const uint32_t* base = desc + (size_t)pass * gridDim.x * 256 + tid;
             long long t = (long long)tile - 1;
-            while (t >= 0) {
-                const uint32_t* pd = desc + ((size_t)pass * gridDim.x + t) * 256 + tid;
-                uint32_t v;
-                do { v = ld_volatile_u32(pd); } while ((v >> 30) == 0);
-                excl += v & RS_VAL_MASK;
-                if ((v >> 30) == 2u) break;
-                t--;
+            bool found = false;
+            while (!found && t >= 0) {
+                uint32_t v[RS_LB];
+#pragma unroll
+                for (int i = 0; i < RS_LB; i++) v[i] = (t - i >= 0) ? ld_volatile_u32(base + (size_t)(t - i) * 256) : RS_FLAG_INCL;
+#pragma unroll
+                for (int i = 0; i < RS_LB; i++) {
+                    if (!found) {
+                        while ((v[i] >> 30) == 0) v[i] = ld_volatile_u32(base + (size_t)(t - i) * 256);
+                        excl += v[i] & RS_VAL_MASK;
+                        if ((v[i] >> 30) == 2u) found = true;
+                    }
+                }
+                t -= RS_LB;
             }
             st_volatile_u32(my_desc, RS_FLAG_INCL | (excl + count));
         }

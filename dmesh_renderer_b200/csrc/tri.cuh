@@ -25,6 +25,7 @@ struct TriRenderParams {
     float* dL_dfopacity;
     float* dL_dvdepth;
     float* dL_dfintense;
+    float* grad_stats;              // [B*F,24] zeroed scratch (face buffer)
 };
 
 int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,

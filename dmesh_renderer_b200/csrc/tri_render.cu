@@ -19,9 +19,9 @@
 // decision and n_contrib are reproduced exactly.  Rays are recomputed per
 // pixel (the reference stores 24 B/px and reads them back twice).
 //
-// Backward: the 23 per-hit gradient terms are reduced across the warp with a
-// 24-shuffle transpose-reduction (each step halves the number of values a
-// lane carries) and leave as ONE red.global instruction with 23 active lanes,
+// Backward: see the design note above tri_render_bwd_kernel (sub-warp groups,
+// sufficient statistics for the vertex-position gradient, transpose-reduction,
+// one statistics record per (view, face) finished by tri_grad_finish_kernel)
 // instead of the reference's 23 atomics per covered pixel.
 #include "tri.cuh"
 
@@ -42,7 +42,8 @@ __device__ __forceinline__ void clamp_bary(float u, float v, float& uc, float& v
 }
 
 // Moeller-Trumbore (t,u,v), no inside test: auxiliary.h:255-286.
-__device__ __forceinline__ bool ray_tri_tuv(float3 ro, float3 rd, float3 p0, float3 p1, float3 p2, float3& tuv)
+__device__ __forceinline__ bool ray_tri_tuv(float3 ro, float3 rd, float3 p0, float3 p1, float3 p2, float3& tuv,
+                                            float& inv_denom_out)
 {
     float3 T = ro - p0;
     float3 E1 = p1 - p0;
@@ -55,7 +56,13 @@ __device__ __forceinline__ bool ray_tri_tuv(float3 ro, float3 rd, float3 p0, flo
     tuv.x = dot3(Q, E2) * inv_denom;
     tuv.y = dot3(Pv, T) * inv_denom;
     tuv.z = dot3(Q, rd) * inv_denom;
+    inv_denom_out = inv_denom;
     return true;
+}
+__device__ __forceinline__ bool ray_tri_tuv(float3 ro, float3 rd, float3 p0, float3 p1, float3 p2, float3& tuv)
+{
+    float unused;
+    return ray_tri_tuv(ro, rd, p0, p1, p2, tuv, unused);
 }
 
 // Can instance `e` cover any pixel of the block [x0,x1] x [y0,y1]?  Exact for
@@ -170,32 +177,6 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
 // backward
 // ---------------------------------------------------------------------------
 
-// auxiliary.h:288-333 (the max(denom,1e-7) there is dead: denom_inv is taken first)
-__device__ __forceinline__ void ray_tri_uv_grad(float3 ro, float3 rd, float3 p0, float3 p1, float3 p2, float3& du_dp0,
-                                                float3& du_dp1, float3& du_dp2, float3& dv_dp0, float3& dv_dp1,
-                                                float3& dv_dp2)
-{
-    float3 T = ro - p0;
-    float3 E1 = p1 - p0;
-    float3 E2 = p2 - p0;
-    float denom_sqrt = dot3(cross3(rd, E2), E1);
-    float denom = denom_sqrt * denom_sqrt;
-    float denom_inv = 1.0f / denom;
-    float v0 = dot3(cross3(rd, E2), T);
-    float v1 = denom_sqrt;
-    float v2 = dot3(cross3(T, E1), E2);
-    float3 du_dE1 = (-1 * cross3(rd, E2) * v0) * denom_inv;
-    float3 du_dE2 = (cross3(T, rd) * v1 - v0 * cross3(E1, rd)) * denom_inv;
-    float3 du_dT = (cross3(rd, E2) * v1) * denom_inv;
-    float3 dv_dE1 = ((cross3(E2, T) * v1) - (v2 * cross3(rd, E2))) * denom_inv;
-    float3 dv_dE2 = ((cross3(T, E1) * v1) - (v2 * cross3(E1, rd))) * denom_inv;
-    float3 dv_dT = cross3(E1, E2) * v1 * denom_inv;
-    du_dp0 = -du_dE1 - du_dE2 - du_dT;
-    dv_dp0 = -dv_dE1 - dv_dE2 - dv_dT;
-    du_dp1 = du_dE1; dv_dp1 = dv_dE1;
-    du_dp2 = du_dE2; dv_dp2 = dv_dE2;
-}
-
 // auxiliary.h:374-400
 __device__ __forceinline__ void clamp_bary_grad(int code, float& duc_du, float& duc_dv, float& dvc_du, float& dvc_dv)
 {
@@ -221,17 +202,38 @@ __device__ __forceinline__ void xreduce_step(float* v, bool hi)
     }
 }
 
-__global__ void __launch_bounds__(256) tri_render_bwd_kernel(TriRenderParams p)
+// Minimum over a pixel range of a*x (a signed coefficient).
+__device__ __forceinline__ int range_min(int a, int lo, int hi) { return a * (a < 0 ? hi : lo); }
+
+// Backward design
+// ---------------
+// * A warp owns an 8x4 pixel block, split into four GROUPS of 8 lanes (4x2 pixels).  Each group walks
+//   ITS OWN list of surviving instances (exact edge-function cull per sub-block), so the four groups
+//   shade four different faces in the same SIMD pass: for the small triangles that dominate real scenes
+//   this multiplies the lane utilisation of the (long) gradient path.
+// * Vertex-position gradients are not formed per pixel.  With u = A/D, A = rd.(E2xT), D = rd.(E2xE1) and
+//   the reference's "v" derivative (ray_tri_intersection_grad, auxiliary.h:288-333, actually the derivative
+//   of t = Nt/D, Nt = (TxE1).E2), the per-face sums only need
+//       S1  = sum dL_du/D * rd          S24 = sum (dL_du*u + dL_dv*t)/D * rd          S3 = sum dL_dv/D
+//   (7 floats); tri_grad_finish_kernel turns them into dL_dp0..2 once per (view, face):
+//       g_E1 = S3 (E2xT) - S24xE2,  g_E2 = TxS1 - E1xS24 + S3 (TxE1),  g_T = S1xE2 + S3 (E1xE2).
+//   This is the same derivative the reference evaluates per covered pixel with ~150 instructions.
+// * All 21 per-hit terms of a group are reduced over its 8 lanes with a transpose-reduction
+//   (12+6+3 = 21 shuffles) and added to ONE contiguous 96-byte statistics record per (view, face)
+//   -> 3 red.global instructions per SIMD pass, all lanes of a group on one cache line.
+// Statistics record (24 floats): S1[3] S24[3] S3 dL_dopacity dL_dintense dL_ddepth[3] dL_dcolor[3][3] pad[3]
+__global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams p)
 {
     __shared__ uint4 s_rec[RB * 9];
     __shared__ uint32_t s_face[RB];
     __shared__ int s_max[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 3, l = lane & 7;
     const int b = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int bx0 = blockIdx.x * DMR_TILE + (warp & 1) * 8, by0 = blockIdx.y * DMR_TILE + (warp >> 1) * 4;
-    const uint32_t px = bx0 + (lane & 7);
-    const uint32_t py = by0 + (lane >> 3);
+    const uint32_t px = bx0 + (g & 1) * 4 + (l & 3);
+    const uint32_t py = by0 + (g >> 1) * 2 + (l >> 2);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
     const size_t HW = (size_t)p.W * p.H;
     const size_t pix = (size_t)py * p.W + px;
@@ -263,10 +265,13 @@ __global__ void __launch_bounds__(256) tri_render_bwd_kernel(TriRenderParams p)
     float acc0 = 0, acc1 = 0, acc2 = 0, accd = 0;
     float last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, ld = 0;
 
-    // The tile walks only the prefix some pixel of it composited; the warp only its own.
-    int warp_last = last_contributor;
+    // The tile walks only the prefix some pixel of it composited; a warp / a group only its own.
+    int group_last = last_contributor;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+    for (int o = 4; o > 0; o >>= 1) group_last = max(group_last, __shfl_xor_sync(0xffffffffu, group_last, o));
+    int warp_last = group_last;
+    warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, 16));
+    warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, 8));
     if (lane == 0) s_max[warp] = warp_last;
     __syncthreads();
     int tile_last = 0;
@@ -274,23 +279,9 @@ __global__ void __launch_bounds__(256) tri_render_bwd_kernel(TriRenderParams p)
     for (int w = 0; w < 8; w++) tile_last = max(tile_last, s_max[w]);
     const int nchunk = (tile_last + RB - 1) / RB;   // chunk c covers list positions [c*RB, c*RB+RB)
 
-    // Destination of the value this lane owns after the transpose-reduction:
-    // value index = 3*(lane>>2) + (lane&3); (lane&3)==3 is padding.
-    //   0..8   dL_dverts  of vertex 0,1,2 (xyz)      9..17  dL_dvcolor of vertex 0,1,2 (rgb)
-    //   18..20 dL_dvdepth of vertex 0,1,2            21 dL_dfopacity   22 dL_dfintense
-    const int g = lane >> 2, cidx = lane & 3;
-    float* out_base;
-    int out_mul, out_add, out_sel;   // address = out_base + out_mul * id[out_sel] + out_add
-    bool out_valid = cidx < 3;
-    if (g < 3) { out_base = p.dL_dverts; out_mul = 3; out_add = cidx; out_sel = g; }
-    else if (g < 6) { out_base = p.dL_dvcolor; out_mul = 3; out_add = cidx; out_sel = g - 3; }
-    else if (g == 6) { out_base = p.dL_dvdepth + (size_t)b * p.P; out_mul = 1; out_add = 0; out_sel = cidx; }
-    else {
-        out_base = cidx == 0 ? p.dL_dfopacity : p.dL_dfintense + (size_t)b * p.F;
-        out_mul = 1; out_add = 0; out_sel = 3;
-        out_valid = cidx < 2;
-    }
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+    // pixel ranges of the four sub-blocks: x in {bx0..bx0+3, bx0+4..bx0+7}, y in {by0..by0+1, by0+2..by0+3}
+    const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+    float* const stats = p.grad_stats;
 
     for (int c = nchunk - 1; c >= 0; c--) {
         __syncthreads();
@@ -308,122 +299,201 @@ __global__ void __launch_bounds__(256) tri_render_bwd_kernel(TriRenderParams p)
         __syncthreads();
         const int cnt = min(RB, warp_last - c * RB);       // this warp's share of the chunk
         for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0 && cnt > 0; c0 -= 32) {
-            const int jl = c0 + lane;
-            bool keep = false;
-            if (jl < cnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
-            unsigned mask = __ballot_sync(0xffffffffu, keep);
-            while (mask) {
-                const int bit = 31 - __clz(mask);
-                mask &= ~(1u << bit);
-                const int j = c0 + bit;
-                const int contributor = c * RB + j;      // 0-based list index (reference: after decrement)
-                const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1], e2 = s_rec[j * 9 + 2];
-                uint32_t s0 = e0.x * px + e0.y * py + e0.z;
-                uint32_t s1 = e1.x * px + e1.y * py + e1.z;
-                uint32_t s2 = e2.x * px + e2.y * py + e2.z;
-                bool hit = contributor < last_contributor && (int)(s0 & s1 & s2) < 0;
-                const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
-                float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
-                float3 tuv = f3(0, 0, 0);
-                if (hit) hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv);
-                if (!__any_sync(0xffffffffu, hit)) continue;
+            // ---- cull: lane tests instance c0+lane against the four sub-blocks
+            unsigned k4 = 0;   // bit s: instance may cover sub-block s
+            {
+                const int jl = c0 + lane;
+                if (jl < cnt) {
+                    const uint4 e0 = s_rec[jl * 9 + 0], e1 = s_rec[jl * 9 + 1], e2 = s_rec[jl * 9 + 2];
+                    if (!(e2.w & DMR_REC_SAFE)) k4 = 0xf;
+                    else {
+                        const int a[3] = { (int)e0.x, (int)e1.x, (int)e2.x }, bb[3] = { (int)e0.y, (int)e1.y, (int)e2.y };
+                        const int cc[3] = { (int)e0.z, (int)e1.z, (int)e2.z };
+                        int m[4] = { -1, -1, -1, -1 };
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const int xl = range_min(a[k], bx0, bx0 + 3), xh = range_min(a[k], bx0 + 4, bx0 + 7);
+                            const int yl = cc[k] + range_min(bb[k], by0, by0 + 1), yh = cc[k] + range_min(bb[k], by0 + 2, by0 + 3);
+                            m[0] &= xl + yl; m[1] &= xh + yl; m[2] &= xl + yh; m[3] &= xh + yh;
+                        }
+                        k4 = (m[0] < 0 ? 1u : 0u) | (m[1] < 0 ? 2u : 0u) | (m[2] < 0 ? 4u : 0u) | (m[3] < 0 ? 8u : 0u);
+                    }
+                }
+            }
+            const unsigned m0 = __ballot_sync(0xffffffffu, k4 & 1u), m1 = __ballot_sync(0xffffffffu, k4 & 2u);
+            const unsigned m2 = __ballot_sync(0xffffffffu, k4 & 4u), m3 = __ballot_sync(0xffffffffu, k4 & 8u);
+            unsigned mymask = g == 0 ? m0 : g == 1 ? m1 : g == 2 ? m2 : m3;
+            {   // drop list positions at or beyond this group's last contributor
+                const int lim = group_last - (c * RB + c0);
+                if (lim < 32) mymask &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
+            }
 
+            for (;;) {
+                // ---- find: advance every group to its next instance with at least one covered pixel
+                bool have = false, cov = false;
+                int j = 0;
+                for (;;) {
+                    const bool searching = !have && mymask != 0u;
+                    bool cj = false;
+                    int jj = 0;
+                    if (searching) {
+                        const int bit = 31 - __clz(mymask);
+                        mymask &= ~(1u << bit);
+                        jj = c0 + bit;
+                        const uint4 e0 = s_rec[jj * 9 + 0], e1 = s_rec[jj * 9 + 1], e2 = s_rec[jj * 9 + 2];
+                        const uint32_t s0 = e0.x * px + e0.y * py + e0.z;
+                        const uint32_t s1 = e1.x * px + e1.y * py + e1.z;
+                        const uint32_t s2 = e2.x * px + e2.y * py + e2.z;
+                        // reference: skip when contributor >= last_contributor (backward.cu:192-194)
+                        cj = (c * RB + jj) < last_contributor && (int)(s0 & s1 & s2) < 0;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, cj);
+                    if (searching && ((bal >> (lane & 24)) & 0xffu)) { have = true; j = jj; cov = cj; }
+                    if (!__any_sync(0xffffffffu, !have && mymask != 0u)) break;
+                }
+                if (!__any_sync(0xffffffffu, have)) break;
+
+                // ---- shade: lanes with a covered pixel evaluate the gradient terms of their group's face
                 float v[24];
 #pragma unroll
                 for (int k = 0; k < 24; k++) v[k] = 0.0f;
-                if (hit) {
-                    float uc, vc;
-                    int code;
-                    clamp_bary(tuv.y, tuv.z, uc, vc, code);
-                    float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
-                    const float intense = __uint_as_float(e1.w);
-                    const float alpha = __uint_as_float(e0.w);
-                    float iC0 = (i0 * w[9] + i1 * w[12] + i2 * w[15]) * intense;
-                    float iC1 = (i0 * w[10] + i1 * w[13] + i2 * w[16]) * intense;
-                    float iC2 = (i0 * w[11] + i1 * w[14] + i2 * w[17]) * intense;
-                    float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
+                if (have && cov) {
+                    const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
+                    const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
+                    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
+                    float3 tuv = f3(0, 0, 0);
+                    float inv_denom = 0.0f;
+                    if (ray_tri_tuv(ro, rd, v0, v1, v2, tuv, inv_denom)) {
+                        float uc, vc;
+                        int code;
+                        clamp_bary(tuv.y, tuv.z, uc, vc, code);
+                        const float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
+                        const float intense = __uint_as_float(e1.w);
+                        const float alpha = __uint_as_float(e0.w);
+                        const float iC0 = (i0 * w[9] + i1 * w[12] + i2 * w[15]) * intense;
+                        const float iC1 = (i0 * w[10] + i1 * w[13] + i2 * w[16]) * intense;
+                        const float iC2 = (i0 * w[11] + i1 * w[14] + i2 * w[17]) * intense;
+                        const float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
 
-                    // backward.cu:244-252
-                    if (!T_first) T = T / (1.f - alpha);
-                    T_first = false;
+                        // backward.cu:244-252
+                        if (!T_first) T = T / (1.f - alpha);
+                        T_first = false;
 
-                    float dL_dalpha = 0.0f;
-                    // colour, backward.cu:262-272
-                    acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = iC0;
-                    float dic0 = dLc0 * alpha * T; dL_dalpha += (iC0 - acc0) * dLc0;
-                    acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = iC1;
-                    float dic1 = dLc1 * alpha * T; dL_dalpha += (iC1 - acc1) * dLc1;
-                    acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = iC2;
-                    float dic2 = dLc2 * alpha * T; dL_dalpha += (iC2 - acc2) * dLc2;
-                    // depth, backward.cu:275-284
-                    accd = last_alpha * ld + (1.f - last_alpha) * accd; ld = iD;
-                    float did = dLd * alpha * T; dL_dalpha += (iD - accd) * dLd;
+                        float dL_dalpha = 0.0f;
+                        // colour, backward.cu:262-272
+                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = iC0;
+                        const float dic0 = dLc0 * alpha * T; dL_dalpha += (iC0 - acc0) * dLc0;
+                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = iC1;
+                        const float dic1 = dLc1 * alpha * T; dL_dalpha += (iC1 - acc1) * dLc1;
+                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = iC2;
+                        const float dic2 = dLc2 * alpha * T; dL_dalpha += (iC2 - acc2) * dLc2;
+                        // depth, backward.cu:275-284
+                        accd = last_alpha * ld + (1.f - last_alpha) * accd; ld = iD;
+                        const float did = dLd * alpha * T; dL_dalpha += (iD - accd) * dLd;
 
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    // background term, backward.cu:299-308
-                    if (alpha == 1.0f) {
-                        dL_dalpha += (-prev_T_final) * bg_dot;
-                        dL_dalpha += (-prev_T_final) * bd_dot;
-                    } else {
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bd_dot;
-                    }
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        // background term, backward.cu:299-308
+                        if (alpha == 1.0f) {
+                            dL_dalpha += (-prev_T_final) * bg_dot;
+                            dL_dalpha += (-prev_T_final) * bd_dot;
+                        } else {
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                            dL_dalpha += (-T_final / (1.f - alpha)) * bd_dot;
+                        }
 
-                    // backward.cu:327-349
-                    float dL_di0 = 0, dL_di1 = 0, dL_di2 = 0, dL_dint = 0;
-                    const float dic[3] = { dic0, dic1, dic2 };
+                        // backward.cu:327-349
+                        float dL_di0 = 0, dL_di1 = 0, dL_di2 = 0, dL_dint = 0;
+                        const float dic[3] = { dic0, dic1, dic2 };
 #pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        dL_di0 += w[9 + ch] * dic[ch] * intense;
-                        dL_di1 += w[12 + ch] * dic[ch] * intense;
-                        dL_di2 += w[15 + ch] * dic[ch] * intense;
-                        v[9 + ch] = i0 * dic[ch] * intense;
-                        v[12 + ch] = i1 * dic[ch] * intense;
-                        v[15 + ch] = i2 * dic[ch] * intense;
-                        dL_dint += (i0 * w[9 + ch] + i1 * w[12 + ch] + i2 * w[15 + ch]) * dic[ch];
-                    }
-                    dL_di0 += w[18] * did;
-                    dL_di1 += w[19] * did;
-                    dL_di2 += w[20] * did;
-                    v[18] = i0 * did; v[19] = i1 * did; v[20] = i2 * did;
-                    v[21] = dL_dalpha;
-                    v[22] = dL_dint;
+                        for (int ch = 0; ch < 3; ch++) {
+                            dL_di0 += w[9 + ch] * dic[ch] * intense;
+                            dL_di1 += w[12 + ch] * dic[ch] * intense;
+                            dL_di2 += w[15 + ch] * dic[ch] * intense;
+                            v[12 + ch] = i0 * dic[ch] * intense;
+                            v[15 + ch] = i1 * dic[ch] * intense;
+                            v[18 + ch] = i2 * dic[ch] * intense;
+                            dL_dint += (i0 * w[9 + ch] + i1 * w[12 + ch] + i2 * w[15 + ch]) * dic[ch];
+                        }
+                        dL_di0 += w[18] * did;
+                        dL_di1 += w[19] * did;
+                        dL_di2 += w[20] * did;
+                        v[9] = i0 * did; v[10] = i1 * did; v[11] = i2 * did;
+                        v[7] = dL_dalpha;
+                        v[8] = dL_dint;
 
-                    // backward.cu:354-382
-                    float duc_du, duc_dv, dvc_du, dvc_dv;
-                    clamp_bary_grad(code, duc_du, duc_dv, dvc_du, dvc_dv);
-                    float di0_du = -1 * duc_du + -1 * dvc_du, di0_dv = -1 * duc_dv + -1 * dvc_dv;
-                    float di1_du = 1 * duc_du + 0 * dvc_du, di1_dv = 1 * duc_dv + 0 * dvc_dv;
-                    float di2_du = 0 * duc_du + 1 * dvc_du, di2_dv = 0 * duc_dv + 1 * dvc_dv;
-                    float dL_du = dL_di0 * di0_du + dL_di1 * di1_du + dL_di2 * di2_du;
-                    float dL_dv = dL_di0 * di0_dv + dL_di1 * di1_dv + dL_di2 * di2_dv;
-                    float3 du0, du1, du2, dv0, dv1, dv2;
-                    ray_tri_uv_grad(ro, rd, v0, v1, v2, du0, du1, du2, dv0, dv1, dv2);
-                    float3 dp0 = dL_du * du0 + dL_dv * dv0;
-                    float3 dp1 = dL_du * du1 + dL_dv * dv1;
-                    float3 dp2 = dL_du * du2 + dL_dv * dv2;
-                    v[0] = dp0.x; v[1] = dp0.y; v[2] = dp0.z;
-                    v[3] = dp1.x; v[4] = dp1.y; v[5] = dp1.z;
-                    v[6] = dp2.x; v[7] = dp2.y; v[8] = dp2.z;
+                        // backward.cu:354-369: chain through the clamp
+                        float duc_du, duc_dv, dvc_du, dvc_dv;
+                        clamp_bary_grad(code, duc_du, duc_dv, dvc_du, dvc_dv);
+                        const float di0_du = -1 * duc_du + -1 * dvc_du, di0_dv = -1 * duc_dv + -1 * dvc_dv;
+                        const float di1_du = 1 * duc_du + 0 * dvc_du, di1_dv = 1 * duc_dv + 0 * dvc_dv;
+                        const float di2_du = 0 * duc_du + 1 * dvc_du, di2_dv = 0 * duc_dv + 1 * dvc_dv;
+                        const float dL_du = dL_di0 * di0_du + dL_di1 * di1_du + dL_di2 * di2_du;
+                        const float dL_dv = dL_di0 * di0_dv + dL_di1 * di1_dv + dL_di2 * di2_dv;
+                        // sufficient statistics of the vertex-position gradient (see header comment)
+                        const float k1 = dL_du * inv_denom;
+                        const float k24 = (dL_du * tuv.y + dL_dv * tuv.x) * inv_denom;
+                        v[0] = k1 * rd.x; v[1] = k1 * rd.y; v[2] = k1 * rd.z;
+                        v[3] = k24 * rd.x; v[4] = k24 * rd.y; v[5] = k24 * rd.z;
+                        v[6] = dL_dv * inv_denom;
+                    }
                 }
 
-                // warp transpose-reduction: 24 -> 12 -> 6 -> 3(+1 pad) -> 2 -> 1 value per lane
-                xreduce_step<12, 16>(v, h16);
-                xreduce_step<6, 8>(v, h8);
-                xreduce_step<3, 4>(v, h4);
-                v[3] = 0.0f;
-                xreduce_step<2, 2>(v, h2);
-                xreduce_step<1, 1>(v, h1);
-
-                if (out_valid) {
-                    const int vi0 = __float_as_int(w[21]), vi1 = __float_as_int(w[22]), vi2 = __float_as_int(w[23]);
-                    const int id = out_sel == 0 ? vi0 : out_sel == 1 ? vi1 : out_sel == 2 ? vi2 : (int)s_face[j];
-                    atomicAdd(out_base + (size_t)out_mul * id + out_add, v[0]);
+                // ---- reduce over the 8 lanes of each group: 24 -> 12 -> 6 -> 3 values per lane
+                xreduce_step<12, 4>(v, h4);
+                xreduce_step<6, 2>(v, h2);
+                xreduce_step<3, 1>(v, h1);
+                if (have && l < 7) {   // lane l owns slots 3l..3l+2 (slots 21..23 are padding)
+                    float* dst = stats + ((size_t)b * p.F + s_face[j]) * 24 + 3 * l;
+                    if (v[0] != 0.0f) atomicAdd(dst + 0, v[0]);
+                    if (v[1] != 0.0f) atomicAdd(dst + 1, v[1]);
+                    if (v[2] != 0.0f) atomicAdd(dst + 2, v[2]);
                 }
             }
         }
     }
+}
+
+// Once per (view, face): statistics -> gradients of the five inputs (see tri_render_bwd_kernel).
+__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t BF = (size_t)p.B * p.F;
+    if (idx >= BF) return;
+    const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + idx * 24);
+    float st[24];
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        float4 t = st4[q];
+        st[4 * q] = t.x; st[4 * q + 1] = t.y; st[4 * q + 2] = t.z; st[4 * q + 3] = t.w;
+        any = any || t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f;
+    }
+    if (!any) return;
+    const int b = (int)(idx / (size_t)p.F);
+    const size_t f = idx - (size_t)b * p.F;
+    const float* w = reinterpret_cast<const float*>(p.records + idx) + 12;
+    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
+    const int vi[3] = { __float_as_int(w[21]), __float_as_int(w[22]), __float_as_int(w[23]) };
+    const float* imv = p.inv_mv + 16 * b;
+    const float3 ro = f3(imv[12], imv[13], imv[14]);
+    const float3 T = ro - v0, E1 = v1 - v0, E2 = v2 - v0;
+    const float3 S1 = f3(st[0], st[1], st[2]), S24 = f3(st[3], st[4], st[5]);
+    const float S3 = st[6];
+    const float3 gE1 = S3 * cross3(E2, T) - cross3(S24, E2);
+    const float3 gE2 = cross3(T, S1) - cross3(E1, S24) + S3 * cross3(T, E1);
+    const float3 gT = cross3(S1, E2) + S3 * cross3(E1, E2);
+    const float3 dp[3] = { -gE1 - gE2 - gT, gE1, gE2 };
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float* dv = p.dL_dverts + 3 * (size_t)vi[k];
+        atomicAdd(dv + 0, dp[k].x); atomicAdd(dv + 1, dp[k].y); atomicAdd(dv + 2, dp[k].z);
+        float* dc = p.dL_dvcolor + 3 * (size_t)vi[k];
+        atomicAdd(dc + 0, st[12 + 3 * k]); atomicAdd(dc + 1, st[13 + 3 * k]); atomicAdd(dc + 2, st[14 + 3 * k]);
+        atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+    }
+    atomicAdd(p.dL_dfopacity + f, st[7]);
+    p.dL_dfintense[idx] = st[8];
 }
 
 int tri_render_forward(const TriRenderParams& p, cudaStream_t stream)
@@ -440,9 +510,17 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
 {
     if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
-    ProfScope prof(ST_TRI_BWD, stream);
-    tri_render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
-    DMR_LAUNCH_CHECK("tri_render_bwd_kernel");
+    {
+        ProfScope prof(ST_TRI_BWD, stream);
+        tri_render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tri_render_bwd_kernel");
+    }
+    {
+        ProfScope prof(ST_TRI_BWD_FINISH, stream);
+        const size_t BF = (size_t)p.B * p.F;
+        tri_grad_finish_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tri_grad_finish_kernel");
+    }
     return 0;
 }
 
