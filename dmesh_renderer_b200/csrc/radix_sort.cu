@@ -24,7 +24,7 @@ namespace dmr {
 #define RS_TILE (RS_THREADS * RS_KPT)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_MAX_PASS 8
-#define RS_LB 8          // look-back descriptors fetched per step
+#define RS_LB 16         // look-back descriptors fetched per step (see the stability note at the look-back)
 
 #define RS_FLAG_AGG  (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
@@ -264,6 +264,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(RsBuffers bu
         // The walk back over predecessors that have only published their aggregate is a chain of
         // dependent L2 round trips when done one descriptor at a time (and ~300 tiles are in flight):
         // fetch RS_LB descriptors per step so the latencies overlap, then consume them in order.
+        // (Stability: with one L2 round trip (~600 cycles) per descriptor and a new tile starting
+        // every ~70 cycles chip-wide, a serial walk takes longer per entry than new unfinished
+        // predecessors arrive, and every tile ends up walking back over ALL ~300 tiles in flight --
+        // measured: 21k cycles per tile.  RS_LB = 16 brings the cost per entry to ~40 cycles.)
         uint32_t excl = 0;
         if (tile > 0) {
             const uint32_t* base = desc + (size_t)pass * gridDim.x * 256 + tid;
