@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
     __shared__ uint32_t s_incl[256];
     __shared__ uint2 s_rect[256];
     __shared__ uint32_t s_depth[256];
+    __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance 64-bit divisions hoisted)
+    __shared__ uint32_t s_fid[256];     // face id inside its view
     const int tid = threadIdx.x;
     const size_t f0 = (size_t)blockIdx.x * 256;
     const size_t f = f0 + tid;
@@ -164,6 +166,9 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
         my_incl = offsets[f];
         s_rect[tid] = rect[f];
         s_depth[tid] = depth_key[f];
+        const uint32_t bview = (uint32_t)((uint32_t)f / (uint32_t)F);   // B*F < 2^31 (checked by the caller)
+        s_tile0[tid] = (uint32_t)tiles_per_view * bview;
+        s_fid[tid] = (uint32_t)f - bview * (uint32_t)F;
     }
     s_incl[tid] = my_incl;
     __syncthreads();
@@ -184,13 +189,10 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
         const uint32_t x0 = r.x & 0xffffu, x1 = r.x >> 16, y0 = r.y & 0xffffu;
         const uint32_t w = x1 - x0;
         const uint32_t ty = y0 + k / w, tx = x0 + k % w;
-        const size_t gf = f0 + i;
-        const uint32_t b = (uint32_t)(gf / (size_t)F);
-        const uint32_t face = (uint32_t)(gf - (size_t)b * F);
-        uint64_t key = (uint64_t)(ty * (uint32_t)tiles_x + tx) + (uint64_t)tiles_per_view * b;
+        uint64_t key = (uint64_t)(ty * (uint32_t)tiles_x + tx + s_tile0[i]);
         key = (key << 32) | (uint64_t)s_depth[i];
         keys[o] = key;
-        vals[o] = face;
+        vals[o] = s_fid[i];
     }
 }
 
