@@ -16,13 +16,11 @@
 //                      global stores are coalesced per digit run.
 // Algorithmic bytes: 8 B/key (histogram) + 24 B/key per executed pass.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace dmr {
 
-#define RS_THREADS 512
-#define RS_KPT 8
-#define RS_TILE (RS_THREADS * RS_KPT)
-#define RS_WARPS (RS_THREADS / 32)
+#define RS_MIN_TILE 2048   // smallest tile of any configuration (sizes the descriptor array)
 #define RS_MAX_PASS 8
 #define RS_LB 16         // look-back descriptors fetched per step (see the stability note at the look-back)
 
@@ -44,7 +42,7 @@ struct SortTempLayout {
     __host__ static SortTempLayout make(size_t n)
     {
         SortTempLayout L;
-        L.ntile = (n + RS_TILE - 1) / RS_TILE;
+        L.ntile = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
         size_t o = 0;
         L.keys_tmp = o; o = align_up(o + 8 * n, 256);
         L.vals_tmp = o; o = align_up(o + 4 * n, 256);
@@ -171,10 +169,13 @@ struct RsBuffers {
 // after ranking), and the look-back only has to walk over the few predecessors that have not yet
 // published their inclusive prefix -- RS_LB descriptors are fetched per step so that walk costs one
 // L2 round trip per RS_LB tiles.
-__global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(RsBuffers buf, size_t n, int pass, int end_bit,
-                                                                     const uint32_t* __restrict__ hist_excl,
-                                                                     SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
+template <int RS_THREADS, int RS_KPT, int RS_MINB>
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers buf, size_t n, int pass, int end_bit,
+                                                                          const uint32_t* __restrict__ hist_excl,
+                                                                          SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
 {
+    constexpr int RS_TILE = RS_THREADS * RS_KPT;
+    constexpr int RS_WARPS = RS_THREADS / 32;
     if (!ctl->exec[pass]) return;
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_smem);                       // RS_TILE
@@ -316,7 +317,25 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_onesweep_kernel(RsBuffers bu
     }
 }
 
-static const size_t RS_SMEM_BYTES = 8 * RS_TILE + 4 * RS_TILE + 4 * RS_WARPS * 256 + 4 * 256 + 4 * 256;
+template <int THREADS, int KPT, int MINB>
+static int launch_onesweep(const RsBuffers& buf, size_t n, int npass, int end_bit, const uint32_t* hist, SortCtl* ctl,
+                           uint32_t* desc, cudaStream_t stream)
+{
+    constexpr size_t tile = (size_t)THREADS * KPT;
+    constexpr size_t smem = 8 * tile + 4 * tile + 4 * (THREADS / 32) * 256 + 4 * 256 + 4 * 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMR_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<THREADS, KPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const unsigned ntile = (unsigned)((n + tile - 1) / tile);
+    for (int p = 0; p < npass; p++) {
+        ProfScope prof(ST_SORT_PASS0 + p, stream);
+        rs_onesweep_kernel<THREADS, KPT, MINB><<<ntile, THREADS, smem, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
+        DMR_LAUNCH_CHECK("rs_onesweep_kernel");
+    }
+    return 0;
+}
 
 int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
                int end_bit, void* temp, cudaStream_t stream)
@@ -330,16 +349,23 @@ int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_
     uint32_t* hist = reinterpret_cast<uint32_t*>(t + L.hist);
     SortCtl* ctl = reinterpret_cast<SortCtl*>(t + L.ctl);
     uint32_t* desc = reinterpret_cast<uint32_t*>(t + L.desc);
-    size_t zero_bytes = (L.desc - L.zero_begin) + 4 * 256 * L.ntile * (size_t)npass;
-    DMR_CUDA(cudaMemsetAsync(t + L.zero_begin, 0, zero_bytes, stream));
 
-    static int sm_count = 0;
+    static int sm_count = 0, cfg = -1;
     if (sm_count == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
+        const char* e = getenv("DMR_SORT_CFG");   // tuning knob for profiles/; the default is the measured best
+        cfg = e ? atoi(e) : 0;
     }
+    // tile size of the chosen configuration (descriptor rows actually used)
+    static const size_t tile_of[] = { 4096, 4096, 2048, 8192, 6144 };
+    const size_t tile = tile_of[(cfg >= 0 && cfg < 5) ? cfg : 0];
+    const size_t ntile = (n + tile - 1) / tile;
+    size_t zero_bytes = (L.desc - L.zero_begin) + 4 * 256 * ntile * (size_t)npass;
+    DMR_CUDA(cudaMemsetAsync(t + L.zero_begin, 0, zero_bytes, stream));
+
     size_t hblocks = (n + 256 * RSH_KPT - 1) / (256 * RSH_KPT);
     size_t hmax = (size_t)sm_count * 8;   // 8 resident CTAs per SM
     if (hblocks > hmax) hblocks = hmax;
@@ -353,22 +379,17 @@ int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_
         rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
         DMR_LAUNCH_CHECK("rs_plan_kernel");
     }
-
-    static bool attr_set = false;
-    if (!attr_set) {
-        DMR_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
-        attr_set = true;
-    }
     RsBuffers buf;
     buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
     buf.ktmp = reinterpret_cast<uint64_t*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
-    for (int p = 0; p < npass; p++) {
-        ProfScope prof(ST_SORT_PASS0 + p, stream);
-        rs_onesweep_kernel<<<(unsigned)L.ntile, RS_THREADS, RS_SMEM_BYTES, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
-        DMR_LAUNCH_CHECK("rs_onesweep_kernel");
+    switch (cfg) {
+    case 1:  return launch_onesweep<256, 16, 2>(buf, n, npass, end_bit, hist, ctl, desc, stream);
+    case 2:  return launch_onesweep<256, 8, 4>(buf, n, npass, end_bit, hist, ctl, desc, stream);
+    case 3:  return launch_onesweep<512, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, stream);
+    case 4:  return launch_onesweep<384, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, stream);
+    default: return launch_onesweep<512, 8, 2>(buf, n, npass, end_bit, hist, ctl, desc, stream);
     }
-    return 0;
 }
 
 }  // namespace dmr
