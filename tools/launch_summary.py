@@ -10,6 +10,8 @@ for path in sys.argv[1:]:
     agg = collections.OrderedDict()
     for r in rows[1:]:
         k = r[ki]
+        if k.startswith("void dmr::"):
+            k = k[5:]
         k = k[:k.index("(")] if "(" in k and k.startswith("dmr::") else k[:70]
         agg.setdefault(k, []).append(float(r[vi].replace(",", "")))
     ours = {k: v for k, v in agg.items() if k.startswith("dmr::")}

@@ -1,0 +1,51 @@
+"""Summarise an ncu --set full report (.ncu-rep) into a small csv: one row per profiled launch with the
+metrics the roofline discussion needs.  usage: ncu_summary.py report.ncu-rep out.csv"""
+import csv
+import subprocess
+import sys
+
+WANT = [
+    ("Kernel Name", "kernel"),
+    ("gpu__time_duration.sum", "duration_us"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("launch__registers_per_thread", "regs"),
+    ("launch__occupancy_limit_registers", "occ_limit_regs_blocks"),
+    ("launch__occupancy_limit_shared_mem", "occ_limit_smem_blocks"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved_occupancy_pct"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_throughput_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+    ("smsp__inst_executed.sum", "warp_instructions"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active_lanes_per_inst"),
+    ("dram__bytes_read.sum", "dram_read"),
+    ("dram__bytes_write.sum", "dram_write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_throughput_pct"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
+    ("lts__t_sectors_op_red.sum", "l2_red_sectors"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_scoreboard"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_selected"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall_lg_throttle"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math_pipe"),
+]
+
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+with open(out, "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow([n for _, n in WANT] + ["units: " + "; ".join("%s=%s" % (n, units[idx[m]]) for m, n in WANT if m in idx and units[idx[m]])])
+    for r in rows[2:]:
+        vals = []
+        for m, n in WANT:
+            v = r[idx[m]] if m in idx else ""
+            if n == "kernel":
+                v = v.split("(")[0].replace("dmr::", "")
+            vals.append(v)
+        w.writerow(vals)
+print("wrote", out, len(rows) - 2, "launches")
