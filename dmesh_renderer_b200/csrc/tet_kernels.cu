@@ -60,40 +60,47 @@ __device__ __forceinline__ float3 outward_normal(float3 p0, float3 p1, float3 p2
 // ---------------------------------------------------------------------------
 // record builders (view independent, once per forward call)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tet_build_tetrec_kernel(
+__global__ void __launch_bounds__(128) tet_build_tetrec_kernel(
     int T, const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ tets,
     const int* __restrict__ face_tets, const int* __restrict__ tet_faces, TetRec* __restrict__ out)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const int4 tv = reinterpret_cast<const int4*>(tets)[t];
-    const int4 tf = reinterpret_cast<const int4*>(tet_faces)[t];
-    float3 q0 = ld3(verts + 3 * (size_t)tv.x), q1 = ld3(verts + 3 * (size_t)tv.y);
-    float3 q2 = ld3(verts + 3 * (size_t)tv.z), q3 = ld3(verts + 3 * (size_t)tv.w);
-    const int fid[4] = { tf.x, tf.y, tf.z, tf.w };
-    int nxt[4];
-    uint4* o = reinterpret_cast<uint4*>(out + t);
+    __shared__ uint4 s_rec[128 * 14];   // 224 B per tet; written per thread, read back coalesced
+    const int t0 = blockIdx.x * 128;
+    const int t = t0 + threadIdx.x;
+    if (t < T) {
+        const int4 tv = reinterpret_cast<const int4*>(tets)[t];
+        const int4 tf = reinterpret_cast<const int4*>(tet_faces)[t];
+        float3 q0 = ld3(verts + 3 * (size_t)tv.x), q1 = ld3(verts + 3 * (size_t)tv.y);
+        float3 q2 = ld3(verts + 3 * (size_t)tv.z), q3 = ld3(verts + 3 * (size_t)tv.w);
+        const int fid[4] = { tf.x, tf.y, tf.z, tf.w };
+        int nxt[4];
+        uint4* o = s_rec + threadIdx.x * 14;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int f = fid[k];
-        const int a = faces[3 * (size_t)f], b = faces[3 * (size_t)f + 1], c = faces[3 * (size_t)f + 2];
-        float3 p0 = ld3(verts + 3 * (size_t)a), p1 = ld3(verts + 3 * (size_t)b), p2 = ld3(verts + 3 * (size_t)c);
-        float3 n = outward_normal(p0, p1, p2, q0, q1, q2, q3);
-        // forward.cu:761-767
-        int nt = -1;
-        for (int i = 0; i < 2; i++) {
-            int cand = face_tets[2 * (size_t)f + i];
-            if (cand == t || cand == -1) continue;
-            nt = cand;
-            break;
+        for (int k = 0; k < 4; k++) {
+            const int f = fid[k];
+            const int a = faces[3 * (size_t)f], b = faces[3 * (size_t)f + 1], c = faces[3 * (size_t)f + 2];
+            float3 p0 = ld3(verts + 3 * (size_t)a), p1 = ld3(verts + 3 * (size_t)b), p2 = ld3(verts + 3 * (size_t)c);
+            float3 n = outward_normal(p0, p1, p2, q0, q1, q2, q3);
+            // forward.cu:761-767
+            int nt = -1;
+            for (int i = 0; i < 2; i++) {
+                int cand = face_tets[2 * (size_t)f + i];
+                if (cand == t || cand == -1) continue;
+                nt = cand;
+                break;
+            }
+            nxt[k] = nt;
+            o[2 + 3 * k + 0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), __float_as_uint(p1.x));
+            o[2 + 3 * k + 1] = make_uint4(__float_as_uint(p1.y), __float_as_uint(p1.z), __float_as_uint(p2.x), __float_as_uint(p2.y));
+            o[2 + 3 * k + 2] = make_uint4(__float_as_uint(p2.z), __float_as_uint(n.x), __float_as_uint(n.y), __float_as_uint(n.z));
         }
-        nxt[k] = nt;
-        o[2 + 3 * k + 0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), __float_as_uint(p1.x));
-        o[2 + 3 * k + 1] = make_uint4(__float_as_uint(p1.y), __float_as_uint(p1.z), __float_as_uint(p2.x), __float_as_uint(p2.y));
-        o[2 + 3 * k + 2] = make_uint4(__float_as_uint(p2.z), __float_as_uint(n.x), __float_as_uint(n.y), __float_as_uint(n.z));
+        o[0] = make_uint4(fid[0], fid[1], fid[2], fid[3]);
+        o[1] = make_uint4(nxt[0], nxt[1], nxt[2], nxt[3]);
     }
-    o[0] = make_uint4(fid[0], fid[1], fid[2], fid[3]);
-    o[1] = make_uint4(nxt[0], nxt[1], nxt[2], nxt[3]);
+    __syncthreads();
+    const int nvalid = min(128, T - t0);
+    uint4* dst = reinterpret_cast<uint4*>(out + t0);
+    for (int i = threadIdx.x; i < nvalid * 14; i += 128) dst[i] = s_rec[i];
 }
 
 __global__ void __launch_bounds__(256) tet_build_shade_kernel(
@@ -119,7 +126,7 @@ int tet_build_records(int P, int F, int T, const float* verts, const int* faces,
     ProfScope prof(ST_TET_RECORDS, stream);
     if (T > 0 && F > 0) count_launch(1);   // two kernels under one scope
     if (T > 0) {
-        tet_build_tetrec_kernel<<<(T + 255) / 256, 256, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
+        tet_build_tetrec_kernel<<<(T + 127) / 128, 128, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
         DMR_LAUNCH_CHECK("tet_build_tetrec_kernel");
     }
     if (F > 0) {
@@ -283,6 +290,11 @@ int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 // ---------------------------------------------------------------------------
 // forward march
 // ---------------------------------------------------------------------------
+// The march is independent per pixel (no shared memory, no tile lists) and its cost per ray has a
+// long tail (rays along the cube diagonal cross several times more faces than the mean), so it is
+// launched as many small CTAs: 64 threads = 8x8 pixels = two 8x4 warps.
+#define MARCH_THREADS 64
+
 struct TetStep {   // result of looking for the exit (or entry) face of a tet
     int face, tet;
     float rt, iu, iv;
@@ -330,12 +342,12 @@ __device__ __forceinline__ TetStep tet_step(const TetRec* __restrict__ tr, int c
     return s;
 }
 
-__global__ void __launch_bounds__(256) tet_march_fwd_kernel(TetParams p)
+__global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams p)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const uint32_t px = blockIdx.x * DMR_TILE + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * DMR_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t px = blockIdx.x * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * 8 + warp * 4 + (lane >> 3);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
     const size_t HW = (size_t)p.W * p.H;
     const size_t pix = (size_t)py * p.W + px;
@@ -424,9 +436,9 @@ __global__ void __launch_bounds__(256) tet_march_fwd_kernel(TetParams p)
 
 int tet_march_forward(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
     ProfScope prof(ST_TET_FWD, stream);
-    tet_march_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+    tet_march_fwd_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_march_fwd_kernel");
     return 0;
 }
@@ -434,12 +446,12 @@ int tet_march_forward(const TetParams& p, cudaStream_t stream)
 // ---------------------------------------------------------------------------
 // backward march
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tet_march_bwd_kernel(TetParams p)
+__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams p)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const uint32_t px = blockIdx.x * DMR_TILE + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * DMR_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const uint32_t px = blockIdx.x * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * 8 + warp * 4 + (lane >> 3);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
     const size_t HW = (size_t)p.W * p.H;
     const size_t pix = (size_t)py * p.W + px;
@@ -561,9 +573,9 @@ __global__ void __launch_bounds__(256) tet_march_bwd_kernel(TetParams p)
 
 int tet_march_backward(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
     ProfScope prof(ST_TET_BWD, stream);
-    tet_march_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    tet_march_bwd_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_march_bwd_kernel");
     return 0;
 }
