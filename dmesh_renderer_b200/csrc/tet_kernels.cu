@@ -176,21 +176,27 @@ __device__ __forceinline__ void tet_pixel_ray(const TetParams& p, int b, uint32_
 // ---------------------------------------------------------------------------
 // first intersection: per tile, faces sorted by min depth
 // ---------------------------------------------------------------------------
-#define FI_RB 256
+#define FI_RB 128
+#define FI_THREADS 64
 
 // Hierarchical search: per group of 32 staged faces each lane tests one face's screen bbox against
 // the warp's 8x4 pixel block; survivors are walked in list order, and a pixel runs the (expensive)
 // ray/triangle test only when it lies inside the face's bbox.  Faces are sorted by min depth, so
 // deferring the reference's early-out check (forward.cu:388-391) to the next processed face cannot
 // change the result: every later face has a min depth at least as large.
-__global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
+// Launch shape: one CTA of 64 threads (two 8x4 warps) per 8x8-pixel QUADRANT of a tile, i.e. four CTAs
+// walk the same tile list.  With one 256-thread CTA per tile the 512x512 benchmark has only 1024 CTAs
+// whose cost is dominated by a few hundred heavy tiles (measured: 45 M warp instructions took 733 us,
+// 25% occupancy, barrier-stalled); quadrants give 4x more, 4x lighter CTAs.
+__global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetParams p)
 {
     __shared__ uint4 s_rec[FI_RB * 4];
     __shared__ int s_face[FI_RB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
-    const uint32_t bx0 = blockIdx.x * DMR_TILE + (warp & 1) * 8, by0 = blockIdx.y * DMR_TILE + (warp >> 1) * 4;
+    const int tiles_x = (p.W + DMR_TILE - 1) / DMR_TILE, tiles_y = (p.H + DMR_TILE - 1) / DMR_TILE;
+    const int tile_x = blockIdx.x >> 1, tile_y = blockIdx.y >> 1;
+    const uint32_t bx0 = tile_x * DMR_TILE + (blockIdx.x & 1) * 8, by0 = tile_y * DMR_TILE + (blockIdx.y & 1) * 8 + warp * 4;
     const uint32_t px = bx0 + (lane & 7);
     const uint32_t py = by0 + (lane >> 3);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
     float3 ro = f3(0, 0, 0), rd = f3(0, 0, 1);
     if (inside) tet_pixel_ray(p, b, px, py, bpix, ro, rd);
 
-    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + blockIdx.y * tiles_x + blockIdx.x];
+    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + tile_y * tiles_x + tile_x];
     const int total = (int)(range.y - range.x);
     const int rounds = (total + FI_RB - 1) / FI_RB;
 
@@ -208,17 +214,17 @@ __global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
     int first_face = -1;
 
     for (int r = 0; r < rounds; r++) {
-        if (__syncthreads_count(done) == 256) break;
-        {
-            uint32_t pos = range.x + (uint32_t)r * FI_RB + tid;
+        if (__syncthreads_count(done) == FI_THREADS) break;
+        for (int t = tid; t < FI_RB; t += FI_THREADS) {
+            uint32_t pos = range.x + (uint32_t)r * FI_RB + t;
             if (pos < range.y) {
                 uint32_t face = p.face_list[pos];
-                s_face[tid] = (int)face;
+                s_face[t] = (int)face;
                 const uint4* src = reinterpret_cast<const uint4*>(p.face_rec + (size_t)b * p.F + face);
-                s_rec[tid * 4 + 0] = src[0];
-                s_rec[tid * 4 + 1] = src[1];
-                s_rec[tid * 4 + 2] = src[2];
-                s_rec[tid * 4 + 3] = src[3];
+                s_rec[t * 4 + 0] = src[0];
+                s_rec[t * 4 + 1] = src[1];
+                s_rec[t * 4 + 2] = src[2];
+                s_rec[t * 4 + 3] = src[3];
             }
         }
         __syncthreads();
@@ -280,9 +286,9 @@ __global__ void __launch_bounds__(256) tet_first_intersect_kernel(TetParams p)
 
 int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    dim3 grid(2 * ((p.W + DMR_TILE - 1) / DMR_TILE), 2 * ((p.H + DMR_TILE - 1) / DMR_TILE), p.B);
     ProfScope prof(ST_TET_FIRST, stream);
-    tet_first_intersect_kernel<<<grid, 256, 0, stream>>>(p);
+    tet_first_intersect_kernel<<<grid, FI_THREADS, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
     return 0;
 }
@@ -304,8 +310,15 @@ struct TetStep {   // result of looking for the exit (or entry) face of a tet
 // Among the sides of `tet` other than `curr_face`, the unique one hit by the ray whose
 // outward normal has the requested sign against the ray: forward.cu:672-768 (EXIT: normal
 // along the ray) and backward.cu:382-477 (ENTRY: normal against the ray).
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// The march is a chain of dependent loads (next tet known only after ~250 instructions of hit tests).
+// As soon as the 4 face / neighbour ids of the current tet are known, the records of all candidate
+// next tets and faces are prefetched into L2, so the one that turns out to be needed is (mostly)
+// there when the step completes: latency is traded for ~3x of a bandwidth that is 93% idle.
 template <bool EXIT>
-__device__ __forceinline__ TetStep tet_step(const TetRec* __restrict__ tr, int curr_face, float3 ro, float3 rd)
+__device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const TetRec* __restrict__ tr, int curr_face,
+                                            float3 ro, float3 rd)
 {
     TetStep s;
     s.ok = true;
@@ -314,6 +327,18 @@ __device__ __forceinline__ TetStep tet_step(const TetRec* __restrict__ tr, int c
     const int4 nxt = *reinterpret_cast<const int4*>(tr->next_tet);
     const int f[4] = { fid.x, fid.y, fid.z, fid.w };
     const int nt[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (f[k] == curr_face) continue;
+        if (nt[k] >= 0) {
+            const char* t = reinterpret_cast<const char*>(p.tet_rec + nt[k]);
+            prefetch_l2(t); prefetch_l2(t + 128); prefetch_l2(t + 223);
+        }
+        if ((unsigned)f[k] < (unsigned)p.F) {
+            prefetch_l2(p.shade + f[k]);
+            prefetch_l2(p.faces_intense + (size_t)b * p.F + f[k]);
+        }
+    }
     int cnt = 0, hits = 0;
     bool have_curr = false;
 #pragma unroll
@@ -405,7 +430,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
         // 2. next face (forward.cu:662-775)
         if (curr_tet == -1) { active = true; done = true; }
         if (!done) {
-            TetStep s = tet_step<true>(p.tet_rec + curr_tet, curr_face, ro, rd);
+            TetStep s = tet_step<true>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
             if (!s.ok) { done = true; }   // numerical failure: pixel stays inactive
             curr_face = s.face; curr_tet = s.tet;
             rt = s.rt; iu = s.iu; iv = s.iv;
@@ -564,7 +589,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
 
         if (curr_face == first_face) break;          // backward.cu:363-366
         if (curr_tet == -1) break;                   // backward.cu:373-376
-        TetStep s = tet_step<false>(p.tet_rec + curr_tet, curr_face, ro, rd);
+        TetStep s = tet_step<false>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
         if (!s.ok) done = true;
         curr_face = s.face; curr_tet = s.tet;
         rt = s.rt; iu = s.iu; iv = s.iv;
