@@ -310,12 +310,9 @@ struct TetStep {   // result of looking for the exit (or entry) face of a tet
 // Among the sides of `tet` other than `curr_face`, the unique one hit by the ray whose
 // outward normal has the requested sign against the ray: forward.cu:672-768 (EXIT: normal
 // along the ray) and backward.cu:382-477 (ENTRY: normal against the ray).
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
-// The march is a chain of dependent loads (next tet known only after ~250 instructions of hit tests).
-// As soon as the 4 face / neighbour ids of the current tet are known, the records of all candidate
-// next tets and faces are prefetched into L2, so the one that turns out to be needed is (mostly)
-// there when the step completes: latency is traded for ~3x of a bandwidth that is 93% idle.
+// (Measured and rejected: prefetching the records of all candidate next tets / faces into L2 as soon
+// as the current tet's ids are known made the march SLOWER -- fwd 0.91 -> 1.03 ms, bwd 1.51 -> 2.25 ms
+// at C3: the extra address arithmetic and L2 requests cost more than the latency they hide.)
 template <bool EXIT>
 __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const TetRec* __restrict__ tr, int curr_face,
                                             float3 ro, float3 rd)
@@ -327,18 +324,6 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
     const int4 nxt = *reinterpret_cast<const int4*>(tr->next_tet);
     const int f[4] = { fid.x, fid.y, fid.z, fid.w };
     const int nt[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (f[k] == curr_face) continue;
-        if (nt[k] >= 0) {
-            const char* t = reinterpret_cast<const char*>(p.tet_rec + nt[k]);
-            prefetch_l2(t); prefetch_l2(t + 128); prefetch_l2(t + 223);
-        }
-        if ((unsigned)f[k] < (unsigned)p.F) {
-            prefetch_l2(p.shade + f[k]);
-            prefetch_l2(p.faces_intense + (size_t)b * p.F + f[k]);
-        }
-    }
     int cnt = 0, hits = 0;
     bool have_curr = false;
 #pragma unroll
