@@ -147,6 +147,25 @@ int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* st
 // rasterizer_impl.cu:84-96:  key = (tile + tiles*b) << 32 | depth_bits,
 // value = face id within the view.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void emit_one(uint32_t o, uint32_t start, int nface, const uint32_t* s_incl, const uint2* s_rect,
+                                         const uint32_t* s_depth, const uint32_t* s_tile0, const uint32_t* s_fid,
+                                         int tiles_x, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    int lo = 0, hi = nface - 1;   // smallest i with s_incl[i] > o
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (s_incl[mid] > o) hi = mid; else lo = mid + 1;
+    }
+    const int i = lo;
+    const uint32_t excl = (i == 0) ? start : s_incl[i - 1];
+    const uint32_t k = o - excl;
+    const uint2 r = s_rect[i];
+    const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
+    const uint32_t q = k / w;
+    keys[o] = ((uint64_t)((y0 + q) * (uint32_t)tiles_x + x0 + (k - q * w) + s_tile0[i]) << 32) | (uint64_t)s_depth[i];
+    vals[o] = s_fid[i];
+}
+
 __global__ void __launch_bounds__(256) duplicate_kernel(
     size_t BF, int F, int tiles_x, int tiles_per_view,
     const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, const uint32_t* __restrict__ depth_key,
@@ -175,24 +194,40 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
     const int nface = (int)((BF - f0 < 256) ? (BF - f0) : 256);
     const uint32_t end = s_incl[nface - 1];
 
-    for (uint32_t o = start + tid; o < end; o += 256) {
-        // smallest i with s_incl[i] > o
+    // Each thread emits 4 consecutive instances per step: one binary search, then cheap "same face or
+    // next face" advances; the 4 keys / 4 values leave as two 16-byte + one 16-byte store, so a warp
+    // writes 1 KB + 512 B contiguous.  Head/tail elements that break 16-byte alignment go out scalar.
+    const uint32_t first4 = (start + 3u) & ~3u;                      // first 4-aligned output index of the block
+    for (uint32_t o = start + tid; o < min(first4, end); o += 256) emit_one(o, start, nface, s_incl, s_rect, s_depth, s_tile0, s_fid, tiles_x, keys, vals);
+    for (uint32_t o4 = first4 + 4u * tid; o4 < end; o4 += 4u * 256u) {
+        if (o4 + 4u > end) {
+            for (uint32_t o = o4; o < end; o++) emit_one(o, start, nface, s_incl, s_rect, s_depth, s_tile0, s_fid, tiles_x, keys, vals);
+            break;
+        }
         int lo = 0, hi = nface - 1;
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            if (s_incl[mid] > o) hi = mid; else lo = mid + 1;
+            if (s_incl[mid] > o4) hi = mid; else lo = mid + 1;
         }
-        const int i = lo;
-        const uint32_t excl = (i == 0) ? start : s_incl[i - 1];
-        const uint32_t k = o - excl;
-        const uint2 r = s_rect[i];
-        const uint32_t x0 = r.x & 0xffffu, x1 = r.x >> 16, y0 = r.y & 0xffffu;
-        const uint32_t w = x1 - x0;
-        const uint32_t ty = y0 + k / w, tx = x0 + k % w;
-        uint64_t key = (uint64_t)(ty * (uint32_t)tiles_x + tx + s_tile0[i]);
-        key = (key << 32) | (uint64_t)s_depth[i];
-        keys[o] = key;
-        vals[o] = s_fid[i];
+        int i = lo;
+        uint64_t k[4];
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t o = o4 + e;
+            while (s_incl[i] <= o) i++;                               // skips faces with no instances
+            const uint32_t excl = (i == 0) ? start : s_incl[i - 1];
+            const uint32_t kk = o - excl;
+            const uint2 r = s_rect[i];
+            const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
+            const uint32_t q = kk / w;
+            k[e] = ((uint64_t)((y0 + q) * (uint32_t)tiles_x + x0 + (kk - q * w) + s_tile0[i]) << 32) | (uint64_t)s_depth[i];
+            v[e] = s_fid[i];
+        }
+        uint4* kd = reinterpret_cast<uint4*>(keys + o4);
+        kd[0] = make_uint4((uint32_t)k[0], (uint32_t)(k[0] >> 32), (uint32_t)k[1], (uint32_t)(k[1] >> 32));
+        kd[1] = make_uint4((uint32_t)k[2], (uint32_t)(k[2] >> 32), (uint32_t)k[3], (uint32_t)(k[3] >> 32));
+        *reinterpret_cast<uint4*>(vals + o4) = make_uint4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -212,29 +247,40 @@ int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32
 // ranges must be zero on entry (tiles without instances keep (0,0),
 // rasterizer_impl.cu:330).
 // ---------------------------------------------------------------------------
+#define TR_KPT 8
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, size_t L,
                                                           uint2* __restrict__ ranges)
 {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    uint32_t cur = (uint32_t)(keys[idx] >> 32);
-    if (idx == 0) {
-        ranges[cur].x = 0;
+    // 8 consecutive keys per thread (4 x 16-byte loads) plus the one before them
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * TR_KPT;
+    if (i0 >= L) return;
+    uint32_t t[TR_KPT + 1];
+    t[0] = (i0 == 0) ? 0u : (uint32_t)(keys[i0 - 1] >> 32);
+    if (i0 + TR_KPT <= L) {
+        const uint4* p = reinterpret_cast<const uint4*>(keys + i0);
+#pragma unroll
+        for (int q = 0; q < TR_KPT / 2; q++) { uint4 v = p[q]; t[1 + 2 * q] = v.y; t[2 + 2 * q] = v.w; }
     } else {
-        uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-        if (cur != prev) {
-            ranges[prev].y = (uint32_t)idx;
-            ranges[cur].x = (uint32_t)idx;
-        }
+#pragma unroll
+        for (int e = 0; e < TR_KPT; e++) t[1 + e] = (i0 + e < L) ? (uint32_t)(keys[i0 + e] >> 32) : 0u;
     }
-    if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+#pragma unroll
+    for (int e = 0; e < TR_KPT; e++) {
+        const size_t idx = i0 + e;
+        if (idx >= L) break;
+        const uint32_t cur = t[1 + e];
+        if (idx == 0) ranges[cur].x = 0;
+        else if (cur != t[e]) { ranges[t[e]].y = (uint32_t)idx; ranges[cur].x = (uint32_t)idx; }
+        if (idx == L - 1) ranges[cur].y = (uint32_t)L;
+    }
 }
 
 int identify_tile_ranges(const uint64_t* keys_sorted, size_t R, uint2* ranges, cudaStream_t stream)
 {
     if (R == 0) return 0;
     ProfScope prof(ST_RANGES, stream);
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(keys_sorted, R, ranges);
+    const size_t nthreads = (R + TR_KPT - 1) / TR_KPT;
+    tile_ranges_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(keys_sorted, R, ranges);
     DMR_LAUNCH_CHECK("tile_ranges_kernel");
     return 0;
 }
