@@ -42,13 +42,17 @@ class _RenderTri(th.autograd.Function):
     @staticmethod
     def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
                 render_settings):
-        inv_mv_mats = th.inverse(mv_mats)
-        inv_proj_mats = th.inverse(proj_mats)
-        args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
-                inv_proj_mats, verts_depth, faces_intense, render_settings.image_height, render_settings.image_width)
         try:
+            # Same computation as _C.render_tris(*13 args) (reference __init__.py:62-88), issued in two halves so
+            # that the host-bound torch.inverse calls overlap the GPU's phase 1 (preprocess + scan).
             # depth in [-1, 1]: -1 near, 1 far
-            num_rendered, color, depth, pointBuffer, faceBuffer, binningBuffer, imgBuffer = _C.render_tris(*args)
+            pending = _C.tri_forward_begin(render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats,
+                                           proj_mats, verts_depth, faces_intense, render_settings.image_height,
+                                           render_settings.image_width)
+            inv_mv_mats = th.inverse(mv_mats)
+            inv_proj_mats = th.inverse(proj_mats)
+            num_rendered, color, depth, pointBuffer, faceBuffer, binningBuffer, imgBuffer = \
+                _C.tri_forward_finish(pending, inv_mv_mats, inv_proj_mats)
         except Exception as ex:
             print("\nAn error occured in forward.")
             print(ex)
