@@ -31,7 +31,7 @@ static const char* const g_stage_names[ST_COUNT] = {
     "preprocess_points", "preprocess_faces", "scan", "duplicate_with_keys", "sort_histogram", "sort_plan",
     "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "sort_pass4", "sort_pass5", "sort_pass6", "sort_pass7",
     "tile_ranges", "tri_render_forward", "tri_render_backward", "tri_grad_finish", "tet_build_records", "tet_jitter",
-    "tet_first_intersect", "tet_march_forward", "tet_march_backward" };
+    "tet_first_intersect", "tet_march_forward", "tet_march_backward", "tet_grad_finish" };
 struct Prof {
     bool on = false, created = false;
     cudaEvent_t ev[ST_COUNT][2];

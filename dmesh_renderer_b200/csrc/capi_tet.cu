@@ -169,6 +169,9 @@ int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_se
                 faces_intense, face_buffer, image_buffer);
     p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
     p.dL_dverts_color = dL_dverts_color; p.dL_dfaces_opacity = dL_dfaces_opacity;
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T);
+    p.grad_stats = const_cast<float*>(at<float>(face_buffer, FL.grad_stats));
+    DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (size_t)48 * F, stream));
     return tet_march_backward(p, stream);
 }
 

@@ -36,12 +36,12 @@ struct __align__(16) TetShade {
     float opacity;
     int i0, i1, i2;              // vertex ids (gradient scatter)
     int t0, t1;                  // face_tets[2f], face_tets[2f+1]
-    uint32_t pad;
+    float log1m_opacity;         // logf(1 - opacity)
 };
 static_assert(sizeof(TetShade) == 64, "TetShade must be 4 x 16 bytes");
 
 struct TetFaceLayout {
-    size_t tiles_touched, offsets, depth_key, rect, scan_state, face_rec, tet_rec, shade, total;
+    size_t tiles_touched, offsets, depth_key, rect, scan_state, face_rec, tet_rec, shade, grad_stats, total;
     __host__ static TetFaceLayout make(size_t BF, size_t F, size_t T)
     {
         TetFaceLayout L;
@@ -55,6 +55,7 @@ struct TetFaceLayout {
         L.face_rec = o;      o = align_up(o + sizeof(TetFaceRec) * BF, 256);
         L.tet_rec = o;       o = align_up(o + sizeof(TetRec) * T, 256);
         L.shade = o;         o = align_up(o + sizeof(TetShade) * F, 256);
+        L.grad_stats = o;    o = align_up(o + 48 * F, 256);   // backward scratch: 12 floats per face (summed over views)
         L.total = o + 256;
         return L;
     }
@@ -103,6 +104,7 @@ struct TetParams {
     // backward
     const float* dL_dcolor; const float* dL_ddepth;
     float* dL_dverts_color; float* dL_dfaces_opacity;
+    float* grad_stats;            // [F,12] zeroed scratch: dL_dcolor[3 verts][3], dL_dopacity, 2 pad
 };
 
 int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,

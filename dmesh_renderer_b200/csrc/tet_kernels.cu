@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(256) tet_build_shade_kernel(
     o[0] = make_uint4(__float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c0.z), __float_as_uint(c1.x));
     o[1] = make_uint4(__float_as_uint(c1.y), __float_as_uint(c1.z), __float_as_uint(c2.x), __float_as_uint(c2.y));
     o[2] = make_uint4(__float_as_uint(c2.z), __float_as_uint(faces_opacity[f]), a, b);
-    o[3] = make_uint4(c, face_tets[2 * (size_t)f], face_tets[2 * (size_t)f + 1], 0);
+    // log(1 - opacity) is a per-face constant of the march (forward.cu:636-642, backward.cu:272-279):
+    // same logf on the same input, evaluated once per face instead of once per step
+    const float op = faces_opacity[f];
+    o[3] = make_uint4(c, face_tets[2 * (size_t)f], face_tets[2 * (size_t)f + 1], __float_as_uint(logf(1.0f - op)));
 }
 
 int tet_build_records(int P, int F, int T, const float* verts, const int* faces, const float* verts_color,
@@ -381,6 +384,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
 
     float3 C = f3(0, 0, 0);
     float D = 0.0f, log_T = 0.0f, prev_log_T = 0.0f;
+    float T_cur = expf(log_T);
     int last_face = -1, last_tet = -1;
     bool active = false;
     uint32_t n_contrib = 0;
@@ -390,12 +394,13 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
         // 1. composite the current face (forward.cu:600-653)
         const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
         const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2];
+        const float log1m = reinterpret_cast<const float*>(sh4)[15];
         const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
         const float opacity = s2.y;
         const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
         float3 col = (c0 + (c1 - c0) * iu + (c2 - c0) * iv);
         col = col * intense;
-        float tmp_T = expf(log_T);
+        const float tmp_T = T_cur;   // = expf(log_T), carried over from the termination test below
         C = C + tmp_T * opacity * col;
         float3 pt = ro + (rd * rt);
         float4 pn = xform44(xform43(pt, mv), pj);
@@ -404,9 +409,10 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
         D += tmp_T * opacity * pd;
 
         prev_log_T = log_T;
-        if (opacity < 1.0f) log_T += logf(1.0f - opacity);
+        if (opacity < 1.0f) log_T += log1m;
         else log_T = logf(DMR_T_EPS * 0.1f);
-        if (expf(log_T) < DMR_T_EPS) { done = true; active = true; }
+        T_cur = expf(log_T);
+        if (T_cur < DMR_T_EPS) { done = true; active = true; }
 
         n_contrib++;
         last_face = curr_face;
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
     p.n_contrib[bpix] = n_contrib;
     p.active[bpix] = active ? 1 : 0;
     if (active) {
-        float fT = expf(log_T);
+        float fT = T_cur;
         p.out_color[(size_t)b * 3 * HW + 0 * HW + pix] = C.x + fT * p.bg[0];
         p.out_color[(size_t)b * 3 * HW + 1 * HW + pix] = C.y + fT * p.bg[1];
         p.out_color[(size_t)b * 3 * HW + 2 * HW + pix] = C.z + fT * p.bg[2];
@@ -522,7 +528,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
         const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2], s3 = sh4[3];
         const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
         const float opacity = s2.y;
-        const int vi0 = __float_as_int(s2.z), vi1 = __float_as_int(s2.w), vi2 = __float_as_int(s3.x);
+        const float log1m = s3.w;
         const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
 
         // backward.cu:252-270
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
         float pw = 1.0f / clamp_w(pn.w);
         float pd = pn.z * pw;
 
-        if (!first_iter) prev_log_T = prev_log_T - logf(1.0f - opacity);
+        if (!first_iter) prev_log_T = prev_log_T - log1m;
         first_iter = false;
         float prev_T = expf(prev_log_T);
 
@@ -563,14 +569,18 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
             dL_dopa += (-final_T / (1.f - opacity)) * bd_dot;
         }
 
-        // backward.cu:341-360
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            atomicAdd(&p.dL_dverts_color[3 * (size_t)vi0 + ch], i0 * dL_dcol[ch] * intense);
-            atomicAdd(&p.dL_dverts_color[3 * (size_t)vi1 + ch], i1 * dL_dcol[ch] * intense);
-            atomicAdd(&p.dL_dverts_color[3 * (size_t)vi2 + ch], i2 * dL_dcol[ch] * intense);
+        // backward.cu:341-360: the reference issues 10 scalar atomics per crossed face (9 vertex-colour
+        // terms + opacity), which bounds its backward pass by the reduction rate of the LSU/L2
+        // (measured, tools/ubench_red.cu).  Here the ten terms go to ONE 48-byte record per face as three
+        // 16-byte vector reductions; tet_grad_finish_kernel scatters the records to the vertices.
+        {
+            float* st = p.grad_stats + (size_t)curr_face * 12;
+            red_add_v4(st + 0, i0 * dL_dcol[0] * intense, i0 * dL_dcol[1] * intense, i0 * dL_dcol[2] * intense,
+                       i1 * dL_dcol[0] * intense);
+            red_add_v4(st + 4, i1 * dL_dcol[1] * intense, i1 * dL_dcol[2] * intense, i2 * dL_dcol[0] * intense,
+                       i2 * dL_dcol[1] * intense);
+            red_add_v4(st + 8, i2 * dL_dcol[2] * intense, dL_dopa, 0.0f, 0.0f);
         }
-        atomicAdd(&p.dL_dfaces_opacity[curr_face], dL_dopa);
 
         if (curr_face == first_face) break;          // backward.cu:363-366
         if (curr_tet == -1) break;                   // backward.cu:373-376
@@ -581,12 +591,42 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
     }
 }
 
+// Once per face: 12-float statistics record -> dL_dverts_color (9 atomics, only for faces some ray
+// crossed) and dL_dfaces_opacity.
+__global__ void __launch_bounds__(256) tet_grad_finish_kernel(TetParams p)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.F) return;
+    const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + (size_t)f * 12);
+    const float4 a = st4[0], b = st4[1], c = st4[2];
+    const float st[10] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y };
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < 10; q++) any = any || st[q] != 0.0f;
+    if (!any) return;
+    const TetShade* sh = p.shade + f;
+    const int vi[3] = { sh->i0, sh->i1, sh->i2 };
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++)
+            if (st[3 * k + ch] != 0.0f) atomicAdd(&p.dL_dverts_color[3 * (size_t)vi[k] + ch], st[3 * k + ch]);
+    p.dL_dfaces_opacity[f] += st[9];   // one thread per face: no atomic needed
+}
+
 int tet_march_backward(const TetParams& p, cudaStream_t stream)
 {
     dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
-    ProfScope prof(ST_TET_BWD, stream);
-    tet_march_bwd_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
-    DMR_LAUNCH_CHECK("tet_march_bwd_kernel");
+    {
+        ProfScope prof(ST_TET_BWD, stream);
+        tet_march_bwd_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tet_march_bwd_kernel");
+    }
+    {
+        ProfScope prof(ST_TET_BWD_FINISH, stream);
+        tet_grad_finish_kernel<<<(p.F + 255) / 256, 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tet_grad_finish_kernel");
+    }
     return 0;
 }
 

@@ -223,6 +223,11 @@ __device__ __forceinline__ void xreduce_step(float* v, bool hi)
     }
 }
 
+// Position of logical statistic i (0..23) inside the 24-float record.  The transpose-reduction leaves
+// lane class c = i / 6 (lane bits 2,1) with the six sums 6c..6c+5; its even lane adds the first four
+// as ONE 16-byte vector reduction to quad c, its odd lane the last two as one 8-byte reduction.
+__host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i / 6) + (i % 6) : 16 + 2 * (i / 6) + (i % 6) - 4; }
+
 // Backward design
 // ---------------
 // * A warp owns an 8x4 pixel block, split into four GROUPS of 8 lanes (4x2 pixels).  Each group walks
@@ -237,9 +242,12 @@ __device__ __forceinline__ void xreduce_step(float* v, bool hi)
 //       g_E1 = S3 (E2xT) - S24xE2,  g_E2 = TxS1 - E1xS24 + S3 (TxE1),  g_T = S1xE2 + S3 (E1xE2).
 //   This is the same derivative the reference evaluates per covered pixel with ~150 instructions.
 // * All 21 per-hit terms of a group are reduced over its 8 lanes with a transpose-reduction
-//   (12+6+3 = 21 shuffles) and added to ONE contiguous 96-byte statistics record per (view, face)
-//   -> 3 red.global instructions per SIMD pass, all lanes of a group on one cache line.
-// Statistics record (24 floats): S1[3] S24[3] S3 dL_dopacity dL_dintense dL_ddepth[3] dL_dcolor[3][3] pad[3]
+//   (12+6+4 = 22 shuffles) and added to ONE contiguous 96-byte statistics record per (view, face)
+//   with vector reductions: per SIMD pass 2 instructions / 8 lane-operations per group (one
+//   red.v4 from each even lane, one red.v2 from each odd lane) instead of 21 scalar reductions --
+//   the kernel was co-limited by the ~0.6 lane-reductions/clk/SM the LSU sustains.
+// Statistics (logical order, 24 floats; memory position = stat_slot(i)):
+//   S1[3] S24[3] S3 dL_dopacity dL_dintense dL_ddepth[3] dL_dcolor[3][3] pad[3]
 __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams p)
 {
     __shared__ uint4 s_rec[RB * 9];
@@ -373,9 +381,10 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                         const float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
                         const float intense = __uint_as_float(e1.w);
                         const float alpha = __uint_as_float(e0.w);
-                        const float iC0 = (i0 * w[9] + i1 * w[12] + i2 * w[15]) * intense;
-                        const float iC1 = (i0 * w[10] + i1 * w[13] + i2 * w[16]) * intense;
-                        const float iC2 = (i0 * w[11] + i1 * w[14] + i2 * w[17]) * intense;
+                        const float raw0 = i0 * w[9] + i1 * w[12] + i2 * w[15];
+                        const float raw1 = i0 * w[10] + i1 * w[13] + i2 * w[16];
+                        const float raw2 = i0 * w[11] + i1 * w[14] + i2 * w[17];
+                        const float iC0 = raw0 * intense, iC1 = raw1 * intense, iC2 = raw2 * intense;
                         const float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
 
                         // backward.cu:244-252
@@ -401,29 +410,24 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                             dL_dalpha += (-prev_T_final) * bg_dot;
                             dL_dalpha += (-prev_T_final) * bd_dot;
                         } else {
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                            dL_dalpha += (-T_final / (1.f - alpha)) * bd_dot;
+                            const float k = -T_final / (1.f - alpha);
+                            dL_dalpha += k * bg_dot;
+                            dL_dalpha += k * bd_dot;
                         }
 
-                        // backward.cu:327-349
-                        float dL_di0 = 0, dL_di1 = 0, dL_di2 = 0, dL_dint = 0;
-                        const float dic[3] = { dic0, dic1, dic2 };
-#pragma unroll
-                        for (int ch = 0; ch < 3; ch++) {
-                            dL_di0 += w[9 + ch] * dic[ch] * intense;
-                            dL_di1 += w[12 + ch] * dic[ch] * intense;
-                            dL_di2 += w[15 + ch] * dic[ch] * intense;
-                            v[12 + ch] = i0 * dic[ch] * intense;
-                            v[15 + ch] = i1 * dic[ch] * intense;
-                            v[18 + ch] = i2 * dic[ch] * intense;
-                            dL_dint += (i0 * w[9 + ch] + i1 * w[12 + ch] + i2 * w[15 + ch]) * dic[ch];
-                        }
-                        dL_di0 += w[18] * did;
-                        dL_di1 += w[19] * did;
-                        dL_di2 += w[20] * did;
+                        // backward.cu:327-349.  The per-term products are the reference's; the common factor
+                        // dic*intense is formed once (the reference multiplies (x*dic)*intense per term: one
+                        // rounding apart, far inside the 1e-4 gradient tolerance).
+                        const float dI0 = dic0 * intense, dI1 = dic1 * intense, dI2 = dic2 * intense;
+                        const float dL_di0 = w[9] * dI0 + w[10] * dI1 + w[11] * dI2 + w[18] * did;
+                        const float dL_di1 = w[12] * dI0 + w[13] * dI1 + w[14] * dI2 + w[19] * did;
+                        const float dL_di2 = w[15] * dI0 + w[16] * dI1 + w[17] * dI2 + w[20] * did;
+                        v[12] = i0 * dI0; v[13] = i0 * dI1; v[14] = i0 * dI2;
+                        v[15] = i1 * dI0; v[16] = i1 * dI1; v[17] = i1 * dI2;
+                        v[18] = i2 * dI0; v[19] = i2 * dI1; v[20] = i2 * dI2;
                         v[9] = i0 * did; v[10] = i1 * did; v[11] = i2 * did;
                         v[7] = dL_dalpha;
-                        v[8] = dL_dint;
+                        v[8] = raw0 * dic0 + raw1 * dic1 + raw2 * dic2;
 
                         // backward.cu:354-369: chain through the clamp
                         float duc_du, duc_dv, dvc_du, dvc_dv;
@@ -442,15 +446,26 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                     }
                 }
 
-                // ---- reduce over the 8 lanes of each group: 24 -> 12 -> 6 -> 3 values per lane
+                // ---- reduce over the 8 lanes of each group: 24 -> 12 -> 6 values per lane, then the even
+                //      lane of each pair completes sums 0..3 and the odd lane sums 4..5 of its class
                 xreduce_step<12, 4>(v, h4);
                 xreduce_step<6, 2>(v, h2);
-                xreduce_step<3, 1>(v, h1);
-                if (have && l < 7) {   // lane l owns slots 3l..3l+2 (slots 21..23 are padding)
-                    float* dst = stats + ((size_t)b * p.F + s_face[j]) * 24 + 3 * l;
-                    if (v[0] != 0.0f) atomicAdd(dst + 0, v[0]);
-                    if (v[1] != 0.0f) atomicAdd(dst + 1, v[1]);
-                    if (v[2] != 0.0f) atomicAdd(dst + 2, v[2]);
+                {
+                    const float r0 = __shfl_xor_sync(0xffffffffu, h1 ? v[0] : v[4], 1);
+                    const float r1 = __shfl_xor_sync(0xffffffffu, h1 ? v[1] : v[5], 1);
+                    const float r2 = __shfl_xor_sync(0xffffffffu, v[2], 1);
+                    const float r3 = __shfl_xor_sync(0xffffffffu, v[3], 1);
+                    if (have) {
+                        float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
+                        const int cls = (lane >> 1) & 3;
+                        if (!h1) {
+                            const float a0 = v[0] + r0, a1 = v[1] + r1, a2 = v[2] + r2, a3 = v[3] + r3;
+                            if (a0 != 0.0f || a1 != 0.0f || a2 != 0.0f || a3 != 0.0f) red_add_v4(rec + 4 * cls, a0, a1, a2, a3);
+                        } else if (cls < 3) {   // class 3's odd lane owns logical 22..23 = padding
+                            const float a4 = v[4] + r0, a5 = v[5] + r1;
+                            if (a4 != 0.0f || a5 != 0.0f) red_add_v2(rec + 16 + 2 * cls, a4, a5);
+                        }
+                    }
                 }
             }
         }
@@ -464,15 +479,17 @@ __global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p)
     const size_t BF = (size_t)p.B * p.F;
     if (idx >= BF) return;
     const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + idx * 24);
-    float st[24];
+    float sm[24], st[24];
     bool any = false;
 #pragma unroll
     for (int q = 0; q < 6; q++) {
         float4 t = st4[q];
-        st[4 * q] = t.x; st[4 * q + 1] = t.y; st[4 * q + 2] = t.z; st[4 * q + 3] = t.w;
+        sm[4 * q] = t.x; sm[4 * q + 1] = t.y; sm[4 * q + 2] = t.z; sm[4 * q + 3] = t.w;
         any = any || t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f;
     }
     if (!any) return;
+#pragma unroll
+    for (int i = 0; i < 24; i++) st[i] = sm[stat_slot(i)];
     const int b = (int)(idx / (size_t)p.F);
     const size_t f = idx - (size_t)b * p.F;
     const float* w = reinterpret_cast<const float*>(p.records + idx) + 12;
