@@ -31,7 +31,7 @@ static const char* const g_stage_names[ST_COUNT] = {
     "preprocess_points", "preprocess_faces", "scan", "duplicate_with_keys", "sort_histogram", "sort_plan",
     "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "sort_pass4", "sort_pass5", "sort_pass6", "sort_pass7",
     "tile_ranges", "tri_render_forward", "tri_render_backward", "tri_grad_finish", "tet_build_records", "tet_jitter",
-    "tet_first_intersect", "tet_march_forward", "tet_march_backward", "tet_grad_finish" };
+    "tet_first_intersect", "tet_march_forward", "tet_march_backward", "tet_grad_vertex" };
 struct Prof {
     bool on = false, created = false;
     cudaEvent_t ev[ST_COUNT][2];
@@ -291,7 +291,7 @@ int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, in
         default: set_error("unknown view kind %d", kind); return DMR_EINVAL;
         }
     } else {
-        TetFaceLayout FL = TetFaceLayout::make(BF, (size_t)F, (size_t)T);
+        TetFaceLayout FL = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
         TetImageLayout IL = TetImageLayout::make(B, W, H);
         switch (kind) {
         case DMR_VIEW_TILES_TOUCHED: off = FL.tiles_touched; n = BF; break;

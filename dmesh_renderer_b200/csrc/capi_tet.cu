@@ -7,6 +7,8 @@
 
 using namespace dmr;
 
+namespace dmr { int g_tet_trail_cap_override = 0; }
+
 namespace {
 
 template <typename T>
@@ -37,7 +39,7 @@ int dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[3])
     if (!out) { set_error("out is null"); return DMR_EINVAL; }
     if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
     out[0] = align_up(sizeof(float4) * (size_t)B * P, 256) + 256;
-    out[1] = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T).total;
+    out[1] = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P).total;
     out[2] = TetImageLayout::make(B, W, H).total;
     return DMR_OK;
 }
@@ -54,7 +56,7 @@ int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* v
     if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats || !face_tets ||
         (T > 0 && (!tets || !tet_faces)) || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
     const size_t BF = (size_t)B * F;
-    TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F, (size_t)T);
+    TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
     float4* vimg = static_cast<float4*>(point_buffer);
     size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
     DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.scan_state), 0, 4 * (ntile + 64), stream));
@@ -78,7 +80,7 @@ static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, 
                         const float* mv, const float* proj, const float* inv_mv, const float* inv_proj,
                         const float* faces_intense, const void* face_buffer, const void* image_buffer)
 {
-    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T);
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
     TetImageLayout IL = TetImageLayout::make(B, W, H);
     p = TetParams{};
     p.B = B; p.P = P; p.F = F; p.T = T; p.W = W; p.H = H;
@@ -98,6 +100,8 @@ static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, 
     p.prev_log_T = at<float>(ib, IL.prev_log_T);
     p.n_contrib = at<uint32_t>(ib, IL.n_contrib);
     p.active = at<uint8_t>(ib, IL.active);
+    p.trail = at<int>(ib, IL.trail);
+    p.trail_cap = (int)IL.trail_cap;
 }
 
 int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int ray_random_seed,
@@ -115,7 +119,7 @@ int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int 
         return DMR_EINVAL;
     }
     (void)point_buffer;
-    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T);
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
     TetImageLayout IL = TetImageLayout::make(B, W, H);
     const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
     const size_t tiles = (size_t)B * tx * ty;
@@ -169,10 +173,16 @@ int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_se
                 faces_intense, face_buffer, image_buffer);
     p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
     p.dL_dverts_color = dL_dverts_color; p.dL_dfaces_opacity = dL_dfaces_opacity;
-    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T);
-    p.grad_stats = const_cast<float*>(at<float>(face_buffer, FL.grad_stats));
-    DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (size_t)48 * F, stream));
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
+    p.grad_vacc = const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc));
+    DMR_CUDA(cudaMemsetAsync(p.grad_vacc, 0, sizeof(float4) * (size_t)P, stream));
     return tet_march_backward(p, stream);
+}
+
+int dmr_debug_set_tet_trail_cap(int cap)
+{
+    g_tet_trail_cap_override = cap > 0 ? cap : 0;
+    return DMR_OK;
 }
 
 }  // extern "C"

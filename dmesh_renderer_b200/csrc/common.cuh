@@ -72,14 +72,16 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b)
 
 // Vector reductions (PTX ISA 8.1, sm_90+; SASS REDG.E.ADD.F32x4 / .F32x2).  Measured on B200
 // (tools/ubench_red.cu, 47 M scattered 12-float records): 10 scalar reds 2.7-3.3 ms, 3 x v4 0.74-1.7 ms
-// -- the LSU/L2 cost of a reduction is per lane-operation, not per float.
+// -- the LSU/L2 cost of a reduction is per lane-operation, not per float.  No "memory" clobber: the
+// kernels that issue them never read the reduced locations, and the clobber would stop the compiler from
+// hoisting the next step's loads above a reduction.
 __device__ __forceinline__ void red_add_v4(float* a, float x, float y, float z, float w)
 {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w));
 }
 __device__ __forceinline__ void red_add_v2(float* a, float x, float y)
 {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(x), "f"(y) : "memory");
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(x), "f"(y));
 }
 
 // column-major 4x4 * (p,1): auxiliary.h:71-90

@@ -41,8 +41,8 @@ struct __align__(16) TetShade {
 static_assert(sizeof(TetShade) == 64, "TetShade must be 4 x 16 bytes");
 
 struct TetFaceLayout {
-    size_t tiles_touched, offsets, depth_key, rect, scan_state, face_rec, tet_rec, shade, grad_stats, total;
-    __host__ static TetFaceLayout make(size_t BF, size_t F, size_t T)
+    size_t tiles_touched, offsets, depth_key, rect, scan_state, face_rec, tet_rec, shade, grad_vacc, total;
+    __host__ static TetFaceLayout make(size_t BF, size_t F, size_t T, size_t P)
     {
         TetFaceLayout L;
         size_t o = 0;
@@ -55,14 +55,30 @@ struct TetFaceLayout {
         L.face_rec = o;      o = align_up(o + sizeof(TetFaceRec) * BF, 256);
         L.tet_rec = o;       o = align_up(o + sizeof(TetRec) * T, 256);
         L.shade = o;         o = align_up(o + sizeof(TetShade) * F, 256);
-        L.grad_stats = o;    o = align_up(o + 48 * F, 256);   // backward scratch: 12 floats per face (summed over views)
+        // backward scratch, zeroed per call: float4 per vertex (colour gradient, 16-byte aligned for red.v4)
+        L.grad_vacc = o;     o = align_up(o + 16 * P, 256);
         L.total = o + 256;
         return L;
     }
 };
 
+// Face trail: the forward march records the id of every face it composites, step-major
+// (trail[k * BI + pixel], coalesced across a warp), so that the backward pass walks the SAME faces in
+// reverse with independent, prefetchable loads instead of re-marching through the adjacency with one
+// dependent load chain per step (cuda_renderer/backward.cu:382-477).  Only the first `cap` steps of a ray
+// are recorded; rays that composite more faces re-march the part beyond the cap exactly as before.
+// cap: 512 steps while the trail stays below 512 MiB, never less than 32 (debug override for tests).
+extern int g_tet_trail_cap_override;
+__host__ inline size_t tet_trail_cap(size_t BI)
+{
+    if (g_tet_trail_cap_override > 0) return (size_t)g_tet_trail_cap_override;
+    if (BI == 0) return 32;
+    size_t cap = ((size_t)512 << 20) / (4 * BI);
+    return cap > 512 ? 512 : (cap < 32 ? 32 : cap);
+}
+
 struct TetImageLayout {
-    size_t n_contrib, ranges, final_log_T, prev_log_T, first_face, first_tet, last_face, last_tet, active, jitter, total;
+    size_t n_contrib, ranges, final_log_T, prev_log_T, first_face, first_tet, last_face, last_tet, active, jitter, trail, trail_cap, total;
     __host__ static TetImageLayout make(size_t B, size_t W, size_t H)
     {
         TetImageLayout L;
@@ -79,6 +95,8 @@ struct TetImageLayout {
         L.last_tet = o;    o = align_up(o + 4 * BI, 256);
         L.active = o;      o = align_up(o + BI, 256);
         L.jitter = o;      o = align_up(o + 8 * BI, 256);   // float2 pixel coordinate, written only when seed > 0
+        L.trail_cap = tet_trail_cap(BI);
+        L.trail = o;       o = align_up(o + 4 * BI * L.trail_cap, 256);
         L.total = o + 256;
         return L;
     }
@@ -99,12 +117,13 @@ struct TetParams {
     const float2* jitter;         // null when ray_random_seed <= 0
     int* first_face; int* first_tet; int* last_face; int* last_tet;
     float* final_log_T; float* prev_log_T; uint32_t* n_contrib; uint8_t* active;
+    int* trail; int trail_cap;    // [trail_cap][B*W*H] face ids in march order
     // outputs
     float* out_color; float* out_depth; float* out_active;
     // backward
     const float* dL_dcolor; const float* dL_ddepth;
     float* dL_dverts_color; float* dL_dfaces_opacity;
-    float* grad_stats;            // [F,12] zeroed scratch: dL_dcolor[3 verts][3], dL_dopacity, 2 pad
+    float4* grad_vacc;            // [P] zeroed scratch: per-vertex colour gradient (xyz), summed over views
 };
 
 int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,

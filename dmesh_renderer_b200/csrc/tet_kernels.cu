@@ -20,6 +20,22 @@ namespace dmr {
 // geometry helpers
 // ---------------------------------------------------------------------------
 
+// dot / cross with the contraction nvcc applies to cuda_math.h:1524-1527, 1696-1699 written out
+// (fma(z,z', fma(x,x', y*y')) and fma(a,b,-(c*d)), the same forms oracle/oracle.cpp pins): every call
+// site then yields the SAME bits for the same inputs, whatever the surrounding code.  The backward
+// pass depends on that: it recomputes (t,u,v) of a face from the trail with the hit test below and
+// must get what the forward march got (the depth term (pd - accum_recd) of the opacity gradient
+// amplifies a one-ulp change of t by 1e3..1e4).
+__device__ __forceinline__ float dot3p(float3 a, float3 b)
+{
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
+}
+__device__ __forceinline__ float3 cross3p(float3 a, float3 b)
+{
+    return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+              __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+
 // Moeller-Trumbore with inside test: cuda_renderer/auxiliary.h:265-296.
 // tuv is left untouched when denom == 0 (as in the reference).
 __device__ __forceinline__ bool ray_tri_hit(float3 ro, float3 rd, float3 p0, float3 p1, float3 p2, float3& tuv)
@@ -27,14 +43,14 @@ __device__ __forceinline__ bool ray_tri_hit(float3 ro, float3 rd, float3 p0, flo
     float3 T = ro - p0;
     float3 E1 = p1 - p0;
     float3 E2 = p2 - p0;
-    float3 Pv = cross3(rd, E2);
-    float3 Q = cross3(T, E1);
-    float denom = dot3(Pv, E1);
+    float3 Pv = cross3p(rd, E2);
+    float3 Q = cross3p(T, E1);
+    float denom = dot3p(Pv, E1);
     if (denom == 0.0f) return false;
     float inv_denom = 1.0f / denom;
-    tuv.x = dot3(Q, E2) * inv_denom;
-    tuv.y = dot3(Pv, T) * inv_denom;
-    tuv.z = dot3(Q, rd) * inv_denom;
+    tuv.x = __fmul_rn(dot3p(Q, E2), inv_denom);
+    tuv.y = __fmul_rn(dot3p(Pv, T), inv_denom);
+    tuv.z = __fmul_rn(dot3p(Q, rd), inv_denom);
     return (tuv.x >= 0.0f && tuv.y >= 0.0f && tuv.z >= 0.0f && tuv.y + tuv.z <= 1.0f);
 }
 
@@ -280,7 +296,7 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
             for (int k = 0; k < 4; k++)
                 if (!found && tr->face[k] == first_face) { n = f3(tr->geo[k][9], tr->geo[k][10], tr->geo[k][11]); found = true; }
             if (!found) continue;   // inconsistent adjacency tables
-            if (dot3(n, rd) < 0.0f) first_tet = tet_id;
+            if (dot3p(n, rd) < 0.0f) first_tet = tet_id;
         }
     }
     p.first_face[bpix] = first_face;
@@ -308,6 +324,7 @@ struct TetStep {   // result of looking for the exit (or entry) face of a tet
     int face, tet;
     float rt, iu, iv;
     bool ok;
+    bool opposite;   // some other side is hit with the OPPOSITE normal sign (see the face trail)
 };
 
 // Among the sides of `tet` other than `curr_face`, the unique one hit by the ray whose
@@ -329,12 +346,13 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
     const int nt[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
     int cnt = 0, hits = 0;
     bool have_curr = false;
+    s.opposite = false;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const float4* g4 = reinterpret_cast<const float4*>(tr->geo[k]);
         const float4 g0 = g4[0], g1 = g4[1], g2 = g4[2];
         const float3 n = f3(g2.y, g2.z, g2.w);
-        const float dn = dot3(n, rd);
+        const float dn = dot3p(n, rd);
         if (f[k] == curr_face) {
             // the face we stand on must face the other way (error case 2)
             if (!have_curr) { if (EXIT ? (dn >= 0.0f) : (dn <= 0.0f)) s.ok = false; }
@@ -349,12 +367,20 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
             s.rt = tuv.x; s.iu = tuv.y; s.iv = tuv.z;
             hits++;
         }
+        if (hit && (EXIT ? (dn < 0.0f) : (dn > 0.0f))) s.opposite = true;
     }
     if (cnt != 3) s.ok = false;      // error case 1
     if (hits != 1) s.ok = false;     // error case 3
     return s;
 }
 
+// Loop shape: at the top of a step both the face to composite (curr_face) and the tet to leave
+// (curr_tet) are known, so the shading record and the adjacency record are loaded TOGETHER (one memory
+// latency per step; the reference, and the first version of this kernel, composite first and only then
+// start the dependent gathers of the tet), and the exit search runs unconditionally next to the
+// compositing arithmetic -- two independent dependency chains in one basic block.  Its result is
+// simply discarded when the ray terminates in this step; the decisions are taken in the reference's
+// order (forward.cu:645-648, 667-670, 687-759).
 __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams p)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -363,6 +389,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
     const uint32_t py = blockIdx.y * 8 + warp * 4 + (lane >> 3);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
     const size_t HW = (size_t)p.W * p.H;
+    const size_t BI = (size_t)p.B * HW;
     const size_t pix = (size_t)py * p.W + px;
     const size_t bpix = (size_t)b * HW + pix;
 
@@ -384,23 +411,35 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
 
     float3 C = f3(0, 0, 0);
     float D = 0.0f, log_T = 0.0f, prev_log_T = 0.0f;
-    float T_cur = expf(log_T);
+    float T_cur = expf(log_T);   // expf(log_T) of the termination test is the next step's transmittance
     int last_face = -1, last_tet = -1;
     bool active = false;
     uint32_t n_contrib = 0;
     int curr_face = first_face, curr_tet = first_tet;
+    int* trail = p.trail + bpix;
+    const uint32_t trail_cap = (uint32_t)p.trail_cap;
 
     while (!done) {
-        // 1. composite the current face (forward.cu:600-653)
+        // loads of this step: shading record, intensity, adjacency record (tet 0 stands in when the ray
+        // is about to leave the mesh; its result is not used)
         const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
         const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2];
         const float log1m = reinterpret_cast<const float*>(sh4)[15];
+        const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
+        const TetStep s = tet_step<true>(p, b, p.tet_rec + (curr_tet >= 0 ? curr_tet : 0), curr_face, ro, rd);
+        // Trail entry: face id; bit 31 flags a tet in which a second side is hit with an inward normal.
+        // The reference's reverse march (backward.cu:382-477) finds two entry candidates there and gives
+        // up on the ray (its error case 3), leaving this and all earlier faces without gradient; the
+        // replay reproduces that.  (The side we entered through always qualifies as the first candidate:
+        // it passed the same hit test one step earlier and its normal sign is checked by tet_step.)
+        if (n_contrib < trail_cap) trail[(size_t)n_contrib * BI] = curr_face | (s.opposite ? (int)0x80000000u : 0);
+
+        // 1. composite the current face (forward.cu:600-653)
         const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
         const float opacity = s2.y;
-        const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
         float3 col = (c0 + (c1 - c0) * iu + (c2 - c0) * iv);
         col = col * intense;
-        const float tmp_T = T_cur;   // = expf(log_T), carried over from the termination test below
+        const float tmp_T = T_cur;
         C = C + tmp_T * opacity * col;
         float3 pt = ro + (rd * rt);
         float4 pn = xform44(xform43(pt, mv), pj);
@@ -421,7 +460,6 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams 
         // 2. next face (forward.cu:662-775)
         if (curr_tet == -1) { active = true; done = true; }
         if (!done) {
-            TetStep s = tet_step<true>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
             if (!s.ok) { done = true; }   // numerical failure: pixel stays inactive
             curr_face = s.face; curr_tet = s.tet;
             rt = s.rt; iu = s.iu; iv = s.iv;
@@ -462,6 +500,84 @@ int tet_march_forward(const TetParams& p, cudaStream_t stream)
 // ---------------------------------------------------------------------------
 // backward march
 // ---------------------------------------------------------------------------
+// Per-ray state of the reverse compositing recurrence (backward.cu:272-339).
+struct TetBwdState {
+    float prev_log_T, last_alpha, last_depth, accum_recd;
+    float last_color[3], accum_rec[3];
+    bool first_iter;
+};
+
+// Gradient terms of one crossed face (backward.cu:252-360) and their reduction.
+// The reference issues 10 scalar atomics per crossed face (9 vertex-colour terms + opacity), which
+// bounds its backward pass by the reduction rate of the LSU/L2 (measured, tools/ubench_red.cu).
+// Here the nine colour terms are three 16-byte vector reductions into a float4-per-vertex accumulator
+// (4.4 MB at C3, L2-resident; tet_grad_vertex_kernel folds it into dL_dverts_color[P,3]) + one scalar.
+// (Also measured: one 48-byte statistics record per face + a finish kernel, as in the tri renderer --
+// 0.06 ms slower at C3 because the records (152 MB) have to be zeroed, written and read back.)
+__device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st, int face, float rt, float iu, float iv,
+                                             const float4 s0, const float4 s1, const float4 s2, const float4 s3,
+                                             float intense, float3 ro, float3 rd, const float* mv, const float* pj,
+                                             const float dLc[3], float gd, float bg_dot, float bd_dot, float final_T,
+                                             float final_prev_T)
+{
+    const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
+    const float opacity = s2.y;
+    const float log1m = s3.w;
+
+    // backward.cu:252-270
+    float i0 = 1.0f - iu - iv, i1 = iu, i2 = iv;
+    float3 col = (i0 * c0) + (i1 * c1) + (i2 * c2);
+    col = col * intense;
+    float3 pt = ro + (rd * rt);
+    float4 pn = xform44(xform43(pt, mv), pj);
+    float pw = 1.0f / clamp_w(pn.w);
+    float pd = pn.z * pw;
+
+    if (!st.first_iter) st.prev_log_T = st.prev_log_T - log1m;
+    st.first_iter = false;
+    float prev_T = expf(st.prev_log_T);
+
+    // backward.cu:288-339
+    float dL_dcol[3];
+    float dL_dopa = 0.0f;
+    const float tc[3] = { col.x, col.y, col.z };
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        const float c = tc[ch];
+        st.accum_rec[ch] = st.last_alpha * st.last_color[ch] + (1.f - st.last_alpha) * st.accum_rec[ch];
+        st.last_color[ch] = c;
+        dL_dcol[ch] = dLc[ch] * opacity * prev_T;
+        dL_dopa += (c - st.accum_rec[ch]) * dLc[ch];
+    }
+    st.accum_recd = st.last_alpha * st.last_depth + (1.f - st.last_alpha) * st.accum_recd;
+    st.last_depth = pd;
+    dL_dopa += (pd - st.accum_recd) * gd;
+    dL_dopa *= prev_T;
+    st.last_alpha = opacity;
+    if (opacity == 1.0f) {
+        dL_dopa += (-final_prev_T) * bg_dot;
+        dL_dopa += (-final_prev_T) * bd_dot;
+    } else {
+        dL_dopa += (-final_T / (1.f - opacity)) * bg_dot;
+        dL_dopa += (-final_T / (1.f - opacity)) * bd_dot;
+    }
+
+    // backward.cu:341-360
+    const float g00 = i0 * dL_dcol[0] * intense, g01 = i0 * dL_dcol[1] * intense, g02 = i0 * dL_dcol[2] * intense;
+    const float g10 = i1 * dL_dcol[0] * intense, g11 = i1 * dL_dcol[1] * intense, g12 = i1 * dL_dcol[2] * intense;
+    const float g20 = i2 * dL_dcol[0] * intense, g21 = i2 * dL_dcol[1] * intense, g22 = i2 * dL_dcol[2] * intense;
+    const int vi0 = __float_as_int(s2.z), vi1 = __float_as_int(s2.w), vi2 = __float_as_int(s3.x);
+    red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi0), g00, g01, g02, 0.0f);
+    red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi1), g10, g11, g12, 0.0f);
+    red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi2), g20, g21, g22, 0.0f);
+    atomicAdd(&p.dL_dfaces_opacity[face], dL_dopa);
+}
+
+// Backward march.  Steps recorded in the face trail (all of them unless a ray composited more than
+// trail_cap faces) are replayed in reverse: face id from the trail (coalesced), (t,u,v) from the same
+// hit test on the same vertices the forward pass used, all loads independent of the previous step and
+// issued one step ahead.  Steps beyond the cap are re-marched through the adjacency records exactly like
+// the reference (backward.cu:382-477) until the recorded part is reached.
 __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams p)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,6 +586,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
     const uint32_t py = blockIdx.y * 8 + warp * 4 + (lane >> 3);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
     const size_t HW = (size_t)p.W * p.H;
+    const size_t BI = (size_t)p.B * HW;
     const size_t pix = (size_t)py * p.W + px;
     const size_t bpix = (size_t)b * HW + pix;
 
@@ -478,12 +595,12 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
     if (last_face == -1) return;                    // backward.cu:190-193
     const int last_tet = p.last_tet[bpix];
     const int first_face = p.first_face[bpix];
+    int k = (int)p.n_contrib[bpix] - 1;             // index of the step to process next, counting down
 
     const float fin_prev_log_T = p.prev_log_T[bpix];
     const float fin_log_T = p.final_log_T[bpix];
     const float final_prev_T = expf(fin_prev_log_T);
     const float final_T = expf(fin_log_T);
-    float prev_log_T = fin_prev_log_T;
 
     const float g0 = p.dL_dcolor[(size_t)b * 3 * HW + 0 * HW + pix];
     const float g1 = p.dL_dcolor[(size_t)b * 3 * HW + 1 * HW + pix];
@@ -496,122 +613,101 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
     const float* mv = p.mv + 16 * b;
     const float* pj = p.proj + 16 * b;
 
-    float rt, iu, iv;
-    {
-        const float* w = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F + last_face);
-        float3 tuv = f3(0, 0, 0);
-        ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
-        rt = tuv.x; iu = tuv.y; iv = tuv.z;
-    }
-    int curr_face = last_face, curr_tet = last_tet;
-    // the tet on the near side of the last face: backward.cu:224-232
-    {
-        const TetShade* sh = p.shade + curr_face;
-        const int cand[2] = { sh->t0, sh->t1 };
-        for (int i = 0; i < 2; i++) {
-            if (cand[i] == curr_tet) continue;
-            curr_tet = cand[i];
-            break;
-        }
-    }
-
     // backward.cu:324-329
     float bg_dot = 0; bg_dot += p.bg[0] * g0; bg_dot += p.bg[1] * g1; bg_dot += p.bg[2] * g2;
     float bd_dot = 0; bd_dot += 1.0 * gd;
 
-    float last_alpha = 0.0f, last_depth = 0.0f, accum_recd = 0.0f;
-    float last_color[3] = { 0, 0, 0 }, accum_rec[3] = { 0, 0, 0 };
-    bool first_iter = true, done = false;
-
-    while (!done) {
-        const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
-        const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2], s3 = sh4[3];
-        const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
-        const float opacity = s2.y;
-        const float log1m = s3.w;
-        const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
-
-        // backward.cu:252-270
-        float i0 = 1.0f - iu - iv, i1 = iu, i2 = iv;
-        float3 col = (i0 * c0) + (i1 * c1) + (i2 * c2);
-        col = col * intense;
-        float3 pt = ro + (rd * rt);
-        float4 pn = xform44(xform43(pt, mv), pj);
-        float pw = 1.0f / clamp_w(pn.w);
-        float pd = pn.z * pw;
-
-        if (!first_iter) prev_log_T = prev_log_T - log1m;
-        first_iter = false;
-        float prev_T = expf(prev_log_T);
-
-        // backward.cu:288-339
-        float dL_dcol[3];
-        float dL_dopa = 0.0f;
-        const float tc[3] = { col.x, col.y, col.z };
+    TetBwdState st;
+    st.prev_log_T = fin_prev_log_T;
+    st.last_alpha = 0.0f; st.last_depth = 0.0f; st.accum_recd = 0.0f;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const float c = tc[ch];
-            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-            last_color[ch] = c;
-            dL_dcol[ch] = dLc[ch] * opacity * prev_T;
-            dL_dopa += (c - accum_rec[ch]) * dLc[ch];
-        }
-        accum_recd = last_alpha * last_depth + (1.f - last_alpha) * accum_recd;
-        last_depth = pd;
-        dL_dopa += (pd - accum_recd) * gd;
-        dL_dopa *= prev_T;
-        last_alpha = opacity;
-        if (opacity == 1.0f) {
-            dL_dopa += (-final_prev_T) * bg_dot;
-            dL_dopa += (-final_prev_T) * bd_dot;
-        } else {
-            dL_dopa += (-final_T / (1.f - opacity)) * bg_dot;
-            dL_dopa += (-final_T / (1.f - opacity)) * bd_dot;
-        }
+    for (int ch = 0; ch < 3; ch++) { st.last_color[ch] = 0.0f; st.accum_rec[ch] = 0.0f; }
+    st.first_iter = true;
 
-        // backward.cu:341-360: the reference issues 10 scalar atomics per crossed face (9 vertex-colour
-        // terms + opacity), which bounds its backward pass by the reduction rate of the LSU/L2
-        // (measured, tools/ubench_red.cu).  Here the ten terms go to ONE 48-byte record per face as three
-        // 16-byte vector reductions; tet_grad_finish_kernel scatters the records to the vertices.
+    // ---- part 1 (rare): steps beyond the trail, re-marched through the adjacency records
+    if (k >= p.trail_cap) {
+        float rt, iu, iv;
         {
-            float* st = p.grad_stats + (size_t)curr_face * 12;
-            red_add_v4(st + 0, i0 * dL_dcol[0] * intense, i0 * dL_dcol[1] * intense, i0 * dL_dcol[2] * intense,
-                       i1 * dL_dcol[0] * intense);
-            red_add_v4(st + 4, i1 * dL_dcol[1] * intense, i1 * dL_dcol[2] * intense, i2 * dL_dcol[0] * intense,
-                       i2 * dL_dcol[1] * intense);
-            red_add_v4(st + 8, i2 * dL_dcol[2] * intense, dL_dopa, 0.0f, 0.0f);
+            const float* w = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F + last_face);
+            float3 tuv = f3(0, 0, 0);
+            ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
+            rt = tuv.x; iu = tuv.y; iv = tuv.z;
         }
+        int curr_face = last_face, curr_tet = last_tet;
+        // the tet on the near side of the last face: backward.cu:224-232
+        {
+            const TetShade* sh = p.shade + curr_face;
+            const int cand[2] = { sh->t0, sh->t1 };
+            for (int i = 0; i < 2; i++) {
+                if (cand[i] == curr_tet) continue;
+                curr_tet = cand[i];
+                break;
+            }
+        }
+        while (k >= p.trail_cap) {
+            const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
+            const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2], s3 = sh4[3];
+            const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
+            tet_bwd_face(p, st, curr_face, rt, iu, iv, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
+                         final_T, final_prev_T);
+            k--;
+            if (curr_face == first_face) return;         // backward.cu:363-366
+            if (curr_tet == -1) return;                  // backward.cu:373-376
+            TetStep s = tet_step<false>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
+            if (!s.ok) return;
+            curr_face = s.face; curr_tet = s.tet;
+            rt = s.rt; iu = s.iu; iv = s.iv;
+        }
+    }
 
-        if (curr_face == first_face) break;          // backward.cu:363-366
-        if (curr_tet == -1) break;                   // backward.cu:373-376
-        TetStep s = tet_step<false>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
-        if (!s.ok) done = true;
-        curr_face = s.face; curr_tet = s.tet;
-        rt = s.rt; iu = s.iu; iv = s.iv;
+    // ---- part 2: replay the trail in reverse, loads one step ahead
+    const int* trail = p.trail + bpix;
+    const float* frec = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F);
+    const float* fint = p.faces_intense + (size_t)b * p.F;
+
+    int face = trail[(size_t)k * BI] & 0x7fffffff;
+    int face_next = k > 0 ? trail[(size_t)(k - 1) * BI] : 0;
+    float4 q0, q1, q2, s0, s1, s2, s3;
+    float intense;
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(frec + (size_t)face * 16);
+        q0 = w4[0]; q1 = w4[1]; q2 = w4[2];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shade + face);
+        s0 = sh4[0]; s1 = sh4[1]; s2 = sh4[2]; s3 = sh4[3];
+        intense = fint[face];
+    }
+    for (; k >= 0; k--) {
+        // issue the loads of step k-1 (face id known since the previous iteration), then work on step k
+        const int nf = face_next & 0x7fffffff;
+        const bool stop_here = face_next < 0;   // the reference's reverse march fails between step k and k-1
+        const float4* w4 = reinterpret_cast<const float4*>(frec + (size_t)nf * 16);
+        const float4 nq0 = w4[0], nq1 = w4[1], nq2 = w4[2];
+        const float4* sh4 = reinterpret_cast<const float4*>(p.shade + nf);
+        const float4 ns0 = sh4[0], ns1 = sh4[1], ns2 = sh4[2], ns3 = sh4[3];
+        const float nint = fint[nf];
+        face_next = k > 1 ? trail[(size_t)(k - 2) * BI] : 0;
+
+        float3 tuv = f3(0, 0, 0);
+        ray_tri_hit(ro, rd, f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), tuv);
+        tet_bwd_face(p, st, face, tuv.x, tuv.y, tuv.z, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
+                     final_T, final_prev_T);
+
+        if (stop_here) break;
+        face = nf;
+        q0 = nq0; q1 = nq1; q2 = nq2;
+        s0 = ns0; s1 = ns1; s2 = ns2; s3 = ns3;
+        intense = nint;
     }
 }
 
-// Once per face: 12-float statistics record -> dL_dverts_color (9 atomics, only for faces some ray
-// crossed) and dL_dfaces_opacity.
-__global__ void __launch_bounds__(256) tet_grad_finish_kernel(TetParams p)
+// Once per vertex: float4 accumulator -> dL_dverts_color[P,3].
+__global__ void __launch_bounds__(256) tet_grad_vertex_kernel(TetParams p)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= p.F) return;
-    const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + (size_t)f * 12);
-    const float4 a = st4[0], b = st4[1], c = st4[2];
-    const float st[10] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y };
-    bool any = false;
-#pragma unroll
-    for (int q = 0; q < 10; q++) any = any || st[q] != 0.0f;
-    if (!any) return;
-    const TetShade* sh = p.shade + f;
-    const int vi[3] = { sh->i0, sh->i1, sh->i2 };
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++)
-            if (st[3 * k + ch] != 0.0f) atomicAdd(&p.dL_dverts_color[3 * (size_t)vi[k] + ch], st[3 * k + ch]);
-    p.dL_dfaces_opacity[f] += st[9];   // one thread per face: no atomic needed
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.P) return;
+    const float4 a = p.grad_vacc[v];
+    float* o = p.dL_dverts_color + 3 * (size_t)v;
+    o[0] += a.x; o[1] += a.y; o[2] += a.z;
 }
 
 int tet_march_backward(const TetParams& p, cudaStream_t stream)
@@ -624,8 +720,8 @@ int tet_march_backward(const TetParams& p, cudaStream_t stream)
     }
     {
         ProfScope prof(ST_TET_BWD_FINISH, stream);
-        tet_grad_finish_kernel<<<(p.F + 255) / 256, 256, 0, stream>>>(p);
-        DMR_LAUNCH_CHECK("tet_grad_finish_kernel");
+        tet_grad_vertex_kernel<<<(p.P + 255) / 256, 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tet_grad_vertex_kernel");
     }
     return 0;
 }

@@ -201,6 +201,12 @@ int dmr_debug_view(int renderer /*0=tri,1=tet*/, int kind,
                    int B, int P, int F, int T, int W, int H, size_t R,
                    const void* buffer, const void** ptr, size_t* count);
 
+/* Test hook: number of march steps per ray recorded in the tet renderer's   */
+/* face trail (0 = automatic, see tet.cuh).  Changes the image-buffer size   */
+/* reported by dmr_tet_state_bytes; set it before the forward call and keep  */
+/* it until the matching backward call has been issued.  Not thread-safe.    */
+int dmr_debug_set_tet_trail_cap(int cap);
+
 /* ------------------------------------------------------------------------ */
 /* Stand-alone stable LSD radix sort of (uint64 key, uint32 value) pairs on  */
 /* bits [0, end_bit) -- the hand-written onesweep that replaces              */

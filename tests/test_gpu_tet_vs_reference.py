@@ -82,6 +82,35 @@ def test_tet_gradients(name, seed):
         assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
 
 
+@pytest.mark.parametrize("cap", [1, 7])
+@pytest.mark.parametrize("name", ["small_tet", "C3"])
+def test_tet_gradients_short_trail(name, cap):
+    """Rays that composite more faces than the face trail holds re-march the part beyond the cap
+    through the adjacency records (as the reference does for the whole ray): same gradients."""
+    need_ref()
+    from dmesh_renderer_b200 import _lib
+    lib = _lib.load()
+    s = scenes.to_device(scenes.config(name), "cuda")
+    gc, gd = [t.cuda() for t in scenes.cotangents(s)]
+    ref = ref_harness.ref_tet_forward(s, 0)
+    rg = ref_harness.ref_tet_backward(s, ref, gc, gd)
+    lib.dmr_debug_set_tet_trail_cap(cap)
+    try:
+        vc = s.verts_color.clone().requires_grad_()
+        fo = s.faces_opacity.clone().requires_grad_()
+        renderer = TetRenderer(TetRenderSettings(s.H, s.W, s.bg, 0))
+        color, depth, active = renderer(s.verts, s.faces, vc, fo, s.mv_mats, s.proj_mats, s.verts_depth,
+                                        s.faces_intense, s.tets, s.face_tets, s.tet_faces)
+        torch.autograd.backward([color, depth], [gc, gd])
+        torch.cuda.synchronize()
+    finally:
+        lib.dmr_debug_set_tet_trail_cap(0)
+    assert (color - ref["color"]).abs().max().item() <= IMG_TOL
+    for n, g, r in (("verts_color", vc.grad, rg[0]), ("faces_opacity", fo.grad, rg[1])):
+        e = rel_l2(g, r)
+        assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
+
+
 def test_tet_validation_errors():
     s = scenes.to_device(scenes.config("tiny_tet"), "cuda")
     mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
