@@ -195,89 +195,134 @@ __device__ __forceinline__ void tet_pixel_ray(const TetParams& p, int b, uint32_
 // ---------------------------------------------------------------------------
 // first intersection: per tile, faces sorted by min depth
 // ---------------------------------------------------------------------------
-#define FI_RB 128
-#define FI_THREADS 64
+#define FI_THREADS 256
 
-// Hierarchical search: per group of 32 staged faces each lane tests one face's screen bbox against
-// the warp's 8x4 pixel block; survivors are walked in list order, and a pixel runs the (expensive)
-// ray/triangle test only when it lies inside the face's bbox.  Faces are sorted by min depth, so
-// deferring the reference's early-out check (forward.cu:388-391) to the next processed face cannot
-// change the result: every later face has a min depth at least as large.
-// Launch shape: one CTA of 64 threads (two 8x4 warps) per 8x8-pixel QUADRANT of a tile, i.e. four CTAs
-// walk the same tile list.  With one 256-thread CTA per tile the 512x512 benchmark has only 1024 CTAs
-// whose cost is dominated by a few hundred heavy tiles (measured: 45 M warp instructions took 733 us,
-// 25% occupancy, barrier-stalled); quadrants give 4x more, 4x lighter CTAs.
+// Face-parallel search.  One CTA per 16x16 tile; per round 256 instances of the tile list are staged
+// (one per thread) and EVERY THREAD TAKES ONE FACE: it walks the pixels of the face's screen bounding
+// box inside the tile that are still searching, runs the reference's ray/triangle test and merges hits
+// into the pixel's slot with a 64-bit shared-memory atomicMin on (t bits << 32 | list position) --
+// the lexicographic minimum is exactly what the reference's sequential "cur < min_T" scan keeps (first
+// face in list order among equal t).  Then every thread folds the round's winner of ITS pixel into its
+// running best and applies the reference's early-out (forward.cu:388-391) at round granularity.
+//
+// Why: the reference (and the first two versions of this kernel) walk the list once per pixel block
+// with one warp -- a serial chain whose length is the whole tile list (5-20 k faces at C3) for every
+// block that contains a pixel the mesh does not cover.  The kernel's duration was the latency of that
+// chain in a few hundred silhouette tiles (688 us at C3 with 14% achieved occupancy and 45 M warp
+// instructions, i.e. 40 us of issue work).  Taking faces instead of pixels as the parallel axis makes a
+// round 256 independent tests wide.
+//
+// Equivalence with the sequential scan: faces are sorted by min depth, a face is skipped by the reference
+// only when its min depth exceeds the max depth of the current best hit, and NDC depth is monotone in t
+// along a ray, so the skipped faces cannot hold the minimum; the result is the argmin of t over all hit
+// faces (ties: list order) either way.  The early-out is applied between rounds, and a round winner that
+// the reference would not have reached any more (min depth beyond the previous best's max depth) is
+// discarded like the reference does.
 __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetParams p)
 {
-    __shared__ uint4 s_rec[FI_RB * 4];
-    __shared__ int s_face[FI_RB];
+    __shared__ uint4 s_rec[FI_THREADS * 3];          // p0 p1 p2 | min_depth max_depth bbox_x
+    __shared__ uint32_t s_bby[FI_THREADS];
+    __shared__ int s_face[FI_THREADS];
+    __shared__ unsigned long long s_best[FI_THREADS];
+    __shared__ float4 s_rd[FI_THREADS];
+    __shared__ uint32_t s_open[DMR_TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const int tiles_x = (p.W + DMR_TILE - 1) / DMR_TILE, tiles_y = (p.H + DMR_TILE - 1) / DMR_TILE;
-    const int tile_x = blockIdx.x >> 1, tile_y = blockIdx.y >> 1;
-    const uint32_t bx0 = tile_x * DMR_TILE + (blockIdx.x & 1) * 8, by0 = tile_y * DMR_TILE + (blockIdx.y & 1) * 8 + warp * 4;
-    const uint32_t px = bx0 + (lane & 7);
-    const uint32_t py = by0 + (lane >> 3);
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+    const uint32_t tx0 = blockIdx.x * DMR_TILE, ty0 = blockIdx.y * DMR_TILE;
+    const uint32_t px = tx0 + (tid & 15);
+    const uint32_t py = ty0 + (tid >> 4);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
     const size_t bpix = (size_t)b * p.W * p.H + (size_t)py * p.W + px;
-    bool done = !inside;
 
-    float3 ro = f3(0, 0, 0), rd = f3(0, 0, 1);
+    float3 ro = f3(p.inv_mv[16 * b + 12], p.inv_mv[16 * b + 13], p.inv_mv[16 * b + 14]);   // same for every pixel
+    float3 rd = f3(0, 0, 1);
     if (inside) tet_pixel_ray(p, b, px, py, bpix, ro, rd);
+    s_rd[tid] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+    ro = f3(p.inv_mv[16 * b + 12], p.inv_mv[16 * b + 13], p.inv_mv[16 * b + 14]);
 
-    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + tile_y * tiles_x + tile_x];
+    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + blockIdx.y * tiles_x + blockIdx.x];
     const int total = (int)(range.y - range.x);
-    const int rounds = (total + FI_RB - 1) / FI_RB;
+    const int rounds = (total + FI_THREADS - 1) / FI_THREADS;
 
     float min_T = -1.0f, min_T_max_depth = -1.0f;
     int first_face = -1;
+    bool closed = !inside;
+
+    // register-staged prefetch of the next round
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0;
+    uint32_t nby = 0;
+    int nface = 0;
+    auto fetch = [&](int r) {
+        const uint32_t pos = range.x + (uint32_t)r * FI_THREADS + tid;
+        if (r < rounds && pos < range.y) {
+            nface = (int)p.face_list[pos];
+            const uint4* src = reinterpret_cast<const uint4*>(p.face_rec + (size_t)b * p.F + nface);
+            n0 = src[0]; n1 = src[1]; n2 = src[2];
+            nby = src[3].x;
+        }
+    };
+    fetch(0);
 
     for (int r = 0; r < rounds; r++) {
-        if (__syncthreads_count(done) == FI_THREADS) break;
-        for (int t = tid; t < FI_RB; t += FI_THREADS) {
-            uint32_t pos = range.x + (uint32_t)r * FI_RB + t;
-            if (pos < range.y) {
-                uint32_t face = p.face_list[pos];
-                s_face[t] = (int)face;
-                const uint4* src = reinterpret_cast<const uint4*>(p.face_rec + (size_t)b * p.F + face);
-                s_rec[t * 4 + 0] = src[0];
-                s_rec[t * 4 + 1] = src[1];
-                s_rec[t * 4 + 2] = src[2];
-                s_rec[t * 4 + 3] = src[3];
-            }
-        }
+        s_rec[tid * 3 + 0] = n0; s_rec[tid * 3 + 1] = n1; s_rec[tid * 3 + 2] = n2;
+        s_bby[tid] = nby;
+        s_face[tid] = nface;
+        s_best[tid] = ~0ull;
         __syncthreads();
-        const int cnt = min(FI_RB, total - r * FI_RB);
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
-            if (__all_sync(0xffffffffu, done)) break;
-            const int jl = c0 + lane;
-            bool keep = false;
-            if (jl < cnt) {
-                const uint32_t bx = s_rec[jl * 4 + 2].w, by = s_rec[jl * 4 + 3].x;
-                keep = (bx & 0xffffu) <= bx0 + 7 && (bx >> 16) >= bx0 && (by & 0xffffu) <= by0 + 3 && (by >> 16) >= by0;
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, keep);
-            while (mask) {
-                const int j = c0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (done) continue;
-                const uint4 q2 = s_rec[j * 4 + 2];
-                // forward.cu:388-391
-                if (min_T >= 0.0f && __uint_as_float(q2.y) > min_T_max_depth) { done = true; continue; }
-                const uint32_t by = s_rec[j * 4 + 3].x;
-                if (px < (q2.w & 0xffffu) || px > (q2.w >> 16) || py < (by & 0xffffu) || py > (by >> 16)) continue;
-                const float* w = reinterpret_cast<const float*>(s_rec + j * 4);
-                float3 tuv;
-                bool hit = ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), tuv);
-                if (!hit) continue;
-                float cur = tuv.x;
-                if (min_T < 0.0f || cur < min_T) {
-                    min_T = cur;
-                    min_T_max_depth = w[10];
-                    first_face = s_face[j];
+        // forward.cu:388-391 at round granularity: nothing from this round on can beat the best hit
+        if (!closed && min_T >= 0.0f && __uint_as_float(s_rec[2].y) > min_T_max_depth) closed = true;
+        {
+            const unsigned open = __ballot_sync(0xffffffffu, !closed);   // a warp holds tile rows 2*warp, 2*warp+1
+            if (lane == 0) { s_open[2 * warp] = open & 0xffffu; s_open[2 * warp + 1] = open >> 16; }
+        }
+        if (__syncthreads_count(!closed) == 0) break;
+        fetch(r + 1);
+
+        const int cnt = min(FI_THREADS, total - r * FI_THREADS);
+        // (fetch(r+1) overwrote the staging registers; this round's face is read back from shared memory)
+        if (tid < cnt) {
+            const uint4 q0 = s_rec[tid * 3 + 0], q1 = s_rec[tid * 3 + 1], q2 = s_rec[tid * 3 + 2];
+            const uint32_t bbx = q2.w, bby = s_bby[tid];
+            const int x0 = max((int)(bbx & 0xffffu), (int)tx0), x1 = min((int)(bbx >> 16), (int)tx0 + DMR_TILE - 1);
+            const int y0 = max((int)(bby & 0xffffu), (int)ty0), y1 = min((int)(bby >> 16), (int)ty0 + DMR_TILE - 1);
+            if (x0 <= x1) {
+                const float3 p0 = f3(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z));
+                const float3 p1 = f3(__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y));
+                const float3 p2 = f3(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x));
+                const uint32_t xmask = ((2u << (x1 - (int)tx0)) - 1u) & ~((1u << (x0 - (int)tx0)) - 1u);
+                for (int y = y0; y <= y1; y++) {
+                    uint32_t m = s_open[y - (int)ty0] & xmask;
+                    while (m) {
+                        const int xi = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int pix = (y - (int)ty0) * DMR_TILE + xi;
+                        const float4 d4 = s_rd[pix];
+                        float3 tuv;
+                        if (!ray_tri_hit(ro, f3(d4.x, d4.y, d4.z), p0, p1, p2, tuv)) continue;
+                        const uint32_t tb = tuv.x == 0.0f ? 0u : __float_as_uint(tuv.x);   // t >= 0: bits are monotone
+                        atomicMin(&s_best[pix], ((unsigned long long)tb << 32) | (unsigned)tid);
+                    }
                 }
             }
         }
+        __syncthreads();
+        if (!closed) {
+            const unsigned long long key = s_best[tid];
+            if (key != ~0ull) {
+                const int pos = (int)(key & 0xffffffffu);
+                const float cur = __uint_as_float((uint32_t)(key >> 32));
+                const uint4 q2 = s_rec[pos * 3 + 2];
+                // the reference stops in front of a face whose min depth exceeds the best hit's max depth
+                if (min_T >= 0.0f && __uint_as_float(q2.y) > min_T_max_depth) closed = true;
+                else if (min_T < 0.0f || cur < min_T) {
+                    min_T = cur;
+                    min_T_max_depth = __uint_as_float(q2.z);
+                    first_face = s_face[pos];
+                }
+            }
+        }
+        __syncthreads();
     }
 
     if (!inside) return;
@@ -305,7 +350,7 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
 
 int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid(2 * ((p.W + DMR_TILE - 1) / DMR_TILE), 2 * ((p.H + DMR_TILE - 1) / DMR_TILE), p.B);
+    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
     ProfScope prof(ST_TET_FIRST, stream);
     tet_first_intersect_kernel<<<grid, FI_THREADS, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
