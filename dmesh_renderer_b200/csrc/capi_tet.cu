@@ -19,8 +19,8 @@ const T* at(const void* base, size_t off) { return reinterpret_cast<const T*>(st
 bool tet_sizes_ok(long long B, long long P, long long F, long long T, long long W, long long H)
 {
     if (B < 0 || P < 0 || F < 0 || T < 0 || W <= 0 || H <= 0) { set_error("negative or zero size"); return false; }
-    if (B * P >= (1LL << 31) || B * F >= (1LL << 31) || B * W * H >= (1LL << 31) || T >= (1LL << 31)) {
-        set_error("B*P, B*F, T and B*W*H must stay below 2^31");
+    if (B * P >= (1LL << 31) || B * F >= (1LL << 31) || B * W * H >= (1LL << 31) || T > DMR_TET_MAX_TETS) {
+        set_error("B*P, B*F and B*W*H must stay below 2^31 and T below 2^28 - 1");
         return false;
     }
     if ((W + DMR_TILE - 1) / DMR_TILE >= 65536 || (H + DMR_TILE - 1) / DMR_TILE >= 65536) {

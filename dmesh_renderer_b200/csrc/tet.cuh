@@ -21,14 +21,26 @@ static_assert(sizeof(TetFaceRec) == 64, "TetFaceRec must be 4 x 16 bytes");
 // View-independent per-tet adjacency record used by the ray march.  The
 // reference re-gathers, at every step, tet_faces -> faces -> verts (3 dependent
 // levels), the tet's 4 vertices four times over and face_tets
-// (cuda_renderer/forward.cu:672-768, ~670 B per step).  One 224-byte record per
-// tet turns that into a single dependent load.
+// (cuda_renderer/forward.cu:672-768, ~670 B per step).  One 128-byte record (exactly
+// one cache line) per tet turns that into a single dependent load.
+//
+// The march is bound by the bytes each lane pulls through L1 per step (ncu: l1tex data pipe 55-90%
+// busy, DRAM < 10%), so the four sides do not carry their own copies of the vertices (the first
+// version: 224 B): vert[k] is the tet vertex OPPOSITE side k, side k's triangle is made of the other
+// three, and a 4-bit order code says in which order faces[] lists them -- the hit test must see
+// (p0,p1,p2) in the reference's order to reproduce its (t,u,v) bits.  A tet whose sides are not made
+// of its own four vertices (inconsistent input tables) cannot be represented: it is flagged and the
+// march treats entering it as a numerical failure (pixel inactive).
 struct __align__(16) TetRec {
     int face[4];          // tet_faces[4*t + k]
-    int next_tet[4];      // first entry of face_tets[face[k]] that is neither t nor -1, else -1
-    float geo[4][12];     // per side: p0, p1, p2 (faces[] order), outward unit normal w.r.t. this tet
+    uint32_t next[4];     // bits 0..27: 1 + first entry of face_tets[face[k]] that is neither t nor -1 (0 = none)
+                          // bits 28..31: order code a | b << 2: p0 = cyc[a], p1 = cyc[b], p2 = cyc[3-a-b] with
+                          //              cyc = (vert[(k+1)&3], vert[(k+2)&3], vert[(k+3)&3]); 0xF = irregular tet
+    float vert[4][3];     // vert[k] = position of the vertex opposite side k
+    float nrm[4][3];      // outward unit normal of side k w.r.t. this tet
 };
-static_assert(sizeof(TetRec) == 224, "TetRec must be 14 x 16 bytes");
+static_assert(sizeof(TetRec) == 128, "TetRec must be one 128-byte line");
+#define DMR_TET_MAX_TETS ((1 << 28) - 2)
 
 // View-independent per-face shading record: 64 bytes.
 struct __align__(16) TetShade {

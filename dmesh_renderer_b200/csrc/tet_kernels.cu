@@ -80,23 +80,30 @@ __global__ void __launch_bounds__(128) tet_build_tetrec_kernel(
     int T, const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ tets,
     const int* __restrict__ face_tets, const int* __restrict__ tet_faces, TetRec* __restrict__ out)
 {
-    __shared__ uint4 s_rec[128 * 14];   // 224 B per tet; written per thread, read back coalesced
+    __shared__ uint4 s_rec[128 * 8];   // 128 B per tet; written per thread, read back coalesced
     const int t0 = blockIdx.x * 128;
     const int t = t0 + threadIdx.x;
     if (t < T) {
-        const int4 tv = reinterpret_cast<const int4*>(tets)[t];
+        const int4 tv4 = reinterpret_cast<const int4*>(tets)[t];
         const int4 tf = reinterpret_cast<const int4*>(tet_faces)[t];
-        float3 q0 = ld3(verts + 3 * (size_t)tv.x), q1 = ld3(verts + 3 * (size_t)tv.y);
-        float3 q2 = ld3(verts + 3 * (size_t)tv.z), q3 = ld3(verts + 3 * (size_t)tv.w);
+        const int tv[4] = { tv4.x, tv4.y, tv4.z, tv4.w };
+        float3 q[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = ld3(verts + 3 * (size_t)tv[i]);
         const int fid[4] = { tf.x, tf.y, tf.z, tf.w };
-        int nxt[4];
-        uint4* o = s_rec + threadIdx.x * 14;
+        uint32_t nxt[4];
+        float3 nrm[4];
+        int loc[4][3];      // tet-local index (0..3) of the side's p0, p1, p2; -1 = not a vertex of this tet
+        int opp[4];         // tet-local index of the vertex opposite side k
+        bool regular = true;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int f = fid[k];
-            const int a = faces[3 * (size_t)f], b = faces[3 * (size_t)f + 1], c = faces[3 * (size_t)f + 2];
-            float3 p0 = ld3(verts + 3 * (size_t)a), p1 = ld3(verts + 3 * (size_t)b), p2 = ld3(verts + 3 * (size_t)c);
-            float3 n = outward_normal(p0, p1, p2, q0, q1, q2, q3);
+            const int fv[3] = { faces[3 * (size_t)f], faces[3 * (size_t)f + 1], faces[3 * (size_t)f + 2] };
+            float3 pp[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) pp[j] = ld3(verts + 3 * (size_t)fv[j]);
+            nrm[k] = outward_normal(pp[0], pp[1], pp[2], q[0], q[1], q[2], q[3]);
             // forward.cu:761-767
             int nt = -1;
             for (int i = 0; i < 2; i++) {
@@ -105,18 +112,56 @@ __global__ void __launch_bounds__(128) tet_build_tetrec_kernel(
                 nt = cand;
                 break;
             }
-            nxt[k] = nt;
-            o[2 + 3 * k + 0] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p0.z), __float_as_uint(p1.x));
-            o[2 + 3 * k + 1] = make_uint4(__float_as_uint(p1.y), __float_as_uint(p1.z), __float_as_uint(p2.x), __float_as_uint(p2.y));
-            o[2 + 3 * k + 2] = make_uint4(__float_as_uint(p2.z), __float_as_uint(n.x), __float_as_uint(n.y), __float_as_uint(n.z));
+            nxt[k] = (uint32_t)(nt + 1);
+            // which tet vertex is p_j?  by id, else by bitwise-equal position (duplicated vertices)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                int l = -1;
+#pragma unroll
+                for (int i = 3; i >= 0; i--)
+                    if (fv[j] == tv[i] || (pp[j].x == q[i].x && pp[j].y == q[i].y && pp[j].z == q[i].z)) l = i;
+                loc[k][j] = l;
+            }
+            const int l0 = loc[k][0], l1 = loc[k][1], l2 = loc[k][2];
+            if (l0 < 0 || l1 < 0 || l2 < 0 || l0 == l1 || l0 == l2 || l1 == l2) { regular = false; opp[k] = 0; }
+            else opp[k] = 6 - l0 - l1 - l2;
         }
+        // the four sides must be opposite four different vertices
+        if (regular && ((1 << opp[0]) | (1 << opp[1]) | (1 << opp[2]) | (1 << opp[3])) != 0xF) regular = false;
+        float3 vout[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t code = 0xFu;
+            vout[k] = q[k];
+            if (regular) {
+                vout[k] = q[0];
+#pragma unroll
+                for (int i = 1; i < 4; i++) if (opp[k] == i) vout[k] = q[i];
+                // position of p0 / p1 inside cyc = (vert[(k+1)&3], vert[(k+2)&3], vert[(k+3)&3])
+                int a = 0, bb = 0;
+#pragma unroll
+                for (int j = 1; j <= 3; j++) {
+                    if (opp[(k + j) & 3] == loc[k][0]) a = j - 1;
+                    if (opp[(k + j) & 3] == loc[k][1]) bb = j - 1;
+                }
+                code = (uint32_t)(a | (bb << 2));
+            }
+            nxt[k] |= code << 28;
+        }
+        uint4* o = s_rec + threadIdx.x * 8;
         o[0] = make_uint4(fid[0], fid[1], fid[2], fid[3]);
         o[1] = make_uint4(nxt[0], nxt[1], nxt[2], nxt[3]);
+        o[2] = make_uint4(__float_as_uint(vout[0].x), __float_as_uint(vout[0].y), __float_as_uint(vout[0].z), __float_as_uint(vout[1].x));
+        o[3] = make_uint4(__float_as_uint(vout[1].y), __float_as_uint(vout[1].z), __float_as_uint(vout[2].x), __float_as_uint(vout[2].y));
+        o[4] = make_uint4(__float_as_uint(vout[2].z), __float_as_uint(vout[3].x), __float_as_uint(vout[3].y), __float_as_uint(vout[3].z));
+        o[5] = make_uint4(__float_as_uint(nrm[0].x), __float_as_uint(nrm[0].y), __float_as_uint(nrm[0].z), __float_as_uint(nrm[1].x));
+        o[6] = make_uint4(__float_as_uint(nrm[1].y), __float_as_uint(nrm[1].z), __float_as_uint(nrm[2].x), __float_as_uint(nrm[2].y));
+        o[7] = make_uint4(__float_as_uint(nrm[2].z), __float_as_uint(nrm[3].x), __float_as_uint(nrm[3].y), __float_as_uint(nrm[3].z));
     }
     __syncthreads();
     const int nvalid = min(128, T - t0);
     uint4* dst = reinterpret_cast<uint4*>(out + t0);
-    for (int i = threadIdx.x; i < nvalid * 14; i += 128) dst[i] = s_rec[i];
+    for (int i = threadIdx.x; i < nvalid * 8; i += 128) dst[i] = s_rec[i];
 }
 
 __global__ void __launch_bounds__(256) tet_build_shade_kernel(
@@ -339,7 +384,7 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
             bool found = false;
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (!found && tr->face[k] == first_face) { n = f3(tr->geo[k][9], tr->geo[k][10], tr->geo[k][11]); found = true; }
+                if (!found && tr->face[k] == first_face) { n = f3(tr->nrm[k][0], tr->nrm[k][1], tr->nrm[k][2]); found = true; }
             if (!found) continue;   // inconsistent adjacency tables
             if (dot3p(n, rd) < 0.0f) first_tet = tet_id;
         }
@@ -364,6 +409,10 @@ int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 // long tail (rays along the cube diagonal cross several times more faces than the mean), so it is
 // launched as many small CTAs: 64 threads = 8x8 pixels = two 8x4 warps.
 #define MARCH_THREADS 64
+// 12 CTAs/SM = 80 registers (measured at C3: uncapped 103 regs 875 us, 80 regs 838 us, 64 regs + spills 947 us)
+#ifndef MARCH_MIN_BLOCKS
+#define MARCH_MIN_BLOCKS 12
+#endif
 
 struct TetStep {   // result of looking for the exit (or entry) face of a tet
     int face, tet;
@@ -378,6 +427,13 @@ struct TetStep {   // result of looking for the exit (or entry) face of a tet
 // (Measured and rejected: prefetching the records of all candidate next tets / faces into L2 as soon
 // as the current tet's ids are known made the march SLOWER -- fwd 0.91 -> 1.03 ms, bwd 1.51 -> 2.25 ms
 // at C3: the extra address arithmetic and L2 requests cost more than the latency they hide.)
+// one of three values by a 2-bit index (0, 1, 2): two selects
+__device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 2 ? c : (i == 1 ? b : a); }
+__device__ __forceinline__ float3 sel3(int i, float3 a, float3 b, float3 c)
+{
+    return f3(sel3(i, a.x, b.x, c.x), sel3(i, a.y, b.y, c.y), sel3(i, a.z, b.z, c.z));
+}
+
 template <bool EXIT>
 __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const TetRec* __restrict__ tr, int curr_face,
                                             float3 ro, float3 rd)
@@ -385,19 +441,21 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
     TetStep s;
     s.ok = true;
     s.face = -1; s.tet = -1; s.rt = 0; s.iu = 0; s.iv = 0;
-    const int4 fid = *reinterpret_cast<const int4*>(tr->face);
-    const int4 nxt = *reinterpret_cast<const int4*>(tr->next_tet);
-    const int f[4] = { fid.x, fid.y, fid.z, fid.w };
-    const int nt[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
+    const uint4* r4 = reinterpret_cast<const uint4*>(tr);
+    const uint4 fid = r4[0], nxt = r4[1];
+    const float4 a0 = reinterpret_cast<const float4*>(tr)[2], a1 = reinterpret_cast<const float4*>(tr)[3];
+    const float4 a2 = reinterpret_cast<const float4*>(tr)[4], n0 = reinterpret_cast<const float4*>(tr)[5];
+    const float4 n1 = reinterpret_cast<const float4*>(tr)[6], n2 = reinterpret_cast<const float4*>(tr)[7];
+    const int f[4] = { (int)fid.x, (int)fid.y, (int)fid.z, (int)fid.w };
+    const uint32_t nx[4] = { nxt.x, nxt.y, nxt.z, nxt.w };
+    const float3 v[4] = { f3(a0.x, a0.y, a0.z), f3(a0.w, a1.x, a1.y), f3(a1.z, a1.w, a2.x), f3(a2.y, a2.z, a2.w) };
+    const float3 nr[4] = { f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w) };
     int cnt = 0, hits = 0;
     bool have_curr = false;
     s.opposite = false;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const float4* g4 = reinterpret_cast<const float4*>(tr->geo[k]);
-        const float4 g0 = g4[0], g1 = g4[1], g2 = g4[2];
-        const float3 n = f3(g2.y, g2.z, g2.w);
-        const float dn = dot3p(n, rd);
+        const float dn = dot3p(nr[k], rd);
         if (f[k] == curr_face) {
             // the face we stand on must face the other way (error case 2)
             if (!have_curr) { if (EXIT ? (dn >= 0.0f) : (dn <= 0.0f)) s.ok = false; }
@@ -405,10 +463,14 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
             continue;
         }
         cnt++;
+        const int code = (int)(nx[k] >> 28);
+        if (code == 0xF) { s.ok = false; continue; }   // irregular tet (see TetRec)
+        const int ia = code & 3, ib = code >> 2, ic = 3 - ia - ib;
+        const float3 A = v[(k + 1) & 3], B = v[(k + 2) & 3], C = v[(k + 3) & 3];
         float3 tuv;
-        bool hit = ray_tri_hit(ro, rd, f3(g0.x, g0.y, g0.z), f3(g0.w, g1.x, g1.y), f3(g1.z, g1.w, g2.x), tuv);
+        bool hit = ray_tri_hit(ro, rd, sel3(ia, A, B, C), sel3(ib, A, B, C), sel3(ic, A, B, C), tuv);
         if (hit && (EXIT ? (dn > 0.0f) : (dn < 0.0f))) {
-            s.face = f[k]; s.tet = nt[k];
+            s.face = f[k]; s.tet = (int)(nx[k] & 0x0fffffffu) - 1;
             s.rt = tuv.x; s.iu = tuv.y; s.iv = tuv.z;
             hits++;
         }
@@ -426,7 +488,7 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
 // compositing arithmetic -- two independent dependency chains in one basic block.  Its result is
 // simply discarded when the ray terminates in this step; the decisions are taken in the reference's
 // order (forward.cu:645-648, 667-670, 687-759).
-__global__ void __launch_bounds__(MARCH_THREADS) tet_march_fwd_kernel(TetParams p)
+__global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd_kernel(TetParams p)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
