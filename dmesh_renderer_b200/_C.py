@@ -64,6 +64,95 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _InverseGraph:
+    """The two torch.linalg.inv_ex calls on [B,4,4] stacks captured ONCE per (device, B) in a CUDA graph and
+    replayed: identical kernels, identical bits, but ~45 us of host time instead of ~170 us for two
+    torch.inverse calls (measured on B200) -- host time that sits on the critical path, because the GPU has
+    nothing queued between phase 1 and the num_rendered read-back.  Inputs are copied into the graph's static
+    buffer, outputs are cloned out of it (autograd keeps them for backward)."""
+    _cache = {}
+
+    def __init__(self, dev, B):
+        self.inp = torch.empty((2, B, 4, 4), dtype=torch.float32, device=dev)
+        self.inp.copy_(torch.eye(4, device=dev).expand(2, B, 4, 4))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):   # warm-up outside the capture (library handles, workspaces)
+                torch.linalg.inv_ex(self.inp[0]); torch.linalg.inv_ex(self.inp[1])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            a, ia = torch.linalg.inv_ex(self.inp[0])
+            b, ib = torch.linalg.inv_ex(self.inp[1])
+            self.out = torch.stack([a, b])
+            self.info = torch.cat([ia.reshape(-1), ib.reshape(-1)])
+
+    @classmethod
+    def get(cls, dev, B):
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), B)
+        g = cls._cache.get(key)
+        if g is None:
+            try:
+                with torch.cuda.device(dev):
+                    g = cls(dev, B)
+            except Exception:   # capture not possible in this context (e.g. another capture running): eager path
+                g = False
+            cls._cache[key] = g
+        return g or None
+
+    def run(self, mv_mats, proj_mats):
+        torch.stack([mv_mats, proj_mats], out=self.inp)
+        self.graph.replay()
+        return self.out.clone(), self.info
+
+
+class _Inverses:
+    """inverse(mv), inverse(proj) exactly as the reference's Python computes them (torch.inverse,
+    dmesh_renderer/__init__.py:62-63, 298-299) -- same LU kernels, same bits -- but without the
+    device synchronisation torch.inverse performs after EACH call to look at the LAPACK `info` vector,
+    and replayed from a CUDA graph (see _InverseGraph).  The info vector is copied to pinned memory
+    asynchronously and examined after the synchronisation the forward call needs anyway (num_rendered);
+    a singular matrix raises the same error, through torch.inverse itself."""
+    __slots__ = ("inv_mv", "inv_proj", "mats", "host")
+    _pinned = {}
+
+    def __init__(self, mv_mats, proj_mats):
+        self.mats = (mv_mats, proj_mats)
+        self.host = None
+        graphable = (mv_mats.is_cuda and proj_mats.is_cuda and mv_mats.dtype == torch.float32 and
+                     proj_mats.dtype == torch.float32 and mv_mats.dim() == 3 and mv_mats.shape == proj_mats.shape and
+                     tuple(mv_mats.shape[1:]) == (4, 4) and 0 < mv_mats.size(0) <= 4096 and
+                     not torch.cuda.is_current_stream_capturing())
+        g = _InverseGraph.get(mv_mats.device, mv_mats.size(0)) if graphable else None
+        if g is not None:
+            with torch.cuda.device(mv_mats.device):
+                out, info = g.run(mv_mats, proj_mats)
+            self.inv_mv, self.inv_proj = out[0], out[1]
+        else:
+            self.inv_mv, info_mv = torch.linalg.inv_ex(mv_mats)
+            self.inv_proj, info_pj = torch.linalg.inv_ex(proj_mats)
+            info = torch.cat([info_mv.reshape(-1), info_pj.reshape(-1)])
+        if mv_mats.is_cuda:
+            n = info.numel()
+            key = (mv_mats.device.index, n)
+            host = _Inverses._pinned.get(key)
+            if host is None:
+                host = _Inverses._pinned[key] = torch.zeros(max(n, 1), dtype=torch.int32).pin_memory()
+            if n:
+                host[:n].copy_(info, non_blocking=True)
+            self.host = host[:n]
+        else:
+            self.check(info)
+
+    def check(self, *infos):
+        """Call after the stream has been synchronised."""
+        bad = any(bool(i.any()) for i in infos) if infos else (self.host is not None and bool(self.host.any()))
+        if bad:
+            torch.inverse(self.mats[0])   # raises torch's own "singular matrix" error
+            torch.inverse(self.mats[1])
+
+
 def _check_common(verts, faces, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats, verts_depth, faces_intense, tri):
     # messages follow render.cu:49-79 (tri) and 237-267 (tet)
     if verts.dim() != 2 or verts.size(1) != 3:
@@ -138,8 +227,9 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
     return st
 
 
-def tri_forward_finish(st, inv_mv_mats, inv_proj_mats):
-    """Phase 2 of a forward call started by tri_forward_begin: the one host sync (R), binning buffer, sort, render."""
+def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
+    """Phase 2 of a forward call started by tri_forward_begin: the one host sync (R), binning buffer, sort, render.
+    `inverses`: the _Inverses object the matrices came from, whose deferred singularity check runs after the sync."""
     for t, n in ((inv_mv_mats, "inv_mv_mats"), (inv_proj_mats, "inv_proj_mats")):
         if t.dim() != 3 or t.size(1) != 4 or t.size(2) != 4:
             _err("%s must have dimensions (B, 4, 4)" % n)
@@ -151,12 +241,17 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats):
         if st.empty:
             # render.cu:88-89,105: zero images (not background), empty state
             z = torch.zeros
+            if inverses is not None:
+                torch.cuda.current_stream().synchronize()
+                inverses.check()
             return (0, z((B, NUM_CHANNELS, H, W), dtype=torch.float32, device=dev),
                     z((B, 1, H, W), dtype=torch.float32, device=dev),
                     torch.empty(0, **u8), torch.empty(0, **u8), torch.empty(0, **u8), torch.empty(0, **u8))
         _require_cuda(inv_mv_mats, inv_proj_mats)
         imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
         torch.cuda.current_stream().synchronize()   # the one sync: R sizes the binning buffer
+        if inverses is not None:
+            inverses.check()
         R = int(st.pinned[0])
         bin_buf = torch.empty(lib.dmr_binning_bytes(R) if R > 0 else 0, **u8)
         point_buf, face_buf, img_buf = st.bufs
@@ -220,9 +315,11 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
 # tet renderer
 # ---------------------------------------------------------------------------
 def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
-                verts_depth, faces_intense, tets, face_tets, tet_faces, image_height, image_width, ray_random_seed):
+                verts_depth, faces_intense, tets, face_tets, tet_faces, image_height, image_width, ray_random_seed,
+                inverses=None):
     """RenderFTetsCUDA (render.cu:213-336).
-    Returns (color[B,3,H,W], depth[B,1,H,W], active_f32[B,H,W], pointBuffer, faceBuffer, binningBuffer, imgBuffer)."""
+    Returns (color[B,3,H,W], depth[B,1,H,W], active_f32[B,H,W], pointBuffer, faceBuffer, binningBuffer, imgBuffer).
+    `inverses` (beyond the reference's 17 arguments): see tri_forward_finish."""
     if verts.dim() != 2 or verts.size(1) != 3:
         _err("verts must have dimensions (num_points, 3)")
     if faces.dim() != 2 or faces.size(1) != 3:
@@ -270,6 +367,8 @@ def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, p
                                            _ptr(mv), _ptr(pj), _ptr(tets_c), _ptr(ft_c), _ptr(tf_c), _ptr(point_buf),
                                            _ptr(face_buf), ctypes.c_void_p(pinned.data_ptr()), stream))
         torch.cuda.current_stream().synchronize()
+        if inverses is not None:
+            inverses.check()
         R = int(pinned[0])
         bin_buf = torch.empty(lib.dmr_binning_bytes(R) if R > 0 else 0, **u8)
         _lib.check(lib.dmr_tet_forward_render(B, P, F, T, W, H, R, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj),

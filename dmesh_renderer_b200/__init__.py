@@ -49,10 +49,10 @@ class _RenderTri(th.autograd.Function):
             pending = _C.tri_forward_begin(render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats,
                                            proj_mats, verts_depth, faces_intense, render_settings.image_height,
                                            render_settings.image_width)
-            inv_mv_mats = th.inverse(mv_mats)
-            inv_proj_mats = th.inverse(proj_mats)
+            inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :62-63) minus its two device syncs
+            inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
             num_rendered, color, depth, pointBuffer, faceBuffer, binningBuffer, imgBuffer = \
-                _C.tri_forward_finish(pending, inv_mv_mats, inv_proj_mats)
+                _C.tri_forward_finish(pending, inv_mv_mats, inv_proj_mats, inv)
         except Exception as ex:
             print("\nAn error occured in forward.")
             print(ex)
@@ -125,11 +125,11 @@ class _RenderTet(th.autograd.Function):
     @staticmethod
     def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
                 face_tets, tet_faces, render_settings):
-        inv_mv_mats = th.inverse(mv_mats)
-        inv_proj_mats = th.inverse(proj_mats)
+        inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :298-299) minus its two device syncs
+        inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
         args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                 inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, render_settings.image_height,
-                render_settings.image_width, render_settings.ray_random_seed)
+                render_settings.image_width, render_settings.ray_random_seed, inv)
         try:
             color, depth, active, pointBuffer, faceBuffer, binningBuffer, imgBuffer = _C.render_tets(*args)
         except Exception as ex:

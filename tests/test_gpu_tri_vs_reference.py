@@ -129,3 +129,18 @@ def test_tri_non_multiple_of_16_image():
     assert R == ref["R"]
     assert (color - ref["color"]).abs().max().item() <= IMG_TOL
     assert (depth - ref["depth"]).abs().max().item() <= IMG_TOL
+
+
+def test_inverses_on_gpu_are_torch_inverse_bits_and_singular_raises():
+    from dmesh_renderer_b200 import TriRenderer, TriRenderSettings
+    s = scenes.to_device(scenes.config("tiny_tri"), "cuda")
+    mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
+    inv = _C._Inverses(mv, pj)
+    torch.cuda.synchronize()
+    inv.check()
+    assert torch.equal(inv.inv_mv, torch.inverse(mv)) and torch.equal(inv.inv_proj, torch.inverse(pj))
+    r = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
+    bad = s.proj_mats.clone()
+    bad[0] = 0
+    with pytest.raises(RuntimeError, match="singular"):
+        r(s.verts, s.faces, s.verts_color, s.faces_opacity, s.mv_mats, bad, s.verts_depth, s.faces_intense)

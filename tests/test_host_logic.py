@@ -86,3 +86,15 @@ def test_scenes_are_deterministic_and_sized():
     assert T == 6 * 4 ** 3 and t.tet_faces.shape == (T, 4) and t.face_tets.shape == (F, 2)
     # every interior face has two tets, every boundary face one
     assert int((t.face_tets[:, 1] < 0).sum()) == 6 * 2 * 4 * 4
+
+
+def test_sync_free_inverses_match_torch_inverse_and_raise_on_singular():
+    """_Inverses = the reference's two th.inverse calls (__init__.py:62-63) without their device syncs."""
+    from dmesh_renderer_b200 import _C
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(3, 4, 4, generator=g), torch.randn(3, 4, 4, generator=g)
+    inv = _C._Inverses(a, b)
+    assert torch.equal(inv.inv_mv, torch.inverse(a)) and torch.equal(inv.inv_proj, torch.inverse(b))
+    a[1] = 0
+    with pytest.raises(RuntimeError, match="singular"):
+        _C._Inverses(a, b)
