@@ -96,6 +96,51 @@ __device__ __forceinline__ unsigned subblock_cull(const uint4 e0, const uint4 e1
     return (m[0] < 0 ? 1u : 0u) | (m[1] < 0 ? 2u : 0u) | (m[2] < 0 ? 4u : 0u) | (m[3] < 0 ? 8u : 0u);
 }
 
+// The same against the eight 2x2 sub-blocks: bit s <-> x quarter = s&3, y half = s>>2.
+__device__ __forceinline__ unsigned subblock_cull8(const uint4 e0, const uint4 e1, const uint4 e2, int bx0, int by0)
+{
+    if (!(e2.w & DMR_REC_SAFE)) return 0xffu;
+    const int a[3] = { (int)e0.x, (int)e1.x, (int)e2.x }, bb[3] = { (int)e0.y, (int)e1.y, (int)e2.y };
+    const int cc[3] = { (int)e0.z, (int)e1.z, (int)e2.z };
+    int m[8] = { -1, -1, -1, -1, -1, -1, -1, -1 };
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int xo = a[k] < 0 ? 1 : 0, yo = bb[k] < 0 ? 1 : 0;
+        const int x0 = a[k] * (bx0 + xo), dx = 2 * a[k];                 // minimum over x in {bx0+2i, bx0+2i+1}
+        const int y0 = cc[k] + bb[k] * (by0 + yo), y1 = y0 + 2 * bb[k];  // minimum over y in {by0+2j, by0+2j+1}
+#pragma unroll
+        for (int i = 0; i < 4; i++) { m[i] &= x0 + i * dx + y0; m[4 + i] &= x0 + i * dx + y1; }
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r |= m[i] < 0 ? (1u << i) : 0u;
+    return r;
+}
+
+// The same against the sixteen 2x1 sub-blocks: bit s <-> x quarter = s&3, row = s>>2.
+__device__ __forceinline__ unsigned subblock_cull16(const uint4 e0, const uint4 e1, const uint4 e2, int bx0, int by0)
+{
+    if (!(e2.w & DMR_REC_SAFE)) return 0xffffu;
+    const int a[3] = { (int)e0.x, (int)e1.x, (int)e2.x }, bb[3] = { (int)e0.y, (int)e1.y, (int)e2.y };
+    const int cc[3] = { (int)e0.z, (int)e1.z, (int)e2.z };
+    int m[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = -1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int x0 = a[k] * (bx0 + (a[k] < 0 ? 1 : 0)), dx = 2 * a[k];
+        const int y0 = cc[k] + bb[k] * by0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) m[4 * j + i] &= x0 + i * dx + y0 + j * bb[k];
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) r |= m[i] < 0 ? (1u << i) : 0u;
+    return r;
+}
+
 // Forward: the whole warp walks one survivor list for its 8x4 block.  (A variant in which the four
 // 4x2 sub-blocks walk their own lists, as the backward kernel does, was measured SLOWER here --
 // 234 vs 211 us at C2: the forward shading path is short, so the extra find-loop bookkeeping costs
@@ -230,10 +275,11 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 
 // Backward design
 // ---------------
-// * A warp owns an 8x4 pixel block, split into four GROUPS of 8 lanes (4x2 pixels).  Each group walks
-//   ITS OWN list of surviving instances (exact edge-function cull per sub-block), so the four groups
-//   shade four different faces in the same SIMD pass: for the small triangles that dominate real scenes
-//   this multiplies the lane utilisation of the (long) gradient path.
+// * A warp owns an 8x4 pixel block, split into GROUPS of GL lanes (sub-blocks of 4x2, 2x2 or 2x1 pixels;
+//   2x1 is the default, table below).  Each group walks ITS OWN list of surviving instances (exact
+//   edge-function cull per sub-block), so the groups shade different faces in the same SIMD pass: for the
+//   small triangles that dominate real scenes this multiplies the lane utilisation of the (long)
+//   gradient path.
 // * Vertex-position gradients are not formed per pixel.  With u = A/D, A = rd.(E2xT), D = rd.(E2xE1) and
 //   the reference's "v" derivative (ray_tri_intersection_grad, auxiliary.h:288-333, actually the derivative
 //   of t = Nt/D, Nt = (TxE1).E2), the per-face sums only need
@@ -241,25 +287,35 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 //   (7 floats); tri_grad_finish_kernel turns them into dL_dp0..2 once per (view, face):
 //       g_E1 = S3 (E2xT) - S24xE2,  g_E2 = TxS1 - E1xS24 + S3 (TxE1),  g_T = S1xE2 + S3 (E1xE2).
 //   This is the same derivative the reference evaluates per covered pixel with ~150 instructions.
-// * All 21 per-hit terms of a group are reduced over its 8 lanes with a transpose-reduction
-//   (12+6+4 = 22 shuffles) and added to ONE contiguous 96-byte statistics record per (view, face)
-//   with vector reductions: per SIMD pass 2 instructions / 8 lane-operations per group (one
-//   red.v4 from each even lane, one red.v2 from each odd lane) instead of 21 scalar reductions --
-//   the kernel was co-limited by the ~0.6 lane-reductions/clk/SM the LSU sustains.
+// * All 21 per-hit terms of a group are reduced over its lanes with a transpose-reduction
+//   (GL = 8: 12+6+4 = 22 shuffles, GL = 2: 12) and added to ONE contiguous 96-byte statistics record per
+//   (view, face) with vector reductions (red.v4 / red.v2) instead of 21 scalar reductions per lane.
 // Statistics (logical order, 24 floats; memory position = stat_slot(i)):
 //   S1[3] S24[3] S3 dL_dopacity dL_dintense dL_ddepth[3] dL_dcolor[3][3] pad[3]
+// GL = lanes per group: 8 (four 4x2 sub-blocks per warp), 4 (eight 2x2) or 2 (sixteen 2x1).
+// Measured tri_render_bwd_kernel, us (B200):      C2      C5     C4 (8 views)
+//                                       GL = 8    537    1172    7808
+//                                       GL = 4    476    1079    6752
+//                                       GL = 2    459    1057    6532
+// Smaller groups shade more different faces per SIMD pass (the triangles of these scenes cover a few
+// pixels of a 4x2 block) and need fewer shuffle steps; GL = 1 would need no shuffles at all but
+// 6 vector reductions per covered pixel, which the LSU/L2 cannot sustain (tools/ubench_red.cu).
+#ifndef DMR_TRI_BWD_GROUP_LANES
+#define DMR_TRI_BWD_GROUP_LANES 2
+#endif
+template <int GL>
 __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams p)
 {
     __shared__ uint4 s_rec[RB * 9];
     __shared__ uint32_t s_face[RB];
     __shared__ int s_max[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 3, l = lane & 7;
+    const int g = lane / GL, l = lane % GL;
     const int b = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int bx0 = blockIdx.x * DMR_TILE + (warp & 1) * 8, by0 = blockIdx.y * DMR_TILE + (warp >> 1) * 4;
-    const uint32_t px = bx0 + (g & 1) * 4 + (l & 3);
-    const uint32_t py = by0 + (g >> 1) * 2 + (l >> 2);
+    const uint32_t px = GL == 8 ? bx0 + (g & 1) * 4 + (l & 3) : bx0 + (g & 3) * 2 + (l & 1);
+    const uint32_t py = GL == 8 ? by0 + (g >> 1) * 2 + (l >> 2) : GL == 4 ? by0 + (g >> 2) * 2 + (l >> 1) : by0 + (g >> 2);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
     const size_t HW = (size_t)p.W * p.H;
     const size_t pix = (size_t)py * p.W + px;
@@ -294,10 +350,10 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
     // The tile walks only the prefix some pixel of it composited; a warp / a group only its own.
     int group_last = last_contributor;
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) group_last = max(group_last, __shfl_xor_sync(0xffffffffu, group_last, o));
+    for (int o = GL / 2; o > 0; o >>= 1) group_last = max(group_last, __shfl_xor_sync(0xffffffffu, group_last, o));
     int warp_last = group_last;
-    warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, 16));
-    warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, 8));
+#pragma unroll
+    for (int o = 16; o >= GL; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
     if (lane == 0) s_max[warp] = warp_last;
     __syncthreads();
     int tile_last = 0;
@@ -325,15 +381,22 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
         __syncthreads();
         const int cnt = min(RB, warp_last - c * RB);       // this warp's share of the chunk
         for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0 && cnt > 0; c0 -= 32) {
-            // ---- cull: lane tests instance c0+lane against the four sub-blocks
+            // ---- cull: lane tests instance c0+lane against the sub-blocks
             unsigned k4 = 0;   // bit s: instance may cover sub-block s
             {
                 const int jl = c0 + lane;
-                if (jl < cnt) k4 = subblock_cull(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
+                if (jl < cnt) {
+                    if (GL == 8) k4 = subblock_cull(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
+                    else if (GL == 4) k4 = subblock_cull8(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
+                    else k4 = subblock_cull16(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
+                }
             }
-            const unsigned m0 = __ballot_sync(0xffffffffu, k4 & 1u), m1 = __ballot_sync(0xffffffffu, k4 & 2u);
-            const unsigned m2 = __ballot_sync(0xffffffffu, k4 & 4u), m3 = __ballot_sync(0xffffffffu, k4 & 8u);
-            unsigned mymask = g == 0 ? m0 : g == 1 ? m1 : g == 2 ? m2 : m3;
+            unsigned mymask = 0;
+#pragma unroll
+            for (int sb = 0; sb < 32 / GL; sb++) {
+                const unsigned msb = __ballot_sync(0xffffffffu, k4 & (1u << sb));
+                if (g == sb) mymask = msb;
+            }
             {   // drop list positions at or beyond this group's last contributor
                 const int lim = group_last - (c * RB + c0);
                 if (lim < 32) mymask &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
@@ -359,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                         cj = (c * RB + jj) < last_contributor && (int)(s0 & s1 & s2) < 0;
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, cj);
-                    if (searching && ((bal >> (lane & 24)) & 0xffu)) { have = true; j = jj; cov = cj; }
+                    if (searching && ((bal >> (lane & (32 - GL))) & ((1u << GL) - 1u))) { have = true; j = jj; cov = cj; }
                     if (!__any_sync(0xffffffffu, !have && mymask != 0u)) break;
                 }
                 if (!__any_sync(0xffffffffu, have)) break;
@@ -446,11 +509,12 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                     }
                 }
 
-                // ---- reduce over the 8 lanes of each group: 24 -> 12 -> 6 values per lane, then the even
-                //      lane of each pair completes sums 0..3 and the odd lane sums 4..5 of its class
-                xreduce_step<12, 4>(v, h4);
-                xreduce_step<6, 2>(v, h2);
-                {
+                // ---- reduce over the lanes of each group
+                if (GL == 8) {
+                    // 24 -> 12 -> 6 values per lane, then the even lane of each pair completes sums 0..3 and the
+                    // odd lane sums 4..5 of its class
+                    xreduce_step<12, 4>(v, h4);
+                    xreduce_step<6, 2>(v, h2);
                     const float r0 = __shfl_xor_sync(0xffffffffu, h1 ? v[0] : v[4], 1);
                     const float r1 = __shfl_xor_sync(0xffffffffu, h1 ? v[1] : v[5], 1);
                     const float r2 = __shfl_xor_sync(0xffffffffu, v[2], 1);
@@ -465,6 +529,27 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                             const float a4 = v[4] + r0, a5 = v[5] + r1;
                             if (a4 != 0.0f || a5 != 0.0f) red_add_v2(rec + 16 + 2 * cls, a4, a5);
                         }
+                    }
+                } else if (GL == 2) {
+                    // 2 lanes: 24 -> 12 values per lane; lane class c = lane & 1 owns logical 12c..12c+11 =
+                    // quads 2c, 2c+1 and the two adjacent pairs 2c, 2c+1 (one more 16-byte vector)
+                    xreduce_step<12, 1>(v, h1);
+                    if (have) {
+                        float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
+                        const int cls = lane & 1;
+                        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
+                        if (v[6] != 0.0f || v[7] != 0.0f || v[8] != 0.0f || v[9] != 0.0f) red_add_v4(rec + 8 * cls + 4, v[6], v[7], v[8], v[9]);
+                        if (v[4] != 0.0f || v[5] != 0.0f || v[10] != 0.0f || v[11] != 0.0f) red_add_v4(rec + 16 + 4 * cls, v[4], v[5], v[10], v[11]);
+                    }
+                } else {
+                    // 4 lanes: 24 -> 12 -> 6 values per lane; lane class = lane & 3 owns logical 6c..6c+5
+                    xreduce_step<12, 2>(v, h2);
+                    xreduce_step<6, 1>(v, h1);
+                    if (have) {
+                        float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
+                        const int cls = lane & 3;
+                        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) red_add_v4(rec + 4 * cls, v[0], v[1], v[2], v[3]);
+                        if (cls < 3 && (v[4] != 0.0f || v[5] != 0.0f)) red_add_v2(rec + 16 + 2 * cls, v[4], v[5]);
                     }
                 }
             }
@@ -532,7 +617,7 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
     {
         ProfScope prof(ST_TRI_BWD, stream);
-        tri_render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+        tri_render_bwd_kernel<DMR_TRI_BWD_GROUP_LANES><<<grid, 256, 0, stream>>>(p);
         DMR_LAUNCH_CHECK("tri_render_bwd_kernel");
     }
     {
