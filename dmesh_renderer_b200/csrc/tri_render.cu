@@ -188,14 +188,30 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
             bool keep = false;
             if (jl < cnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
             unsigned mask = __ballot_sync(0xffffffffu, keep);
+            // (1) coverage: every lane tests its pixel against every survivor (3 broadcast 16-byte reads,
+            //     6 IMAD + 2 LOP3 each) and keeps the result as a bit mask
+            unsigned mine = 0;
             while (mask) {
-                const int j = c0 + __ffs(mask) - 1;
+                const int bit = __ffs(mask) - 1;
                 mask &= mask - 1;
+                const int j = c0 + bit;
                 const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1], e2 = s_rec[j * 9 + 2];
                 uint32_t s0 = e0.x * px + e0.y * py + e0.z;
                 uint32_t s1 = e1.x * px + e1.y * py + e1.z;
                 uint32_t s2 = e2.x * px + e2.y * py + e2.z;
-                if (done || (int)(s0 & s1 & s2) >= 0) continue;   // finished pixel, or not covered (in_tri false)
+                if ((int)(s0 & s1 & s2) < 0) mine |= 1u << bit;   // covered (in_tri true)
+            }
+            if (done) mine = 0;
+            // (2) shading: every lane pops ITS next covered instance, so the lanes of a warp shade different
+            //     faces in the same SIMD pass; per pixel the list order (front to back) is unchanged.
+            //     The triangles of these scenes cover ~5 of a block's 32 pixels: walking the survivors one
+            //     at a time left the (long) shading path at 17 of 32 lanes (ncu) with one pass per survivor;
+            //     now the number of passes is the largest per-pixel hit count of the group.
+            while (__any_sync(0xffffffffu, mine != 0u)) {
+                if (mine == 0u) continue;
+                const int j = c0 + __ffs(mine) - 1;
+                mine &= mine - 1;
+                const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
 
                 const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
                 float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
                 pT = T;
                 T = test_T;
                 last_contributor = (uint32_t)(r * RB + j + 1);
-                if (T < DMR_T_EPS) done = true;
+                if (T < DMR_T_EPS) { done = true; mine = 0; }
             }
         }
     }
