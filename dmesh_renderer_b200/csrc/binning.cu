@@ -1,4 +1,4 @@
-// binning.cu -- prefix sum, (tile|depth) key emission, tile ranges.
+// binning.cu -- prefix sum, tile-key emission, tile ranges, and the two-level binning driver.
 //
 //   inclusive_scan_kernel   replaces cub::DeviceScan::InclusiveSum
 //                           (cuda_rasterizer/rasterizer_impl.cu:278-284,
@@ -6,8 +6,9 @@
 //   duplicate_kernel        replaces duplicateWithKeys
 //                           (rasterizer_impl.cu:44-97, renderer_impl.cu:44-99)
 //   tile_ranges_kernel      replaces identifyTileRanges (rasterizer_impl.cu:102-124)
+//   bin_faces / bin_instances   stage sequencing, see common.cuh
 //
-// All three are HBM-bound; see DESIGN.md for the algorithmic bytes.
+// All of them are HBM-bound; see DESIGN.md for the algorithmic bytes.
 #include "common.cuh"
 
 namespace dmr {
@@ -23,8 +24,8 @@ namespace dmr {
 #define SCAN_VAL_MASK  ((1u << 30) - 1u)
 
 __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
-    const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ state,
-    int32_t* __restrict__ total_mapped)
+    const uint32_t* __restrict__ in, const uint32_t* __restrict__ index, uint32_t* __restrict__ out, size_t n,
+    uint32_t* __restrict__ state, int32_t* __restrict__ total_mapped)
 {
     __shared__ uint32_t s_warp[DMR_SCAN_THREADS / 32];
     __shared__ uint32_t s_tile;
@@ -38,7 +39,19 @@ __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
 
     // blocked arrangement: 16 consecutive items per thread = 4 x 128-bit loads
     uint32_t v[DMR_SCAN_ITEMS];
-    if (base + DMR_SCAN_ITEMS <= n) {
+    if (index) {   // gather: element i of the scanned sequence is in[index[i]]
+        if (base + DMR_SCAN_ITEMS <= n) {
+            const uint4* p = reinterpret_cast<const uint4*>(index + base);
+#pragma unroll
+            for (int q = 0; q < DMR_SCAN_ITEMS / 4; q++) {
+                uint4 t = p[q];
+                v[4 * q] = in[t.x]; v[4 * q + 1] = in[t.y]; v[4 * q + 2] = in[t.z]; v[4 * q + 3] = in[t.w];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < DMR_SCAN_ITEMS; i++) v[i] = (base + i < n) ? in[index[base + i]] : 0u;
+        }
+    } else if (base + DMR_SCAN_ITEMS <= n) {
         const uint4* p = reinterpret_cast<const uint4*>(in + base);
 #pragma unroll
         for (int q = 0; q < DMR_SCAN_ITEMS / 4; q++) {
@@ -119,8 +132,8 @@ __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
     }
 }
 
-int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* state, int32_t* total_host,
-                       cudaStream_t stream)
+int inclusive_scan_u32(const uint32_t* in, const uint32_t* index, uint32_t* out, size_t n, uint32_t* state,
+                       int32_t* total_host, cudaStream_t stream)
 {
     if (n == 0) {
         if (total_host) *total_host = 0;
@@ -129,7 +142,7 @@ int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* st
     size_t ntile = (n + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
     {
     ProfScope prof(ST_SCAN, stream);
-    inclusive_scan_kernel<<<(unsigned)ntile, DMR_SCAN_THREADS, 0, stream>>>(in, out, n, state, nullptr);
+    inclusive_scan_kernel<<<(unsigned)ntile, DMR_SCAN_THREADS, 0, stream>>>(in, index, out, n, state, nullptr);
     DMR_LAUNCH_CHECK("inclusive_scan_kernel");
     }
     if (total_host)
@@ -140,16 +153,18 @@ int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* st
 // ---------------------------------------------------------------------------
 // Key emission.  The reference runs one thread per face with a serial loop
 // over its tile rectangle (strided 12-byte writes, load imbalance on large
-// triangles).  Here a block owns 256 consecutive faces and its 256 threads
-// walk the block's contiguous OUTPUT range, locating the owning face by
-// binary search in shared memory -> every key/value store is coalesced.
-// Emission order (face-major, then y, then x) and key layout are those of
-// rasterizer_impl.cu:84-96:  key = (tile + tiles*b) << 32 | depth_bits,
-// value = face id within the view.
+// triangles).  Here a block owns 256 consecutive faces OF THE DEPTH ORDER and
+// its 256 threads walk the block's contiguous OUTPUT range, locating the
+// owning face by binary search in shared memory -> every key/value store is
+// coalesced.  Emission order inside a face (y, then x) and the tile id are
+// those of rasterizer_impl.cu:84-96:  tile + tiles*b, value = face id within
+// the view; the depth word of the reference's key is implied by the order.
 // ---------------------------------------------------------------------------
+struct DupFace { uint32_t x0, w, y0, tile0, fid; };
+
 __device__ __forceinline__ void emit_one(uint32_t o, uint32_t start, int nface, const uint32_t* s_incl, const uint2* s_rect,
-                                         const uint32_t* s_depth, const uint32_t* s_tile0, const uint32_t* s_fid,
-                                         int tiles_x, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+                                         const uint32_t* s_tile0, const uint32_t* s_fid, int tiles_x,
+                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     int lo = 0, hi = nface - 1;   // smallest i with s_incl[i] > o
     while (lo < hi) {
@@ -162,46 +177,45 @@ __device__ __forceinline__ void emit_one(uint32_t o, uint32_t start, int nface, 
     const uint2 r = s_rect[i];
     const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
     const uint32_t q = k / w;
-    keys[o] = ((uint64_t)((y0 + q) * (uint32_t)tiles_x + x0 + (k - q * w) + s_tile0[i]) << 32) | (uint64_t)s_depth[i];
+    keys[o] = (y0 + q) * (uint32_t)tiles_x + x0 + (k - q * w) + s_tile0[i];
     vals[o] = s_fid[i];
 }
 
 __global__ void __launch_bounds__(256) duplicate_kernel(
-    size_t BF, int F, int tiles_x, int tiles_per_view,
-    const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, const uint32_t* __restrict__ depth_key,
-    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+    size_t BF, int F, int tiles_x, int tiles_per_view, const uint32_t* __restrict__ order,
+    const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
+    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
     __shared__ uint32_t s_incl[256];
     __shared__ uint2 s_rect[256];
-    __shared__ uint32_t s_depth[256];
-    __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance 64-bit divisions hoisted)
+    __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance divisions hoisted)
     __shared__ uint32_t s_fid[256];     // face id inside its view
     const int tid = threadIdx.x;
-    const size_t f0 = (size_t)blockIdx.x * 256;
-    const size_t f = f0 + tid;
-    const uint32_t start = (f0 == 0) ? 0u : offsets[f0 - 1];
+    const size_t i0 = (size_t)blockIdx.x * 256;
+    const size_t i = i0 + tid;          // position in the depth order
+    const uint32_t start = (i0 == 0) ? 0u : offsets[i0 - 1];
     uint32_t my_incl = 0xffffffffu;
-    if (f < BF) {
-        my_incl = offsets[f];
+    if (i < BF) {
+        my_incl = offsets[i];
+        const uint32_t f = order[i];    // b*F + f, B*F < 2^31 (checked by the caller)
         s_rect[tid] = rect[f];
-        s_depth[tid] = depth_key[f];
-        const uint32_t bview = (uint32_t)((uint32_t)f / (uint32_t)F);   // B*F < 2^31 (checked by the caller)
+        const uint32_t bview = f / (uint32_t)F;
         s_tile0[tid] = (uint32_t)tiles_per_view * bview;
-        s_fid[tid] = (uint32_t)f - bview * (uint32_t)F;
+        s_fid[tid] = f - bview * (uint32_t)F;
     }
     s_incl[tid] = my_incl;
     __syncthreads();
-    const int nface = (int)((BF - f0 < 256) ? (BF - f0) : 256);
+    const int nface = (int)((BF - i0 < 256) ? (BF - i0) : 256);
     const uint32_t end = s_incl[nface - 1];
 
     // Each thread emits 4 consecutive instances per step: one binary search, then cheap "same face or
-    // next face" advances; the 4 keys / 4 values leave as two 16-byte + one 16-byte store, so a warp
-    // writes 1 KB + 512 B contiguous.  Head/tail elements that break 16-byte alignment go out scalar.
+    // next face" advances; 4 keys / 4 values leave as two 16-byte stores, so a warp writes 2 x 512 B
+    // contiguous.  Head/tail elements that break 16-byte alignment go out scalar.
     const uint32_t first4 = (start + 3u) & ~3u;                      // first 4-aligned output index of the block
-    for (uint32_t o = start + tid; o < min(first4, end); o += 256) emit_one(o, start, nface, s_incl, s_rect, s_depth, s_tile0, s_fid, tiles_x, keys, vals);
+    for (uint32_t o = start + tid; o < min(first4, end); o += 256) emit_one(o, start, nface, s_incl, s_rect, s_tile0, s_fid, tiles_x, keys, vals);
     for (uint32_t o4 = first4 + 4u * tid; o4 < end; o4 += 4u * 256u) {
         if (o4 + 4u > end) {
-            for (uint32_t o = o4; o < end; o++) emit_one(o, start, nface, s_incl, s_rect, s_depth, s_tile0, s_fid, tiles_x, keys, vals);
+            for (uint32_t o = o4; o < end; o++) emit_one(o, start, nface, s_incl, s_rect, s_tile0, s_fid, tiles_x, keys, vals);
             break;
         }
         int lo = 0, hi = nface - 1;
@@ -209,37 +223,23 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
             int mid = (lo + hi) >> 1;
             if (s_incl[mid] > o4) hi = mid; else lo = mid + 1;
         }
-        int i = lo;
-        uint64_t k[4];
-        uint32_t v[4];
+        int j = lo;
+        uint32_t k[4], v[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const uint32_t o = o4 + e;
-            while (s_incl[i] <= o) i++;                               // skips faces with no instances
-            const uint32_t excl = (i == 0) ? start : s_incl[i - 1];
+            while (s_incl[j] <= o) j++;                               // skips faces with no instances
+            const uint32_t excl = (j == 0) ? start : s_incl[j - 1];
             const uint32_t kk = o - excl;
-            const uint2 r = s_rect[i];
+            const uint2 r = s_rect[j];
             const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
             const uint32_t q = kk / w;
-            k[e] = ((uint64_t)((y0 + q) * (uint32_t)tiles_x + x0 + (kk - q * w) + s_tile0[i]) << 32) | (uint64_t)s_depth[i];
-            v[e] = s_fid[i];
+            k[e] = (y0 + q) * (uint32_t)tiles_x + x0 + (kk - q * w) + s_tile0[j];
+            v[e] = s_fid[j];
         }
-        uint4* kd = reinterpret_cast<uint4*>(keys + o4);
-        kd[0] = make_uint4((uint32_t)k[0], (uint32_t)(k[0] >> 32), (uint32_t)k[1], (uint32_t)(k[1] >> 32));
-        kd[1] = make_uint4((uint32_t)k[2], (uint32_t)(k[2] >> 32), (uint32_t)k[3], (uint32_t)(k[3] >> 32));
+        *reinterpret_cast<uint4*>(keys + o4) = make_uint4(k[0], k[1], k[2], k[3]);
         *reinterpret_cast<uint4*>(vals + o4) = make_uint4(v[0], v[1], v[2], v[3]);
     }
-}
-
-int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32_t* offsets, const uint2* rect,
-                        const uint32_t* depth_key, uint64_t* keys, uint32_t* vals, size_t R, cudaStream_t stream)
-{
-    if (BF == 0 || R == 0) return 0;
-    unsigned nblk = (unsigned)((BF + 255) / 256);
-    ProfScope prof(ST_DUPLICATE, stream);
-    duplicate_kernel<<<nblk, 256, 0, stream>>>(BF, F, tiles_x, tiles_x * tiles_y, offsets, rect, depth_key, keys, vals);
-    DMR_LAUNCH_CHECK("duplicate_kernel");
-    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -248,21 +248,21 @@ int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32
 // rasterizer_impl.cu:330).
 // ---------------------------------------------------------------------------
 #define TR_KPT 8
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, size_t L,
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ keys, size_t L,
                                                           uint2* __restrict__ ranges)
 {
-    // 8 consecutive keys per thread (4 x 16-byte loads) plus the one before them
+    // 8 consecutive keys per thread (2 x 16-byte loads) plus the one before them
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * TR_KPT;
     if (i0 >= L) return;
     uint32_t t[TR_KPT + 1];
-    t[0] = (i0 == 0) ? 0u : (uint32_t)(keys[i0 - 1] >> 32);
+    t[0] = (i0 == 0) ? 0u : keys[i0 - 1];
     if (i0 + TR_KPT <= L) {
         const uint4* p = reinterpret_cast<const uint4*>(keys + i0);
-#pragma unroll
-        for (int q = 0; q < TR_KPT / 2; q++) { uint4 v = p[q]; t[1 + 2 * q] = v.y; t[2 + 2 * q] = v.w; }
+        const uint4 a = p[0], b = p[1];
+        t[1] = a.x; t[2] = a.y; t[3] = a.z; t[4] = a.w; t[5] = b.x; t[6] = b.y; t[7] = b.z; t[8] = b.w;
     } else {
 #pragma unroll
-        for (int e = 0; e < TR_KPT; e++) t[1 + e] = (i0 + e < L) ? (uint32_t)(keys[i0 + e] >> 32) : 0u;
+        for (int e = 0; e < TR_KPT; e++) t[1 + e] = (i0 + e < L) ? keys[i0 + e] : 0u;
     }
 #pragma unroll
     for (int e = 0; e < TR_KPT; e++) {
@@ -275,16 +275,6 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __rest
     }
 }
 
-int identify_tile_ranges(const uint64_t* keys_sorted, size_t R, uint2* ranges, cudaStream_t stream)
-{
-    if (R == 0) return 0;
-    ProfScope prof(ST_RANGES, stream);
-    const size_t nthreads = (R + TR_KPT - 1) / TR_KPT;
-    tile_ranges_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(keys_sorted, R, ranges);
-    DMR_LAUNCH_CHECK("tile_ranges_kernel");
-    return 0;
-}
-
 // Number of key bits above the depth word.  The reference's getHigherMsb
 // (rasterizer_impl.cu:25-40) is a bisection that returns the bit length of n
 // (and 1 for n == 0); the closed form below gives the same value for every n.
@@ -293,6 +283,62 @@ uint32_t higher_msb(uint32_t n)
     uint32_t bits = 0;
     while (n) { bits++; n >>= 1; }
     return bits ? bits : 1u;
+}
+
+namespace {
+template <typename T>
+T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<unsigned char*>(base) + off); }
+template <typename T>
+const T* at(const void* base, size_t off) { return reinterpret_cast<const T*>(static_cast<const unsigned char*>(base) + off); }
+}  // namespace
+
+int bin_faces(size_t BF, void* fb, const FaceBinLayout& L, int32_t* num_rendered_host, cudaStream_t stream)
+{
+    if (BF == 0) { if (num_rendered_host) *num_rendered_host = 0; return 0; }
+    int rc;
+    {
+        // depth keys are non-negative floats: integer order == float order.  All 32 bits take part (the
+        // constant top byte of real scenes is skipped on the device by the sort's plan kernel).
+        ProfScope prof(ST_FACE_SORT, stream);
+        count_launch(-1);   // the scope counted one launch; the sort counts its own kernels
+        if ((rc = sort_pairs_u32(at<uint32_t>(fb, L.depth_key), nullptr, at<uint32_t>(fb, L.depth_sorted),
+                                 at<uint32_t>(fb, L.order), BF, 32, at<void>(fb, L.fsort_temp), false, stream)))
+            return rc;
+    }
+    return inclusive_scan_u32(at<uint32_t>(fb, L.tiles_touched), at<uint32_t>(fb, L.order), at<uint32_t>(fb, L.offsets),
+                              BF, at<uint32_t>(fb, L.scan_state), num_rendered_host, stream);
+}
+
+int bin_instances(int B, int F, int W, int H, size_t R, const void* fb, const FaceBinLayout& L, void* binning_buffer,
+                  uint2* ranges, cudaStream_t stream)
+{
+    const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
+    const size_t tiles = (size_t)B * tx * ty;
+    DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream));
+    if (R == 0) return 0;
+    const size_t BF = (size_t)B * F;
+    BinningLayout BL = BinningLayout::make(R);
+    uint32_t* ku = at<uint32_t>(binning_buffer, BL.keys_unsorted);
+    uint32_t* vu = at<uint32_t>(binning_buffer, BL.vals_unsorted);
+    uint32_t* ks = at<uint32_t>(binning_buffer, BL.keys_sorted);
+    uint32_t* vs = at<uint32_t>(binning_buffer, BL.vals_sorted);
+    {
+        ProfScope prof(ST_DUPLICATE, stream);
+        duplicate_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(
+            BF, F, tx, tx * ty, at<uint32_t>(fb, L.order), at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu);
+        DMR_LAUNCH_CHECK("duplicate_kernel");
+    }
+    // the bits above the depth word of the reference's key: rasterizer_impl.cu:316-324
+    const int tile_bits = (int)higher_msb((uint32_t)tiles);
+    int rc;
+    if ((rc = sort_pairs_u32(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, stream))) return rc;
+    {
+        ProfScope prof(ST_RANGES, stream);
+        const size_t nthreads = (R + TR_KPT - 1) / TR_KPT;
+        tile_ranges_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(ks, R, ranges);
+        DMR_LAUNCH_CHECK("tile_ranges_kernel");
+    }
+    return 0;
 }
 
 }  // namespace dmr

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char* what)
 
 // ---- stage timing ------------------------------------------------------------
 static const char* const g_stage_names[ST_COUNT] = {
-    "preprocess_points", "preprocess_faces", "scan", "duplicate_with_keys", "sort_histogram", "sort_plan",
+    "preprocess_points", "preprocess_faces", "face_depth_sort", "scan", "duplicate_with_keys", "sort_histogram", "sort_plan",
     "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "sort_pass4", "sort_pass5", "sort_pass6", "sort_pass7",
     "tile_ranges", "tri_render_forward", "tri_render_backward", "tri_grad_finish", "tet_build_records", "tet_jitter",
     "tet_first_intersect", "tet_march_forward", "tet_march_backward", "tet_grad_vertex" };
@@ -61,11 +61,11 @@ BinningLayout BinningLayout::make(size_t R)
 {
     BinningLayout L;
     size_t o = 0;
-    L.keys_unsorted = o; o = align_up(o + 8 * R, 256);
+    L.keys_unsorted = o; o = align_up(o + 4 * R, 256);
     L.vals_unsorted = o; o = align_up(o + 4 * R, 256);
-    L.keys_sorted = o;   o = align_up(o + 8 * R, 256);
+    L.keys_sorted = o;   o = align_up(o + 4 * R, 256);
     L.vals_sorted = o;   o = align_up(o + 4 * R, 256);
-    L.sort_temp = o;     o = align_up(o + sort_temp_bytes(R), 256);
+    L.sort_temp = o;     o = align_up(o + sort_temp_bytes_u32(R), 256);
     L.total = o + 256;
     return L;
 }
@@ -161,37 +161,14 @@ int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, c
     TriFaceLayout L = TriFaceLayout::make(BF);
     float4* vimg = static_cast<float4*>(point_buffer);
     size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.scan_state), 0, 4 * (ntile + 64), stream));
+    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.bin.scan_state), 0, 4 * (ntile + 64), stream));
     int rc;
     if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, verts_depth, vimg, stream))) return rc;
     if ((rc = tri_preprocess_faces(B, P, F, W, H, faces, vimg, verts, verts_color, faces_opacity, faces_intense,
-                                   at<uint32_t>(face_buffer, L.tiles_touched), at<uint32_t>(face_buffer, L.depth_key),
-                                   at<uint2>(face_buffer, L.rect), at<TriRecord>(face_buffer, L.records), stream)))
+                                   at<uint32_t>(face_buffer, L.bin.tiles_touched), at<uint32_t>(face_buffer, L.bin.depth_key),
+                                   at<uint2>(face_buffer, L.bin.rect), at<TriRecord>(face_buffer, L.records), stream)))
         return rc;
-    if ((rc = inclusive_scan_u32(at<uint32_t>(face_buffer, L.tiles_touched), at<uint32_t>(face_buffer, L.offsets), BF,
-                                 at<uint32_t>(face_buffer, L.scan_state), num_rendered_host, stream)))
-        return rc;
-    return DMR_OK;
-}
-
-static int bin_sort_ranges(int B, int F, int W, int H, size_t R, const uint32_t* offsets, const uint2* rect,
-                           const uint32_t* depth_key, void* binning_buffer, uint2* ranges, cudaStream_t stream)
-{
-    const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
-    const size_t tiles = (size_t)B * tx * ty;
-    DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream));
-    if (R == 0) return DMR_OK;
-    BinningLayout L = BinningLayout::make(R);
-    uint64_t* ku = at<uint64_t>(binning_buffer, L.keys_unsorted);
-    uint32_t* vu = at<uint32_t>(binning_buffer, L.vals_unsorted);
-    uint64_t* ks = at<uint64_t>(binning_buffer, L.keys_sorted);
-    uint32_t* vs = at<uint32_t>(binning_buffer, L.vals_sorted);
-    int rc;
-    if ((rc = duplicate_with_keys((size_t)B * F, F, tx, ty, offsets, rect, depth_key, ku, vu, R, stream))) return rc;
-    const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);   // rasterizer_impl.cu:316-324
-    if ((rc = sort_pairs(ku, vu, ks, vs, R, end_bit, at<void>(binning_buffer, L.sort_temp), stream))) return rc;
-    if ((rc = identify_tile_ranges(ks, R, ranges, stream))) return rc;
-    return DMR_OK;
+    return bin_faces(BF, face_buffer, L.bin, num_rendered_host, stream);
 }
 
 int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float* background,
@@ -208,9 +185,7 @@ int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float
     TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
     TriImageLayout IL = TriImageLayout::make(B, W, H);
     uint2* ranges = at<uint2>(image_buffer, IL.ranges);
-    int rc = bin_sort_ranges(B, F, W, H, (size_t)R, R ? at<uint32_t>(face_buffer, FL.offsets) : nullptr,
-                             R ? at<uint2>(face_buffer, FL.rect) : nullptr,
-                             R ? at<uint32_t>(face_buffer, FL.depth_key) : nullptr, binning_buffer, ranges, stream);
+    int rc = bin_instances(B, F, W, H, (size_t)R, face_buffer, FL.bin, binning_buffer, ranges, stream);
     if (rc) return rc;
     TriRenderParams p = {};
     p.B = B; p.F = F; p.W = W; p.H = H; p.P = P;
@@ -282,9 +257,10 @@ int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, in
         TriFaceLayout FL = TriFaceLayout::make(BF);
         TriImageLayout IL = TriImageLayout::make(B, W, H);
         switch (kind) {
-        case DMR_VIEW_TILES_TOUCHED: off = FL.tiles_touched; n = BF; break;
-        case DMR_VIEW_FACE_OFFSETS:  off = FL.offsets; n = BF; break;
-        case DMR_VIEW_DEPTH_KEYS:    off = FL.depth_key; n = BF; break;
+        case DMR_VIEW_TILES_TOUCHED: off = FL.bin.tiles_touched; n = BF; break;
+        case DMR_VIEW_FACE_OFFSETS:  off = FL.bin.offsets; n = BF; break;
+        case DMR_VIEW_DEPTH_KEYS:    off = FL.bin.depth_key; n = BF; break;
+        case DMR_VIEW_FACE_ORDER:    off = FL.bin.order; n = BF; break;
         case DMR_VIEW_RANGES:        off = IL.ranges; n = tiles; break;
         case DMR_VIEW_N_CONTRIB:     off = IL.n_contrib; n = BI; break;
         case DMR_VIEW_FINAL_T:       off = IL.final_T; n = BI; break;
@@ -294,9 +270,10 @@ int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, in
         TetFaceLayout FL = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
         TetImageLayout IL = TetImageLayout::make(B, W, H);
         switch (kind) {
-        case DMR_VIEW_TILES_TOUCHED: off = FL.tiles_touched; n = BF; break;
-        case DMR_VIEW_FACE_OFFSETS:  off = FL.offsets; n = BF; break;
-        case DMR_VIEW_DEPTH_KEYS:    off = FL.depth_key; n = BF; break;
+        case DMR_VIEW_TILES_TOUCHED: off = FL.bin.tiles_touched; n = BF; break;
+        case DMR_VIEW_FACE_OFFSETS:  off = FL.bin.offsets; n = BF; break;
+        case DMR_VIEW_DEPTH_KEYS:    off = FL.bin.depth_key; n = BF; break;
+        case DMR_VIEW_FACE_ORDER:    off = FL.bin.order; n = BF; break;
         case DMR_VIEW_RANGES:        off = IL.ranges; n = tiles; break;
         case DMR_VIEW_N_CONTRIB:     off = IL.n_contrib; n = BI; break;
         case DMR_VIEW_FINAL_T:       off = IL.final_log_T; n = BI; break;

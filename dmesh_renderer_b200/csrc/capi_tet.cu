@@ -59,16 +59,14 @@ int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* v
     TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
     float4* vimg = static_cast<float4*>(point_buffer);
     size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.scan_state), 0, 4 * (ntile + 64), stream));
+    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.bin.scan_state), 0, 4 * (ntile + 64), stream));
     int rc;
     if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, nullptr, vimg, stream))) return rc;
-    if ((rc = tet_preprocess_faces(B, P, F, W, H, faces, vimg, verts, at<uint32_t>(face_buffer, L.tiles_touched),
-                                   at<uint32_t>(face_buffer, L.depth_key), at<uint2>(face_buffer, L.rect),
+    if ((rc = tet_preprocess_faces(B, P, F, W, H, faces, vimg, verts, at<uint32_t>(face_buffer, L.bin.tiles_touched),
+                                   at<uint32_t>(face_buffer, L.bin.depth_key), at<uint2>(face_buffer, L.bin.rect),
                                    at<TetFaceRec>(face_buffer, L.face_rec), stream)))
         return rc;
-    if ((rc = inclusive_scan_u32(at<uint32_t>(face_buffer, L.tiles_touched), at<uint32_t>(face_buffer, L.offsets), BF,
-                                 at<uint32_t>(face_buffer, L.scan_state), num_rendered_host, stream)))
-        return rc;
+    if ((rc = bin_faces(BF, face_buffer, L.bin, num_rendered_host, stream))) return rc;
     // view-independent march records; independent of the scan, enqueued behind it
     if ((rc = tet_build_records(P, F, T, verts, faces, verts_color, faces_opacity, tets, face_tets, tet_faces,
                                 at<TetRec>(face_buffer, L.tet_rec), at<TetShade>(face_buffer, L.shade), stream)))
@@ -121,32 +119,15 @@ int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int 
     (void)point_buffer;
     TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
     TetImageLayout IL = TetImageLayout::make(B, W, H);
-    const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
-    const size_t tiles = (size_t)B * tx * ty;
     uint2* ranges = at<uint2>(image_buffer, IL.ranges);
     int rc;
-    DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream));
     TetParams p;
     fill_params(p, B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
                 faces_intense, face_buffer, image_buffer);
     if (ray_random_seed > 0)
         if ((rc = tet_jitter(B, W, H, ray_random_seed, at<float2>(image_buffer, IL.jitter), stream))) return rc;
-    if (R > 0) {
-        BinningLayout BL = BinningLayout::make((size_t)R);
-        uint64_t* ku = at<uint64_t>(binning_buffer, BL.keys_unsorted);
-        uint32_t* vu = at<uint32_t>(binning_buffer, BL.vals_unsorted);
-        uint64_t* ks = at<uint64_t>(binning_buffer, BL.keys_sorted);
-        uint32_t* vs = at<uint32_t>(binning_buffer, BL.vals_sorted);
-        if ((rc = duplicate_with_keys((size_t)B * F, F, tx, ty, at<uint32_t>(face_buffer, FL.offsets),
-                                      at<uint2>(face_buffer, FL.rect), at<uint32_t>(face_buffer, FL.depth_key), ku, vu,
-                                      (size_t)R, stream)))
-            return rc;
-        const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);   // renderer_impl.cu:332-340
-        if ((rc = sort_pairs(ku, vu, ks, vs, (size_t)R, end_bit, at<void>(binning_buffer, BL.sort_temp), stream)))
-            return rc;
-        if ((rc = identify_tile_ranges(ks, (size_t)R, ranges, stream))) return rc;
-        p.face_list = vs;
-    }
+    if ((rc = bin_instances(B, F, W, H, (size_t)R, face_buffer, FL.bin, binning_buffer, ranges, stream))) return rc;
+    if (R > 0) p.face_list = at<uint32_t>(binning_buffer, BinningLayout::make((size_t)R).vals_sorted);
     p.out_color = out_color; p.out_depth = out_depth; p.out_active = out_active;
     if ((rc = tet_first_intersect(p, stream))) return rc;
     if ((rc = tet_march_forward(p, stream))) return rc;

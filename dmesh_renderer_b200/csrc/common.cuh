@@ -38,7 +38,7 @@ int  cuda_fail(cudaError_t e, const char* what);
 // stream around every kernel when enabled; no synchronisation, off by default.
 // ---------------------------------------------------------------------------
 enum Stage {
-    ST_POINTS = 0, ST_FACES, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PLAN,
+    ST_POINTS = 0, ST_FACES, ST_FACE_SORT, ST_SCAN, ST_DUPLICATE, ST_SORT_HIST, ST_SORT_PLAN,
     ST_SORT_PASS0, ST_SORT_PASS1, ST_SORT_PASS2, ST_SORT_PASS3, ST_SORT_PASS4, ST_SORT_PASS5, ST_SORT_PASS6, ST_SORT_PASS7,
     ST_RANGES, ST_TRI_FWD, ST_TRI_BWD, ST_TRI_BWD_FINISH, ST_TET_RECORDS, ST_TET_JITTER, ST_TET_FIRST, ST_TET_FWD, ST_TET_BWD, ST_TET_BWD_FINISH, ST_COUNT
 };
@@ -187,18 +187,41 @@ static_assert(sizeof(TriRecord) == 144, "TriRecord must be 9 x 16 bytes");
 #define DMR_SCAN_ITEMS 16
 #define DMR_SCAN_TILE (DMR_SCAN_THREADS * DMR_SCAN_ITEMS)
 
+size_t sort_temp_bytes_u32(size_t n);
+
+// Per-(view,face) binning scratch at the head of both renderers' face buffers.
+//   tiles_touched, depth_key, rect   written by the face-preprocess kernel, indexed by bf = b*F + f
+//   order          faces stably sorted by depth key (u32 indices bf)          -- see bin_faces()
+//   depth_sorted   the sorted depth keys (sort output, otherwise unused)
+//   offsets        inclusive scan of tiles_touched[order[i]]: instance ranges in DEPTH order
+struct FaceBinLayout {
+    size_t tiles_touched, depth_key, rect, order, depth_sorted, offsets, scan_state, fsort_temp, end;
+    __host__ static FaceBinLayout make(size_t BF)
+    {
+        FaceBinLayout L;
+        size_t o = 0;
+        L.tiles_touched = o; o = align_up(o + 4 * BF, 256);
+        L.depth_key = o;     o = align_up(o + 4 * BF, 256);
+        L.rect = o;          o = align_up(o + 8 * BF, 256);
+        L.order = o;         o = align_up(o + 4 * BF, 256);
+        L.depth_sorted = o;  o = align_up(o + 4 * BF, 256);
+        L.offsets = o;       o = align_up(o + 4 * BF, 256);
+        size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
+        L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);   // [0]=ticket, [1]=total, [32..]=descriptors
+        L.fsort_temp = o;    o = align_up(o + sort_temp_bytes_u32(BF), 256);
+        L.end = o;
+        return L;
+    }
+};
+
 struct TriFaceLayout {
-    size_t tiles_touched, offsets, depth_key, rect, scan_state, records, grad_stats, total;
+    FaceBinLayout bin;
+    size_t records, grad_stats, total;
     __host__ static TriFaceLayout make(size_t BF)
     {
         TriFaceLayout L;
-        size_t o = 0;
-        L.tiles_touched = o; o = align_up(o + 4 * BF, 256);
-        L.offsets = o;       o = align_up(o + 4 * BF, 256);
-        L.depth_key = o;     o = align_up(o + 4 * BF, 256);
-        L.rect = o;          o = align_up(o + 8 * BF, 256);
-        size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-        L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);   // [0]=ticket, [1]=total, [32..]=descriptors
+        L.bin = FaceBinLayout::make(BF);
+        size_t o = L.bin.end;
         L.records = o;       o = align_up(o + sizeof(TriRecord) * BF, 256);
         L.grad_stats = o;    o = align_up(o + 96 * BF, 256);   // backward scratch: 24 floats per (view, face)
         L.total = o + 256;
@@ -223,7 +246,9 @@ struct TriImageLayout {
     }
 };
 
-// binning buffer: A = unsorted (duplicate output), B = sorted, then sort temp
+// binning buffer: A = unsorted (duplicate output), B = sorted, then sort temp.  Keys are 32-bit tile ids
+// (tile + tiles_per_view * view): the depth half of the reference's 64-bit key is already sorted when the
+// instances are emitted (see bin_faces()).
 struct BinningLayout {
     size_t keys_unsorted, vals_unsorted, keys_sorted, vals_sorted, sort_temp, total;
     __host__ static BinningLayout make(size_t R);
@@ -235,14 +260,28 @@ struct BinningLayout {
 size_t sort_temp_bytes(size_t n);
 int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
                int end_bit, void* temp, cudaStream_t stream);
+// 32-bit keys; vals_in == nullptr stands for the identity (0, 1, 2, ...); profile == false: no per-kernel
+// profile stages (the caller wraps the whole sort in one)
+int sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
+                   int end_bit, void* temp, bool profile, cudaStream_t stream);
 
-int inclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* state /* zeroed, ntile+64 words */,
-                       int32_t* total_host /* pinned, may be null */, cudaStream_t stream);
+// inclusive scan of in[index ? index[i] : i]
+int inclusive_scan_u32(const uint32_t* in, const uint32_t* index, uint32_t* out, size_t n,
+                       uint32_t* state /* zeroed, ntile+64 words */, int32_t* total_host /* pinned, may be null */,
+                       cudaStream_t stream);
 
-int duplicate_with_keys(size_t BF, int F, int tiles_x, int tiles_y, const uint32_t* offsets, const uint2* rect,
-                        const uint32_t* depth_key, uint64_t* keys, uint32_t* vals, size_t R, cudaStream_t stream);
-
-int identify_tile_ranges(const uint64_t* keys_sorted, size_t R, uint2* ranges /* zeroed */, cudaStream_t stream);
+// Two-level binning (replaces InclusiveSum + duplicateWithKeys + the 64-bit SortPairs + identifyTileRanges,
+// rasterizer_impl.cu:278-338).  The reference sorts R (tile|depth) keys of 32+bit_length(tiles) bits.  An LSD
+// radix sort is a chain of stable passes from the least significant digit up, so the same order results from
+//   (1) bin_faces:     stable sort of the B*F FACES by their 32-bit depth key, then the scan over
+//                      tiles_touched in that order (R and the instance ranges);
+//   (2) bin_instances: emission of the instances in depth order (key = tile id only) and a stable sort on
+//                      the bit_length(tiles) tile bits -- 1-3 eight-bit passes over 8-byte pairs instead of
+//                      6-7 passes over 12-byte pairs; then the tile ranges.
+// Equal (tile, depth) pairs keep ascending b*F+f order in both formulations (stable sorts all the way).
+int bin_faces(size_t BF, void* face_buffer, const FaceBinLayout& L, int32_t* num_rendered_host, cudaStream_t stream);
+int bin_instances(int B, int F, int W, int H, size_t R, const void* face_buffer, const FaceBinLayout& L,
+                  void* binning_buffer, uint2* ranges /* [B*tiles] */, cudaStream_t stream);
 
 uint32_t higher_msb(uint32_t n);
 

@@ -39,12 +39,12 @@ struct SortCtl {
 struct SortTempLayout {
     size_t keys_tmp, vals_tmp, zero_begin, hist, ctl, desc, total;
     size_t ntile;
-    __host__ static SortTempLayout make(size_t n)
+    __host__ static SortTempLayout make(size_t n, size_t key_bytes)
     {
         SortTempLayout L;
         L.ntile = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
         size_t o = 0;
-        L.keys_tmp = o; o = align_up(o + 8 * n, 256);
+        L.keys_tmp = o; o = align_up(o + key_bytes * n, 256);
         L.vals_tmp = o; o = align_up(o + 4 * n, 256);
         L.zero_begin = o;
         L.hist = o;     o = align_up(o + 4 * 256 * RS_MAX_PASS, 256);
@@ -55,7 +55,8 @@ struct SortTempLayout {
     }
 };
 
-size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n).total; }
+size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n, 8).total; }
+size_t sort_temp_bytes_u32(size_t n) { return SortTempLayout::make(n, 4).total; }
 
 // ---------------------------------------------------------------------------
 // 1. histograms of all passes in one sweep.  8 keys per thread are loaded
@@ -64,7 +65,8 @@ size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n).total; }
 // upper tile bits) costs one shared atomic instead of 256.
 // ---------------------------------------------------------------------------
 #define RSH_KPT 8
-__global__ void __launch_bounds__(256) rs_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int npass, int end_bit,
+template <typename KeyT>
+__global__ void __launch_bounds__(256) rs_hist_kernel(const KeyT* __restrict__ keys, size_t n, int npass, int end_bit,
                                                       uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t s_hist[RS_MAX_PASS * 256];
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(256) rs_hist_kernel(const uint64_t* __restrict
 
     const size_t chunk = 256 * RSH_KPT;
     for (size_t base = (size_t)blockIdx.x * chunk; base < n; base += (size_t)gridDim.x * chunk) {
-        uint64_t k[RSH_KPT];
+        KeyT k[RSH_KPT];
         const bool full = base + chunk <= n;
 #pragma unroll
         for (int i = 0; i < RSH_KPT; i++) {
@@ -154,10 +156,11 @@ __global__ void __launch_bounds__(256) rs_plan_kernel(uint32_t* __restrict__ his
 // ---------------------------------------------------------------------------
 // 3. one onesweep pass
 // ---------------------------------------------------------------------------
+template <typename KeyT>
 struct RsBuffers {
-    const uint64_t* kin; const uint32_t* vin;
-    uint64_t* kout; uint32_t* vout;
-    uint64_t* ktmp; uint32_t* vtmp;
+    const KeyT* kin; const uint32_t* vin;
+    KeyT* kout; uint32_t* vout;
+    KeyT* ktmp; uint32_t* vtmp;
 };
 
 // Phase order per tile (4096 keys, 512 threads x 8 keys):
@@ -169,8 +172,8 @@ struct RsBuffers {
 // after ranking), and the look-back only has to walk over the few predecessors that have not yet
 // published their inclusive prefix -- RS_LB descriptors are fetched per step so that walk costs one
 // L2 round trip per RS_LB tiles.
-template <int RS_THREADS, int RS_KPT, int RS_MINB>
-__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers buf, size_t n, int pass, int end_bit,
+template <typename KeyT, int RS_THREADS, int RS_KPT, int RS_MINB>
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n, int pass, int end_bit,
                                                                           const uint32_t* __restrict__ hist_excl,
                                                                           SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
 {
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     constexpr int RS_WARPS = RS_THREADS / 32;
     if (!ctl->exec[pass]) return;
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_smem);                       // RS_TILE
-    uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + 8 * RS_TILE);         // RS_TILE
+    KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                               // RS_TILE
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE);   // RS_TILE
     uint32_t* s_whist = s_vals + RS_TILE;                                          // RS_WARPS * 256
     uint32_t* s_dbase = s_whist + RS_WARPS * 256;                                  // 256: local exclusive digit base
     int32_t*  s_gbase = reinterpret_cast<int32_t*>(s_dbase + 256);                 // 256: global pos - local pos (wrapping)
@@ -188,9 +191,9 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s = ctl->src[pass], d_sel = ctl->dst[pass];
-    const uint64_t* kin = (s == 0) ? buf.kin : (s == 1 ? buf.kout : buf.ktmp);
-    const uint32_t* vin = (s == 0) ? buf.vin : (s == 1 ? buf.vout : buf.vtmp);
-    uint64_t* kout = (d_sel == 1) ? buf.kout : buf.ktmp;
+    const KeyT* kin = (s == 0) ? buf.kin : (s == 1 ? buf.kout : buf.ktmp);
+    const uint32_t* vin = (s == 0) ? buf.vin : (s == 1 ? buf.vout : buf.vtmp);   // buf.vin may be null: identity
+    KeyT* kout = (d_sel == 1) ? buf.kout : buf.ktmp;
     uint32_t* vout = (d_sel == 1) ? buf.vout : buf.vtmp;
 
     if (tid == 0) s_tile = atomicAdd(&ctl->ticket[pass], 1u);
@@ -206,17 +209,17 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     // warp-striped load: item i of lane l sits at warp_base + i*32 + l, so that
     // (i, lane) order == global order (stability)
     const uint32_t wbase = warp * (32 * RS_KPT);
-    uint64_t key[RS_KPT];
+    KeyT key[RS_KPT];
     uint32_t val[RS_KPT];
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
         uint32_t loc = wbase + i * 32 + lane;
-        key[i] = (loc < nvalid) ? kin[tile_base + loc] : ~0ull;
+        key[i] = (loc < nvalid) ? kin[tile_base + loc] : (KeyT)~(KeyT)0;
     }
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
         uint32_t loc = wbase + i * 32 + lane;
-        val[i] = (loc < nvalid) ? vin[tile_base + loc] : 0u;
+        val[i] = (loc < nvalid) ? (vin ? vin[tile_base + loc] : (uint32_t)(tile_base + loc)) : 0u;   // null = identity
     }
 
     // ---- per-warp digit counts
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
 
     // ---- coalesced write-out
     for (uint32_t p = tid; p < nvalid; p += RS_THREADS) {
-        uint64_t k = s_keys[p];
+        KeyT k = s_keys[p];
         uint32_t d = (uint32_t)(k >> shift) & dmask;
         size_t g = (size_t)(uint32_t)(s_gbase[d] + (int32_t)p);
         kout[g] = k;
@@ -325,34 +328,38 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     }
 }
 
-template <int THREADS, int KPT, int MINB>
-static int launch_onesweep(const RsBuffers& buf, size_t n, int npass, int end_bit, const uint32_t* hist, SortCtl* ctl,
-                           uint32_t* desc, cudaStream_t stream)
+template <typename KeyT, int THREADS, int KPT, int MINB>
+static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int end_bit, const uint32_t* hist, SortCtl* ctl,
+                           uint32_t* desc, bool profile, cudaStream_t stream)
 {
     constexpr size_t tile = (size_t)THREADS * KPT;
-    constexpr size_t smem = 8 * tile + 4 * tile + 4 * (THREADS / 32) * 256 + 4 * 256 + 4 * 256;
+    constexpr size_t smem = sizeof(KeyT) * tile + 4 * tile + 4 * (THREADS / 32) * 256 + 4 * 256 + 4 * 256;
     static bool attr_set = false;
     if (!attr_set) {
-        DMR_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<THREADS, KPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DMR_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, THREADS, KPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const unsigned ntile = (unsigned)((n + tile - 1) / tile);
     for (int p = 0; p < npass; p++) {
-        ProfScope prof(ST_SORT_PASS0 + p, stream);
-        rs_onesweep_kernel<THREADS, KPT, MINB><<<ntile, THREADS, smem, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
+        if (profile) prof_begin(ST_SORT_PASS0 + p, stream); else count_launch(1);
+        rs_onesweep_kernel<KeyT, THREADS, KPT, MINB><<<ntile, THREADS, smem, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
+        if (profile) prof_end(ST_SORT_PASS0 + p, stream);
         DMR_LAUNCH_CHECK("rs_onesweep_kernel");
     }
     return 0;
 }
 
-int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
-               int end_bit, void* temp, cudaStream_t stream)
+// profile == false: the kernels are counted but get no stage events of their own (the face sort is reported as
+// ONE stage by its caller; the per-kernel stages belong to the instance sort).
+template <typename KeyT>
+static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out, size_t n,
+                           int end_bit, void* temp, bool profile, cudaStream_t stream)
 {
     if (n == 0) return 0;
-    if (end_bit < 1 || end_bit > 64) { set_error("sort_pairs: end_bit %d out of range", end_bit); return 1; }
+    if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort_pairs: end_bit %d out of range", end_bit); return 1; }
     if (n >= (1ull << 30)) { set_error("sort_pairs: n=%zu exceeds 2^30", n); return 3; }
     const int npass = (end_bit + 7) / 8;
-    SortTempLayout L = SortTempLayout::make(n);
+    SortTempLayout L = SortTempLayout::make(n, sizeof(KeyT));
     unsigned char* t = static_cast<unsigned char*>(temp);
     uint32_t* hist = reinterpret_cast<uint32_t*>(t + L.hist);
     SortCtl* ctl = reinterpret_cast<SortCtl*>(t + L.ctl);
@@ -378,26 +385,40 @@ int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_
     size_t hmax = (size_t)sm_count * 8;   // 8 resident CTAs per SM
     if (hblocks > hmax) hblocks = hmax;
     {
-        ProfScope prof(ST_SORT_HIST, stream);
-        rs_hist_kernel<<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
+        if (profile) prof_begin(ST_SORT_HIST, stream); else count_launch(1);
+        rs_hist_kernel<KeyT><<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
+        if (profile) prof_end(ST_SORT_HIST, stream);
         DMR_LAUNCH_CHECK("rs_hist_kernel");
     }
     {
-        ProfScope prof(ST_SORT_PLAN, stream);
+        if (profile) prof_begin(ST_SORT_PLAN, stream); else count_launch(1);
         rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
+        if (profile) prof_end(ST_SORT_PLAN, stream);
         DMR_LAUNCH_CHECK("rs_plan_kernel");
     }
-    RsBuffers buf;
+    RsBuffers<KeyT> buf;
     buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
-    buf.ktmp = reinterpret_cast<uint64_t*>(t + L.keys_tmp);
+    buf.ktmp = reinterpret_cast<KeyT*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
     switch (cfg) {
-    case 1:  return launch_onesweep<256, 16, 2>(buf, n, npass, end_bit, hist, ctl, desc, stream);
-    case 2:  return launch_onesweep<256, 8, 4>(buf, n, npass, end_bit, hist, ctl, desc, stream);
-    case 3:  return launch_onesweep<512, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, stream);
-    case 4:  return launch_onesweep<384, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, stream);
-    default: return launch_onesweep<512, 8, 2>(buf, n, npass, end_bit, hist, ctl, desc, stream);
+    case 1:  return launch_onesweep<KeyT, 256, 16, 2>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
+    case 2:  return launch_onesweep<KeyT, 256, 8, 4>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
+    case 3:  return launch_onesweep<KeyT, 512, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
+    case 4:  return launch_onesweep<KeyT, 384, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
+    default: return launch_onesweep<KeyT, 512, 8, 2>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
     }
+}
+
+int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
+               int end_bit, void* temp, cudaStream_t stream)
+{
+    return sort_pairs_impl<uint64_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, true, stream);
+}
+
+int sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
+                   int end_bit, void* temp, bool profile, cudaStream_t stream)
+{
+    return sort_pairs_impl<uint32_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, profile, stream);
 }
 
 }  // namespace dmr

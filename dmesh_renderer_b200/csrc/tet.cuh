@@ -53,17 +53,13 @@ struct __align__(16) TetShade {
 static_assert(sizeof(TetShade) == 64, "TetShade must be 4 x 16 bytes");
 
 struct TetFaceLayout {
-    size_t tiles_touched, offsets, depth_key, rect, scan_state, face_rec, tet_rec, shade, grad_vacc, total;
+    FaceBinLayout bin;
+    size_t face_rec, tet_rec, shade, grad_vacc, total;
     __host__ static TetFaceLayout make(size_t BF, size_t F, size_t T, size_t P)
     {
         TetFaceLayout L;
-        size_t o = 0;
-        L.tiles_touched = o; o = align_up(o + 4 * BF, 256);
-        L.offsets = o;       o = align_up(o + 4 * BF, 256);
-        L.depth_key = o;     o = align_up(o + 4 * BF, 256);
-        L.rect = o;          o = align_up(o + 8 * BF, 256);
-        size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-        L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);
+        L.bin = FaceBinLayout::make(BF);
+        size_t o = L.bin.end;
         L.face_rec = o;      o = align_up(o + sizeof(TetFaceRec) * BF, 256);
         L.tet_rec = o;       o = align_up(o + sizeof(TetRec) * T, 256);
         L.shade = o;         o = align_up(o + sizeof(TetShade) * F, 256);

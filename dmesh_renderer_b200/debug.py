@@ -11,20 +11,36 @@ KINDS = {
     "tiles_touched": (1, np.uint32, 1),
     "offsets": (2, np.uint32, 1),
     "depth_keys": (3, np.uint32, 1),
-    "keys_unsorted": (4, np.uint64, 1),
+    "tile_keys_unsorted": (4, np.uint32, 1),
     "values_unsorted": (5, np.uint32, 1),
-    "keys_sorted": (6, np.uint64, 1),
+    "tile_keys_sorted": (6, np.uint32, 1),
     "values_sorted": (7, np.uint32, 1),
     "ranges": (8, np.uint32, 2),
     "n_contrib": (9, np.uint32, 1),
     "final_T": (10, np.float32, 1),
     "first_face": (11, np.int32, 1),
     "first_tet": (12, np.int32, 1),
+    "face_order": (13, np.uint32, 1),
 }
+# The reference's 64-bit (tile | depth) keys.  The native path sorts FACES by depth and instances by tile
+# id only (csrc/common.cuh: bin_faces / bin_instances), so it never materialises them; they are recomposed
+# here from the tile ids, the face ids and the per-(view, face) depth keys for the bit-exact parity checks.
+COMPOSED = {"keys_unsorted": ("tile_keys_unsorted", "values_unsorted"), "keys_sorted": ("tile_keys_sorted", "values_sorted")}
 
 
-def view(renderer, kind, buffer, B, P, F, W, H, R=0, T=0):
-    """Return a numpy copy of one intermediate.  renderer: "tri" | "tet"."""
+def view(renderer, kind, buffer, B, P, F, W, H, R=0, T=0, face_buffer=None):
+    """Return a numpy copy of one intermediate.  renderer: "tri" | "tet".
+    keys_sorted / keys_unsorted additionally need the face buffer (depth keys)."""
+    if kind in COMPOSED:
+        if face_buffer is None:
+            raise ValueError("%s is recomposed from tile ids and depth keys: pass face_buffer=" % kind)
+        dims = dict(B=B, P=P, F=F, W=W, H=H, R=R, T=T)
+        tile = view(renderer, COMPOSED[kind][0], buffer, **dims).astype(np.uint64)
+        fid = view(renderer, COMPOSED[kind][1], buffer, **dims).astype(np.int64)
+        depth = view(renderer, "depth_keys", face_buffer, **dims).astype(np.uint64)
+        tiles_per_view = ((W + 15) // 16) * ((H + 15) // 16)
+        b = (tile // np.uint64(tiles_per_view)).astype(np.int64)
+        return (tile << np.uint64(32)) | depth[b * F + fid]
     lib = _lib.load()
     k, dtype, width = KINDS[kind]
     ptr = ctypes.c_void_p()

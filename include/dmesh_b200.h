@@ -185,17 +185,20 @@ int dmr_tet_backward(
 enum dmr_view_kind {
     DMR_VIEW_VERTS_IMAGE    = 0,  /* float4[B*P] {img.x,img.y,ndc.z,depth}   point buffer */
     DMR_VIEW_TILES_TOUCHED  = 1,  /* uint32[B*F]                              face buffer  */
-    DMR_VIEW_FACE_OFFSETS   = 2,  /* uint32[B*F] inclusive scan               face buffer  */
+    DMR_VIEW_FACE_OFFSETS   = 2,  /* uint32[B*F] inclusive scan of tiles_touched in FACE_ORDER  face buffer */
     DMR_VIEW_DEPTH_KEYS     = 3,  /* uint32[B*F] float bits of the sort depth face buffer  */
-    DMR_VIEW_KEYS_UNSORTED  = 4,  /* uint64[R]                                binning      */
-    DMR_VIEW_VALUES_UNSORTED= 5,  /* uint32[R]                                binning      */
-    DMR_VIEW_KEYS_SORTED    = 6,  /* uint64[R]                                binning      */
-    DMR_VIEW_VALUES_SORTED  = 7,  /* uint32[R]                                binning      */
+    DMR_VIEW_KEYS_UNSORTED  = 4,  /* uint32[R] tile ids as emitted (depth order)  binning  */
+    DMR_VIEW_VALUES_UNSORTED= 5,  /* uint32[R] face ids as emitted               binning   */
+    DMR_VIEW_KEYS_SORTED    = 6,  /* uint32[R] tile ids, sorted: the upper word of the      */
+                                  /* reference's (tile|depth) key; the lower word is        */
+                                  /* DEPTH_KEYS[view*F + value]                  binning   */
+    DMR_VIEW_VALUES_SORTED  = 7,  /* uint32[R] face ids in final order           binning   */
     DMR_VIEW_RANGES         = 8,  /* uint2[B*tiles]                           image buffer */
     DMR_VIEW_N_CONTRIB      = 9,  /* uint32[B*W*H]                            image buffer */
     DMR_VIEW_FINAL_T        = 10, /* float[B*W*H] (tet: final log T)          image buffer */
     DMR_VIEW_FIRST_FACE     = 11, /* int32[B*W*H] (tet only)                  image buffer */
-    DMR_VIEW_FIRST_TET      = 12  /* int32[B*W*H] (tet only)                  image buffer */
+    DMR_VIEW_FIRST_TET      = 12, /* int32[B*W*H] (tet only)                  image buffer */
+    DMR_VIEW_FACE_ORDER     = 13  /* uint32[B*F] faces (b*F+f) stably sorted by depth key  face buffer */
 };
 int dmr_debug_view(int renderer /*0=tri,1=tet*/, int kind,
                    int B, int P, int F, int T, int W, int H, size_t R,

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch
 
+import binning_checks
 import ref_harness
 from dmesh_renderer_b200 import TetRenderer, TetRenderSettings, _C, debug, scenes
 
@@ -46,10 +47,12 @@ def test_tet_forward(name, seed):
     dims = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=R, T=T)
     tt = debug.view("tet", "tiles_touched", fb, **dims)
     np.testing.assert_array_equal(tt, ri["tiles_touched"])
-    np.testing.assert_array_equal(debug.view("tet", "offsets", fb, **dims), ri["offsets"])
     live = tt > 0
-    np.testing.assert_array_equal(debug.view("tet", "depth_keys", fb, **dims)[live], ri["min_depths"].view(np.uint32)[live])
-    np.testing.assert_array_equal(debug.view("tet", "keys_sorted", bb, **dims), ri["keys_sorted"])
+    dk = debug.view("tet", "depth_keys", fb, **dims)
+    np.testing.assert_array_equal(dk[live], ri["min_depths"].view(np.uint32)[live])
+    binning_checks.check_face_order_and_offsets(debug.view("tet", "face_order", fb, **dims), dk, tt,
+                                                debug.view("tet", "offsets", fb, **dims), ri["offsets"])
+    np.testing.assert_array_equal(debug.view("tet", "keys_sorted", bb, face_buffer=fb, **dims), ri["keys_sorted"])
     np.testing.assert_array_equal(debug.view("tet", "values_sorted", bb, **dims), ri["values_sorted"])
     np.testing.assert_array_equal(debug.view("tet", "ranges", ib, **dims), ri["ranges"])
     np.testing.assert_array_equal(debug.view("tet", "first_face", ib, **dims), ri["first_face"])

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 import torch
 
+import binning_checks
 import ref_harness
 from dmesh_renderer_b200 import TriRenderer, TriRenderSettings, _C, debug, scenes
 
@@ -53,14 +54,16 @@ def test_tri_intermediates_and_images(name):
     np.testing.assert_array_equal(vimg[:, 2].view(np.uint32), ri["ndc_z"].view(np.uint32))
     tt = debug.view("tri", "tiles_touched", fb, **dims)
     np.testing.assert_array_equal(tt, ri["tiles_touched"])
-    np.testing.assert_array_equal(debug.view("tri", "offsets", fb, **dims), ri["offsets"])
     assert R == ref["R"]
     dk = debug.view("tri", "depth_keys", fb, **dims)
     live = tt > 0      # culled faces leave depths[] unwritten in the reference
     np.testing.assert_array_equal(dk[live], ri["depths"].view(np.uint32)[live])
-    np.testing.assert_array_equal(debug.view("tri", "keys_unsorted", bb, **dims), ri["keys_unsorted"])
-    np.testing.assert_array_equal(debug.view("tri", "values_unsorted", bb, **dims), ri["values_unsorted"])
-    np.testing.assert_array_equal(debug.view("tri", "keys_sorted", bb, **dims), ri["keys_sorted"])
+    binning_checks.check_face_order_and_offsets(debug.view("tri", "face_order", fb, **dims), dk, tt,
+                                                debug.view("tri", "offsets", fb, **dims), ri["offsets"])
+    binning_checks.check_same_pairs(debug.view("tri", "keys_unsorted", bb, face_buffer=fb, **dims),
+                                    debug.view("tri", "values_unsorted", bb, **dims),
+                                    ri["keys_unsorted"], ri["values_unsorted"])
+    np.testing.assert_array_equal(debug.view("tri", "keys_sorted", bb, face_buffer=fb, **dims), ri["keys_sorted"])
     np.testing.assert_array_equal(debug.view("tri", "values_sorted", bb, **dims), ri["values_sorted"])
     np.testing.assert_array_equal(debug.view("tri", "ranges", ib, **dims), ri["ranges"])
     np.testing.assert_array_equal(debug.view("tri", "n_contrib", ib, **dims), ri["n_contrib"])

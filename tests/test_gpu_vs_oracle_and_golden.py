@@ -10,6 +10,8 @@ import sys
 
 import numpy as np
 import pytest
+
+import binning_checks
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,8 +58,9 @@ def run_tet(s, mats, gc=None, gd=None, seed=0):
 def tri_views(s, out):
     B, P, F = s.mv_mats.shape[0], s.verts.shape[0], s.faces.shape[0]
     d = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=out[0])
-    v = {k: debug.view("tri", k, out[4], **d) for k in ("tiles_touched", "offsets", "depth_keys")}
-    v.update({k: debug.view("tri", k, out[5], **d) for k in ("keys_unsorted", "values_unsorted", "keys_sorted", "values_sorted")})
+    v = {k: debug.view("tri", k, out[4], **d) for k in ("tiles_touched", "offsets", "depth_keys", "face_order")}
+    v.update({k: debug.view("tri", k, out[5], face_buffer=out[4], **d)
+              for k in ("keys_unsorted", "values_unsorted", "keys_sorted", "values_sorted")})
     v.update({k: debug.view("tri", k, out[6], **d) for k in ("ranges", "n_contrib", "final_T")})
     v["verts_image"] = debug.view("tri", "verts_image", out[3], **d)
     return v
@@ -65,7 +68,8 @@ def tri_views(s, out):
 
 def check_tri_against(v, out, grads, ref, ref_grads, exact_T=False):
     np.testing.assert_array_equal(v["tiles_touched"], ref["tiles_touched"])
-    np.testing.assert_array_equal(v["offsets"], ref["offsets"])
+    binning_checks.check_face_order_and_offsets(v["face_order"], v["depth_keys"], v["tiles_touched"], v["offsets"],
+                                                ref["offsets"])
     assert out[0] == int(ref["R"])
     live = ref["tiles_touched"] > 0
     np.testing.assert_array_equal(v["depth_keys"][live], ref["depth_keys"][live])
@@ -105,7 +109,7 @@ def test_tet_cuda_matches_golden(name):
     B, P, F, T = s.mv_mats.shape[0], s.verts.shape[0], s.faces.shape[0], s.tets.shape[0]
     d = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=int(g["R"]), T=T)
     np.testing.assert_array_equal(debug.view("tet", "tiles_touched", out[4], **d), g["tiles_touched"])
-    np.testing.assert_array_equal(debug.view("tet", "keys_sorted", out[5], **d), g["keys_sorted"])
+    np.testing.assert_array_equal(debug.view("tet", "keys_sorted", out[5], face_buffer=out[4], **d), g["keys_sorted"])
     np.testing.assert_array_equal(debug.view("tet", "values_sorted", out[5], **d), g["values_sorted"])
     np.testing.assert_array_equal(debug.view("tet", "ranges", out[6], **d), g["ranges"])
     np.testing.assert_array_equal(debug.view("tet", "first_face", out[6], **d), g["first_face"])
@@ -148,8 +152,7 @@ def test_tri_cuda_matches_oracle(make):
     o = oracle.TriOracle(cpu, mats=[m.contiguous().cpu().numpy() for m in mats])
     ref = o.outputs()
     v = tri_views(s, out)
-    np.testing.assert_array_equal(v["keys_unsorted"], ref["keys_unsorted"])
-    np.testing.assert_array_equal(v["values_unsorted"], ref["values_unsorted"])
+    binning_checks.check_same_pairs(v["keys_unsorted"], v["values_unsorted"], ref["keys_unsorted"], ref["values_unsorted"])
     check_tri_against(v, out, grads, ref, o.backward(gc.cpu(), gd.cpu()))
 
 
@@ -188,7 +191,7 @@ def test_tri_full_size_properties(name):
     v = tri_views(s, out)
     keys, R = v["keys_sorted"], out[0]
     assert keys.size == R == int(v["offsets"][-1])
-    np.testing.assert_array_equal(np.cumsum(v["tiles_touched"], dtype=np.uint64).astype(np.uint32), v["offsets"])
+    np.testing.assert_array_equal(np.cumsum(v["tiles_touched"][v["face_order"]], dtype=np.uint64).astype(np.uint32), v["offsets"])
     assert np.all(keys[1:] >= keys[:-1])                                             # sortedness
     # the sort is a permutation: order-independent checksums of (key, value) pairs agree
     mix = lambda k, val: int(np.bitwise_xor.reduce((k * np.uint64(0x9E3779B97F4A7C15)) ^ (val.astype(np.uint64) << np.uint64(7))))
