@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
 
     const int shift = 8 * pass;
     const uint32_t dmask = (end_bit - shift >= 8) ? 0xffu : ((1u << (end_bit - shift)) - 1u);
+    const int nbits = (end_bit - shift >= 8) ? 8 : (end_bit - shift);
 
     // warp-striped load: item i of lane l sits at warp_base + i*32 + l, so that
     // (i, lane) order == global order (stability)
@@ -275,8 +276,10 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
         if (!ok) peers = ~peers;
 #pragma unroll
         for (int bit = 0; bit < 8; bit++) {
-            const unsigned m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
-            peers &= ((d >> bit) & 1u) ? m : ~m;
+            if (bit < nbits) {   // the top pass of a sort usually has fewer than 8 digit bits (warp-uniform test)
+                const unsigned m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
+                peers &= ((d >> bit) & 1u) ? m : ~m;
+            }
         }
         int leader = __ffs(peers) - 1;
         uint32_t before = __popc(peers & lt_mask);

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
     __shared__ uint4 s_rec[RB * 9];
     __shared__ uint32_t s_face[RB];
     __shared__ int s_max[8];
+    __shared__ uint32_t s_gmask[8 * (RB / 32) * (32 / GL)];   // [warp][slice][group]: surviving instances
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane / GL, l = lane % GL;
     const int b = blockIdx.z;
@@ -396,8 +397,14 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
         }
         __syncthreads();
         const int cnt = min(RB, warp_last - c * RB);       // this warp's share of the chunk
-        for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0 && cnt > 0; c0 -= 32) {
-            // ---- cull: lane tests instance c0+lane against the sub-blocks
+        const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;      // 32-instance slices of it
+
+        // ---- cull: lane tests instance c0+lane against the sub-blocks; the survivors of every sub-block go to
+        //      shared memory as one bit mask per (slice, group).  Groups then walk the WHOLE staged chunk at their
+        //      own pace: when every group had to finish a 32-instance slice before any could start the next,
+        //      only ~55% of the groups had work in a SIMD pass (ncu: 14 of 32 lanes in the shading path).
+        for (int ch = 0; ch < nch; ch++) {
+            const int c0 = ch << 5;
             unsigned k4 = 0;   // bit s: instance may cover sub-block s
             {
                 const int jl = c0 + lane;
@@ -417,19 +424,26 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                 const int lim = group_last - (c * RB + c0);
                 if (lim < 32) mymask &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
             }
+            if (l == 0) s_gmask[(warp * (RB / 32) + ch) * (32 / GL) + g] = mymask;
+        }
+        __syncwarp();
 
+        int gch = nch - 1;                                                         // slice the group is working on
+        unsigned gm = nch > 0 ? s_gmask[(warp * (RB / 32) + gch) * (32 / GL) + g] : 0u;   // its remaining candidates
+        if (nch > 0) {
             for (;;) {
                 // ---- find: advance every group to its next instance with at least one covered pixel
                 bool have = false, cov = false;
                 int j = 0;
                 for (;;) {
-                    const bool searching = !have && mymask != 0u;
+                    while (!have && gm == 0u && gch > 0) { gch--; gm = s_gmask[(warp * (RB / 32) + gch) * (32 / GL) + g]; }
+                    const bool searching = !have && gm != 0u;
                     bool cj = false;
                     int jj = 0;
                     if (searching) {
-                        const int bit = 31 - __clz(mymask);
-                        mymask &= ~(1u << bit);
-                        jj = c0 + bit;
+                        const int bit = 31 - __clz(gm);
+                        gm &= ~(1u << bit);
+                        jj = (gch << 5) + bit;
                         const uint4 e0 = s_rec[jj * 9 + 0], e1 = s_rec[jj * 9 + 1], e2 = s_rec[jj * 9 + 2];
                         const uint32_t s0 = e0.x * px + e0.y * py + e0.z;
                         const uint32_t s1 = e1.x * px + e1.y * py + e1.z;
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                     }
                     const unsigned bal = __ballot_sync(0xffffffffu, cj);
                     if (searching && ((bal >> (lane & (32 - GL))) & ((1u << GL) - 1u))) { have = true; j = jj; cov = cj; }
-                    if (!__any_sync(0xffffffffu, !have && mymask != 0u)) break;
+                    if (!__any_sync(0xffffffffu, !have && (gm != 0u || gch > 0))) break;
                 }
                 if (!__any_sync(0xffffffffu, have)) break;
 
