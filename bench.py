@@ -289,16 +289,22 @@ def run_ours(args, ws, rank, local):
         return
     # ---- roofline of the dominant kernel
     P, F, px = int(s.verts.shape[0]), int(s.faces.shape[0]), s.H * s.W
-    npass = (32 + bit_length(vpr * ((s.W + 15) // 16) * ((s.H + 15) // 16)) + 7) // 8
-    alg = {   # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md), per rank (vpr views)
-        "preprocess_points": 32 * P * vpr, "preprocess_faces": (12 + 48 + 72 + 8 + 16 + 144) * F * vpr,
-        "scan": 8 * F * vpr, "duplicate_with_keys": (16 * F * vpr + 12 * R), "sort_histogram": 8 * R,
-        "tile_ranges": 8 * R + 8 * vpr * ((s.W + 15) // 16) * ((s.H + 15) // 16),
+    tiles = vpr * ((s.W + 15) // 16) * ((s.H + 15) // 16)
+    npass = (bit_length(tiles) + 7) // 8          # instance sort: tile bits only (two-level binning)
+    BF = F * vpr
+    alg = {   # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md 3), per rank (vpr views)
+        "preprocess_points": 32 * P * vpr, "preprocess_faces": (12 + 48 + 72 + 8 + 16 + 144) * BF,
+        "face_depth_sort": (4 + 4 * 16) * BF,      # histogram read + 4 eight-bit passes over (u32 key, u32 index) pairs
+        "scan": 12 * BF,                           # order + gathered tiles_touched read, offsets written
+        "duplicate_with_keys": 16 * BF + 8 * R,    # order, offsets, rect read; (u32 tile, u32 face) written
+        "sort_histogram": 4 * R,
+        "tile_ranges": 4 * R + 8 * tiles,
         "tri_render_forward": 132 * R + 28 * px * vpr,
         "tri_render_backward": 132 * R + 28 * px * vpr + 4 * (6 * P + F) + 4 * (P + F) * vpr,
+        "tri_grad_finish": (96 + 144) * BF + 4 * (6 * P + F) + 4 * (P + F) * vpr,
     }
     for i in range(8):
-        alg["sort_pass%d" % i] = 24 * R
+        alg["sort_pass%d" % i] = 16 * R
     dom = max(stage_ms, key=stage_ms.get)
     peak, peak_src = peaks()
     achieved = alg.get(dom, 0) / (stage_ms[dom] * 1e-3) / 1e9

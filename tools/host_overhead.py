@@ -49,3 +49,19 @@ for name, fn in [("_C direct fwd+bwd", direct), ("_C fwd only", fwd_only), ("2x 
     g, h = timeit(fn)
     gf, hf = timeit(fn, flush=True)
     print("%-22s gpu %.3f ms (host-side issue %.3f ms) | with L2 flush: gpu %.3f ms" % (name, g, h, gf))
+
+# ---- forward-only / backward-only through the public API
+st = {}
+def api_fwd():
+    st["o"] = r(verts, s.faces, vcol, fopa, s.mv_mats, s.proj_mats, vdep, fint)
+def api_bwd():
+    leaves.zero_(); vdep.grad = None; fint.grad = None
+    torch.autograd.backward(list(st["o"]), [gc, gd], retain_graph=True)
+def c_bwd():
+    o = st["c"]
+    _C.render_tris_backward(*a, gc, gd, o[0], o[3], o[4], o[5], o[6])
+st["c"] = _C.render_tris(*a, s.H, s.W)
+api_fwd()
+for name, fn in [("API fwd only", api_fwd), ("API bwd only", api_bwd), ("_C bwd only", c_bwd)]:
+    g, h = timeit(fn)
+    print("%-22s gpu %.3f ms (host-side issue %.3f ms)" % (name, g, h))
