@@ -9,7 +9,7 @@
 //   bin_faces / bin_instances   stage sequencing, see common.cuh
 //
 // All of them are HBM-bound; see DESIGN.md for the algorithmic bytes.
-#include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace dmr {
 
@@ -162,7 +162,7 @@ int inclusive_scan_u32(const uint32_t* in, const uint32_t* index, uint32_t* out,
 // ---------------------------------------------------------------------------
 struct DupFace { uint32_t x0, w, y0, tile0, fid; };
 
-__device__ __forceinline__ void emit_one(uint32_t o, uint32_t start, int nface, const uint32_t* s_incl, const uint2* s_rect,
+__device__ __forceinline__ uint32_t emit_one(uint32_t o, uint32_t start, int nface, const uint32_t* s_incl, const uint2* s_rect,
                                          const uint32_t* s_tile0, const uint32_t* s_fid, int tiles_x,
                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
 {
@@ -177,20 +177,25 @@ __device__ __forceinline__ void emit_one(uint32_t o, uint32_t start, int nface, 
     const uint2 r = s_rect[i];
     const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
     const uint32_t q = k / w;
-    keys[o] = (y0 + q) * (uint32_t)tiles_x + x0 + (k - q * w) + s_tile0[i];
+    const uint32_t key = (y0 + q) * (uint32_t)tiles_x + x0 + (k - q * w) + s_tile0[i];
+    keys[o] = key;
     vals[o] = s_fid[i];
+    return key;
 }
 
+template <bool HIST>   // HIST: accumulate the tile sort's histograms as a by-product (small inputs only)
 __global__ void __launch_bounds__(256) duplicate_kernel(
     size_t BF, int F, int tiles_x, int tiles_per_view, const uint32_t* __restrict__ order,
     const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
-    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, SortPre sp)
 {
     __shared__ uint32_t s_incl[256];
     __shared__ uint2 s_rect[256];
     __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance divisions hoisted)
     __shared__ uint32_t s_fid[256];     // face id inside its view
+    __shared__ uint32_t s_hist[HIST ? 4 * 256 : 1];   // digit histograms of the emitted tile ids (tile sort, radix_sort.cuh)
     const int tid = threadIdx.x;
+    if (HIST) for (int i = tid; i < 4 * 256; i += 256) s_hist[i] = 0;
     const size_t i0 = (size_t)blockIdx.x * 256;
     const size_t i = i0 + tid;          // position in the depth order
     const uint32_t start = (i0 == 0) ? 0u : offsets[i0 - 1];
@@ -210,36 +215,50 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
 
     // Each thread emits 4 consecutive instances per step: one binary search, then cheap "same face or
     // next face" advances; 4 keys / 4 values leave as two 16-byte stores, so a warp writes 2 x 512 B
-    // contiguous.  Head/tail elements that break 16-byte alignment go out scalar.
+    // contiguous.  Head/tail elements that break 16-byte alignment go out scalar.  All loops have
+    // block-uniform trip counts (the histogram update is a warp-collective).
     const uint32_t first4 = (start + 3u) & ~3u;                      // first 4-aligned output index of the block
-    for (uint32_t o = start + tid; o < min(first4, end); o += 256) emit_one(o, start, nface, s_incl, s_rect, s_tile0, s_fid, tiles_x, keys, vals);
-    for (uint32_t o4 = first4 + 4u * tid; o4 < end; o4 += 4u * 256u) {
-        if (o4 + 4u > end) {
-            for (uint32_t o = o4; o < end; o++) emit_one(o, start, nface, s_incl, s_rect, s_tile0, s_fid, tiles_x, keys, vals);
-            break;
-        }
-        int lo = 0, hi = nface - 1;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (s_incl[mid] > o4) hi = mid; else lo = mid + 1;
-        }
-        int j = lo;
-        uint32_t k[4], v[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const uint32_t o = o4 + e;
-            while (s_incl[j] <= o) j++;                               // skips faces with no instances
-            const uint32_t excl = (j == 0) ? start : s_incl[j - 1];
-            const uint32_t kk = o - excl;
-            const uint2 r = s_rect[j];
-            const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
-            const uint32_t q = kk / w;
-            k[e] = (y0 + q) * (uint32_t)tiles_x + x0 + (kk - q * w) + s_tile0[j];
-            v[e] = s_fid[j];
-        }
-        *reinterpret_cast<uint4*>(keys + o4) = make_uint4(k[0], k[1], k[2], k[3]);
-        *reinterpret_cast<uint4*>(vals + o4) = make_uint4(v[0], v[1], v[2], v[3]);
+    {   // head: at most 3 elements
+        const uint32_t o = start + tid;
+        const bool v[1] = { o < min(first4, end) };
+        uint32_t k[1] = { 0u };
+        if (v[0]) k[0] = emit_one(o, start, nface, s_incl, s_rect, s_tile0, s_fid, tiles_x, keys, vals);
+        if (HIST) rs_pre_add<1>(s_hist, k, v, sp);
     }
+    for (uint32_t base = first4; base < end; base += 4u * 256u) {
+        const uint32_t o4 = base + 4u * tid;
+        uint32_t k[4] = { 0u, 0u, 0u, 0u }, v[4];
+        bool ok[4] = { false, false, false, false };
+        if (o4 + 4u <= end) {
+            int lo = 0, hi = nface - 1;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (s_incl[mid] > o4) hi = mid; else lo = mid + 1;
+            }
+            int j = lo;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t o = o4 + e;
+                while (s_incl[j] <= o) j++;                               // skips faces with no instances
+                const uint32_t excl = (j == 0) ? start : s_incl[j - 1];
+                const uint32_t kk = o - excl;
+                const uint2 r = s_rect[j];
+                const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
+                const uint32_t q = kk / w;
+                k[e] = (y0 + q) * (uint32_t)tiles_x + x0 + (kk - q * w) + s_tile0[j];
+                v[e] = s_fid[j];
+                ok[e] = true;
+            }
+            *reinterpret_cast<uint4*>(keys + o4) = make_uint4(k[0], k[1], k[2], k[3]);
+            *reinterpret_cast<uint4*>(vals + o4) = make_uint4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (o4 + e < end) { k[e] = emit_one(o4 + e, start, nface, s_incl, s_rect, s_tile0, s_fid, tiles_x, keys, vals); ok[e] = true; }
+        }
+        if (HIST) rs_pre_add<4>(s_hist, k, ok, sp);
+    }
+    if (HIST) rs_pre_finish(s_hist, sp, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -292,17 +311,29 @@ template <typename T>
 const T* at(const void* base, size_t off) { return reinterpret_cast<const T*>(static_cast<const unsigned char*>(base) + off); }
 }  // namespace
 
+int bin_faces_begin(size_t BF, void* fb, const FaceBinLayout& L, SortPre* face_sort, cudaStream_t stream)
+{
+    if (BF == 0) return 0;
+    // scan descriptors and the face sort's control words are adjacent: one memset
+    const size_t zero = (L.fsort_temp - L.scan_state) + sort_zero_bytes(BF, 4, 32);
+    DMR_CUDA(cudaMemsetAsync(at<unsigned char>(fb, L.scan_state), 0, zero, stream));
+    // depth keys are non-negative floats: integer order == float order.  All 32 bits take part (the
+    // constant top byte of real scenes is skipped on the device by the sort's plan).
+    int rc = sort_pre_handle(at<void>(fb, L.fsort_temp), BF, 4, 32, face_sort);
+    if (BF > DMR_FUSED_FACE_HIST_MAX) face_sort->npass = 0;   // histogram + plan kernels of the sort itself
+    return rc;
+}
+
 int bin_faces(size_t BF, void* fb, const FaceBinLayout& L, int32_t* num_rendered_host, cudaStream_t stream)
 {
     if (BF == 0) { if (num_rendered_host) *num_rendered_host = 0; return 0; }
     int rc;
     {
-        // depth keys are non-negative floats: integer order == float order.  All 32 bits take part (the
-        // constant top byte of real scenes is skipped on the device by the sort's plan kernel).
         ProfScope prof(ST_FACE_SORT, stream);
         count_launch(-1);   // the scope counted one launch; the sort counts its own kernels
-        if ((rc = sort_pairs_u32(at<uint32_t>(fb, L.depth_key), nullptr, at<uint32_t>(fb, L.depth_sorted),
-                                 at<uint32_t>(fb, L.order), BF, 32, at<void>(fb, L.fsort_temp), false, stream)))
+        if ((rc = sort_pairs_u32_pre(at<uint32_t>(fb, L.depth_key), nullptr, at<uint32_t>(fb, L.depth_sorted),
+                                     at<uint32_t>(fb, L.order), BF, 32, at<void>(fb, L.fsort_temp), false,
+                                     BF <= DMR_FUSED_FACE_HIST_MAX, stream)))
             return rc;
     }
     return inclusive_scan_u32(at<uint32_t>(fb, L.tiles_touched), at<uint32_t>(fb, L.order), at<uint32_t>(fb, L.offsets),
@@ -322,16 +353,24 @@ int bin_instances(int B, int F, int W, int H, size_t R, const void* fb, const Fa
     uint32_t* vu = at<uint32_t>(binning_buffer, BL.vals_unsorted);
     uint32_t* ks = at<uint32_t>(binning_buffer, BL.keys_sorted);
     uint32_t* vs = at<uint32_t>(binning_buffer, BL.vals_sorted);
-    {
-        ProfScope prof(ST_DUPLICATE, stream);
-        duplicate_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(
-            BF, F, tx, tx * ty, at<uint32_t>(fb, L.order), at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu);
-        DMR_LAUNCH_CHECK("duplicate_kernel");
-    }
     // the bits above the depth word of the reference's key: rasterizer_impl.cu:316-324
     const int tile_bits = (int)higher_msb((uint32_t)tiles);
     int rc;
-    if ((rc = sort_pairs_u32(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, stream))) return rc;
+    SortPre sp;
+    const bool fused = R <= DMR_FUSED_TILE_HIST_MAX;
+    if ((rc = sort_pre_begin(at<void>(binning_buffer, BL.sort_temp), R, 4, tile_bits, &sp, stream))) return rc;
+    {
+        ProfScope prof(ST_DUPLICATE, stream);
+        const unsigned nblk = (unsigned)((BF + 255) / 256);
+        if (fused)
+            duplicate_kernel<true><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
+                                                            at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp);
+        else
+            duplicate_kernel<false><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
+                                                             at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp);
+        DMR_LAUNCH_CHECK("duplicate_kernel");
+    }
+    if ((rc = sort_pairs_u32_pre(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, fused, stream))) return rc;
     {
         ProfScope prof(ST_RANGES, stream);
         const size_t nthreads = (R + TR_KPT - 1) / TR_KPT;

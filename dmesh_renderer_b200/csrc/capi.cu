@@ -160,13 +160,14 @@ int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, c
     const size_t BF = (size_t)B * F;
     TriFaceLayout L = TriFaceLayout::make(BF);
     float4* vimg = static_cast<float4*>(point_buffer);
-    size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.bin.scan_state), 0, 4 * (ntile + 64), stream));
     int rc;
+    SortPre face_sort;
+    if ((rc = bin_faces_begin(BF, face_buffer, L.bin, &face_sort, stream))) return rc;
     if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, verts_depth, vimg, stream))) return rc;
     if ((rc = tri_preprocess_faces(B, P, F, W, H, faces, vimg, verts, verts_color, faces_opacity, faces_intense,
                                    at<uint32_t>(face_buffer, L.bin.tiles_touched), at<uint32_t>(face_buffer, L.bin.depth_key),
-                                   at<uint2>(face_buffer, L.bin.rect), at<TriRecord>(face_buffer, L.records), stream)))
+                                   at<uint2>(face_buffer, L.bin.rect), at<TriRecord>(face_buffer, L.records), face_sort,
+                                   stream)))
         return rc;
     return bin_faces(BF, face_buffer, L.bin, num_rendered_host, stream);
 }

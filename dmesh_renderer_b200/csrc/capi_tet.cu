@@ -58,13 +58,13 @@ int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* v
     const size_t BF = (size_t)B * F;
     TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
     float4* vimg = static_cast<float4*>(point_buffer);
-    size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-    DMR_CUDA(cudaMemsetAsync(at<uint32_t>(face_buffer, L.bin.scan_state), 0, 4 * (ntile + 64), stream));
     int rc;
+    SortPre face_sort;
+    if ((rc = bin_faces_begin(BF, face_buffer, L.bin, &face_sort, stream))) return rc;
     if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, nullptr, vimg, stream))) return rc;
     if ((rc = tet_preprocess_faces(B, P, F, W, H, faces, vimg, verts, at<uint32_t>(face_buffer, L.bin.tiles_touched),
                                    at<uint32_t>(face_buffer, L.bin.depth_key), at<uint2>(face_buffer, L.bin.rect),
-                                   at<TetFaceRec>(face_buffer, L.face_rec), stream)))
+                                   at<TetFaceRec>(face_buffer, L.face_rec), face_sort, stream)))
         return rc;
     if ((rc = bin_faces(BF, face_buffer, L.bin, num_rendered_host, stream))) return rc;
     // view-independent march records; independent of the scan, enqueued behind it

@@ -279,6 +279,16 @@ int inclusive_scan_u32(const uint32_t* in, const uint32_t* index, uint32_t* out,
 //                      the bit_length(tiles) tile bits -- 1-3 eight-bit passes over 8-byte pairs instead of
 //                      6-7 passes over 12-byte pairs; then the tile ranges.
 // Equal (tile, depth) pairs keep ascending b*F+f order in both formulations (stable sorts all the way).
+struct SortPre;
+// bin_faces_begin zeroes the scan / face-sort control words (one memset) and returns the handle the
+// face-preprocess kernel needs to accumulate the depth-key histograms as a by-product (radix_sort.cuh)
+int bin_faces_begin(size_t BF, void* face_buffer, const FaceBinLayout& L, SortPre* face_sort, cudaStream_t stream);
+// Above this many faces the by-product histogram costs more than it saves (every block of the face kernel
+// flushes up to 1024 bins with global atomics: +51 us at 4 M faces against a 20 us histogram kernel); below it
+// the two saved launches win (C1/C2: -15 us).
+#define DMR_FUSED_FACE_HIST_MAX (1u << 20)
+// same for the tile sort's histogram in duplicate_kernel (C4 with 8 views, R = 16.8 M: +209 us fused)
+#define DMR_FUSED_TILE_HIST_MAX (1u << 21)
 int bin_faces(size_t BF, void* face_buffer, const FaceBinLayout& L, int32_t* num_rendered_host, cudaStream_t stream);
 int bin_instances(int B, int F, int W, int H, size_t R, const void* face_buffer, const FaceBinLayout& L,
                   void* binning_buffer, uint2* ranges /* [B*tiles] */, cudaStream_t stream);

@@ -14,6 +14,7 @@
 // write of a block's 256 records is one contiguous 36 KB burst.
 #include "tri.cuh"
 #include "tet.cuh"
+#include "radix_sort.cuh"
 
 namespace dmr {
 
@@ -135,20 +136,27 @@ __device__ __forceinline__ void edge_setup(float2 p1, float2 p2, float2 p3, int 
 // algorithmic bytes per (b,f): read 12 (idx) + 3*16 (vimg) + 3*12 (pos) +
 // 3*12 (colour) + 4 + 4, write 4 + 4 + 8 + 144.
 // ---------------------------------------------------------------------------
+template <bool HIST>   // HIST: accumulate the face sort's histograms as a by-product (small inputs only)
 __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
     int B, int P, int F, int W, int H, int gx, int gy,
     const int* __restrict__ faces, const float4* __restrict__ vimg,
     const float* __restrict__ verts, const float* __restrict__ verts_color,
     const float* __restrict__ faces_opacity, const float* __restrict__ faces_intense,
     uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
-    TriRecord* __restrict__ records)
+    TriRecord* __restrict__ records, SortPre sp)
 {
     __shared__ uint4 s_rec[256 * 9];
+    __shared__ uint32_t s_hist[HIST ? 4 * 256 : 1];   // digit histograms of the depth keys for the face sort (radix_sort.cuh)
     const int tid = threadIdx.x;
+    if (HIST) {
+        for (int i = tid; i < 4 * 256; i += 256) s_hist[i] = 0;
+        __syncthreads();
+    }
     const size_t f0 = (size_t)blockIdx.x * 256;
     const int b = blockIdx.y;
     const size_t f = f0 + tid;
     const bool valid = f < (size_t)F;
+    uint32_t sort_key[1] = { 0u };
 
     if (valid) {
         int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
@@ -177,6 +185,7 @@ __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
         size_t bf = (size_t)b * F + f;
         tiles_touched[bf] = touched;
         depth_key[bf] = __float_as_uint(dk);
+        sort_key[0] = __float_as_uint(dk);
         rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
 
         uint32_t ea[3], eb[3], ec[3], flags;
@@ -205,20 +214,31 @@ __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
     size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
     uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
     for (size_t i = tid; i < nvalid * 9; i += 256) dst[i] = s_rec[i];
+    // by-product: digit histograms of the depth keys + (last block) the plan of the face sort
+    if (HIST) {
+        const bool sort_valid[1] = { valid };
+        rs_pre_add<1>(s_hist, sort_key, sort_valid, sp);
+        rs_pre_finish(s_hist, sp, gridDim.x * gridDim.y);
+    }
 }
 
 int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          const float* verts_color, const float* faces_opacity, const float* faces_intense,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TriRecord* records,
-                         cudaStream_t stream)
+                         const SortPre& sp, cudaStream_t stream)
 {
     if (B <= 0 || F <= 0) return 0;
     int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
     dim3 grid((F + 255) / 256, B);
     ProfScope prof(ST_FACES, stream);
-    tri_preprocess_faces_kernel<<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
-                                                         faces_opacity, faces_intense, tiles_touched, depth_key, rect,
-                                                         records);
+    if (sp.npass > 0)
+        tri_preprocess_faces_kernel<true><<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
+                                                                   faces_opacity, faces_intense, tiles_touched, depth_key,
+                                                                   rect, records, sp);
+    else
+        tri_preprocess_faces_kernel<false><<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
+                                                                    faces_opacity, faces_intense, tiles_touched, depth_key,
+                                                                    rect, records, sp);
     DMR_LAUNCH_CHECK("tri_preprocess_faces_kernel");
     return 0;
 }
@@ -229,17 +249,24 @@ int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
 // the world-space triangle plus min/max depth for firstIntersect.
 // algorithmic bytes per (b,f): read 12 + 3*16 + 3*12, write 4 + 4 + 8 + 64.
 // ---------------------------------------------------------------------------
+template <bool HIST>
 __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
     int B, int P, int F, int gx, int gy,
     const int* __restrict__ faces, const float4* __restrict__ vimg, const float* __restrict__ verts,
     uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
-    TetFaceRec* __restrict__ records)
+    TetFaceRec* __restrict__ records, SortPre sp)
 {
     __shared__ uint4 s_rec[256 * 4];
+    __shared__ uint32_t s_hist[HIST ? 4 * 256 : 1];   // digit histograms of the depth keys for the face sort (radix_sort.cuh)
     const int tid = threadIdx.x;
+    if (HIST) {
+        for (int i = tid; i < 4 * 256; i += 256) s_hist[i] = 0;
+        __syncthreads();
+    }
     const size_t f0 = (size_t)blockIdx.x * 256;
     const int b = blockIdx.y;
     const size_t f = f0 + tid;
+    uint32_t sort_key[1] = { 0u };
     if (f < (size_t)F) {
         int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
         const float4* vb = vimg + (size_t)b * P;
@@ -281,6 +308,7 @@ __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
         size_t bf = (size_t)b * F + f;
         tiles_touched[bf] = touched;
         depth_key[bf] = __float_as_uint(mn);
+        sort_key[0] = __float_as_uint(mn);
         rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
 
         const float* q0 = verts + 3 * (size_t)i0; const float* q1 = verts + 3 * (size_t)i1; const float* q2 = verts + 3 * (size_t)i2;
@@ -294,18 +322,27 @@ __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
     size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
     uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
     for (size_t i = tid; i < nvalid * 4; i += 256) dst[i] = s_rec[i];
+    if (HIST) {
+        const bool sort_valid[1] = { f < (size_t)F };
+        rs_pre_add<1>(s_hist, sort_key, sort_valid, sp);
+        rs_pre_finish(s_hist, sp, gridDim.x * gridDim.y);
+    }
 }
 
 int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
-                         cudaStream_t stream)
+                         const SortPre& sp, cudaStream_t stream)
 {
     if (B <= 0 || F <= 0) return 0;
     int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
     dim3 grid((F + 255) / 256, B);
     ProfScope prof(ST_FACES, stream);
-    tet_preprocess_faces_kernel<<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched, depth_key,
-                                                         rect, rec);
+    if (sp.npass > 0)
+        tet_preprocess_faces_kernel<true><<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched,
+                                                                   depth_key, rect, rec, sp);
+    else
+        tet_preprocess_faces_kernel<false><<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched,
+                                                                    depth_key, rect, rec, sp);
     DMR_LAUNCH_CHECK("tet_preprocess_faces_kernel");
     return 0;
 }

@@ -15,44 +15,36 @@
 //                      per-digit global prefix, scatter through shared memory so
 //                      global stores are coalesced per digit run.
 // Algorithmic bytes: 8 B/key (histogram) + 24 B/key per executed pass.
-#include "common.cuh"
-#include <cstdlib>
+#include "radix_sort.cuh"
 
 namespace dmr {
 
 #define RS_MIN_TILE 2048   // smallest tile of any configuration (sizes the descriptor array)
-#define RS_MAX_PASS 8
 #define RS_LB 16         // look-back descriptors fetched per step (see the stability note at the look-back)
 
 #define RS_FLAG_AGG  (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
 #define RS_VAL_MASK  ((1u << 30) - 1u)
 
-// control block living in the temp buffer (zeroed before every sort)
-struct SortCtl {
-    uint32_t ticket[RS_MAX_PASS];
-    uint32_t exec[RS_MAX_PASS];
-    uint32_t src[RS_MAX_PASS];   // 0 = input, 1 = output, 2 = temp
-    uint32_t dst[RS_MAX_PASS];
-};
-
-struct SortTempLayout {
-    size_t keys_tmp, vals_tmp, zero_begin, hist, ctl, desc, total;
+struct SortTempLayout {   // zeroed part first, so that a caller can merge the memset with a neighbouring one
+    size_t hist, ctl, desc, zero_end_base, keys_tmp, vals_tmp, total;
     size_t ntile;
     __host__ static SortTempLayout make(size_t n, size_t key_bytes)
     {
         SortTempLayout L;
         L.ntile = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
         size_t o = 0;
-        L.keys_tmp = o; o = align_up(o + key_bytes * n, 256);
-        L.vals_tmp = o; o = align_up(o + 4 * n, 256);
-        L.zero_begin = o;
         L.hist = o;     o = align_up(o + 4 * 256 * RS_MAX_PASS, 256);
         L.ctl = o;      o = align_up(o + sizeof(SortCtl), 256);
         L.desc = o;     o = align_up(o + 4 * 256 * L.ntile * RS_MAX_PASS, 256);
+        L.zero_end_base = o;
+        L.keys_tmp = o; o = align_up(o + key_bytes * n, 256);
+        L.vals_tmp = o; o = align_up(o + 4 * n, 256);
         L.total = o + 256;
         return L;
     }
+    // bytes from the start of the buffer that must be zero before a sort of npass passes
+    size_t zero_bytes(size_t n, int npass) const { return desc + 4 * 256 * ((n + 4095) / 4096) * (size_t)npass; }
 };
 
 size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n, 8).total; }
@@ -118,39 +110,7 @@ __global__ void __launch_bounds__(256) rs_plan_kernel(uint32_t* __restrict__ his
 {
     __shared__ uint32_t s_scan[256];
     __shared__ uint32_t s_skip[RS_MAX_PASS];
-    const int tid = threadIdx.x;
-    for (int p = 0; p < npass; p++) {
-        uint32_t c = hist[p * 256 + tid];
-        if (tid == 0) s_skip[p] = 0;
-        __syncthreads();
-        if ((size_t)c == n) s_skip[p] = 1;   // every key has the same digit -> identity pass
-        s_scan[tid] = c;
-        __syncthreads();
-        for (int d = 1; d < 256; d <<= 1) {
-            uint32_t t = (tid >= d) ? s_scan[tid - d] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
-        }
-        hist[p * 256 + tid] = s_scan[tid] - c;   // exclusive
-        __syncthreads();
-    }
-    if (tid == 0) {
-        int nexec = 0;
-        for (int p = 0; p < npass; p++) nexec += s_skip[p] ? 0 : 1;
-        if (nexec == 0) { s_skip[0] = 0; nexec = 1; }   // always move input -> output
-        int k = 0;
-        uint32_t cur = 0;   // where the data currently lives
-        for (int p = 0; p < npass; p++) {
-            if (s_skip[p]) { ctl->exec[p] = 0; continue; }
-            uint32_t dst = ((nexec - 1 - k) % 2 == 0) ? 1u : 2u;
-            ctl->exec[p] = 1;
-            ctl->src[p] = cur;
-            ctl->dst[p] = dst;
-            cur = dst;
-            k++;
-        }
-    }
+    rs_plan_block(hist, ctl, (uint32_t)n, npass, s_scan, s_skip);
 }
 
 // ---------------------------------------------------------------------------
@@ -172,8 +132,10 @@ struct RsBuffers {
 // after ranking), and the look-back only has to walk over the few predecessors that have not yet
 // published their inclusive prefix -- RS_LB descriptors are fetched per step so that walk costs one
 // L2 round trip per RS_LB tiles.
-template <typename KeyT, int RS_THREADS, int RS_KPT, int RS_MINB>
-__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n, int pass, int end_bit,
+// NBITS = digit bits of this pass (8 except for the top pass of a sort): a compile-time constant so that the
+// ranking loop is exactly NBITS ballots with no run-time tests.
+template <typename KeyT, int RS_THREADS, int RS_KPT, int RS_MINB, int NBITS>
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n, int pass,
                                                                           const uint32_t* __restrict__ hist_excl,
                                                                           SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
 {
@@ -204,8 +166,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     const uint32_t nvalid = (uint32_t)((n - tile_base < RS_TILE) ? (n - tile_base) : RS_TILE);
 
     const int shift = 8 * pass;
-    const uint32_t dmask = (end_bit - shift >= 8) ? 0xffu : ((1u << (end_bit - shift)) - 1u);
-    const int nbits = (end_bit - shift >= 8) ? 8 : (end_bit - shift);
+    constexpr uint32_t dmask = (1u << NBITS) - 1u;
 
     // warp-striped load: item i of lane l sits at warp_base + i*32 + l, so that
     // (i, lane) order == global order (stability)
@@ -275,11 +236,9 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
         unsigned peers = __ballot_sync(0xffffffffu, ok);
         if (!ok) peers = ~peers;
 #pragma unroll
-        for (int bit = 0; bit < 8; bit++) {
-            if (bit < nbits) {   // the top pass of a sort usually has fewer than 8 digit bits (warp-uniform test)
-                const unsigned m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
-                peers &= ((d >> bit) & 1u) ? m : ~m;
-            }
+        for (int bit = 0; bit < NBITS; bit++) {
+            const unsigned m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
+            peers &= ((d >> bit) & 1u) ? m : ~m;
         }
         int leader = __ffs(peers) - 1;
         uint32_t before = __popc(peers & lt_mask);
@@ -337,15 +296,23 @@ static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int 
 {
     constexpr size_t tile = (size_t)THREADS * KPT;
     constexpr size_t smem = sizeof(KeyT) * tile + 4 * tile + 4 * (THREADS / 32) * 256 + 4 * 256 + 4 * 256;
+    typedef void (*Kern)(RsBuffers<KeyT>, size_t, int, const uint32_t*, SortCtl*, uint32_t*);
+    static const Kern kern[8] = {
+        rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 1>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 2>,
+        rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 3>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 4>,
+        rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 5>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 6>,
+        rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 7>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 8> };
     static bool attr_set = false;
     if (!attr_set) {
-        DMR_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, THREADS, KPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int i = 0; i < 8; i++)
+            DMR_CUDA(cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const unsigned ntile = (unsigned)((n + tile - 1) / tile);
     for (int p = 0; p < npass; p++) {
+        const int nbits = (end_bit - 8 * p >= 8) ? 8 : (end_bit - 8 * p);
         if (profile) prof_begin(ST_SORT_PASS0 + p, stream); else count_launch(1);
-        rs_onesweep_kernel<KeyT, THREADS, KPT, MINB><<<ntile, THREADS, smem, stream>>>(buf, n, p, end_bit, hist, ctl, desc);
+        kern[nbits - 1]<<<ntile, THREADS, smem, stream>>>(buf, n, p, hist, ctl, desc);
         if (profile) prof_end(ST_SORT_PASS0 + p, stream);
         DMR_LAUNCH_CHECK("rs_onesweep_kernel");
     }
@@ -354,9 +321,11 @@ static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int 
 
 // profile == false: the kernels are counted but get no stage events of their own (the face sort is reported as
 // ONE stage by its caller; the per-kernel stages belong to the instance sort).
+// prehist == true: the producer of the keys has already zeroed the control region (sort_pre_begin), accumulated
+// the histograms and computed the plan (radix_sort.cuh); only the passes run here.
 template <typename KeyT>
 static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out, size_t n,
-                           int end_bit, void* temp, bool profile, cudaStream_t stream)
+                           int end_bit, void* temp, bool profile, int prehist /* 0 no, 1 yes, 2 zeroed only */, cudaStream_t stream)
 {
     if (n == 0) return 0;
     if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort_pairs: end_bit %d out of range", end_bit); return 1; }
@@ -368,60 +337,85 @@ static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* k
     SortCtl* ctl = reinterpret_cast<SortCtl*>(t + L.ctl);
     uint32_t* desc = reinterpret_cast<uint32_t*>(t + L.desc);
 
-    static int sm_count = 0, cfg = -1;
+    static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
-        const char* e = getenv("DMR_SORT_CFG");   // tuning knob for profiles/; the default is the measured best
-        cfg = e ? atoi(e) : 0;
     }
-    // tile size of the chosen configuration (descriptor rows actually used)
-    static const size_t tile_of[] = { 4096, 4096, 2048, 8192, 6144 };
-    const size_t tile = tile_of[(cfg >= 0 && cfg < 5) ? cfg : 0];
-    const size_t ntile = (n + tile - 1) / tile;
-    size_t zero_bytes = (L.desc - L.zero_begin) + 4 * 256 * ntile * (size_t)npass;
-    DMR_CUDA(cudaMemsetAsync(t + L.zero_begin, 0, zero_bytes, stream));
-
-    size_t hblocks = (n + 256 * RSH_KPT - 1) / (256 * RSH_KPT);
-    size_t hmax = (size_t)sm_count * 8;   // 8 resident CTAs per SM
-    if (hblocks > hmax) hblocks = hmax;
-    {
-        if (profile) prof_begin(ST_SORT_HIST, stream); else count_launch(1);
-        rs_hist_kernel<KeyT><<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
-        if (profile) prof_end(ST_SORT_HIST, stream);
-        DMR_LAUNCH_CHECK("rs_hist_kernel");
-    }
-    {
-        if (profile) prof_begin(ST_SORT_PLAN, stream); else count_launch(1);
-        rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
-        if (profile) prof_end(ST_SORT_PLAN, stream);
-        DMR_LAUNCH_CHECK("rs_plan_kernel");
+    // 512 threads x 8 keys, 2 CTAs/SM.  Measured alternatives (tools/bench_sort.py, 32 M 64-bit keys): 256x16,
+    // 256x8, 512x16 and 384x16 tiles all land within 3% of this one.
+    if (prehist != 1) {
+        if (prehist == 0) DMR_CUDA(cudaMemsetAsync(t, 0, L.zero_bytes(n, npass), stream));
+        size_t hblocks = (n + 256 * RSH_KPT - 1) / (256 * RSH_KPT);
+        size_t hmax = (size_t)sm_count * 8;   // 8 resident CTAs per SM
+        if (hblocks > hmax) hblocks = hmax;
+        {
+            if (profile) prof_begin(ST_SORT_HIST, stream); else count_launch(1);
+            rs_hist_kernel<KeyT><<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
+            if (profile) prof_end(ST_SORT_HIST, stream);
+            DMR_LAUNCH_CHECK("rs_hist_kernel");
+        }
+        {
+            if (profile) prof_begin(ST_SORT_PLAN, stream); else count_launch(1);
+            rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
+            if (profile) prof_end(ST_SORT_PLAN, stream);
+            DMR_LAUNCH_CHECK("rs_plan_kernel");
+        }
     }
     RsBuffers<KeyT> buf;
     buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
     buf.ktmp = reinterpret_cast<KeyT*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
-    switch (cfg) {
-    case 1:  return launch_onesweep<KeyT, 256, 16, 2>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
-    case 2:  return launch_onesweep<KeyT, 256, 8, 4>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
-    case 3:  return launch_onesweep<KeyT, 512, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
-    case 4:  return launch_onesweep<KeyT, 384, 16, 1>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
-    default: return launch_onesweep<KeyT, 512, 8, 2>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
-    }
+    return launch_onesweep<KeyT, 512, 8, 2>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
 }
 
 int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
                int end_bit, void* temp, cudaStream_t stream)
 {
-    return sort_pairs_impl<uint64_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, true, stream);
+    return sort_pairs_impl<uint64_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, true, 0, stream);
 }
 
 int sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
                    int end_bit, void* temp, bool profile, cudaStream_t stream)
 {
-    return sort_pairs_impl<uint32_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, profile, stream);
+    return sort_pairs_impl<uint32_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, profile, 0, stream);
+}
+
+// have_hist == false: the control region is already zero (the caller's memset) but nobody has built the
+// histograms: run the histogram + plan kernels here
+int sort_pairs_u32_pre(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
+                       int end_bit, void* temp, bool profile, bool have_hist, cudaStream_t stream)
+{
+    return sort_pairs_impl<uint32_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, profile, have_hist ? 1 : 2, stream);
+}
+
+size_t sort_zero_bytes(size_t n, size_t key_bytes, int end_bit)
+{
+    return SortTempLayout::make(n, key_bytes).zero_bytes(n, (end_bit + 7) / 8);
+}
+
+int sort_pre_handle(void* temp, size_t n, size_t key_bytes, int end_bit, SortPre* out)
+{
+    if (end_bit < 1 || end_bit > (int)(8 * key_bytes)) { set_error("sort: end_bit %d out of range", end_bit); return 1; }
+    if (n >= (1ull << 30)) { set_error("sort: n=%zu exceeds 2^30", n); return 3; }
+    SortTempLayout L = SortTempLayout::make(n, key_bytes);
+    unsigned char* t = static_cast<unsigned char*>(temp);
+    out->hist = reinterpret_cast<uint32_t*>(t + L.hist);
+    out->ctl = reinterpret_cast<SortCtl*>(t + L.ctl);
+    out->n = (uint32_t)n;
+    out->npass = (end_bit + 7) / 8;
+    out->end_bit = end_bit;
+    return 0;
+}
+
+int sort_pre_begin(void* temp, size_t n, size_t key_bytes, int end_bit, SortPre* out, cudaStream_t stream)
+{
+    int rc = sort_pre_handle(temp, n, key_bytes, end_bit, out);
+    if (rc) return rc;
+    DMR_CUDA(cudaMemsetAsync(temp, 0, sort_zero_bytes(n, key_bytes, end_bit), stream));
+    return 0;
 }
 
 }  // namespace dmr

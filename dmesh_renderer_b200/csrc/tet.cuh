@@ -1,6 +1,7 @@
 // tet.cuh -- records, workspace layouts and launch interface of the tet renderer.
 #pragma once
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace dmr {
 
@@ -138,7 +139,7 @@ int preprocess_points(int B, int P, int W, int H, const float* verts, const floa
                       const float* verts_depth, float4* vimg, cudaStream_t stream);
 int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
-                         cudaStream_t stream);
+                         const SortPre& face_sort, cudaStream_t stream);
 int tet_build_records(int P, int F, int T, const float* verts, const int* faces, const float* verts_color,
                       const float* faces_opacity, const int* tets, const int* face_tets, const int* tet_faces,
                       TetRec* tet_rec, TetShade* shade, cudaStream_t stream);

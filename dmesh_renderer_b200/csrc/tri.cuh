@@ -1,6 +1,7 @@
 // tri.cuh -- launch interface of the tri renderer's kernels.
 #pragma once
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace dmr {
 
@@ -31,7 +32,7 @@ struct TriRenderParams {
 int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          const float* verts_color, const float* faces_opacity, const float* faces_intense,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TriRecord* records,
-                         cudaStream_t stream);
+                         const SortPre& face_sort, cudaStream_t stream);
 int tri_render_forward(const TriRenderParams& p, cudaStream_t stream);
 int tri_render_backward(const TriRenderParams& p, cudaStream_t stream);
 
