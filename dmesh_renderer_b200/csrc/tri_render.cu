@@ -319,16 +319,21 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 // Smaller groups shade more different faces per SIMD pass (the triangles of these scenes cover a few
 // pixels of a 4x2 block) and need fewer shuffle steps; GL = 1 would need no shuffles at all but
 // 6 vector reductions per covered pixel, which the LSU/L2 cannot sustain (tools/ubench_red.cu).
+#ifndef DMR_TRI_BWD_MINB
+#define DMR_TRI_BWD_MINB 3
+#endif
 #ifndef DMR_TRI_BWD_GROUP_LANES
 #define DMR_TRI_BWD_GROUP_LANES 2
 #endif
 template <int GL>
-__global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams p)
+__global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(TriRenderParams p)
 {
     __shared__ uint4 s_rec[RB * 9];
     __shared__ uint32_t s_face[RB];
     __shared__ int s_max[8];
     __shared__ uint32_t s_gmask[8 * (RB / 32) * (32 / GL)];   // [warp][slice][group]: surviving instances
+    __shared__ int s_glast[8 * (32 / GL)];                    // [warp][group]: largest n_contrib of the group's pixels
+    __shared__ unsigned char s_cidx[8 * RB];                  // [warp][compacted position] -> position in the chunk
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane / GL, l = lane % GL;
     const int b = blockIdx.z;
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
 #pragma unroll
     for (int o = 16; o >= GL; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
     if (lane == 0) s_max[warp] = warp_last;
+    if (l == 0) s_glast[warp * (32 / GL) + g] = group_last;
     __syncthreads();
     int tile_last = 0;
 #pragma unroll
@@ -400,21 +406,43 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
         }
         __syncthreads();
         const int cnt = min(RB, warp_last - c * RB);       // this warp's share of the chunk
-        const int nch = cnt > 0 ? (cnt + 31) >> 5 : 0;      // 32-instance slices of it
 
-        // ---- cull: lane tests instance c0+lane against the sub-blocks; the survivors of every sub-block go to
-        //      shared memory as one bit mask per (slice, group).  Groups then walk the WHOLE staged chunk at their
-        //      own pace: when every group had to finish a 32-instance slice before any could start the next,
-        //      only ~55% of the groups had work in a SIMD pass (ncu: 14 of 32 lanes in the shading path).
+        // ---- cull, step 1: instances that can touch the warp's 8x4 block at all (3 edge minima per instance,
+        //      one lane per instance) are COMPACTED, in list order, into a per-warp index list.  A tile's
+        //      list holds every face that touches the 16x16 tile; ~1/3 of them reach a given 8x4 block, and
+        //      the exact 16-way sub-block test below (270 instructions per 32 instances) only runs on those.
+        int ncomp = 0;
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            const int jl = c0 + lane;
+            bool keep = false;
+            if (jl < cnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) s_cidx[warp * RB + ncomp + __popc(m & ((1u << lane) - 1u))] = (unsigned char)jl;
+            ncomp += __popc(m);
+        }
+        __syncwarp();
+        const int nch = (ncomp + 31) >> 5;      // 32-entry slices of the compacted list
+
+        // ---- cull, step 2: lane tests one compacted instance against the sub-blocks; the survivors of every
+        //      sub-block go to shared memory as one bit mask per (slice, group).  Groups then walk the WHOLE
+        //      staged chunk at their own pace: when every group had to finish a 32-instance slice before any
+        //      could start the next, only ~55% of the groups had work in a SIMD pass (ncu: 14 of 32 lanes in
+        //      the shading path).
         for (int ch = 0; ch < nch; ch++) {
-            const int c0 = ch << 5;
             unsigned k4 = 0;   // bit s: instance may cover sub-block s
             {
-                const int jl = c0 + lane;
-                if (jl < cnt) {
+                const int jc = (ch << 5) + lane;
+                if (jc < ncomp) {
+                    const int jl = s_cidx[warp * RB + jc];
                     if (GL == 8) k4 = subblock_cull(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
                     else if (GL == 4) k4 = subblock_cull8(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
                     else k4 = subblock_cull16(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
+                    // drop the sub-blocks whose pixels all stopped compositing before this list position
+                    const int pos = c * RB + jl;
+                    unsigned alive = 0;
+#pragma unroll
+                    for (int sb = 0; sb < 32 / GL; sb++) alive |= (s_glast[warp * (32 / GL) + sb] > pos ? 1u : 0u) << sb;
+                    k4 &= alive;
                 }
             }
             unsigned mymask = 0;
@@ -422,10 +450,6 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
             for (int sb = 0; sb < 32 / GL; sb++) {
                 const unsigned msb = __ballot_sync(0xffffffffu, k4 & (1u << sb));
                 if (g == sb) mymask = msb;
-            }
-            {   // drop list positions at or beyond this group's last contributor
-                const int lim = group_last - (c * RB + c0);
-                if (lim < 32) mymask &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
             }
             if (l == 0) s_gmask[(warp * (RB / 32) + ch) * (32 / GL) + g] = mymask;
         }
@@ -446,7 +470,7 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                     if (searching) {
                         const int bit = 31 - __clz(gm);
                         gm &= ~(1u << bit);
-                        jj = (gch << 5) + bit;
+                        jj = s_cidx[warp * RB + (gch << 5) + bit];   // compacted position -> position in the chunk
                         const uint4 e0 = s_rec[jj * 9 + 0], e1 = s_rec[jj * 9 + 1], e2 = s_rec[jj * 9 + 2];
                         const uint32_t s0 = e0.x * px + e0.y * py + e0.z;
                         const uint32_t s1 = e1.x * px + e1.y * py + e1.z;
@@ -570,9 +594,10 @@ __global__ void __launch_bounds__(256, 3) tri_render_bwd_kernel(TriRenderParams 
                     if (have) {
                         float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
                         const int cls = lane & 1;
-                        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
-                        if (v[6] != 0.0f || v[7] != 0.0f || v[8] != 0.0f || v[9] != 0.0f) red_add_v4(rec + 8 * cls + 4, v[6], v[7], v[8], v[9]);
-                        if (v[4] != 0.0f || v[5] != 0.0f || v[10] != 0.0f || v[11] != 0.0f) red_add_v4(rec + 16 + 4 * cls, v[4], v[5], v[10], v[11]);
+                        // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
+                        red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
+                        red_add_v4(rec + 8 * cls + 4, v[6], v[7], v[8], v[9]);
+                        red_add_v4(rec + 16 + 4 * cls, v[4], v[5], v[10], v[11]);
                     }
                 } else {
                     // 4 lanes: 24 -> 12 -> 6 values per lane; lane class = lane & 3 owns logical 6c..6c+5
