@@ -67,7 +67,9 @@ int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* v
                                    at<TetFaceRec>(face_buffer, L.face_rec), face_sort, stream)))
         return rc;
     if ((rc = bin_faces(BF, face_buffer, L.bin, num_rendered_host, stream))) return rc;
-    // view-independent march records; independent of the scan, enqueued behind it
+    // view-independent march records; independent of the scan, enqueued behind it.  (Measured and rejected:
+    // building them on a second stream concurrently with the binning chain -- the chain's preprocess and sort
+    // kernels are HBM-bound like the record builders, they just slow each other down: C3 forward 1.78 ms both ways.)
     if ((rc = tet_build_records(P, F, T, verts, faces, verts_color, faces_opacity, tets, face_tets, tet_faces,
                                 at<TetRec>(face_buffer, L.tet_rec), at<TetShade>(face_buffer, L.shade), stream)))
         return rc;
