@@ -130,7 +130,7 @@ int dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3])
     if (!out) { set_error("out is null"); return DMR_EINVAL; }
     if (!sizes_ok(B, P, F, W, H)) return DMR_ETOOLARGE;
     out[0] = align_up(sizeof(float4) * (size_t)B * P, 256) + 256;
-    out[1] = TriFaceLayout::make((size_t)B * F).total;
+    out[1] = TriFaceLayout::make((size_t)B * F, (size_t)P).total;
     out[2] = TriImageLayout::make(B, W, H).total;
     return DMR_OK;
 }
@@ -158,7 +158,7 @@ int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, c
     if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats || !verts_depth ||
         !faces_intense || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
     const size_t BF = (size_t)B * F;
-    TriFaceLayout L = TriFaceLayout::make(BF);
+    TriFaceLayout L = TriFaceLayout::make(BF, (size_t)P);
     float4* vimg = static_cast<float4*>(point_buffer);
     int rc;
     SortPre face_sort;
@@ -183,7 +183,7 @@ int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float
     if (!background || !inv_mv_mats || !inv_proj_mats || !image_buffer || !out_color || !out_depth ||
         (R > 0 && (!binning_buffer || !face_buffer))) { set_error("null pointer"); return DMR_EINVAL; }
     (void)point_buffer;
-    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
+    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F, (size_t)P);
     TriImageLayout IL = TriImageLayout::make(B, W, H);
     uint2* ranges = at<uint2>(image_buffer, IL.ranges);
     int rc = bin_instances(B, F, W, H, (size_t)R, face_buffer, FL.bin, binning_buffer, ranges, stream);
@@ -219,7 +219,7 @@ int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* back
         return DMR_EINVAL;
     }
     (void)point_buffer;
-    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
+    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F, (size_t)P);
     TriImageLayout IL = TriImageLayout::make(B, W, H);
     BinningLayout BL = BinningLayout::make((size_t)R);
     TriRenderParams p = {};
@@ -236,7 +236,10 @@ int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* back
     p.dL_dvdepth = dL_dvdepth; p.dL_dfintense = dL_dfintense;
     // backward scratch lives in the face buffer (opaque state owned by autograd ctx)
     p.grad_stats = const_cast<float*>(at<float>(face_buffer, FL.grad_stats));
-    DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (size_t)96 * B * F, stream));
+    // per-vertex vector accumulators only when there are at least two (view, face) records per vertex
+    const bool use_vacc = (size_t)B * F >= 2 * (size_t)P;
+    p.grad_vacc = use_vacc ? const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc)) : nullptr;
+    DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (use_vacc ? FL.grad_end : FL.grad_vacc) - FL.grad_stats, stream));
     return tri_render_backward(p, stream);
 }
 
@@ -255,7 +258,7 @@ int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, in
         off = kind == DMR_VIEW_KEYS_UNSORTED ? L.keys_unsorted : kind == DMR_VIEW_VALUES_UNSORTED ? L.vals_unsorted
             : kind == DMR_VIEW_KEYS_SORTED ? L.keys_sorted : L.vals_sorted;
     } else if (renderer == 0) {
-        TriFaceLayout FL = TriFaceLayout::make(BF);
+        TriFaceLayout FL = TriFaceLayout::make(BF, (size_t)P);
         TriImageLayout IL = TriImageLayout::make(B, W, H);
         switch (kind) {
         case DMR_VIEW_TILES_TOUCHED: off = FL.bin.tiles_touched; n = BF; break;

@@ -216,14 +216,17 @@ struct FaceBinLayout {
 
 struct TriFaceLayout {
     FaceBinLayout bin;
-    size_t records, grad_stats, total;
-    __host__ static TriFaceLayout make(size_t BF)
+    size_t records, grad_stats, grad_vacc, grad_end, total;
+    __host__ static TriFaceLayout make(size_t BF, size_t P)
     {
         TriFaceLayout L;
         L.bin = FaceBinLayout::make(BF);
         size_t o = L.bin.end;
         L.records = o;       o = align_up(o + sizeof(TriRecord) * BF, 256);
-        L.grad_stats = o;    o = align_up(o + 96 * BF, 256);   // backward scratch: 24 floats per (view, face)
+        // backward scratch, zeroed per call as one range [grad_stats, grad_end)
+        L.grad_stats = o;    o = align_up(o + 96 * BF, 256);   // 24 floats per (view, face)
+        L.grad_vacc = o;     o = align_up(o + 32 * P, 256);    // float4[2][P]: dL_dverts, dL_dvcolor (16-byte aligned for red.v4)
+        L.grad_end = o;
         L.total = o + 256;
         return L;
     }

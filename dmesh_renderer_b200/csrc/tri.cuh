@@ -27,6 +27,7 @@ struct TriRenderParams {
     float* dL_dvdepth;
     float* dL_dfintense;
     float* grad_stats;              // [B*F,24] zeroed scratch (face buffer)
+    float4* grad_vacc;              // [2][P] zeroed scratch: per-vertex dL_dverts / dL_dvcolor accumulators
 };
 
 int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,

@@ -647,16 +647,43 @@ __global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p)
     const float3 gE2 = cross3(T, S1) - cross3(E1, S24) + S3 * cross3(T, E1);
     const float3 gT = cross3(S1, E2) + S3 * cross3(E1, E2);
     const float3 dp[3] = { -gE1 - gE2 - gT, gE1, gE2 };
+    // The reference scatters 6 scalar atomics per vertex here (backward.cu:389-407); two 16-byte vector
+    // reductions into float4-per-vertex accumulators cost a third of the lane-operations
+    // (tri_grad_vertex_kernel folds them into dL_dverts / dL_dvcolor [P,3]).
+    // Used when there are many (view, face) records per vertex (multi-view batches, shared vertices): the
+    // accumulators cost 56 B of extra streaming per VERTEX (C4, 8 views: finish 705 -> 536 us; C5 with one
+    // view of 12 M unshared vertices: 92 -> 175 us, hence the switch in tri_render_backward).
+    if (p.grad_vacc) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        float* dv = p.dL_dverts + 3 * (size_t)vi[k];
-        atomicAdd(dv + 0, dp[k].x); atomicAdd(dv + 1, dp[k].y); atomicAdd(dv + 2, dp[k].z);
-        float* dc = p.dL_dvcolor + 3 * (size_t)vi[k];
-        atomicAdd(dc + 0, st[12 + 3 * k]); atomicAdd(dc + 1, st[13 + 3 * k]); atomicAdd(dc + 2, st[14 + 3 * k]);
-        atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+        for (int k = 0; k < 3; k++) {
+            red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi[k]), dp[k].x, dp[k].y, dp[k].z, 0.0f);
+            red_add_v4(reinterpret_cast<float*>(p.grad_vacc + (size_t)p.P + vi[k]), st[12 + 3 * k], st[13 + 3 * k], st[14 + 3 * k], 0.0f);
+            atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float* dv = p.dL_dverts + 3 * (size_t)vi[k];
+            atomicAdd(dv + 0, dp[k].x); atomicAdd(dv + 1, dp[k].y); atomicAdd(dv + 2, dp[k].z);
+            float* dc = p.dL_dvcolor + 3 * (size_t)vi[k];
+            atomicAdd(dc + 0, st[12 + 3 * k]); atomicAdd(dc + 1, st[13 + 3 * k]); atomicAdd(dc + 2, st[14 + 3 * k]);
+            atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+        }
     }
     atomicAdd(p.dL_dfopacity + f, st[7]);
     p.dL_dfintense[idx] = st[8];
+}
+
+// Once per vertex: float4 accumulators -> dL_dverts[P,3], dL_dvcolor[P,3].
+__global__ void __launch_bounds__(256) tri_grad_vertex_kernel(TriRenderParams p)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.P) return;
+    const float4 a = p.grad_vacc[v], c = p.grad_vacc[(size_t)p.P + v];
+    float* dv = p.dL_dverts + 3 * (size_t)v;
+    float* dc = p.dL_dvcolor + 3 * (size_t)v;
+    if (a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) { dv[0] += a.x; dv[1] += a.y; dv[2] += a.z; }
+    if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f) { dc[0] += c.x; dc[1] += c.y; dc[2] += c.z; }
 }
 
 int tri_render_forward(const TriRenderParams& p, cudaStream_t stream)
@@ -683,6 +710,11 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
         const size_t BF = (size_t)p.B * p.F;
         tri_grad_finish_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(p);
         DMR_LAUNCH_CHECK("tri_grad_finish_kernel");
+        if (p.grad_vacc) {
+            count_launch(1);   // two kernels under one scope
+            tri_grad_vertex_kernel<<<(unsigned)((p.P + 255) / 256), 256, 0, stream>>>(p);
+            DMR_LAUNCH_CHECK("tri_grad_vertex_kernel");
+        }
     }
     return 0;
 }

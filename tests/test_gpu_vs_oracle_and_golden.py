@@ -142,7 +142,9 @@ def edge_scene():
     return base._replace(verts=verts, faces=faces, faces_opacity=op, verts_depth=depth)
 
 
-@pytest.mark.parametrize("make", [edge_scene, lambda: scenes.random_tri_scene("mid", 5, 6000, 0.06, 176, 208, B=3)])
+@pytest.mark.parametrize("make", [edge_scene, lambda: scenes.random_tri_scene("mid", 5, 6000, 0.06, 176, 208, B=3),
+                                  # 8 views: B*F >= 2*P, the per-vertex vector accumulators of tri_grad_finish
+                                  lambda: scenes.random_tri_scene("mv8", 6, 2500, 0.07, 96, 112, B=8)])
 def test_tri_cuda_matches_oracle(make):
     cpu = make()
     s = scenes.to_device(cpu, "cuda")
