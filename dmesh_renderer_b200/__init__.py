@@ -46,11 +46,11 @@ class _RenderTri(th.autograd.Function):
             # Same computation as _C.render_tris(*13 args) (reference __init__.py:62-88), issued in two halves so
             # that the host-bound torch.inverse calls overlap the GPU's phase 1 (preprocess + scan).
             # depth in [-1, 1]: -1 near, 1 far
+            inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :62-63) minus its two device syncs
+            inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
             pending = _C.tri_forward_begin(render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats,
                                            proj_mats, verts_depth, faces_intense, render_settings.image_height,
                                            render_settings.image_width)
-            inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :62-63) minus its two device syncs
-            inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
             num_rendered, color, depth, pointBuffer, faceBuffer, binningBuffer, imgBuffer = \
                 _C.tri_forward_finish(pending, inv_mv_mats, inv_proj_mats, inv)
         except Exception as ex:

@@ -47,9 +47,9 @@ static_assert(sizeof(TetRec) == 128, "TetRec must be one 128-byte line");
 struct __align__(16) TetShade {
     float c0[3], c1[3], c2[3];   // vertex colours
     float opacity;
+    float log1m_opacity;         // logf(1 - opacity)      -- the first 48 bytes are all the forward march reads
     int i0, i1, i2;              // vertex ids (gradient scatter)
     int t0, t1;                  // face_tets[2f], face_tets[2f+1]
-    float log1m_opacity;         // logf(1 - opacity)
 };
 static_assert(sizeof(TetShade) == 64, "TetShade must be 4 x 16 bytes");
 

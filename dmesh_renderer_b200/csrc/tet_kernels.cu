@@ -175,11 +175,10 @@ __global__ void __launch_bounds__(256) tet_build_shade_kernel(
     uint4* o = reinterpret_cast<uint4*>(out + f);
     o[0] = make_uint4(__float_as_uint(c0.x), __float_as_uint(c0.y), __float_as_uint(c0.z), __float_as_uint(c1.x));
     o[1] = make_uint4(__float_as_uint(c1.y), __float_as_uint(c1.z), __float_as_uint(c2.x), __float_as_uint(c2.y));
-    o[2] = make_uint4(__float_as_uint(c2.z), __float_as_uint(faces_opacity[f]), a, b);
+    o[2] = make_uint4(__float_as_uint(c2.z), __float_as_uint(faces_opacity[f]), __float_as_uint(logf(1.0f - faces_opacity[f])), a);
     // log(1 - opacity) is a per-face constant of the march (forward.cu:636-642, backward.cu:272-279):
     // same logf on the same input, evaluated once per face instead of once per step
-    const float op = faces_opacity[f];
-    o[3] = make_uint4(c, face_tets[2 * (size_t)f], face_tets[2 * (size_t)f + 1], __float_as_uint(logf(1.0f - op)));
+    o[3] = make_uint4(b, c, face_tets[2 * (size_t)f], face_tets[2 * (size_t)f + 1]);
 }
 
 int tet_build_records(int P, int F, int T, const float* verts, const int* faces, const float* verts_color,
@@ -531,7 +530,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
         // is about to leave the mesh; its result is not used)
         const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
         const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2];
-        const float log1m = reinterpret_cast<const float*>(sh4)[15];
+        const float log1m = s2.z;
         const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
         const TetStep s = tet_step<true>(p, b, p.tet_rec + (curr_tet >= 0 ? curr_tet : 0), curr_face, ro, rd);
         // Trail entry: face id; bit 31 flags a tet in which a second side is hit with an inward normal.
@@ -629,7 +628,7 @@ __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st
 {
     const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
     const float opacity = s2.y;
-    const float log1m = s3.w;
+    const float log1m = s2.z;
 
     // backward.cu:252-270
     float i0 = 1.0f - iu - iv, i1 = iu, i2 = iv;
@@ -673,7 +672,7 @@ __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st
     const float g00 = i0 * dL_dcol[0] * intense, g01 = i0 * dL_dcol[1] * intense, g02 = i0 * dL_dcol[2] * intense;
     const float g10 = i1 * dL_dcol[0] * intense, g11 = i1 * dL_dcol[1] * intense, g12 = i1 * dL_dcol[2] * intense;
     const float g20 = i2 * dL_dcol[0] * intense, g21 = i2 * dL_dcol[1] * intense, g22 = i2 * dL_dcol[2] * intense;
-    const int vi0 = __float_as_int(s2.z), vi1 = __float_as_int(s2.w), vi2 = __float_as_int(s3.x);
+    const int vi0 = __float_as_int(s2.w), vi1 = __float_as_int(s3.x), vi2 = __float_as_int(s3.y);
     red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi0), g00, g01, g02, 0.0f);
     red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi1), g10, g11, g12, 0.0f);
     red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi2), g20, g21, g22, 0.0f);
