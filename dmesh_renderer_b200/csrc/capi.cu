@@ -125,6 +125,20 @@ int dmr_profile_read(float* ms_out)
     return DMR_OK;
 }
 
+int dmr_wait_i32(volatile int32_t* host_value, int32_t sentinel, dmr_stream_t stream_)
+{
+    // Spin on the pinned word (the D2H copy of num_rendered lands a few microseconds before a
+    // cudaStreamSynchronize would return); after ~2 s fall back to the stream synchronisation, which also
+    // reports a faulted stream instead of spinning forever.
+    if (!host_value) { set_error("host_value is null"); return DMR_EINVAL; }
+    for (long long spin = 0; spin < 2000000000LL; spin++) {
+        if (*host_value != sentinel) return DMR_OK;
+        if ((spin & 0xffff) == 0xffff && cudaStreamQuery((cudaStream_t)stream_) != cudaErrorNotReady) break;
+    }
+    DMR_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+    return DMR_OK;
+}
+
 int dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3])
 {
     if (!out) { set_error("out is null"); return DMR_EINVAL; }

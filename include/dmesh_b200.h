@@ -54,6 +54,14 @@ int    dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[
 /* Replaces required<BinningState>(R): rasterizer_impl.cu:297-299.           */
 size_t dmr_binning_bytes(size_t R);
 
+/* Host-side wait for the num_rendered read-back of *_forward_bin: the caller  */
+/* stores `sentinel` (a value num_rendered cannot take, e.g. INT32_MIN) in the  */
+/* pinned word before calling *_forward_bin and waits here until the copy has  */
+/* overwritten it.  Replaces the blocking 4-byte cudaMemcpy + device sync of   */
+/* rasterizer_impl.cu:287-292 / renderer_impl.cu:305-310 with a spin on the    */
+/* pinned word (falls back to cudaStreamSynchronize(stream)).                  */
+int dmr_wait_i32(volatile int32_t* host_value, int32_t sentinel, dmr_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* Tri renderer, forward, phase 1: preprocess + per-face records + scan.     */
 /* Replaces stages T1-T4 of CudaRasterizer::Rasterizer::forward              */
