@@ -236,18 +236,30 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
                 if (s_incl[mid] > o4) hi = mid; else lo = mid + 1;
             }
             int j = lo;
+            while (s_incl[j] <= o4) j++;                                  // skips faces with no instances
+            // first instance: position inside its face's rectangle by one division; the next three advance
+            // incrementally (next column, next row, or the first tile of the next face that has instances)
+            uint2 r = s_rect[j];
+            uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
+            uint32_t kk = o4 - ((j == 0) ? start : s_incl[j - 1]);
+            uint32_t row = kk / w, col = kk - row * w;
+            uint32_t fend = s_incl[j], base_t = s_tile0[j] + x0, fid = s_fid[j];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-                const uint32_t o = o4 + e;
-                while (s_incl[j] <= o) j++;                               // skips faces with no instances
-                const uint32_t excl = (j == 0) ? start : s_incl[j - 1];
-                const uint32_t kk = o - excl;
-                const uint2 r = s_rect[j];
-                const uint32_t x0 = r.x & 0xffffu, w = (r.x >> 16) - x0, y0 = r.y & 0xffffu;
-                const uint32_t q = kk / w;
-                k[e] = (y0 + q) * (uint32_t)tiles_x + x0 + (kk - q * w) + s_tile0[j];
-                v[e] = s_fid[j];
+                k[e] = (y0 + row) * (uint32_t)tiles_x + base_t + col;
+                v[e] = fid;
                 ok[e] = true;
+                if (e < 3) {
+                    if (o4 + e + 1 < fend) {
+                        if (++col == w) { col = 0; row++; }
+                    } else {
+                        do { j++; } while (s_incl[j] <= o4 + e + 1);
+                        r = s_rect[j];
+                        x0 = r.x & 0xffffu; w = (r.x >> 16) - x0; y0 = r.y & 0xffffu;
+                        row = 0; col = 0;
+                        fend = s_incl[j]; base_t = s_tile0[j] + x0; fid = s_fid[j];
+                    }
+                }
             }
             *reinterpret_cast<uint4*>(keys + o4) = make_uint4(k[0], k[1], k[2], k[3]);
             *reinterpret_cast<uint4*>(vals + o4) = make_uint4(v[0], v[1], v[2], v[3]);
