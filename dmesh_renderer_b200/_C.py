@@ -56,7 +56,8 @@ class _Pinned:
     def get(cls, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in cls._slots:
-            cls._slots[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+            t = torch.zeros(1, dtype=torch.int32).pin_memory()
+            cls._slots[key] = (t, t.numpy(), ctypes.c_void_p(t.data_ptr()))   # tensor, numpy view (cheap host reads), pointer
         return cls._slots[key]
 
 
@@ -69,7 +70,7 @@ _last_R = {}                  # (renderer, B, P, F, T, W, H) -> num_rendered of 
 
 
 def _arm(pinned):
-    pinned[0] = _SENTINEL
+    pinned[1][0] = _SENTINEL
 
 
 def _speculative_binning(lib, key, u8):
@@ -85,8 +86,8 @@ def _speculative_binning(lib, key, u8):
 def _wait_R(lib, pinned, key, spec, u8):
     """The one host<->device synchronisation of a forward call (rasterizer_impl.cu:287-292): wait for
     num_rendered, return (R, binning buffer)."""
-    _lib.check(lib.dmr_wait_i32(ctypes.c_void_p(pinned.data_ptr()), _SENTINEL, _stream()))
-    R = int(pinned[0])
+    _lib.check(lib.dmr_wait_i32(pinned[2], _SENTINEL, _stream()))
+    R = int(pinned[1][0])
     _last_R[key] = R
     need = lib.dmr_binning_bytes(R) if R > 0 else 0
     if spec is not None and spec.numel() >= need:
@@ -105,7 +106,9 @@ class _InverseGraph:
     def __init__(self, dev, B):
         self.inp = torch.empty((2, B, 4, 4), dtype=torch.float32, device=dev)
         self.inp.copy_(torch.eye(4, device=dev).expand(2, B, 4, 4))
-        side = torch.cuda.Stream(device=dev)
+        self.host = torch.zeros(2 * B, dtype=torch.int32).pin_memory()
+        self.host_np = self.host.numpy()
+        side = self.side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):   # warm-up outside the capture (library handles, workspaces)
@@ -132,9 +135,15 @@ class _InverseGraph:
         return g or None
 
     def run(self, mv_mats, proj_mats):
+        """Replay on the caller's stream.  (Measured and rejected: replaying on a side stream so that the ~25 tiny
+        LU kernels, ~90 us back to back, run concurrently with phase 1 -- the host is the bottleneck in that
+        window: the extra stream bookkeeping delayed the phase-1 launches by more than the overlap gained,
+        1013 vs 949 us per step.  On one stream the GPU runs the inverses while the host prepares phase 1.)"""
         torch.stack([mv_mats, proj_mats], out=self.inp)
         self.graph.replay()
-        return self.out.clone(), self.info
+        out = self.out.clone()
+        self.host.copy_(self.info, non_blocking=True)
+        return out, None
 
 
 class _Inverses:
@@ -144,12 +153,13 @@ class _Inverses:
     and replayed from a CUDA graph (see _InverseGraph).  The info vector is copied to pinned memory
     asynchronously and examined after the synchronisation the forward call needs anyway (num_rendered);
     a singular matrix raises the same error, through torch.inverse itself."""
-    __slots__ = ("inv_mv", "inv_proj", "mats", "host")
+    __slots__ = ("inv_mv", "inv_proj", "mats", "host_np", "event")
     _pinned = {}
 
     def __init__(self, mv_mats, proj_mats):
         self.mats = (mv_mats, proj_mats)
-        self.host = None
+        self.host_np = None
+        self.event = None
         graphable = (mv_mats.is_cuda and proj_mats.is_cuda and mv_mats.dtype == torch.float32 and
                      proj_mats.dtype == torch.float32 and mv_mats.dim() == 3 and mv_mats.shape == proj_mats.shape and
                      tuple(mv_mats.shape[1:]) == (4, 4) and 0 < mv_mats.size(0) <= 4096 and
@@ -157,12 +167,13 @@ class _Inverses:
         g = _InverseGraph.get(mv_mats.device, mv_mats.size(0)) if graphable else None
         if g is not None:
             with torch.cuda.device(mv_mats.device):
-                out, info = g.run(mv_mats, proj_mats)
+                out, self.event = g.run(mv_mats, proj_mats)
             self.inv_mv, self.inv_proj = out[0], out[1]
-        else:
-            self.inv_mv, info_mv = torch.linalg.inv_ex(mv_mats)
-            self.inv_proj, info_pj = torch.linalg.inv_ex(proj_mats)
-            info = torch.cat([info_mv.reshape(-1), info_pj.reshape(-1)])
+            self.host_np = g.host_np
+            return
+        self.inv_mv, info_mv = torch.linalg.inv_ex(mv_mats)
+        self.inv_proj, info_pj = torch.linalg.inv_ex(proj_mats)
+        info = torch.cat([info_mv.reshape(-1), info_pj.reshape(-1)])
         if mv_mats.is_cuda:
             n = info.numel()
             key = (mv_mats.device.index, n)
@@ -171,13 +182,23 @@ class _Inverses:
                 host = _Inverses._pinned[key] = torch.zeros(max(n, 1), dtype=torch.int32).pin_memory()
             if n:
                 host[:n].copy_(info, non_blocking=True)
-            self.host = host[:n]
+            self.host_np = host[:n].numpy()
         else:
             self.check(info)
 
+    def join(self):
+        """Make the current stream wait for the inverses (no-op when they were computed on it)."""
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+
     def check(self, *infos):
-        """Call after the stream has been synchronised."""
-        bad = any(bool(i.any()) for i in infos) if infos else (self.host is not None and bool(self.host.any()))
+        """Call after the current stream has been synchronised (and join() has been issued)."""
+        if infos:
+            bad = any(bool(i.any()) for i in infos)
+        else:
+            if self.event is not None:
+                self.event.synchronize()      # long complete; makes the pinned info words valid
+            bad = self.host_np is not None and bool(self.host_np.any())
         if bad:
             torch.inverse(self.mats[0])   # raises torch's own "singular matrix" error
             torch.inverse(self.mats[1])
@@ -254,7 +275,7 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
         _arm(st.pinned)
         _lib.check(lib.dmr_tri_forward_bin(B, P, F, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa), _ptr(mv),
                                            _ptr(pj), _ptr(vdep), _ptr(fint), _ptr(st.bufs[0]), _ptr(st.bufs[1]),
-                                           ctypes.c_void_p(st.pinned.data_ptr()), _stream()))
+                                           st.pinned[2], _stream()))
     return st
 
 
@@ -273,6 +294,7 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
             # render.cu:88-89,105: zero images (not background), empty state
             z = torch.zeros
             if inverses is not None:
+                inverses.join()
                 torch.cuda.current_stream().synchronize()
                 inverses.check()
             return (0, z((B, NUM_CHANNELS, H, W), dtype=torch.float32, device=dev),
@@ -282,14 +304,17 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
         imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
         key = ("tri", B, P, F, 0, W, H)
         spec = _speculative_binning(lib, key, u8)
-        R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
-        if inverses is not None:
-            inverses.check()
         point_buf, face_buf, img_buf = st.bufs
         out_color, out_depth = st.outs
-        _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, _ptr(st.bg), _ptr(imv), _ptr(ipj), _ptr(point_buf),
-                                              _ptr(face_buf), _ptr(bin_buf), _ptr(img_buf), _ptr(out_color),
-                                              _ptr(out_depth), _stream()))
+        # everything that does not depend on R is prepared before the wait
+        a = (_ptr(st.bg), _ptr(imv), _ptr(ipj), _ptr(point_buf), _ptr(face_buf))
+        b2 = (_ptr(img_buf), _ptr(out_color), _ptr(out_depth), _stream())
+        if inverses is not None:
+            inverses.join()
+        R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
+        _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, *a, _ptr(bin_buf), *b2))
+        if inverses is not None:
+            inverses.check()
     return R, out_color, out_depth, point_buf, face_buf, bin_buf, img_buf
 
 
@@ -325,20 +350,21 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
             offs.append(o)
             o += (n + 3) // 4 * 4
         flat = torch.zeros(max(o, 1), dtype=torch.float32, device=dev)
-        dL_dverts = flat[offs[0]:offs[0] + sizes[0]].view(P, 3)
-        dL_dvcolor = flat[offs[1]:offs[1] + sizes[1]].view(P, NUM_CHANNELS)
-        dL_dfopacity = flat[offs[2]:offs[2] + sizes[2]]
-        dL_dvdepth = flat[offs[3]:offs[3] + sizes[3]].view(B, P)
-        dL_dfintense = flat[offs[4]:offs[4] + sizes[4]].view(B, F)
         if F != 0 and P != 0 and R > 0:
             _require_cuda(dL_dout_color, dL_dout_depth)
             bg = _f32(background, "background")
             imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
             gc, gd = _f32(dL_dout_color, "dL_dout_color"), _f32(dL_dout_depth, "dL_dout_depth")
+            base = flat.data_ptr()   # the kernels are enqueued before the five views below are even created
+            gp = [ctypes.c_void_p(base + 4 * off) for off in offs]
             _lib.check(lib.dmr_tri_backward(B, P, F, W, H, int(R), _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(pointBuffer),
                                             _ptr(faceBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd),
-                                            _ptr(dL_dverts), _ptr(dL_dvcolor), _ptr(dL_dfopacity), _ptr(dL_dvdepth),
-                                            _ptr(dL_dfintense), _stream()))
+                                            gp[0], gp[1], gp[2], gp[3], gp[4], _stream()))
+        dL_dverts = flat[offs[0]:offs[0] + sizes[0]].view(P, 3)
+        dL_dvcolor = flat[offs[1]:offs[1] + sizes[1]].view(P, NUM_CHANNELS)
+        dL_dfopacity = flat[offs[2]:offs[2] + sizes[2]]
+        dL_dvdepth = flat[offs[3]:offs[3] + sizes[3]].view(B, P)
+        dL_dfintense = flat[offs[4]:offs[4] + sizes[4]].view(B, F)
     return dL_dverts, dL_dvcolor, dL_dfopacity, dL_dvdepth, dL_dfintense
 
 
@@ -397,9 +423,11 @@ def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, p
         stream = _stream()
         _lib.check(lib.dmr_tet_forward_bin(B, P, F, T, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa),
                                            _ptr(mv), _ptr(pj), _ptr(tets_c), _ptr(ft_c), _ptr(tf_c), _ptr(point_buf),
-                                           _ptr(face_buf), ctypes.c_void_p(pinned.data_ptr()), stream))
+                                           _ptr(face_buf), pinned[2], stream))
         key = ("tet", B, P, F, T, W, H)
         spec = _speculative_binning(lib, key, u8)
+        if inverses is not None:
+            inverses.join()
         R, bin_buf = _wait_R(lib, pinned, key, spec, u8)
         if inverses is not None:
             inverses.check()
