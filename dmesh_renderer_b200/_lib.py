@@ -33,6 +33,7 @@ SIGNATURES = {
     "dmr_debug_view": (c_int, [c_int] * 8 + [c_size_t, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t)]),
     "dmr_launch_count": (ctypes.c_ulonglong, []),
     "dmr_debug_set_tet_trail_cap": (c_int, [c_int]),
+    "dmr_debug_set_tet_first_split": (c_int, [c_int]),
     "dmr_profile_enable": (c_int, [c_int]),
     "dmr_profile_stage_count": (c_int, []),
     "dmr_profile_stage_name": (ctypes.c_char_p, [c_int]),

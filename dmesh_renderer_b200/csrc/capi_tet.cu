@@ -8,6 +8,7 @@
 using namespace dmr;
 
 namespace dmr { int g_tet_trail_cap_override = 0; }
+static int g_tet_first_split_override = 0;
 
 namespace {
 
@@ -102,6 +103,16 @@ static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, 
     p.active = at<uint8_t>(ib, IL.active);
     p.trail = at<int>(ib, IL.trail);
     p.trail_cap = (int)IL.trail_cap;
+    p.fi_key = at<unsigned long long>(ib, IL.fi_key);
+    p.fi_close = reinterpret_cast<uint32_t*>(p.fi_key + (size_t)B * W * H);
+    // CTAs per tile of the first-intersection search.  Measured at C3 (1024 tiles): 1 -> 259 us, 2 -> 200 us,
+    // 4 -> 275 us, 8 -> 433 us: two CTAs halve the chain of the silhouette tiles; more of them only repeat, for
+    // every interior tile, rounds a single CTA would have skipped after its first hits.
+    {
+        const size_t tiles = (size_t)B * ((W + DMR_TILE - 1) / DMR_TILE) * ((H + DMR_TILE - 1) / DMR_TILE);
+        p.fi_split = tiles <= 4096 ? 2 : 1;
+        if (g_tet_first_split_override > 0) p.fi_split = g_tet_first_split_override;
+    }
 }
 
 int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int ray_random_seed,
@@ -160,6 +171,12 @@ int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_se
     p.grad_vacc = const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc));
     DMR_CUDA(cudaMemsetAsync(p.grad_vacc, 0, sizeof(float4) * (size_t)P, stream));
     return tet_march_backward(p, stream);
+}
+
+int dmr_debug_set_tet_first_split(int split)
+{
+    g_tet_first_split_override = (split > 0 && split <= 16) ? split : 0;
+    return DMR_OK;
 }
 
 int dmr_debug_set_tet_trail_cap(int cap)

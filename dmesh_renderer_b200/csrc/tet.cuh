@@ -87,7 +87,7 @@ __host__ inline size_t tet_trail_cap(size_t BI)
 }
 
 struct TetImageLayout {
-    size_t n_contrib, ranges, final_log_T, prev_log_T, first_face, first_tet, last_face, last_tet, active, jitter, trail, trail_cap, total;
+    size_t n_contrib, ranges, final_log_T, prev_log_T, first_face, first_tet, last_face, last_tet, active, jitter, fi_key, trail, trail_cap, total;
     __host__ static TetImageLayout make(size_t B, size_t W, size_t H)
     {
         TetImageLayout L;
@@ -104,6 +104,9 @@ struct TetImageLayout {
         L.last_tet = o;    o = align_up(o + 4 * BI, 256);
         L.active = o;      o = align_up(o + BI, 256);
         L.jitter = o;      o = align_up(o + 8 * BI, 256);   // float2 pixel coordinate, written only when seed > 0
+        // first-intersect partial results: u64 (t bits << 32 | list position) per pixel, directly followed by
+        // u32 max-depth bits per pixel (one memset)
+        L.fi_key = o;      o = align_up(o + 12 * BI, 256);
         L.trail_cap = tet_trail_cap(BI);
         L.trail = o;       o = align_up(o + 4 * BI * L.trail_cap, 256);
         L.total = o + 256;
@@ -127,6 +130,9 @@ struct TetParams {
     int* first_face; int* first_tet; int* last_face; int* last_tet;
     float* final_log_T; float* prev_log_T; uint32_t* n_contrib; uint8_t* active;
     int* trail; int trail_cap;    // [trail_cap][B*W*H] face ids in march order
+    unsigned long long* fi_key;   // [B*W*H] split first-intersect: per-pixel atomicMin slot
+    uint32_t* fi_close;           // [B*W*H] smallest max depth (float bits) of any hit found so far
+    int fi_split;                 // CTAs per tile in tet_first_intersect_kernel
     // outputs
     float* out_color; float* out_depth; float* out_active;
     // backward

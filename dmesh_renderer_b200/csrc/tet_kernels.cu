@@ -240,6 +240,7 @@ __device__ __forceinline__ void tet_pixel_ray(const TetParams& p, int b, uint32_
 // first intersection: per tile, faces sorted by min depth
 // ---------------------------------------------------------------------------
 #define FI_THREADS 256
+__device__ __forceinline__ void tet_first_finish(const TetParams& p, int b, size_t bpix, int first_face, float3 rd);
 
 // Face-parallel search.  One CTA per 16x16 tile; per round 256 instances of the tile list are staged
 // (one per thread) and EVERY THREAD TAKES ONE FACE: it walks the pixels of the face's screen bounding
@@ -272,8 +273,13 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
     __shared__ uint32_t s_open[DMR_TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
-    const uint32_t tx0 = blockIdx.x * DMR_TILE, ty0 = blockIdx.y * DMR_TILE;
+    // fi_split CTAs share a tile: CTA `part` takes rounds part, part + fi_split, ... of the tile list and the
+    // partial results meet in a global 64-bit atomicMin per pixel (tet_first_resolve_kernel turns the winner
+    // into first_face / first_tet).  The kernel's duration is the longest tile list (a few hundred silhouette
+    // tiles at C3); splitting it shortens exactly that chain.
+    const int split = p.fi_split, part = (int)(blockIdx.x % (unsigned)split), tile_x = (int)(blockIdx.x / (unsigned)split);
+    const int tiles_x = (int)(gridDim.x / (unsigned)split), tiles_y = gridDim.y;
+    const uint32_t tx0 = tile_x * DMR_TILE, ty0 = blockIdx.y * DMR_TILE;
     const uint32_t px = tx0 + (tid & 15);
     const uint32_t py = ty0 + (tid >> 4);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
@@ -285,12 +291,13 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
     s_rd[tid] = make_float4(rd.x, rd.y, rd.z, 0.0f);
     ro = f3(p.inv_mv[16 * b + 12], p.inv_mv[16 * b + 13], p.inv_mv[16 * b + 14]);
 
-    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + blockIdx.y * tiles_x + blockIdx.x];
+    const uint2 range = p.ranges[(size_t)b * tiles_x * tiles_y + blockIdx.y * tiles_x + tile_x];
     const int total = (int)(range.y - range.x);
     const int rounds = (total + FI_THREADS - 1) / FI_THREADS;
 
     float min_T = -1.0f, min_T_max_depth = -1.0f;
     int first_face = -1;
+    uint32_t first_pos = 0;     // list position of the best hit (split mode)
     bool closed = !inside;
 
     // register-staged prefetch of the next round
@@ -306,9 +313,9 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
             nby = src[3].x;
         }
     };
-    fetch(0);
+    fetch(part);
 
-    for (int r = 0; r < rounds; r++) {
+    for (int r = part; r < rounds; r += split) {
         s_rec[tid * 3 + 0] = n0; s_rec[tid * 3 + 1] = n1; s_rec[tid * 3 + 2] = n2;
         s_bby[tid] = nby;
         s_face[tid] = nface;
@@ -316,12 +323,15 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
         __syncthreads();
         // forward.cu:388-391 at round granularity: nothing from this round on can beat the best hit
         if (!closed && min_T >= 0.0f && __uint_as_float(s_rec[2].y) > min_T_max_depth) closed = true;
+        // split mode: ... nor a hit found by one of the other CTAs of this tile (smallest max depth of any hit
+        // so far; a face whose min depth lies beyond it cannot hold the first intersection)
+        if (!closed && split > 1 && __uint_as_float(s_rec[2].y) > __uint_as_float(__ldcg(p.fi_close + bpix))) closed = true;
         {
             const unsigned open = __ballot_sync(0xffffffffu, !closed);   // a warp holds tile rows 2*warp, 2*warp+1
             if (lane == 0) { s_open[2 * warp] = open & 0xffffu; s_open[2 * warp + 1] = open >> 16; }
         }
         if (__syncthreads_count(!closed) == 0) break;
-        fetch(r + 1);
+        fetch(r + split);
 
         const int cnt = min(FI_THREADS, total - r * FI_THREADS);
         // (fetch(r+1) overwrote the staging registers; this round's face is read back from shared memory)
@@ -363,6 +373,8 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
                     min_T = cur;
                     min_T_max_depth = __uint_as_float(q2.z);
                     first_face = s_face[pos];
+                    first_pos = (uint32_t)(r * FI_THREADS + pos);
+                    if (split > 1) atomicMin(p.fi_close + bpix, q2.z);   // max depth bits (non-negative float)
                 }
             }
         }
@@ -370,7 +382,20 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
     }
 
     if (!inside) return;
-    // forward.cu:419-444: the adjacent tet whose outward normal opposes the ray
+    if (split > 1) {   // partial result: (t, list position) into the pixel's global slot
+        if (first_face >= 0) {
+            const uint32_t tb = min_T == 0.0f ? 0u : __float_as_uint(min_T);
+            atomicMin(p.fi_key + bpix, ((unsigned long long)tb << 32) | first_pos);
+        }
+        return;
+    }
+    tet_first_finish(p, b, bpix, first_face, rd);
+}
+
+// first_tet of a pixel (forward.cu:419-444: the adjacent tet whose outward normal opposes the ray) + stores
+__device__ __forceinline__ void tet_first_finish(const TetParams& p, int b, size_t bpix, int first_face, float3 rd)
+{
+    (void)b;
     int first_tet = -1;
     if (first_face >= 0) {
         const TetShade* sh = p.shade + first_face;
@@ -392,12 +417,38 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
     p.first_tet[bpix] = first_tet;
 }
 
+// split mode: winner of the pixel's partial results -> first_face, first_tet
+__global__ void __launch_bounds__(256) tet_first_resolve_kernel(TetParams p)
+{
+    const int b = blockIdx.z;
+    const uint32_t px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
+    const size_t bpix = (size_t)b * p.W * p.H + (size_t)py * p.W + px;
+    const unsigned long long key = p.fi_key[bpix];
+    int first_face = -1;
+    if (key != ~0ull) {
+        const uint2 range = p.ranges[((size_t)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+        first_face = (int)p.face_list[range.x + (uint32_t)(key & 0xffffffffu)];
+    }
+    float3 ro, rd;
+    tet_pixel_ray(p, b, px, py, bpix, ro, rd);
+    tet_first_finish(p, b, bpix, first_face, rd);
+}
+
 int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    const int tx = (p.W + DMR_TILE - 1) / DMR_TILE, ty = (p.H + DMR_TILE - 1) / DMR_TILE;
     ProfScope prof(ST_TET_FIRST, stream);
-    tet_first_intersect_kernel<<<grid, FI_THREADS, 0, stream>>>(p);
+    if (p.fi_split > 1) {
+        count_launch(1);   // two kernels under one scope
+        DMR_CUDA(cudaMemsetAsync(p.fi_key, 0xff, 12 * (size_t)p.B * p.W * p.H, stream));   // fi_key + fi_close
+    }
+    tet_first_intersect_kernel<<<dim3(tx * p.fi_split, ty, p.B), FI_THREADS, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
+    if (p.fi_split > 1) {
+        tet_first_resolve_kernel<<<dim3(tx, ty, p.B), 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tet_first_resolve_kernel");
+    }
     return 0;
 }
 

@@ -114,6 +114,27 @@ def test_tet_gradients_short_trail(name, cap):
         assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
 
 
+@pytest.mark.parametrize("split", [1, 3, 4])
+def test_tet_first_intersection_does_not_depend_on_the_tile_split(split):
+    need_ref()
+    from dmesh_renderer_b200 import _lib
+    lib = _lib.load()
+    s = scenes.to_device(scenes.config("small_tet"), "cuda")
+    B, P, F, T = s.mv_mats.shape[0], s.verts.shape[0], s.faces.shape[0], s.tets.shape[0]
+    ref = ref_harness.ref_tet_forward(s, 0)
+    ri = ref_harness.ref_tet_intermediates(s, ref)
+    lib.dmr_debug_set_tet_first_split(split)
+    try:
+        color, depth, active, pb, fb, bb, ib = ours_forward(s, 0)
+        torch.cuda.synchronize()
+    finally:
+        lib.dmr_debug_set_tet_first_split(0)
+    dims = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=ri["R"], T=T)
+    np.testing.assert_array_equal(debug.view("tet", "first_face", ib, **dims), ri["first_face"])
+    np.testing.assert_array_equal(debug.view("tet", "first_tet", ib, **dims), ri["first_tet"])
+    np.testing.assert_array_equal(debug.view("tet", "n_contrib", ib, **dims), ri["n_contrib"])
+
+
 def test_tet_validation_errors():
     s = scenes.to_device(scenes.config("tiny_tet"), "cuda")
     mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
