@@ -20,7 +20,7 @@ python tools/launch_summary.py $out/${tag}_launches_C2.csv $out/${tag}_launches_
 # full captures of the dominant kernels (one launch each)
 ncu --set full --clock-control none --import-source on -k regex:"tri_render" -c 2 -o $out/${tag}_full_C2 -f python tools/run_once.py C2 1 > $out/ncu_full_C2.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full_C2.ncu-rep $out/${tag}_ncu_full_C2.csv
-ncu --set full --clock-control none --import-source on -k regex:"tet_march|tet_first" -c 3 -o $out/${tag}_full_C3 -f python tools/run_once.py C3 1 > $out/ncu_full_C3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"tet_march|tet_first" -c 4 -o $out/${tag}_full_C3 -f python tools/run_once.py C3 1 > $out/ncu_full_C3.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full_C3.ncu-rep $out/${tag}_ncu_full_C3.csv
 ncu --set full --clock-control none --import-source on -k regex:"rs_onesweep|duplicate|tile_ranges|preprocess|inclusive_scan" -c 12 -o $out/${tag}_full_bin_C5 -f python tools/run_once.py C5 1 > $out/ncu_full_bin_C5.log 2>&1
 python tools/ncu_summary.py $out/${tag}_full_bin_C5.ncu-rep $out/${tag}_ncu_full_bin_C5.csv
