@@ -105,12 +105,13 @@ static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, 
     p.trail_cap = (int)IL.trail_cap;
     p.fi_key = at<unsigned long long>(ib, IL.fi_key);
     p.fi_close = reinterpret_cast<uint32_t*>(p.fi_key + (size_t)B * W * H);
-    // CTAs per tile of the first-intersection search.  Measured at C3 (1024 tiles): 1 -> 259 us, 2 -> 200 us,
-    // 4 -> 275 us, 8 -> 433 us: two CTAs halve the chain of the silhouette tiles; more of them only repeat, for
-    // every interior tile, rounds a single CTA would have skipped after its first hits.
+    // CTAs per tile of the first-intersection search.  Measured at C3 (1024 tiles), later parts scheduled
+    // after all part-0 CTAs: 1 -> 260 us, 2 -> 189 us, 4 -> 166 us, 8 -> 168 us.  (With the parts of a tile
+    // adjacent in the grid: 2 -> 200, 4 -> 275, 8 -> 433 us -- every interior tile then repeats rounds a single
+    // CTA would have skipped after its first hits.)
     {
         const size_t tiles = (size_t)B * ((W + DMR_TILE - 1) / DMR_TILE) * ((H + DMR_TILE - 1) / DMR_TILE);
-        p.fi_split = tiles <= 4096 ? 2 : 1;
+        p.fi_split = tiles <= 4096 ? 4 : tiles <= 16384 ? 2 : 1;
         if (g_tet_first_split_override > 0) p.fi_split = g_tet_first_split_override;
     }
 }

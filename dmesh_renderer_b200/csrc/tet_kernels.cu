@@ -272,13 +272,15 @@ __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetPara
     __shared__ float4 s_rd[FI_THREADS];
     __shared__ uint32_t s_open[DMR_TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z;
     // fi_split CTAs share a tile: CTA `part` takes rounds part, part + fi_split, ... of the tile list and the
     // partial results meet in a global 64-bit atomicMin per pixel (tet_first_resolve_kernel turns the winner
     // into first_face / first_tet).  The kernel's duration is the longest tile list (a few hundred silhouette
-    // tiles at C3); splitting it shortens exactly that chain.
-    const int split = p.fi_split, part = (int)(blockIdx.x % (unsigned)split), tile_x = (int)(blockIdx.x / (unsigned)split);
-    const int tiles_x = (int)(gridDim.x / (unsigned)split), tiles_y = gridDim.y;
+    // tiles at C3); splitting it shortens exactly that chain.  `part` is the SLOWEST grid dimension: the
+    // part-0 CTAs of all tiles are scheduled first, so that by the time a later part starts, the interior
+    // tiles (finished by part 0 in one or two rounds) have published their closing depths and it stops at once.
+    const int split = p.fi_split, part = (int)(blockIdx.z / (unsigned)p.B), b = (int)(blockIdx.z % (unsigned)p.B);
+    const int tile_x = blockIdx.x;
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const uint32_t tx0 = tile_x * DMR_TILE, ty0 = blockIdx.y * DMR_TILE;
     const uint32_t px = tx0 + (tid & 15);
     const uint32_t py = ty0 + (tid >> 4);
@@ -443,7 +445,7 @@ int tet_first_intersect(const TetParams& p, cudaStream_t stream)
         count_launch(1);   // two kernels under one scope
         DMR_CUDA(cudaMemsetAsync(p.fi_key, 0xff, 12 * (size_t)p.B * p.W * p.H, stream));   // fi_key + fi_close
     }
-    tet_first_intersect_kernel<<<dim3(tx * p.fi_split, ty, p.B), FI_THREADS, 0, stream>>>(p);
+    tet_first_intersect_kernel<<<dim3(tx, ty, p.B * p.fi_split), FI_THREADS, 0, stream>>>(p);
     DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
     if (p.fi_split > 1) {
         tet_first_resolve_kernel<<<dim3(tx, ty, p.B), 256, 0, stream>>>(p);

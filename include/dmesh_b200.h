@@ -217,8 +217,8 @@ int dmr_debug_view(int renderer /*0=tri,1=tet*/, int kind,
 /* reported by dmr_tet_state_bytes; set it before the forward call and keep  */
 /* it until the matching backward call has been issued.  Not thread-safe.    */
 int dmr_debug_set_tet_trail_cap(int cap);
-/* Test hook: CTAs per tile of the tet first-intersection search (0 = automatic: 2 up to 4096 tiles,  */
-/* else 1).  Results do not depend on it.                                                              */
+/* Test hook: CTAs per tile of the tet first-intersection search (0 = automatic: 4 up to 4096 tiles,  */
+/* 2 up to 16384, else 1).  Results do not depend on it.                                              */
 int dmr_debug_set_tet_first_split(int split);
 
 /* ------------------------------------------------------------------------ */

@@ -114,7 +114,7 @@ def test_tet_gradients_short_trail(name, cap):
         assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
 
 
-@pytest.mark.parametrize("split", [1, 3, 4])
+@pytest.mark.parametrize("split", [1, 2, 3])
 def test_tet_first_intersection_does_not_depend_on_the_tile_split(split):
     need_ref()
     from dmesh_renderer_b200 import _lib
