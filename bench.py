@@ -168,7 +168,7 @@ def describe(name, s, ws, views_per_rank, total_views):
         "workload": {"C1": "configs[0]", "C2": "configs[1]", "C4": "configs[3]", "C5": "configs[4]"}[name] +
         ": tri renderer fwd+bwd, %d triangles, %dx%d, %d view(s) per rank and step" % (s.faces.shape[0], s.W, s.H, views_per_rank),
         "triangles": int(s.faces.shape[0]), "vertices": int(s.verts.shape[0]), "image": [s.H, s.W],
-        "views_per_step_total": total_views, "parallelism": "camera-sharded x%d, 1 all-reduce of (6P+F) fp32" % ws if ws > 1 else "single GPU",
+        "views_per_step_total": total_views, "parallelism": "camera-sharded x%d, 1 all-reduce of (6P+F) fp32 (NVLS multimem kernel over symmetric memory, NCCL fallback)" % ws if ws > 1 else "single GPU",
         "l2_flush": "256 MB device fill between timed steps, outside the timed events",
     }
 

@@ -26,12 +26,29 @@ def shard_views(num_views: int, rank: int, world_size: int) -> range:
 
 class PackedSceneGrads:
     """Scene leaves (verts, verts_color, faces_opacity) whose .grad tensors are
-    views into ONE contiguous fp32 buffer, so the step needs a single collective."""
+    views into ONE contiguous fp32 buffer, so the step needs a single collective.
 
-    def __init__(self, verts: torch.Tensor, verts_color: torch.Tensor, faces_opacity: torch.Tensor):
+    On a CUDA job with world_size > 1 the buffer is allocated in SYMMETRIC memory
+    (torch.distributed._symmetric_memory: peer-mapped on every rank + an NVLS multicast
+    address) and the all-reduce is the hand-written in-switch reduction kernel of
+    csrc/collective.cu (multimem.ld_reduce / multimem.st); without multicast support
+    (or on CPU / gloo) it is torch.distributed.all_reduce.  Construct it collectively:
+    every rank of `group` must create its PackedSceneGrads at the same point."""
+
+    def __init__(self, verts: torch.Tensor, verts_color: torch.Tensor, faces_opacity: torch.Tensor, group=None,
+                 use_nvls: Optional[bool] = None):
         self.leaves = [verts, verts_color, faces_opacity]
+        self.group = group
+        self._fused = True             # barriers inside the all-reduce kernel (False: separate signal-pad barriers)
         n = sum(t.numel() for t in self.leaves)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=verts.device)
+        self._nvls = None
+        full = None
+        if use_nvls is not False:
+            full = self._try_symmetric(n, verts.device, group)
+        if full is None:
+            full = torch.zeros(n, dtype=torch.float32, device=verts.device)
+        self._full = full              # padded to a multiple of 4 * world_size floats in the NVLS case
+        self.flat = full[:n]
         o = 0
         for t in self.leaves:
             if not t.requires_grad:
@@ -39,10 +56,69 @@ class PackedSceneGrads:
             t.grad = self.flat[o:o + t.numel()].view_as(t)
             o += t.numel()
 
+    def _try_symmetric(self, n, device, group):
+        if not (device.type == "cuda" and dist.is_available() and dist.is_initialized()):
+            return None
+        ws = dist.get_world_size(group)
+        if ws <= 1 or dist.get_backend(group) != "nccl":
+            return None
+        ok, full, hdl = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = group if group is not None else dist.group.WORLD
+            if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    symm_mem.enable_symm_mem_for_group(pg.group_name)
+            n_pad = -(-n // (4 * ws)) * (4 * ws)
+            full = symm_mem.empty(n_pad, dtype=torch.float32, device=device)
+            full.zero_()
+            hdl = symm_mem.rendezvous(full, pg)
+            if not hdl.multicast_ptr:     # no NVLS multicast object behind the allocation (no NVSwitch / disabled)
+                ok = 0
+            # flag words for the in-kernel cross-GPU barriers (symmetric, zeroed) + this GPU's control words
+            flags = symm_mem.empty(256, dtype=torch.int32, device=device)
+            flags.zero_()
+            fh = symm_mem.rendezvous(flags, pg)
+            ctl = torch.zeros(4, dtype=torch.int32, device=device)
+        except Exception:
+            ok = 0
+        # all ranks must take the same path
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            return None
+        torch.cuda.synchronize(device)
+        dist.barrier(group)            # every rank's flag words are zero before anybody signals
+        self._nvls = (hdl, int(hdl.multicast_ptr) + int(getattr(hdl, "offset", 0) or 0), full.numel(), dist.get_rank(group), ws)
+        self._flags = (flags, fh, int(fh.buffer_ptrs_dev), ctl)
+        self._epoch = 0
+        return full
+
     def zero_(self):
-        self.flat.zero_()
+        self._full.zero_()
 
     def all_reduce(self, group=None, async_op=False):
+        if self._nvls is not None:
+            import ctypes
+            from . import _lib
+            hdl, mc, n_pad, rank, ws = self._nvls
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if self._fused and self._epoch < (1 << 30) - 2:
+                # one launch: barrier ("every rank's gradients are complete") -> in-switch reduce + broadcast of this
+                # rank's slice -> barrier ("every slice has been broadcast"), all inside the kernel
+                self._epoch += 1
+                flags, fh, peer_ptrs, ctl = self._flags
+                _lib.check(_lib.load().dmr_nvls_allreduce_sum_f32_fused(ctypes.c_void_p(mc), n_pad, rank, ws,
+                                                                        ctypes.c_void_p(peer_ptrs), ctypes.c_void_p(ctl.data_ptr()),
+                                                                        self._epoch, stream))
+                return None
+            hdl.barrier(channel=0)        # signal-pad barriers as separate launches
+            _lib.check(_lib.load().dmr_nvls_allreduce_sum_f32(ctypes.c_void_p(mc), n_pad, rank, ws, stream))
+            hdl.barrier(channel=0)
+            return None
+        group = group if group is not None else self.group
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         return None
