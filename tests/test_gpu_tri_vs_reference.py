@@ -147,3 +147,28 @@ def test_inverses_on_gpu_are_torch_inverse_bits_and_singular_raises():
     bad[0] = 0
     with pytest.raises(RuntimeError, match="singular"):
         r(s.verts, s.faces, s.verts_color, s.faces_opacity, s.mv_mats, bad, s.verts_depth, s.faces_intense)
+
+
+def test_speculative_binning_buffer_when_num_rendered_grows():
+    """The binning buffer is pre-sized from the previous call with the same shapes; a call whose num_rendered
+    outgrows it must fall back to an exact allocation (same shapes, camera far -> near)."""
+    need_ref()
+    far = scenes.random_tri_scene("far", 11, 4000, 0.05, 160, 160, dist=8.0, far=12.0)
+    near = scenes.random_tri_scene("near", 11, 4000, 0.12, 160, 160, dist=2.0)
+    R = []
+    for cpu in (far, near, far):
+        s = scenes.to_device(cpu, "cuda")
+        gc, gd = [t.cuda() for t in scenes.cotangents(cpu)]
+        ref = ref_harness.ref_tri_forward(s)
+        rg = ref_harness.ref_tri_backward(s, ref, gc, gd)
+        leaves = [s.verts.clone().requires_grad_(), s.verts_color.clone().requires_grad_(),
+                  s.faces_opacity.clone().requires_grad_(), s.verts_depth.clone().requires_grad_(),
+                  s.faces_intense.clone().requires_grad_()]
+        color, depth = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))(leaves[0], s.faces, leaves[1], leaves[2], s.mv_mats,
+                                                                      s.proj_mats, leaves[3], leaves[4])
+        torch.autograd.backward([color, depth], [gc, gd])
+        assert (color - ref["color"]).abs().max().item() <= IMG_TOL
+        for leaf, r in zip(leaves, rg):
+            assert rel_l2(leaf.grad, r) <= GRAD_TOL
+        R.append(ref["R"])
+    assert R[1] > 1.25 * R[0] + 1024      # the second call really outgrew the speculative buffer
