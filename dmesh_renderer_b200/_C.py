@@ -62,7 +62,28 @@ class _Pinned:
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of the current stream of the current device; torch.cuda.current_stream() costs ~10 us of Python
+    # per call (device-index resolution, Stream object), and a forward+backward needs it four times
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` without its cost when `dev` already is the current device (the normal case:
+    one process per GPU, torch.cuda.set_device(rank))."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        idx = dev.index
+        self.ctx = None if idx is None or idx == torch._C._cuda_getDevice() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 _SENTINEL = -2 ** 31          # num_rendered is never negative
@@ -127,7 +148,7 @@ class _InverseGraph:
         g = cls._cache.get(key)
         if g is None:
             try:
-                with torch.cuda.device(dev):
+                with _on_device(dev):
                     g = cls(dev, B)
             except Exception:   # capture not possible in this context (e.g. another capture running): eager path
                 g = False
@@ -166,7 +187,7 @@ class _Inverses:
                      not torch.cuda.is_current_stream_capturing())
         g = _InverseGraph.get(mv_mats.device, mv_mats.size(0)) if graphable else None
         if g is not None:
-            with torch.cuda.device(mv_mats.device):
+            with _on_device(mv_mats.device):
                 out, self.event = g.run(mv_mats, proj_mats)
             self.inv_mv, self.inv_proj = out[0], out[1]
             self.host_np = g.host_np
@@ -259,7 +280,7 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
     st.dims, st.dev, st.empty = (B, P, F, W, H), dev, P == 0
     if st.empty:
         return st
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         u8 = dict(dtype=torch.uint8, device=dev)
         st.bg = _f32(background, "background")
         verts_c, faces_c = _f32(verts, "verts"), _i32(faces, "faces")
@@ -288,7 +309,7 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
     B, P, F, W, H = st.dims
     dev = st.dev
     lib = _lib.load()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         u8 = dict(dtype=torch.uint8, device=dev)
         if st.empty:
             # render.cu:88-89,105: zero images (not background), empty state
@@ -341,7 +362,7 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
     B, P, F = mv_mats.size(0), verts.size(0), faces.size(0)
     H, W = dL_dout_color.size(2), dL_dout_color.size(3)
     dev = verts.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         # the five zero-initialised gradient tensors of render.cu:166-171, carved out of ONE allocation
         # (one memset instead of five); each starts on a 16-byte boundary
         sizes = [3 * P, NUM_CHANNELS * P, F, B * P, B * F]
@@ -398,7 +419,7 @@ def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, p
     B, P, F, T = mv_mats.size(0), verts.size(0), faces.size(0), tets.size(0)
     H, W = int(image_height), int(image_width)
     dev = verts.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         u8 = dict(dtype=torch.uint8, device=dev)
         bg = _f32(background, "background")
         verts_c, faces_c = _f32(verts, "verts"), _i32(faces, "faces")
@@ -452,7 +473,7 @@ def render_tets_backward(background, verts, faces, verts_color, faces_opacity, m
     dev = verts.device
     if ray_random_seed is None:
         ray_random_seed = 0
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         z = dict(dtype=torch.float32, device=dev)
         dL_dverts_color = torch.zeros((P, 3), **z)
         dL_dfaces_opacity = torch.zeros((F,), **z)
