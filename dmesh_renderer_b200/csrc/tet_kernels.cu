@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
         // up on the ray (its error case 3), leaving this and all earlier faces without gradient; the
         // replay reproduces that.  (The side we entered through always qualifies as the first candidate:
         // it passed the same hit test one step earlier and its normal sign is checked by tet_step.)
-        if (n_contrib < trail_cap) trail[(size_t)n_contrib * BI] = curr_face | (s.opposite ? (int)0x80000000u : 0);
+        if (n_contrib < trail_cap) __stcs(trail + (size_t)n_contrib * BI, curr_face | (s.opposite ? (int)0x80000000u : 0));   // streaming: read once, by the backward pass
 
         // 1. composite the current face (forward.cu:600-653)
         const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
@@ -824,8 +824,8 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
     const float* frec = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F);
     const float* fint = p.faces_intense + (size_t)b * p.F;
 
-    int face = trail[(size_t)k * BI] & 0x7fffffff;
-    int face_next = k > 0 ? trail[(size_t)(k - 1) * BI] : 0;
+    int face = __ldcs(trail + (size_t)k * BI) & 0x7fffffff;
+    int face_next = k > 0 ? __ldcs(trail + (size_t)(k - 1) * BI) : 0;
     float4 q0, q1, q2, s0, s1, s2, s3;
     float intense;
     {
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
         const float4* sh4 = reinterpret_cast<const float4*>(p.shade + nf);
         const float4 ns0 = sh4[0], ns1 = sh4[1], ns2 = sh4[2], ns3 = sh4[3];
         const float nint = fint[nf];
-        face_next = k > 1 ? trail[(size_t)(k - 2) * BI] : 0;
+        face_next = k > 1 ? __ldcs(trail + (size_t)(k - 2) * BI) : 0;
 
         float3 tuv = f3(0, 0, 0);
         ray_tri_hit(ro, rd, f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), tuv);
