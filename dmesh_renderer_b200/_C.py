@@ -265,11 +265,14 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
     for t, n in ((mv_mats, "mv_mats"), (proj_mats, "proj_mats")):
         if t.dim() != 3 or t.size(1) != 4 or t.size(2) != 4:
             _err("%s must have dimensions (B, 4, 4)" % n)
-    if verts_depth.dim() != 2 or verts_depth.size(1) != verts.size(0):
+    # verts_depth=None (an extension of the reference API): the renderer uses the NDC z it computes itself
+    if verts_depth is not None and (verts_depth.dim() != 2 or verts_depth.size(1) != verts.size(0)):
         _err("verts_depth must have dimensions (B, num_points,)")
     if faces_intense.dim() != 2 or faces_intense.size(1) != faces.size(0):
         _err("faces_intense must have dimensions (B, num_faces,)")
-    _require_cuda(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense)
+    _require_cuda(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, faces_intense)
+    if verts_depth is not None:
+        _require_cuda(verts_depth)
     lib = _lib.load()
     B, P, F = mv_mats.size(0), verts.size(0), faces.size(0)
     H, W = int(image_height), int(image_width)
@@ -286,7 +289,8 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
         verts_c, faces_c = _f32(verts, "verts"), _i32(faces, "faces")
         vcol, fopa = _f32(verts_color, "verts_color"), _f32(faces_opacity, "faces_opacity")
         mv, pj = _f32(mv_mats, "mv_mats"), _f32(proj_mats, "proj_mats")
-        vdep, fint = _f32(verts_depth, "verts_depth"), _f32(faces_intense, "faces_intense")
+        vdep = _f32(verts_depth, "verts_depth") if verts_depth is not None else None
+        fint = _f32(faces_intense, "faces_intense")
         sizes = (ctypes.c_size_t * 3)()
         _lib.check(lib.dmr_tri_state_bytes(B, P, F, W, H, sizes))
         st.bufs = [torch.empty(sizes[0], **u8), torch.empty(sizes[1], **u8), torch.empty(sizes[2], **u8)]
@@ -387,6 +391,18 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
         dL_dvdepth = flat[offs[3]:offs[3] + sizes[3]].view(B, P)
         dL_dfintense = flat[offs[4]:offs[4] + sizes[4]].view(B, F)
     return dL_dverts, dL_dvcolor, dL_dfopacity, dL_dvdepth, dL_dfintense
+
+
+def tri_depth_chain(verts, mv_mats, proj_mats, dL_dvdepth, dL_dverts):
+    """Fused vertex depth (verts_depth=None): dL_dverts += sum_b dL_dvdepth[b] * d ndc_z / d verts, in place."""
+    lib = _lib.load()
+    B, P = mv_mats.size(0), verts.size(0)
+    with _on_device(verts.device):
+        # keep the contiguous copies alive in locals until the launch is enqueued (a temporary would be freed, and
+        # its memory handed to the next .contiguous(), before the call)
+        v, mv, pj = _f32(verts, "verts"), _f32(mv_mats, "mv_mats"), _f32(proj_mats, "proj_mats")
+        _lib.check(lib.dmr_tri_depth_chain(B, P, _ptr(v), _ptr(mv), _ptr(pj), _ptr(dL_dvdepth), _ptr(dL_dverts), _stream()))
+    return dL_dverts
 
 
 # ---------------------------------------------------------------------------

@@ -59,6 +59,7 @@ class _RenderTri(th.autograd.Function):
             raise ex
         ctx.render_settings = render_settings
         ctx.num_rendered = num_rendered
+        ctx.fused_depth = verts_depth is None
         ctx.save_for_backward(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
                               verts_depth, faces_intense, pointBuffer, faceBuffer, binningBuffer, imgBuffer)
         return color, depth
@@ -78,6 +79,10 @@ class _RenderTri(th.autograd.Function):
         except Exception as ex:
             print("\nAn error occured in backward.\n")
             raise ex
+        if ctx.fused_depth:
+            # verts_depth=None: the depth was the vertex's own NDC z -> chain its gradient into the vertex positions
+            _C.tri_depth_chain(verts, mv_mats, proj_mats, grad_verts_depth, grad_verts)
+            grad_verts_depth = None
         # gradient positions: reference __init__.py:156-168
         return (grad_verts, None, grad_verts_color, grad_faces_opacity, None, None, grad_verts_depth,
                 grad_faces_intense, None)
@@ -95,6 +100,8 @@ class TriRenderer(th.nn.Module):
         verts [P,3] f32, faces [F,3] int, verts_color [P,3], faces_opacity [F]   (view independent)
         mv_mats, proj_mats [B,4,4] in maths convention (transposed here, as the reference does)
         verts_depth [B,P], faces_intense [B,F]                                   (per view)
+        verts_depth=None (extension): use each vertex's own NDC z, computed and differentiated inside the
+        renderer (what DMesh's callers otherwise compute upstream in PyTorch, a [B,P] tensor per step)
         returns color [B,3,H,W], depth [B,1,H,W]
         """
         return render_tri(verts, faces.to(dtype=th.int32), verts_color, faces_opacity, mv_mats.transpose(1, 2),

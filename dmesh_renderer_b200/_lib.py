@@ -25,6 +25,7 @@ SIGNATURES = {
     "dmr_binning_bytes": (c_size_t, [c_size_t]),
     "dmr_wait_i32": (c_int, [c_void_p, ctypes.c_int32, c_void_p]),
     "dmr_tri_forward_bin": (c_int, [c_int] * 5 + [c_void_p] * 11 + [c_void_p]),
+    "dmr_tri_depth_chain": (c_int, [c_int, c_int] + [c_void_p] * 5 + [c_void_p]),
     "dmr_tri_forward_render": (c_int, [c_int] * 6 + [c_void_p] * 9 + [c_void_p]),
     "dmr_tri_backward": (c_int, [c_int] * 6 + [c_void_p] * 14 + [c_void_p]),
     "dmr_tet_forward_bin": (c_int, [c_int] * 6 + [c_void_p] * 12 + [c_void_p]),

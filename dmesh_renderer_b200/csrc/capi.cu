@@ -169,7 +169,8 @@ int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, c
     if (!sizes_ok(B, P, F, W, H)) return DMR_ETOOLARGE;
     if (!num_rendered_host) { set_error("num_rendered_host is null"); return DMR_EINVAL; }
     if (B == 0 || P == 0 || F == 0) { *num_rendered_host = 0; return DMR_OK; }
-    if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats || !verts_depth ||
+    // verts_depth == NULL selects the fused vertex depth (the vertex's own NDC z, dmr_tri_depth_chain in backward)
+    if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats ||
         !faces_intense || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
     const size_t BF = (size_t)B * F;
     TriFaceLayout L = TriFaceLayout::make(BF, (size_t)P);
@@ -177,13 +178,22 @@ int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, c
     int rc;
     SortPre face_sort;
     if ((rc = bin_faces_begin(BF, face_buffer, L.bin, &face_sort, stream))) return rc;
-    if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, verts_depth, vimg, stream))) return rc;
+    if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, verts_depth, 1, vimg, stream))) return rc;
     if ((rc = tri_preprocess_faces(B, P, F, W, H, faces, vimg, verts, verts_color, faces_opacity, faces_intense,
                                    at<uint32_t>(face_buffer, L.bin.tiles_touched), at<uint32_t>(face_buffer, L.bin.depth_key),
                                    at<uint2>(face_buffer, L.bin.rect), at<TriRecord>(face_buffer, L.records), face_sort,
                                    stream)))
         return rc;
     return bin_faces(BF, face_buffer, L.bin, num_rendered_host, stream);
+}
+
+int dmr_tri_depth_chain(int B, int P, const float* verts, const float* mv_mats, const float* proj_mats,
+                        const float* dL_dvdepth, float* dL_dverts, dmr_stream_t stream)
+{
+    if (B < 0 || P < 0) { set_error("negative size"); return DMR_EINVAL; }
+    if (B == 0 || P == 0) return DMR_OK;
+    if (!verts || !mv_mats || !proj_mats || !dL_dvdepth || !dL_dverts) { set_error("null pointer"); return DMR_EINVAL; }
+    return depth_chain(B, P, verts, mv_mats, proj_mats, dL_dvdepth, dL_dverts, (cudaStream_t)stream);
 }
 
 int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float* background,

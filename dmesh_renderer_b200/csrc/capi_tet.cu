@@ -62,7 +62,7 @@ int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* v
     int rc;
     SortPre face_sort;
     if ((rc = bin_faces_begin(BF, face_buffer, L.bin, &face_sort, stream))) return rc;
-    if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, nullptr, vimg, stream))) return rc;
+    if ((rc = preprocess_points(B, P, W, H, verts, mv_mats, proj_mats, nullptr, 0, vimg, stream))) return rc;
     if ((rc = tet_preprocess_faces(B, P, F, W, H, faces, vimg, verts, at<uint32_t>(face_buffer, L.bin.tiles_touched),
                                    at<uint32_t>(face_buffer, L.bin.depth_key), at<uint2>(face_buffer, L.bin.rect),
                                    at<TetFaceRec>(face_buffer, L.face_rec), face_sort, stream)))

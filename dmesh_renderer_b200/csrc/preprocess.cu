@@ -26,7 +26,8 @@ namespace dmr {
 __global__ void __launch_bounds__(256) preprocess_points_kernel(
     int B, int P, int W, int H,
     const float* __restrict__ verts, const float* __restrict__ mv_mats, const float* __restrict__ proj_mats,
-    const float* __restrict__ verts_depth,   // may be null (tet path: unused lane)
+    const float* __restrict__ verts_depth,   // may be null, see depth_mode
+    int depth_mode,                          // 4th lane when verts_depth is null: 0 = clip-space w (tet), 1 = NDC z
     float4* __restrict__ vimg)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -45,18 +46,71 @@ __global__ void __launch_bounds__(256) preprocess_points_kernel(
     o.x = ndc2pix(ndc.x, W);
     o.y = ndc2pix(ndc.y, H);
     o.z = ndc.z;
-    o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : pp.w;   // tet path: clip-space w (bbox validity)
+    // tet path: clip-space w (bbox validity); tri path without a verts_depth tensor: the vertex's own NDC z
+    o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : (depth_mode == 1 ? ndc.z : pp.w);
     vimg[(size_t)b * P + idx] = o;
 }
 
 int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
-                      const float* verts_depth, float4* vimg, cudaStream_t stream)
+                      const float* verts_depth, int depth_mode, float4* vimg, cudaStream_t stream)
 {
     if (B <= 0 || P <= 0) return 0;
     dim3 grid((P + 255) / 256, B);
     ProfScope prof(ST_POINTS, stream);
-    preprocess_points_kernel<<<grid, 256, 0, stream>>>(B, P, W, H, verts, mv, proj, verts_depth, vimg);
+    preprocess_points_kernel<<<grid, 256, 0, stream>>>(B, P, W, H, verts, mv, proj, verts_depth, depth_mode, vimg);
     DMR_LAUNCH_CHECK("preprocess_points_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Fused vertex depth: when the caller passes no verts_depth tensor the renderer uses the NDC z
+// it computes anyway.  The caller's usual upstream op  verts_depth[b,p] = ndc_z(P_b M_b p)  then has to be
+// differentiated here: dL/dp += sum_b dL/dverts_depth[b,p] * d ndc_z / dp, with
+//   ndc_z = z_clip / clamp_w(w_clip),  d ndc_z/dp = (dz_clip/dp - ndc_z * dw_clip/dp) / w   (w not clamped)
+// One thread per vertex, loop over the views (coalesced reads of dL_dvdepth rows), no atomics.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) depth_chain_kernel(int B, int P, const float* __restrict__ verts,
+                                                          const float* __restrict__ mv_mats, const float* __restrict__ proj_mats,
+                                                          const float* __restrict__ dL_dvdepth, float* __restrict__ dL_dverts)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P) return;
+    const float3 p = f3(verts[3 * idx + 0], verts[3 * idx + 1], verts[3 * idx + 2]);
+    float3 acc = f3(0, 0, 0);
+    for (int b = 0; b < B; b++) {
+        const float g = dL_dvdepth[(size_t)b * P + idx];
+        if (g == 0.0f) continue;
+        const float* mv = mv_mats + 16 * b;
+        const float* pj = proj_mats + 16 * b;
+        const float3 pv = xform43(p, mv);
+        const float4 pp = xform44(pv, pj);
+        const float wc = clamp_w(pp.w);
+        const float pw = 1.0f / wc;
+        const float ndc_z = pp.z * pw;
+        const bool clamped = wc != pp.w;     // |w| < 1e-4: the reciprocal is a constant
+        float az[3], aw[3];                  // rows 2 and 3 of (Proj * MV)[:, 0:3]
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            az[c] = pj[2] * mv[4 * c + 0] + pj[6] * mv[4 * c + 1] + pj[10] * mv[4 * c + 2];
+            aw[c] = pj[3] * mv[4 * c + 0] + pj[7] * mv[4 * c + 1] + pj[11] * mv[4 * c + 2];
+        }
+        const float k = g * pw;
+        acc.x += k * (az[0] - (clamped ? 0.0f : ndc_z * aw[0]));
+        acc.y += k * (az[1] - (clamped ? 0.0f : ndc_z * aw[1]));
+        acc.z += k * (az[2] - (clamped ? 0.0f : ndc_z * aw[2]));
+    }
+    dL_dverts[3 * idx + 0] += acc.x;
+    dL_dverts[3 * idx + 1] += acc.y;
+    dL_dverts[3 * idx + 2] += acc.z;
+}
+
+int depth_chain(int B, int P, const float* verts, const float* mv, const float* proj, const float* dL_dvdepth,
+                float* dL_dverts, cudaStream_t stream)
+{
+    if (B <= 0 || P <= 0) return 0;
+    count_launch(1);
+    depth_chain_kernel<<<(P + 255) / 256, 256, 0, stream>>>(B, P, verts, mv, proj, dL_dvdepth, dL_dverts);
+    DMR_LAUNCH_CHECK("depth_chain_kernel");
     return 0;
 }
 

@@ -142,7 +142,9 @@ struct TetParams {
 };
 
 int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
-                      const float* verts_depth, float4* vimg, cudaStream_t stream);
+                      const float* verts_depth, int depth_mode, float4* vimg, cudaStream_t stream);
+int depth_chain(int B, int P, const float* verts, const float* mv, const float* proj, const float* dL_dvdepth,
+                float* dL_dverts, cudaStream_t stream);
 int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
                          const SortPre& face_sort, cudaStream_t stream);

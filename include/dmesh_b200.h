@@ -79,11 +79,19 @@ int dmr_tri_forward_bin(
     const float* faces_opacity,  /* [F]     */
     const float* mv_mats,        /* [B,16]  */
     const float* proj_mats,      /* [B,16]  */
-    const float* verts_depth,    /* [B,P]   */
+    const float* verts_depth,    /* [B,P] or NULL = fused NDC z */
     const float* faces_intense,  /* [B,F]   */
     void* point_buffer, void* face_buffer,
     int32_t* num_rendered_host,
     dmr_stream_t stream);
+
+/* Fused vertex depth (no reference counterpart).  With verts_depth == NULL in                  */
+/* dmr_tri_forward_bin the per-view vertex depth is the vertex's own NDC z (what DMesh's callers compute         */
+/* upstream and pass in as verts_depth[B,P]); dmr_tri_backward still returns dL_dvdepth[B,P] and this call        */
+/* adds its chain through the projection to dL_dverts[P,3]:  dL/dp += sum_b dL_dvdepth[b,p] * d ndc_z / dp.       */
+int dmr_tri_depth_chain(int B, int P, const float* verts, const float* mv_mats, const float* proj_mats,
+                        const float* dL_dvdepth, float* dL_dverts, dmr_stream_t stream);
+
 
 /* ------------------------------------------------------------------------ */
 /* Tri renderer, forward, phase 2: binning + sort + tile ranges + render.    */

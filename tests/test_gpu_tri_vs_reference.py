@@ -172,3 +172,37 @@ def test_speculative_binning_buffer_when_num_rendered_grows():
             assert rel_l2(leaf.grad, r) <= GRAD_TOL
         R.append(ref["R"])
     assert R[1] > 1.25 * R[0] + 1024      # the second call really outgrew the speculative buffer
+
+
+def test_fused_vertex_depth_matches_the_upstream_torch_computation():
+    """verts_depth=None: the renderer's own NDC z + its chain rule into the vertex positions must
+    equal passing verts_depth = ndc_z(proj @ mv @ p) computed (and differentiated) upstream in PyTorch."""
+    cpu = scenes.random_tri_scene("fd", 21, 3000, 0.07, 144, 176, B=3)
+    s = scenes.to_device(cpu, "cuda")
+    gc, gd = [t.cuda() for t in scenes.cotangents(cpu)]
+    renderer = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
+
+    def leaves():
+        return [s.verts.clone().requires_grad_(), s.verts_color.clone().requires_grad_(),
+                s.faces_opacity.clone().requires_grad_(), s.faces_intense.clone().requires_grad_()]
+
+    # upstream: depth computed by the caller, gradient flows back through torch
+    a = leaves()
+    vh = torch.cat([a[0], torch.ones_like(a[0][:, :1])], dim=1)
+    clip = torch.einsum("bij,bjk,pk->bpi", s.proj_mats, s.mv_mats, vh)
+    vdepth = (clip[..., 2] / clip[..., 3]).contiguous()
+    c0, d0 = renderer(a[0], s.faces, a[1], a[2], s.mv_mats, s.proj_mats, vdepth, a[3])
+    torch.autograd.backward([c0, d0], [gc, gd])
+    # fused
+    b = leaves()
+    c1, d1 = renderer(b[0], s.faces, b[1], b[2], s.mv_mats, s.proj_mats, None, b[3])
+    torch.autograd.backward([c1, d1], [gc, gd])
+    assert (c1 - c0).abs().max().item() <= IMG_TOL and (d1 - d0).abs().max().item() <= IMG_TOL
+    for n, x, y in zip(("verts", "verts_color", "faces_opacity", "faces_intense"), b, a):
+        e = rel_l2(x.grad, y.grad)
+        assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
+    # the depth term really contributes to the vertex gradient (the test would be vacuous otherwise)
+    c = leaves()
+    c2, d2 = renderer(c[0], s.faces, c[1], c[2], s.mv_mats, s.proj_mats, vdepth.detach(), c[3])
+    torch.autograd.backward([c2, d2], [gc, gd])
+    assert rel_l2(c[0].grad, a[0].grad) > 1e-3
