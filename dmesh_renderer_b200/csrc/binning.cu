@@ -341,8 +341,7 @@ int bin_faces(size_t BF, void* fb, const FaceBinLayout& L, int32_t* num_rendered
     if (BF == 0) { if (num_rendered_host) *num_rendered_host = 0; return 0; }
     int rc;
     {
-        ProfScope prof(ST_FACE_SORT, stream);
-        count_launch(-1);   // the scope counted one launch; the sort counts its own kernels
+        ProfScope prof(ST_FACE_SORT, stream, /*count=*/false);   // the sort counts its own kernels
         if ((rc = sort_pairs_u32_pre(at<uint32_t>(fb, L.depth_key), nullptr, at<uint32_t>(fb, L.depth_sorted),
                                      at<uint32_t>(fb, L.order), BF, 32, at<void>(fb, L.fsort_temp), false,
                                      BF <= DMR_FUSED_FACE_HIST_MAX, stream)))

@@ -40,9 +40,9 @@ struct Prof {
 static Prof g_prof;
 static unsigned long long g_launches = 0;   // kernels launched by this library (bench.py: gpu_launches)
 void count_launch(int n) { g_launches += (unsigned long long)n; }
-void prof_begin(int stage, cudaStream_t s)
+void prof_begin(int stage, cudaStream_t s, bool count)
 {
-    g_launches++;
+    if (count) g_launches++;
     if (!g_prof.on) return;
     if (!g_prof.created) {
         for (int i = 0; i < ST_COUNT; i++) { cudaEventCreate(&g_prof.ev[i][0]); cudaEventCreate(&g_prof.ev[i][1]); g_prof.used[i] = false; }

@@ -43,11 +43,12 @@ enum Stage {
     ST_RANGES, ST_TRI_FWD, ST_TRI_BWD, ST_TRI_BWD_FINISH, ST_TET_RECORDS, ST_TET_JITTER, ST_TET_FIRST, ST_TET_FWD, ST_TET_BWD, ST_TET_BWD_FINISH, ST_COUNT
 };
 void count_launch(int n);
-void prof_begin(int stage, cudaStream_t s);   // also counts one kernel launch
+void prof_begin(int stage, cudaStream_t s, bool count = true);   // count: also counts one kernel launch
 void prof_end(int stage, cudaStream_t s);
 struct ProfScope {
     int st; cudaStream_t s;
-    ProfScope(int stage, cudaStream_t stream) : st(stage), s(stream) { prof_begin(st, s); }
+    // count = false: a scope around a sequence of launches that count themselves
+    ProfScope(int stage, cudaStream_t stream, bool count = true) : st(stage), s(stream) { prof_begin(st, s, count); }
     ~ProfScope() { prof_end(st, s); }
 };
 
