@@ -305,11 +305,13 @@ static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int 
         rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 3>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 4>,
         rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 5>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 6>,
         rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 7>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 8> };
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // function attributes are per device
+    int dev = 0;
+    DMR_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         for (int i = 0; i < 8; i++)
             DMR_CUDA(cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const unsigned ntile = (unsigned)((n + tile - 1) / tile);
     for (int p = 0; p < npass; p++) {
