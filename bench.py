@@ -433,10 +433,11 @@ def run_reference(args, ws, rank, local):
     clocks = sampler.stop()
     ms = total_ms / args.steps
     value = vpr / (ms / 1e3)
-    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": ws, "ranks_used": 1, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, SURVEY.md App. E)", "config": cfg,
            "impl": "reference", "clocks": clocks,
+           "note": "the reference has no multi-GPU path: rank 0 alone runs it on one B200 (launched with %d rank(s))" % ws,
            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "reference",
                             "sample": "the reference has no CPU path: its unmodified CUDA extension (oracle/_ref) ran the full "
                                       "workload on one B200, driven by 1 host thread"},
