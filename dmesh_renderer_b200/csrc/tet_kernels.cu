@@ -672,7 +672,9 @@ struct TetBwdState {
 // Here the nine colour terms are three 16-byte vector reductions into a float4-per-vertex accumulator
 // (4.4 MB at C3, L2-resident; tet_grad_vertex_kernel folds it into dL_dverts_color[P,3]) + one scalar.
 // (Also measured: one 48-byte statistics record per face + a finish kernel, as in the tri renderer --
-// 0.06 ms slower at C3 because the records (152 MB) have to be zeroed, written and read back.)
+// 0.06 ms slower at C3 because the records (152 MB) have to be zeroed, written and read back; and opportunistic
+// warp aggregation of the lanes that hold the same face (match.any + one shuffle round per extra lane): no gain,
+// 779 vs 770 us.)
 __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st, int face, float rt, float iu, float iv,
                                              const float4 s0, const float4 s1, const float4 s2, const float4 s3,
                                              float intense, float3 ro, float3 rd, const float* mv, const float* pj,
