@@ -322,16 +322,26 @@ def run_ours(args, ws, rank, local):
     dom = max(stage_ms, key=stage_ms.get)
     peak, peak_src = peaks()
     achieved = alg.get(dom, 0) / (stage_ms[dom] * 1e-3) / 1e9
-    traffic = None
+    traffic, winst = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+            tj = json.load(f)
+        traffic = tj.get(args.workload, {}).get(dom)
+        winst = tj.get(args.workload + "_warp_instructions", {}).get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": round(stage_ms[dom], 4), "algorithmic_bytes": alg.get(dom, 0),
                 "note": "render kernels are issue-bound (coverage tests + shading), not HBM-bound; see DESIGN.md",
                 "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "instances_R": R, "sort_passes": npass}
+    if winst:
+        # the bound that actually limits the dominant kernel: warp-instruction issue (148 SMs x 4 schedulers x SM clock);
+        # instruction count from the committed ncu capture, duration measured live above
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak_issue = 148 * 4 * sm_mhz * 1e6
+        roofline["issue_bound"] = {"warp_instructions": winst, "achieved_ginst_per_s": round(winst / (stage_ms[dom] * 1e-3) / 1e9, 1),
+                                   "peak_ginst_per_s": round(peak_issue / 1e9, 1),
+                                   "frac": round(winst / (stage_ms[dom] * 1e-3) / peak_issue, 3)}
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample
     cpu = cpu_baseline(args.workload) if ws == 1 else None
