@@ -116,88 +116,44 @@ def _wait_R(lib, pinned, key, spec, u8):
     return R, torch.empty(need, **u8)
 
 
-class _InverseGraph:
-    """The two torch.linalg.inv_ex calls on [B,4,4] stacks captured ONCE per (device, B) in a CUDA graph and
-    replayed: identical kernels, identical bits, but ~45 us of host time instead of ~170 us for two
-    torch.inverse calls (measured on B200) -- host time that sits on the critical path, because the GPU has
-    nothing queued between phase 1 and the num_rendered read-back.  Inputs are copied into the graph's static
-    buffer, outputs are cloned out of it (autograd keeps them for backward)."""
-    _cache = {}
-
-    def __init__(self, dev, B):
-        self.inp = torch.empty((2, B, 4, 4), dtype=torch.float32, device=dev)
-        self.inp.copy_(torch.eye(4, device=dev).expand(2, B, 4, 4))
-        self.host = torch.zeros(2 * B, dtype=torch.int32).pin_memory()
-        self.host_np = self.host.numpy()
-        side = self.side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):   # warm-up outside the capture (library handles, workspaces)
-                torch.linalg.inv_ex(self.inp[0]); torch.linalg.inv_ex(self.inp[1])
-        torch.cuda.current_stream(dev).wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            a, ia = torch.linalg.inv_ex(self.inp[0])
-            b, ib = torch.linalg.inv_ex(self.inp[1])
-            self.out = torch.stack([a, b])
-            self.info = torch.cat([ia.reshape(-1), ib.reshape(-1)])
-
-    @classmethod
-    def get(cls, dev, B):
-        key = (dev.index if dev.index is not None else torch.cuda.current_device(), B)
-        g = cls._cache.get(key)
-        if g is None:
-            try:
-                with _on_device(dev):
-                    g = cls(dev, B)
-            except Exception:   # capture not possible in this context (e.g. another capture running): eager path
-                g = False
-            cls._cache[key] = g
-        return g or None
-
-    def run(self, mv_mats, proj_mats):
-        """Replay on the caller's stream.  (Measured and rejected: replaying on a side stream so that the ~25 tiny
-        LU kernels, ~90 us back to back, run concurrently with phase 1 -- the host is the bottleneck in that
-        window: the extra stream bookkeeping delayed the phase-1 launches by more than the overlap gained,
-        1013 vs 949 us per step.  On one stream the GPU runs the inverses while the host prepares phase 1.)"""
-        torch.stack([mv_mats, proj_mats], out=self.inp)
-        self.graph.replay()
-        out = self.out.clone()
-        self.host.copy_(self.info, non_blocking=True)
-        return out, None
-
-
 class _Inverses:
-    """inverse(mv), inverse(proj) exactly as the reference's Python computes them (torch.inverse,
-    dmesh_renderer/__init__.py:62-63, 298-299) -- same LU kernels, same bits -- but without the
-    device synchronisation torch.inverse performs after EACH call to look at the LAPACK `info` vector,
-    and replayed from a CUDA graph (see _InverseGraph).  The info vector is copied to pinned memory
-    asynchronously and examined after the synchronisation the forward call needs anyway (num_rendered);
-    a singular matrix raises the same error, through torch.inverse itself."""
-    __slots__ = ("inv_mv", "inv_proj", "mats", "host_np", "event")
+    """inverse(mv), inverse(proj) with the bits torch.inverse produces (reference dmesh_renderer/__init__.py:62-63,
+    298-299) from ONE kernel launch (csrc/inverse.cu: the same LU / triangular-solve arithmetic, one thread per
+    matrix) instead of ~24 library kernels and the two device synchronisations torch.inverse performs to look at
+    LAPACK's `info` vector.  The kernel writes `info` straight into pinned host memory; it is examined after the
+    synchronisation the forward call needs anyway (num_rendered), and a singular matrix raises the same error,
+    through torch.inverse itself.  `mv` / `proj` are contiguous copies of the inputs written by the same kernel
+    (the API passes transposed views).  Anything but fp32 CUDA [B,4,4] stacks takes torch.linalg.inv_ex."""
+    __slots__ = ("inv_mv", "inv_proj", "mv", "proj", "mats", "host_np")
     _pinned = {}
 
     def __init__(self, mv_mats, proj_mats):
         self.mats = (mv_mats, proj_mats)
+        self.mv, self.proj = mv_mats, proj_mats
         self.host_np = None
-        self.event = None
-        graphable = (mv_mats.is_cuda and proj_mats.is_cuda and mv_mats.dtype == torch.float32 and
-                     proj_mats.dtype == torch.float32 and mv_mats.dim() == 3 and mv_mats.shape == proj_mats.shape and
-                     tuple(mv_mats.shape[1:]) == (4, 4) and 0 < mv_mats.size(0) <= 4096 and
-                     not torch.cuda.is_current_stream_capturing())
-        g = _InverseGraph.get(mv_mats.device, mv_mats.size(0)) if graphable else None
-        if g is not None:
-            with _on_device(mv_mats.device):
-                out, self.event = g.run(mv_mats, proj_mats)
-            self.inv_mv, self.inv_proj = out[0], out[1]
-            self.host_np = g.host_np
+        native = (mv_mats.is_cuda and proj_mats.is_cuda and mv_mats.device == proj_mats.device and
+                  mv_mats.dtype == torch.float32 and proj_mats.dtype == torch.float32 and mv_mats.dim() == 3 and
+                  mv_mats.shape == proj_mats.shape and tuple(mv_mats.shape[1:]) == (4, 4) and mv_mats.size(0) > 0)
+        if native:
+            dev, B = mv_mats.device, mv_mats.size(0)
+            key = (dev.index, B)
+            slot = _Inverses._pinned.get(key)
+            if slot is None:
+                host = torch.zeros(2 * B, dtype=torch.int32).pin_memory()
+                slot = _Inverses._pinned[key] = (host, host.numpy(), ctypes.c_void_p(host.data_ptr()))
+            with _on_device(dev):
+                out = torch.empty((4, B, 4, 4), dtype=torch.float32, device=dev)
+                _lib.check(_lib.load().dmr_camera_inverses(B, _ptr(mv_mats), *mv_mats.stride(), _ptr(proj_mats),
+                                                           *proj_mats.stride(), _ptr(out), slot[2], _stream()))
+            self.mv, self.proj, self.inv_mv, self.inv_proj = out[0], out[1], out[2], out[3]
+            self.host_np = slot[1]
             return
         self.inv_mv, info_mv = torch.linalg.inv_ex(mv_mats)
         self.inv_proj, info_pj = torch.linalg.inv_ex(proj_mats)
         info = torch.cat([info_mv.reshape(-1), info_pj.reshape(-1)])
         if mv_mats.is_cuda:
             n = info.numel()
-            key = (mv_mats.device.index, n)
+            key = (mv_mats.device.index, -n)
             host = _Inverses._pinned.get(key)
             if host is None:
                 host = _Inverses._pinned[key] = torch.zeros(max(n, 1), dtype=torch.int32).pin_memory()
@@ -208,17 +164,13 @@ class _Inverses:
             self.check(info)
 
     def join(self):
-        """Make the current stream wait for the inverses (no-op when they were computed on it)."""
-        if self.event is not None:
-            torch.cuda.current_stream().wait_event(self.event)
+        """The inverses are computed on the current stream: nothing to wait for."""
 
     def check(self, *infos):
-        """Call after the current stream has been synchronised (and join() has been issued)."""
+        """Call after the current stream has been synchronised."""
         if infos:
             bad = any(bool(i.any()) for i in infos)
         else:
-            if self.event is not None:
-                self.event.synchronize()      # long complete; makes the pinned info words valid
             bad = self.host_np is not None and bool(self.host_np.any())
         if bad:
             torch.inverse(self.mats[0])   # raises torch's own "singular matrix" error

@@ -43,11 +43,12 @@ class _RenderTri(th.autograd.Function):
     def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
                 render_settings):
         try:
-            # Same computation as _C.render_tris(*13 args) (reference __init__.py:62-88), issued in two halves so
-            # that the host-bound torch.inverse calls overlap the GPU's phase 1 (preprocess + scan).
+            # Same computation as _C.render_tris(*13 args) (reference __init__.py:62-88), issued in two halves
+            # (phase 1: preprocess + scan; phase 2 after the num_rendered read-back).
             # depth in [-1, 1]: -1 near, 1 far
-            inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :62-63) minus its two device syncs
+            inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :62-63): one launch, no device sync
             inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
+            mv_mats, proj_mats = inv.mv, inv.proj    # contiguous copies written by the same launch
             pending = _C.tri_forward_begin(render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats,
                                            proj_mats, verts_depth, faces_intense, render_settings.image_height,
                                            render_settings.image_width)
@@ -132,8 +133,9 @@ class _RenderTet(th.autograd.Function):
     @staticmethod
     def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
                 face_tets, tet_faces, render_settings):
-        inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :298-299) minus its two device syncs
+        inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :298-299): one launch, no device sync
         inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
+        mv_mats, proj_mats = inv.mv, inv.proj    # contiguous copies written by the same launch
         args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                 inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, render_settings.image_height,
                 render_settings.image_width, render_settings.ray_random_seed, inv)

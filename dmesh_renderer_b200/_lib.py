@@ -34,6 +34,8 @@ SIGNATURES = {
     "dmr_debug_view": (c_int, [c_int] * 8 + [c_size_t, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t)]),
     "dmr_nvls_allreduce_sum_f32": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dmr_nvls_allreduce_sum_f32_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, ctypes.c_uint, c_void_p]),
+    "dmr_camera_inverses": (c_int, [c_int, c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, c_void_p, ctypes.c_int64,
+                                   ctypes.c_int64, ctypes.c_int64, c_void_p, c_void_p, c_void_p]),
     "dmr_launch_count": (ctypes.c_ulonglong, []),
     "dmr_debug_set_tet_trail_cap": (c_int, [c_int]),
     "dmr_debug_set_tet_first_split": (c_int, [c_int]),

@@ -63,6 +63,23 @@ size_t dmr_binning_bytes(size_t R);
 int dmr_wait_i32(volatile int32_t* host_value, int32_t sentinel, dmr_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
+/* inverse(mv_mats), inverse(proj_mats) of B cameras in one launch.          */
+/* Replaces the two th.inverse calls of the reference's Python wrapper        */
+/* (dmesh_renderer/__init__.py:62-63 tri, 298-299 tet) -- ~24 library kernels  */
+/* and two device synchronisations -- with the same LU / triangular-solve      */
+/* arithmetic done by one thread per matrix; bit-identical to torch.inverse on */
+/* this stack (csrc/inverse.cu).  Inputs are [B,4,4] fp32 with arbitrary       */
+/* element strides (the API passes transposed views).  `out`: 4*B*16 floats,   */
+/* 16-byte aligned = contiguous [mv | proj | inverse(mv) | inverse(proj)].     */
+/* `info`: 2*B int32, device-accessible (device memory or mapped pinned host   */
+/* memory): LAPACK getrf info per matrix, > 0 = singular (the caller raises).  */
+/* ------------------------------------------------------------------------ */
+int dmr_camera_inverses(int B, const float* mv_mats, int64_t mv_batch_stride, int64_t mv_row_stride,
+                        int64_t mv_col_stride, const float* proj_mats, int64_t proj_batch_stride,
+                        int64_t proj_row_stride, int64_t proj_col_stride, float* out, int32_t* info,
+                        dmr_stream_t stream);
+
+/* ------------------------------------------------------------------------ */
 /* Tri renderer, forward, phase 1: preprocess + per-face records + scan.     */
 /* Replaces stages T1-T4 of CudaRasterizer::Rasterizer::forward              */
 /* (cuda_rasterizer/rasterizer_impl.cu:226-292): preprocessPointCUDA         */

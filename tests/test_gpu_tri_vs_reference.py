@@ -142,6 +142,22 @@ def test_inverses_on_gpu_are_torch_inverse_bits_and_singular_raises():
     torch.cuda.synchronize()
     inv.check()
     assert torch.equal(inv.inv_mv, torch.inverse(mv)) and torch.equal(inv.inv_proj, torch.inverse(pj))
+    assert inv.mv.is_contiguous() and torch.equal(inv.mv, mv) and torch.equal(inv.proj, pj)
+    # csrc/inverse.cu against torch.inverse, bit for bit: random matrices, the cameras of every benchmark scene,
+    # contiguous and transposed views, B = 1 and B > 1 (torch takes different library paths for the two)
+    g = torch.Generator().manual_seed(5)
+    stacks = [(torch.randn(4096, 4, 4, generator=g), torch.randn(4096, 4, 4, generator=g) * 100.0)]
+    for name in ("C1", "C2", "C4", "C3"):
+        c = scenes.config(name)
+        stacks.append((c.mv_mats, c.proj_mats))
+    for a, b in stacks:
+        a, b = a.cuda(), b.cuda()
+        for x, y in ((a, b), (a.transpose(1, 2), b.transpose(1, 2)), (a[:1], b[:1]), (a[:1].transpose(1, 2), b[:1].transpose(1, 2))):
+            inv = _C._Inverses(x, y)
+            torch.cuda.synchronize()
+            inv.check()
+            assert torch.equal(inv.inv_mv.view(torch.int32), torch.inverse(x).view(torch.int32))
+            assert torch.equal(inv.inv_proj.view(torch.int32), torch.inverse(y).view(torch.int32))
     r = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
     bad = s.proj_mats.clone()
     bad[0] = 0
