@@ -192,9 +192,10 @@ def run_ours(args, ws, rank, local):
         leaves.zero_()
         vdep.grad = None
         fint.grad = None
-        color, depth = renderer(verts, s.faces, vcol, fopa, s.mv_mats, s.proj_mats, vdep, fint)
-        # image loss gradient as cotangent (device resident targets)
-        torch.autograd.backward([color, depth], [color.detach() - tgt_c, depth.detach() - tgt_d])
+        with leaves.direct():   # backward kernels accumulate straight into the packed gradient buffer
+            color, depth = renderer(verts, s.faces, vcol, fopa, s.mv_mats, s.proj_mats, vdep, fint)
+            # image loss gradient as cotangent (device resident targets)
+            torch.autograd.backward([color, depth], [color.detach() - tgt_c, depth.detach() - tgt_d])
         leaves.all_reduce()
 
     dbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
@@ -220,11 +221,12 @@ def run_ours(args, ws, rank, local):
         leaves.zero_()
         vd = dbuf["verts_depth"].requires_grad_()
         fi = dbuf["faces_intense"].requires_grad_()
-        color, depth = renderer(verts, s.faces, vcol, fopa, dbuf["mv"], dbuf["proj"], vd, fi)
-        main.wait_event(targets_ready)
-        dc, dd = color.detach() - dbuf["target_color"], depth.detach() - dbuf["target_depth"]
-        loss = 0.5 * (dc.square().sum() + dd.square().sum())
-        torch.autograd.backward([color, depth], [dc, dd])
+        with leaves.direct():
+            color, depth = renderer(verts, s.faces, vcol, fopa, dbuf["mv"], dbuf["proj"], vd, fi)
+            main.wait_event(targets_ready)
+            dc, dd = color.detach() - dbuf["target_color"], depth.detach() - dbuf["target_depth"]
+            loss = 0.5 * (dc.square().sum() + dd.square().sum())
+            torch.autograd.backward([color, depth], [dc, dd])
         leaves.all_reduce()
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -309,11 +309,35 @@ def render_tris(background, verts, faces, verts_color, faces_opacity, mv_mats, p
     return tri_forward_finish(st, inv_mv_mats, inv_proj_mats)
 
 
+# Gradient sinks (multiview.PackedSceneGrads.direct()): while one is active, a renderer call whose scene tensors ARE
+# the sink's leaves lets its backward kernels accumulate straight into the leaves' .grad buffers (the C ABI
+# accumulates into whatever it is given) and returns None for them, instead of filling three fresh tensors that
+# autograd then adds to .grad with three more kernels.  Module-global: autograd runs backward on its own thread.
+_grad_sinks = []
+
+
+def grad_sink_for(verts, verts_color, faces_opacity):
+    for sink in reversed(_grad_sinks):
+        ok = True
+        for x, leaf in zip((verts, verts_color, faces_opacity), sink.leaves):
+            g = leaf.grad
+            if not (x is leaf or (x.data_ptr() == leaf.data_ptr() and x.shape == leaf.shape and x.dtype == leaf.dtype)) \
+                    or g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != leaf.shape \
+                    or g.device != x.device or not leaf.is_leaf:
+                ok = False
+                break
+        if ok:
+            return sink
+    return None
+
+
 def render_tris_backward(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                          inv_proj_mats, verts_depth, faces_intense, dL_dout_color, dL_dout_depth, R, pointBuffer,
-                         faceBuffer, binningBuffer, imageBuffer):
+                         faceBuffer, binningBuffer, imageBuffer, accumulate_into=None):
     """RasterizeTrianglesBackwardCUDA (render.cu:134-208).
-    Returns (dL_dverts[P,3], dL_dvcolor[P,3], dL_dfopacity[F], dL_dvdepth[B,P], dL_dfintense[B,F])."""
+    Returns (dL_dverts[P,3], dL_dvcolor[P,3], dL_dfopacity[F], dL_dvdepth[B,P], dL_dfintense[B,F]).
+    `accumulate_into` (beyond the reference's 18 arguments): existing contiguous fp32 (dL_dverts, dL_dvcolor,
+    dL_dfopacity) tensors that the gradients are ADDED to (and that are returned) instead of fresh zero tensors."""
     lib = _lib.load()
     B, P, F = mv_mats.size(0), verts.size(0), faces.size(0)
     H, W = dL_dout_color.size(2), dL_dout_color.size(3)
@@ -322,6 +346,8 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
         # the five zero-initialised gradient tensors of render.cu:166-171, carved out of ONE allocation
         # (one memset instead of five); each starts on a 16-byte boundary
         sizes = [3 * P, NUM_CHANNELS * P, F, B * P, B * F]
+        if accumulate_into is not None:
+            sizes[0] = sizes[1] = sizes[2] = 0
         offs, o = [], 0
         for n in sizes:
             offs.append(o)
@@ -334,12 +360,17 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
             gc, gd = _f32(dL_dout_color, "dL_dout_color"), _f32(dL_dout_depth, "dL_dout_depth")
             base = flat.data_ptr()   # the kernels are enqueued before the five views below are even created
             gp = [ctypes.c_void_p(base + 4 * off) for off in offs]
+            if accumulate_into is not None:
+                gp[:3] = [ctypes.c_void_p(t.data_ptr()) for t in accumulate_into]
             _lib.check(lib.dmr_tri_backward(B, P, F, W, H, int(R), _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(pointBuffer),
                                             _ptr(faceBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd),
                                             gp[0], gp[1], gp[2], gp[3], gp[4], _stream()))
-        dL_dverts = flat[offs[0]:offs[0] + sizes[0]].view(P, 3)
-        dL_dvcolor = flat[offs[1]:offs[1] + sizes[1]].view(P, NUM_CHANNELS)
-        dL_dfopacity = flat[offs[2]:offs[2] + sizes[2]]
+        if accumulate_into is not None:
+            dL_dverts, dL_dvcolor, dL_dfopacity = accumulate_into
+        else:
+            dL_dverts = flat[offs[0]:offs[0] + sizes[0]].view(P, 3)
+            dL_dvcolor = flat[offs[1]:offs[1] + sizes[1]].view(P, NUM_CHANNELS)
+            dL_dfopacity = flat[offs[2]:offs[2] + sizes[2]]
         dL_dvdepth = flat[offs[3]:offs[3] + sizes[3]].view(B, P)
         dL_dfintense = flat[offs[4]:offs[4] + sizes[4]].view(B, F)
     return dL_dverts, dL_dvcolor, dL_dfopacity, dL_dvdepth, dL_dfintense

@@ -61,6 +61,7 @@ class _RenderTri(th.autograd.Function):
         ctx.render_settings = render_settings
         ctx.num_rendered = num_rendered
         ctx.fused_depth = verts_depth is None
+        ctx.grad_sink = _C.grad_sink_for(verts, verts_color, faces_opacity)   # multiview.PackedSceneGrads.direct()
         ctx.save_for_backward(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
                               verts_depth, faces_intense, pointBuffer, faceBuffer, binningBuffer, imgBuffer)
         return color, depth
@@ -74,9 +75,11 @@ class _RenderTri(th.autograd.Function):
         args = (render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                 inv_proj_mats, verts_depth, faces_intense, grad_out_color, grad_out_depth, num_rendered, pointBuffer,
                 faceBuffer, binningBuffer, imgBuffer)
+        sink = ctx.grad_sink
+        into = None if sink is None else tuple(leaf.grad for leaf in sink.leaves)
         try:
             grad_verts, grad_verts_color, grad_faces_opacity, grad_verts_depth, grad_faces_intense = \
-                _C.render_tris_backward(*args)
+                _C.render_tris_backward(*args, accumulate_into=into)
         except Exception as ex:
             print("\nAn error occured in backward.\n")
             raise ex
@@ -84,6 +87,9 @@ class _RenderTri(th.autograd.Function):
             # verts_depth=None: the depth was the vertex's own NDC z -> chain its gradient into the vertex positions
             _C.tri_depth_chain(verts, mv_mats, proj_mats, grad_verts_depth, grad_verts)
             grad_verts_depth = None
+        if into is not None:
+            # already added to the leaves' .grad by the kernels
+            grad_verts = grad_verts_color = grad_faces_opacity = None
         # gradient positions: reference __init__.py:156-168
         return (grad_verts, None, grad_verts_color, grad_faces_opacity, None, None, grad_verts_depth,
                 grad_faces_intense, None)

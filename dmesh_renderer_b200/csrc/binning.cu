@@ -187,8 +187,12 @@ template <bool HIST>   // HIST: accumulate the tile sort's histograms as a by-pr
 __global__ void __launch_bounds__(256) duplicate_kernel(
     size_t BF, int F, int tiles_x, int tiles_per_view, const uint32_t* __restrict__ order,
     const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
-    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, SortPre sp)
+    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, SortPre sp, uint2* __restrict__ ranges, size_t n_ranges)
 {
+    // tiles without instances keep the empty range (0,0): zero the table here (tile_ranges_kernel runs after the
+    // sort) instead of with one more memset between the num_rendered read-back and this launch
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n_ranges; t += (size_t)gridDim.x * 256)
+        ranges[t] = make_uint2(0u, 0u);
     __shared__ uint32_t s_incl[256];
     __shared__ uint2 s_rect[256];
     __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance divisions hoisted)
@@ -356,8 +360,7 @@ int bin_instances(int B, int F, int W, int H, size_t R, const void* fb, const Fa
 {
     const int tx = (W + DMR_TILE - 1) / DMR_TILE, ty = (H + DMR_TILE - 1) / DMR_TILE;
     const size_t tiles = (size_t)B * tx * ty;
-    DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream));
-    if (R == 0) return 0;
+    if (R == 0) { DMR_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * tiles, stream)); return 0; }
     const size_t BF = (size_t)B * F;
     BinningLayout BL = BinningLayout::make(R);
     uint32_t* ku = at<uint32_t>(binning_buffer, BL.keys_unsorted);
@@ -375,10 +378,12 @@ int bin_instances(int B, int F, int W, int H, size_t R, const void* fb, const Fa
         const unsigned nblk = (unsigned)((BF + 255) / 256);
         if (fused)
             duplicate_kernel<true><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
-                                                            at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp);
+                                                            at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp,
+                                                            ranges, tiles);
         else
             duplicate_kernel<false><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
-                                                             at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp);
+                                                             at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp,
+                                                             ranges, tiles);
         DMR_LAUNCH_CHECK("duplicate_kernel");
     }
     if ((rc = sort_pairs_u32_pre(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, fused, stream))) return rc;

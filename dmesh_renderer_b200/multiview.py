@@ -10,6 +10,7 @@ that has to be exchanged.  Per-view gradients (verts_depth, faces_intense rows)
 stay rank-local.  One process per GPU, torch.distributed (NCCL over NVLink 5 /
 NVSwitch on the B200 box, gloo in the CPU tests); nothing else communicates.
 """
+import contextlib
 from typing import Callable, Optional, Sequence, Tuple
 
 import torch
@@ -99,6 +100,19 @@ class PackedSceneGrads:
     def zero_(self):
         self._full.zero_()
 
+    @contextlib.contextmanager
+    def direct(self):
+        """While active, TriRenderer calls on these leaves accumulate their scene gradients straight into the packed
+        buffer from the backward kernels (no intermediate gradient tensors, no autograd accumulation kernels).
+        The leaves must be passed to the renderer themselves (not views or functions of them); gradient hooks on
+        them do not see this contribution.  The choice is made at forward time, so backward may run later."""
+        from . import _C
+        _C._grad_sinks.append(self)
+        try:
+            yield self
+        finally:
+            _C._grad_sinks.remove(self)
+
     def all_reduce(self, group=None, async_op=False):
         if self._nvls is not None:
             import ctypes
@@ -144,12 +158,13 @@ def multiview_step(render: Callable, scene_grads: PackedSceneGrads, faces: torch
     B = mv_mats.shape[0]
     step = views_per_call or max(B, 1)
     outs = []
-    for s in range(0, B, step):
-        e = min(B, s + step)
-        color, depth = render(verts, faces, verts_color, faces_opacity, mv_mats[s:e], proj_mats[s:e], verts_depth[s:e],
-                              faces_intense[s:e])
-        gc, gd = cotangent_fn(color, depth)
-        torch.autograd.backward([color, depth], [gc, gd])
-        outs.append((color.detach(), depth.detach()))
+    with scene_grads.direct():
+        for s in range(0, B, step):
+            e = min(B, s + step)
+            color, depth = render(verts, faces, verts_color, faces_opacity, mv_mats[s:e], proj_mats[s:e],
+                                  verts_depth[s:e], faces_intense[s:e])
+            gc, gd = cotangent_fn(color, depth)
+            torch.autograd.backward([color, depth], [gc, gd])
+            outs.append((color.detach(), depth.detach()))
     scene_grads.all_reduce(group)
     return outs

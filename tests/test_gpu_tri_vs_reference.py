@@ -222,3 +222,57 @@ def test_fused_vertex_depth_matches_the_upstream_torch_computation():
     c2, d2 = renderer(c[0], s.faces, c[1], c[2], s.mv_mats, s.proj_mats, vdepth.detach(), c[3])
     torch.autograd.backward([c2, d2], [gc, gd])
     assert rel_l2(c[0].grad, a[0].grad) > 1e-3
+
+
+@pytest.mark.parametrize("fused_depth", [False, True])
+def test_direct_gradient_sink_equals_autograd_accumulation(fused_depth):
+    """PackedSceneGrads.direct(): the backward kernels add into the packed .grad buffer themselves; the result must
+    equal what autograd's own accumulation produces, across several calls per step (views_per_call) and with the
+    fused vertex depth, and a call on other tensors must not be redirected."""
+    from dmesh_renderer_b200.multiview import PackedSceneGrads, multiview_step
+    cpu = scenes.random_tri_scene("sink", 33, 2500, 0.08, 128, 160, B=4)
+    s = scenes.to_device(cpu, "cuda")
+    gc, gd = [t.cuda() for t in scenes.cotangents(cpu)]
+    renderer = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
+    vd = None if fused_depth else s.verts_depth
+
+    # plain autograd, all views in one call
+    ref = [s.verts.clone().requires_grad_(), s.verts_color.clone().requires_grad_(), s.faces_opacity.clone().requires_grad_()]
+    fi0 = s.faces_intense.clone().requires_grad_()
+    c0, d0 = renderer(ref[0], s.faces, ref[1], ref[2], s.mv_mats, s.proj_mats, vd, fi0)
+    torch.autograd.backward([c0, d0], [gc, gd])
+
+    class Render:   # multiview_step slices verts_depth; None stays None
+        def __call__(self, v, f, vc, fo, mv, pj, vdep, fint):
+            return renderer(v, f, vc, fo, mv, pj, None if fused_depth else vdep, fint)
+
+    g = PackedSceneGrads(s.verts.clone(), s.verts_color.clone(), s.faces_opacity.clone())
+    fi1 = s.faces_intense.clone().requires_grad_()
+    launches = []
+    orig = _C.render_tris_backward
+
+    def spy(*a, **k):
+        launches.append(k.get("accumulate_into") is not None)
+        return orig(*a, **k)
+    _C.render_tris_backward = spy
+    try:
+        def cotangents(c, d):   # call i renders views 2i, 2i+1; its backward has not run yet
+            first = 2 * len(launches)
+            return gc[first:first + c.shape[0]], gd[first:first + c.shape[0]]
+        multiview_step(Render(), g, s.faces, s.mv_mats, s.proj_mats, s.verts_depth, fi1, cotangents, views_per_call=2)
+        assert launches == [True, True]
+        for n, leaf, r in zip(("verts", "verts_color", "faces_opacity"), g.leaves, ref):
+            assert rel_l2(leaf.grad, r.grad) <= GRAD_TOL, n
+            assert leaf.grad.data_ptr() >= g.flat.data_ptr() and leaf.grad.data_ptr() < g.flat.data_ptr() + 4 * g.flat.numel()
+        assert rel_l2(fi1.grad, fi0.grad) <= GRAD_TOL
+        # tensors that are not the sink's leaves: ordinary autograd path even while the sink is active
+        other = [t.detach().clone().requires_grad_() for t in ref]
+        with g.direct():
+            c2, d2 = renderer(other[0], s.faces, other[1], other[2], s.mv_mats, s.proj_mats, vd, s.faces_intense)
+            torch.autograd.backward([c2, d2], [gc, gd])
+        assert launches[-1] is False
+        for o, r in zip(other, ref):
+            assert rel_l2(o.grad, r.grad) <= GRAD_TOL
+        assert not _C._grad_sinks
+    finally:
+        _C.render_tris_backward = orig
