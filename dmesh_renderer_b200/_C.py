@@ -288,6 +288,8 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
         b2 = (_ptr(img_buf), _ptr(out_color), _ptr(out_depth), _stream())
         if inverses is not None:
             inverses.join()
+        # (Measured and rejected: one native call that waits for R and launches phase 2 without returning to Python
+        # in between -- 1163 vs 1159 views/s at C2: the bubble is the D2H + launch latency, not the interpreter.)
         R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
         _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, *a, _ptr(bin_buf), *b2))
         if inverses is not None:
