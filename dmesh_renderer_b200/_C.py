@@ -335,11 +335,12 @@ def grad_sink_for(verts, verts_color, faces_opacity):
 
 def render_tris_backward(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                          inv_proj_mats, verts_depth, faces_intense, dL_dout_color, dL_dout_depth, R, pointBuffer,
-                         faceBuffer, binningBuffer, imageBuffer, accumulate_into=None):
+                         faceBuffer, binningBuffer, imageBuffer, accumulate_into=None, deterministic=False):
     """RasterizeTrianglesBackwardCUDA (render.cu:134-208).
     Returns (dL_dverts[P,3], dL_dvcolor[P,3], dL_dfopacity[F], dL_dvdepth[B,P], dL_dfintense[B,F]).
     `accumulate_into` (beyond the reference's 18 arguments): existing contiguous fp32 (dL_dverts, dL_dvcolor,
-    dL_dfopacity) tensors that the gradients are ADDED to (and that are returned) instead of fresh zero tensors."""
+    dL_dfopacity) tensors that the gradients are ADDED to (and that are returned) instead of fresh zero tensors.
+    `deterministic`: run-to-run reproducible gradients (64-bit fixed-point accumulation, dmr_tri_backward_deterministic)."""
     lib = _lib.load()
     B, P, F = mv_mats.size(0), verts.size(0), faces.size(0)
     H, W = dL_dout_color.size(2), dL_dout_color.size(3)
@@ -364,9 +365,13 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
             gp = [ctypes.c_void_p(base + 4 * off) for off in offs]
             if accumulate_into is not None:
                 gp[:3] = [ctypes.c_void_p(t.data_ptr()) for t in accumulate_into]
-            _lib.check(lib.dmr_tri_backward(B, P, F, W, H, int(R), _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(pointBuffer),
-                                            _ptr(faceBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd),
-                                            gp[0], gp[1], gp[2], gp[3], gp[4], _stream()))
+            a = (B, P, F, W, H, int(R), _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(pointBuffer), _ptr(faceBuffer),
+                 _ptr(binningBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd), gp[0], gp[1], gp[2], gp[3], gp[4])
+            if deterministic:
+                ws = torch.empty(lib.dmr_tri_backward_deterministic_bytes(B, P, F), dtype=torch.uint8, device=dev)
+                _lib.check(lib.dmr_tri_backward_deterministic(*a, _ptr(ws), ws.numel(), _stream()))
+            else:
+                _lib.check(lib.dmr_tri_backward(*a, _stream()))
         if accumulate_into is not None:
             dL_dverts, dL_dvcolor, dL_dfopacity = accumulate_into
         else:

@@ -29,11 +29,25 @@ class TriRenderSettings(NamedTuple):      # reference __init__.py:13-16
     bg: th.Tensor
 
 
+_deterministic_default = False
+
+
+def set_deterministic(flag: bool) -> bool:
+    """Process-wide default for the tri renderer's backward pass (extension): True = run-to-run
+    reproducible gradients (64-bit fixed-point accumulation instead of fp32 atomics; same values within fp32
+    accumulation noise, slower).  `TriRenderer(settings, deterministic=...)` / `render_tri(..., deterministic=...)`
+    override it per renderer / call.  Returns the previous value.  The tet renderer is not covered."""
+    global _deterministic_default
+    old, _deterministic_default = _deterministic_default, bool(flag)
+    return old
+
+
 def render_tri(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
-               render_settings: TriRenderSettings):
-    """reference __init__.py:18-43"""
+               render_settings: TriRenderSettings, deterministic=None):
+    """reference __init__.py:18-43 (`deterministic`: see set_deterministic)"""
+    det = _deterministic_default if deterministic is None else bool(deterministic)
     return _RenderTri.apply(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
-                            render_settings)
+                            render_settings, det)
 
 
 class _RenderTri(th.autograd.Function):
@@ -41,7 +55,8 @@ class _RenderTri(th.autograd.Function):
 
     @staticmethod
     def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
-                render_settings):
+                render_settings, deterministic=False):
+        ctx.deterministic = deterministic
         try:
             # Same computation as _C.render_tris(*13 args) (reference __init__.py:62-88), issued in two halves
             # (phase 1: preprocess + scan; phase 2 after the num_rendered read-back).
@@ -79,7 +94,7 @@ class _RenderTri(th.autograd.Function):
         into = None if sink is None else tuple(leaf.grad for leaf in sink.leaves)
         try:
             grad_verts, grad_verts_color, grad_faces_opacity, grad_verts_depth, grad_faces_intense = \
-                _C.render_tris_backward(*args, accumulate_into=into)
+                _C.render_tris_backward(*args, accumulate_into=into, deterministic=ctx.deterministic)
         except Exception as ex:
             print("\nAn error occured in backward.\n")
             raise ex
@@ -92,15 +107,16 @@ class _RenderTri(th.autograd.Function):
             grad_verts = grad_verts_color = grad_faces_opacity = None
         # gradient positions: reference __init__.py:156-168
         return (grad_verts, None, grad_verts_color, grad_faces_opacity, None, None, grad_verts_depth,
-                grad_faces_intense, None)
+                grad_faces_intense, None, None)
 
 
 class TriRenderer(th.nn.Module):
     """reference __init__.py:172-225"""
 
-    def __init__(self, render_settings: TriRenderSettings):
+    def __init__(self, render_settings: TriRenderSettings, deterministic=None):
         super().__init__()
         self.render_settings = render_settings
+        self.deterministic = deterministic     # None: the process-wide default (set_deterministic)
 
     def forward(self, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense):
         """
@@ -112,7 +128,8 @@ class TriRenderer(th.nn.Module):
         returns color [B,3,H,W], depth [B,1,H,W]
         """
         return render_tri(verts, faces.to(dtype=th.int32), verts_color, faces_opacity, mv_mats.transpose(1, 2),
-                          proj_mats.transpose(1, 2), verts_depth, faces_intense, self.render_settings)
+                          proj_mats.transpose(1, 2), verts_depth, faces_intense, self.render_settings,
+                          self.deterministic)
 
 
 # =============================================================================

@@ -28,6 +28,8 @@ SIGNATURES = {
     "dmr_tri_depth_chain": (c_int, [c_int, c_int] + [c_void_p] * 5 + [c_void_p]),
     "dmr_tri_forward_render": (c_int, [c_int] * 6 + [c_void_p] * 9 + [c_void_p]),
     "dmr_tri_backward": (c_int, [c_int] * 6 + [c_void_p] * 14 + [c_void_p]),
+    "dmr_tri_backward_deterministic_bytes": (c_size_t, [c_int] * 3),
+    "dmr_tri_backward_deterministic": (c_int, [c_int] * 6 + [c_void_p] * 14 + [c_void_p, c_size_t] + [c_void_p]),
     "dmr_tet_forward_bin": (c_int, [c_int] * 6 + [c_void_p] * 12 + [c_void_p]),
     "dmr_tet_forward_render": (c_int, [c_int] * 8 + [c_void_p] * 13 + [c_void_p]),
     "dmr_tet_backward": (c_int, [c_int] * 7 + [c_void_p] * 13 + [c_void_p]),

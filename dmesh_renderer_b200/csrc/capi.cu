@@ -228,11 +228,12 @@ int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float
     return tri_render_forward(p, stream);
 }
 
-int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* background, const float* inv_mv_mats,
-                     const float* inv_proj_mats, const void* point_buffer, const void* face_buffer,
-                     const void* binning_buffer, const void* image_buffer, const float* dL_dcolor,
-                     const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity,
-                     float* dL_dvdepth, float* dL_dfintense, dmr_stream_t stream_)
+static int tri_backward_impl(int B, int P, int F, int W, int H, int R, const float* background, const float* inv_mv_mats,
+                             const float* inv_proj_mats, const void* point_buffer, const void* face_buffer,
+                             const void* binning_buffer, const void* image_buffer, const float* dL_dcolor,
+                             const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity,
+                             float* dL_dvdepth, float* dL_dfintense, void* det_workspace, size_t det_workspace_bytes,
+                             bool deterministic, dmr_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!sizes_ok(B, P, F, W, H) || R < 0) return DMR_ETOOLARGE;
@@ -258,6 +259,20 @@ int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* back
     p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
     p.dL_dverts = dL_dverts; p.dL_dvcolor = dL_dvcolor; p.dL_dfopacity = dL_dfopacity;
     p.dL_dvdepth = dL_dvdepth; p.dL_dfintense = dL_dfintense;
+    if (deterministic) {
+        TriDetLayout DL = TriDetLayout::make((size_t)B, (size_t)P, (size_t)F);
+        if (!det_workspace || det_workspace_bytes < DL.total) {
+            set_error("deterministic backward needs a workspace of %zu bytes (dmr_tri_backward_deterministic_bytes)", DL.total);
+            return DMR_EINVAL;
+        }
+        p.det_gmax = at<uint32_t>(det_workspace, DL.gmax);
+        p.det_stats = at<long long>(det_workspace, DL.stats);
+        p.det_vert = at<long long>(det_workspace, DL.vert);
+        p.det_vdepth = at<long long>(det_workspace, DL.vdepth);
+        p.det_fopa = at<long long>(det_workspace, DL.fopa);
+        DMR_CUDA(cudaMemsetAsync(det_workspace, 0, DL.total, stream));
+        return tri_render_backward_deterministic(p, stream);
+    }
     // backward scratch lives in the face buffer (opaque state owned by autograd ctx)
     p.grad_stats = const_cast<float*>(at<float>(face_buffer, FL.grad_stats));
     // per-vertex vector accumulators only when there are at least two (view, face) records per vertex
@@ -265,6 +280,35 @@ int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* back
     p.grad_vacc = use_vacc ? const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc)) : nullptr;
     DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (use_vacc ? FL.grad_end : FL.grad_vacc) - FL.grad_stats, stream));
     return tri_render_backward(p, stream);
+}
+
+int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* background, const float* inv_mv_mats,
+                     const float* inv_proj_mats, const void* point_buffer, const void* face_buffer,
+                     const void* binning_buffer, const void* image_buffer, const float* dL_dcolor,
+                     const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity,
+                     float* dL_dvdepth, float* dL_dfintense, dmr_stream_t stream)
+{
+    return tri_backward_impl(B, P, F, W, H, R, background, inv_mv_mats, inv_proj_mats, point_buffer, face_buffer,
+                             binning_buffer, image_buffer, dL_dcolor, dL_ddepth, dL_dverts, dL_dvcolor, dL_dfopacity,
+                             dL_dvdepth, dL_dfintense, nullptr, 0, false, stream);
+}
+
+size_t dmr_tri_backward_deterministic_bytes(int B, int P, int F)
+{
+    if (B < 0 || P < 0 || F < 0) return 0;
+    return TriDetLayout::make((size_t)B, (size_t)P, (size_t)F).total;
+}
+
+int dmr_tri_backward_deterministic(int B, int P, int F, int W, int H, int R, const float* background,
+                                   const float* inv_mv_mats, const float* inv_proj_mats, const void* point_buffer,
+                                   const void* face_buffer, const void* binning_buffer, const void* image_buffer,
+                                   const float* dL_dcolor, const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor,
+                                   float* dL_dfopacity, float* dL_dvdepth, float* dL_dfintense, void* workspace,
+                                   size_t workspace_bytes, dmr_stream_t stream)
+{
+    return tri_backward_impl(B, P, F, W, H, R, background, inv_mv_mats, inv_proj_mats, point_buffer, face_buffer,
+                             binning_buffer, image_buffer, dL_dcolor, dL_ddepth, dL_dverts, dL_dvcolor, dL_dfopacity,
+                             dL_dvdepth, dL_dfintense, workspace, workspace_bytes, true, stream);
 }
 
 int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, int H, size_t R, const void* buffer,

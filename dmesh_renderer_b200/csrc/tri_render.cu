@@ -325,9 +325,41 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 #ifndef DMR_TRI_BWD_GROUP_LANES
 #define DMR_TRI_BWD_GROUP_LANES 2
 #endif
-template <int GL>
-__global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(TriRenderParams p)
+// Deterministic mode
+// ----------------------------------
+// Everything up to the gradient accumulation is already run-to-run reproducible (stable sorts, fixed per-pixel
+// compositing order); only the ORDER in which the groups' partial sums reach a (view, face) record, and the faces'
+// contributions reach a vertex, varies -- and fp32 addition is not associative.  The deterministic variant
+// accumulates the same partial sums as 64-bit FIXED-POINT integers (integer addition is associative, so any
+// arrival order gives the same bits): value * 2^k rounded to nearest, added with red.global.add.u64.
+// All gradients are linear in the cotangent, so k is chosen relative to g = max |dL_dout| (found by a max-reduction,
+// itself order-independent): with 2^(e-1) <= g < 2^e,
+//     colour / opacity / intensity / depth terms:  k = 38 - e   (|sum| < 3.4e7 g, resolution 3.6e-12 g)
+//     vertex-position terms (carry 1/det):          k = 28 - e   (|sum| < 3.4e10 g, resolution 3.7e-9 g)
+// A term beyond the range saturates (cvt.rni.s64.f32) instead of wrapping.
+#define DMR_DET_VALUE_BITS 38
+#define DMR_DET_GEOM_BITS 28
+__device__ __forceinline__ void det_scales(uint32_t gmax_bits, float& sv, float& sg)
 {
+    const float g = __uint_as_float(gmax_bits);
+    sv = sg = 0.0f;
+    if (!(g > 0.0f) || !(g <= 3.0e38f)) return;      // zero (all gradients are zero), inf or NaN cotangents
+    int e;
+    frexpf(g, &e);
+    e = max(e, -80);
+    sv = ldexpf(1.0f, DMR_DET_VALUE_BITS - e);
+    sg = ldexpf(1.0f, DMR_DET_GEOM_BITS - e);
+}
+__device__ __forceinline__ void det_add(long long* dst, float v, float scale)
+{
+    const long long q = __float2ll_rn(v * scale);
+    if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(q));
+}
+
+template <int GL, bool DET>
+__device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
+{
+    static_assert(!DET || GL == 2, "the deterministic variant exists for 2-lane groups only");
     __shared__ uint4 s_rec[RB * 9];
     __shared__ uint32_t s_face[RB];
     __shared__ int s_max[8];
@@ -390,6 +422,8 @@ __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(T
     // pixel ranges of the four sub-blocks: x in {bx0..bx0+3, bx0+4..bx0+7}, y in {by0..by0+1, by0+2..by0+3}
     const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
     float* const stats = p.grad_stats;
+    float det_sv = 0.0f, det_sg = 0.0f;
+    if (DET) det_scales(*p.det_gmax, det_sv, det_sg);
 
     for (int c = nchunk - 1; c >= 0; c--) {
         __syncthreads();
@@ -591,7 +625,18 @@ __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(T
                     // 2 lanes: 24 -> 12 values per lane; lane class c = lane & 1 owns logical 12c..12c+11 =
                     // quads 2c, 2c+1 and the two adjacent pairs 2c, 2c+1 (one more 16-byte vector)
                     xreduce_step<12, 1>(v, h1);
-                    if (have) {
+                    if (DET) {
+                        if (have) {
+                            // fixed-point record in LOGICAL order: this lane holds sums 12*cls .. 12*cls+11
+                            const int cls = lane & 1;
+                            long long* rec = p.det_stats + ((size_t)b * p.F + s_face[j]) * 24 + 12 * cls;
+#pragma unroll
+                            for (int k = 0; k < 12; k++) {
+                                if (cls == 1 && k >= 9) break;                       // logical 21..23: padding
+                                det_add(rec + k, v[k], (cls == 0 && k < 7) ? det_sg : det_sv);
+                            }
+                        }
+                    } else if (have) {
                         float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
                         const int cls = lane & 1;
                         // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
@@ -615,24 +660,67 @@ __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(T
     }
 }
 
+template <int GL>
+__global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(TriRenderParams p)
+{
+    tri_render_bwd_body<GL, false>(p);
+}
+
+__global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_det_kernel(TriRenderParams p)
+{
+    tri_render_bwd_body<2, true>(p);
+}
+
+// Deterministic mode: g = max |dL_dout| over both cotangent images, as float bits (non-negative floats order like
+// unsigned integers; the maximum does not depend on the order of the comparisons).
+__global__ void __launch_bounds__(256) tri_det_gmax_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
+                                                           size_t nb, uint32_t* __restrict__ gmax)
+{
+    uint32_t m = 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < na + nb; i += (size_t)gridDim.x * 256) {
+        const float x = i < na ? a[i] : b[i - na];
+        m = max(m, __float_as_uint(fabsf(x)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(gmax, m);
+}
+
 // Once per (view, face): statistics -> gradients of the five inputs (see tri_render_bwd_kernel).
-__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p)
+template <bool DET>
+__device__ __forceinline__ void tri_grad_finish_body(const TriRenderParams& p)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t BF = (size_t)p.B * p.F;
     if (idx >= BF) return;
-    const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + idx * 24);
-    float sm[24], st[24];
+    float st[24];
     bool any = false;
+    float det_sv = 0.0f, det_sg = 0.0f;
+    if (DET) {
+        det_scales(*p.det_gmax, det_sv, det_sg);
+        if (det_sv == 0.0f) return;
+        const double iv = 1.0 / (double)det_sv, ig = 1.0 / (double)det_sg;
+        const long long* r = p.det_stats + idx * 24;
 #pragma unroll
-    for (int q = 0; q < 6; q++) {
-        float4 t = st4[q];
-        sm[4 * q] = t.x; sm[4 * q + 1] = t.y; sm[4 * q + 2] = t.z; sm[4 * q + 3] = t.w;
-        any = any || t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f;
+        for (int i = 0; i < 21; i++) {
+            const long long q = r[i];
+            any = any || q != 0;
+            st[i] = (float)((double)q * (i < 7 ? ig : iv));
+        }
+        st[21] = st[22] = st[23] = 0.0f;
+    } else {
+        const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + idx * 24);
+        float sm[24];
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            float4 t = st4[q];
+            sm[4 * q] = t.x; sm[4 * q + 1] = t.y; sm[4 * q + 2] = t.z; sm[4 * q + 3] = t.w;
+            any = any || t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 24; i++) st[i] = sm[stat_slot(i)];
     }
     if (!any) return;
-#pragma unroll
-    for (int i = 0; i < 24; i++) st[i] = sm[stat_slot(i)];
     const int b = (int)(idx / (size_t)p.F);
     const size_t f = idx - (size_t)b * p.F;
     const float* w = reinterpret_cast<const float*>(p.records + idx) + 12;
@@ -653,6 +741,18 @@ __global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p)
     // Used when there are many (view, face) records per vertex (multi-view batches, shared vertices): the
     // accumulators cost 56 B of extra streaming per VERTEX (C4, 8 views: finish 705 -> 536 us; C5 with one
     // view of 12 M unshared vertices: 92 -> 175 us, hence the switch in tri_render_backward).
+    if (DET) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            long long* a = p.det_vert + 8 * (size_t)vi[k];
+            det_add(a + 0, dp[k].x, det_sg); det_add(a + 1, dp[k].y, det_sg); det_add(a + 2, dp[k].z, det_sg);
+            det_add(a + 4, st[12 + 3 * k], det_sv); det_add(a + 5, st[13 + 3 * k], det_sv); det_add(a + 6, st[14 + 3 * k], det_sv);
+            det_add(p.det_vdepth + (size_t)b * p.P + vi[k], st[9 + k], det_sv);
+        }
+        det_add(p.det_fopa + f, st[7], det_sv);
+        p.dL_dfintense[idx] = st[8];
+        return;
+    }
     if (p.grad_vacc) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -672,6 +772,42 @@ __global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p)
     }
     atomicAdd(p.dL_dfopacity + f, st[7]);
     p.dL_dfintense[idx] = st[8];
+}
+
+__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p) { tri_grad_finish_body<false>(p); }
+__global__ void __launch_bounds__(256) tri_grad_finish_det_kernel(TriRenderParams p) { tri_grad_finish_body<true>(p); }
+
+// Deterministic mode, last step: fixed-point accumulators -> += into the caller's fp32 gradient tensors.
+// One thread per vertex, then per (view, vertex), then per face.
+__global__ void __launch_bounds__(256) tri_det_convert_kernel(TriRenderParams p)
+{
+    float sv, sg;
+    det_scales(*p.det_gmax, sv, sg);
+    if (sv == 0.0f) return;
+    const double iv = 1.0 / (double)sv, ig = 1.0 / (double)sg;
+    const size_t P = (size_t)p.P, BP = (size_t)p.B * p.P, F = (size_t)p.F;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < P) {
+        const long long* a = p.det_vert + 8 * i;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const long long q = a[c], r = a[4 + c];
+            if (q != 0) p.dL_dverts[3 * i + c] += (float)((double)q * ig);
+            if (r != 0) p.dL_dvcolor[3 * i + c] += (float)((double)r * iv);
+        }
+        return;
+    }
+    i -= P;
+    if (i < BP) {
+        const long long q = p.det_vdepth[i];
+        if (q != 0) p.dL_dvdepth[i] += (float)((double)q * iv);
+        return;
+    }
+    i -= BP;
+    if (i < F) {
+        const long long q = p.det_fopa[i];
+        if (q != 0) p.dL_dfopacity[i] += (float)((double)q * iv);
+    }
 }
 
 // Once per vertex: float4 accumulators -> dL_dverts[P,3], dL_dvcolor[P,3].
@@ -715,6 +851,32 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
             tri_grad_vertex_kernel<<<(unsigned)((p.P + 255) / 256), 256, 0, stream>>>(p);
             DMR_LAUNCH_CHECK("tri_grad_vertex_kernel");
         }
+    }
+    return 0;
+}
+
+int tri_render_backward_deterministic(const TriRenderParams& p, cudaStream_t stream)
+{
+    if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
+    dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
+    const size_t HW = (size_t)p.W * p.H, BF = (size_t)p.B * p.F;
+    {
+        ProfScope prof(ST_TRI_BWD, stream);
+        count_launch(1);   // two kernels under one scope
+        tri_det_gmax_kernel<<<592, 256, 0, stream>>>(p.dL_dcolor, 3 * p.B * HW, p.dL_ddepth, p.B * HW,
+                                                     const_cast<uint32_t*>(p.det_gmax));
+        DMR_LAUNCH_CHECK("tri_det_gmax_kernel");
+        tri_render_bwd_det_kernel<<<grid, 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tri_render_bwd_det_kernel");
+    }
+    {
+        ProfScope prof(ST_TRI_BWD_FINISH, stream);
+        count_launch(1);
+        tri_grad_finish_det_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tri_grad_finish_det_kernel");
+        const size_t n = (size_t)p.P + (size_t)p.B * p.P + (size_t)p.F;
+        tri_det_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tri_det_convert_kernel");
     }
     return 0;
 }

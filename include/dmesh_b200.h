@@ -151,6 +151,26 @@ int dmr_tri_backward(
     float* dL_dfintense,         /* [B,F]  */
     dmr_stream_t stream);
 
+/* The same with run-to-run REPRODUCIBLE gradients (the reference's scalar atomics,             */
+/* cuda_rasterizer/backward.cu:389-415, give different low-order bits on every run).  Identical kernels up to     */
+/* the accumulation; the partial sums are accumulated as 64-bit fixed-point integers, scaled relative to           */
+/* max |dL_dout| (integer addition is associative, so the arrival order no longer matters), and converted once.    */
+/* Resolution 2^-38 of max |dL_dout| for colour / opacity / intensity / depth terms, 2^-28 for vertex positions;   */
+/* results agree with dmr_tri_backward within fp32 accumulation noise.  `workspace`: device scratch of            */
+/* dmr_tri_backward_deterministic_bytes(B, P, F) bytes (zeroed by the call).  The gradients are ADDED to the five  */
+/* output buffers, as in dmr_tri_backward.                                                                        */
+size_t dmr_tri_backward_deterministic_bytes(int B, int P, int F);
+int dmr_tri_backward_deterministic(
+    int B, int P, int F, int W, int H, int R,
+    const float* background,
+    const float* inv_mv_mats, const float* inv_proj_mats,
+    const void* point_buffer, const void* face_buffer,
+    const void* binning_buffer, const void* image_buffer,
+    const float* dL_dcolor, const float* dL_ddepth,
+    float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity, float* dL_dvdepth, float* dL_dfintense,
+    void* workspace, size_t workspace_bytes,
+    dmr_stream_t stream);
+
 /* ------------------------------------------------------------------------ */
 /* Tet renderer, forward, phase 1.  Replaces E1, E4, E5 of                   */
 /* CudaRenderer::Renderer::forward (cuda_renderer/renderer_impl.cu:241-310): */

@@ -276,3 +276,71 @@ def test_direct_gradient_sink_equals_autograd_accumulation(fused_depth):
         assert not _C._grad_sinks
     finally:
         _C.render_tris_backward = orig
+
+
+def _tri_grads(s, gc, gd, deterministic, sink=False):
+    leaves = [s.verts.clone().requires_grad_(), s.verts_color.clone().requires_grad_(),
+              s.faces_opacity.clone().requires_grad_(), s.verts_depth.clone().requires_grad_(),
+              s.faces_intense.clone().requires_grad_()]
+    renderer = TriRenderer(TriRenderSettings(s.H, s.W, s.bg), deterministic=deterministic)
+    color, depth = renderer(leaves[0], s.faces, leaves[1], leaves[2], s.mv_mats, s.proj_mats, leaves[3], leaves[4])
+    torch.autograd.backward([color, depth], [gc, gd])
+    return [leaf.grad for leaf in leaves]
+
+
+@pytest.mark.parametrize("name", ["small_tri", "C1", "C2", "mv4"])
+def test_deterministic_backward_is_reproducible_and_matches(name):
+    """TriRenderer(..., deterministic=True) must give bit-identical gradients on every run (64-bit
+    fixed-point accumulation) that agree with the reference extension within the gradient tolerance, for any scale
+    of the cotangents (the fixed-point format is relative to max |dL_dout|)."""
+    need_ref()
+    cpu = scenes.random_tri_scene("mv4", 44, 3000, 0.09, 160, 144, B=4) if name == "mv4" else scenes.config(name)
+    s = scenes.to_device(cpu, "cuda")
+    gc, gd = [t.cuda() for t in scenes.cotangents(cpu)]
+    ref = ref_harness.ref_tri_forward(s)
+    rg = ref_harness.ref_tri_backward(s, ref, gc, gd)
+    names = ["verts", "verts_color", "faces_opacity", "verts_depth", "faces_intense"]
+    runs = [_tri_grads(s, gc, gd, True) for _ in range(4)]
+    for r in runs[1:]:
+        for n, a, b in zip(names, runs[0], r):
+            assert torch.equal(a, b), "%s differs between two deterministic runs" % n
+    for n, a, r in zip(names, runs[0], rg):
+        e = rel_l2(a, r)
+        assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
+    # linear in the cotangent, at any magnitude: powers of two scale exactly, so even the bits must follow
+    for k in (2.0 ** -30, 2.0 ** 20):
+        scaled = _tri_grads(s, gc * k, gd * k, True)
+        for n, a, b in zip(names, runs[0], scaled):
+            assert torch.equal(a * k, b), "%s: not exactly linear under cotangent scale %g" % (n, k)
+    zero = _tri_grads(s, gc * 0, gd * 0, True)
+    assert all(float(z.abs().max()) == 0.0 for z in zero)
+
+
+def test_deterministic_mode_default_switch_and_gradient_sink():
+    """set_deterministic() flips the process-wide default; the deterministic kernels also serve the direct gradient
+    sink (PackedSceneGrads.direct) -- there the result is reproducible as long as the sink starts from the same values."""
+    import dmesh_renderer_b200 as pkg
+    from dmesh_renderer_b200.multiview import PackedSceneGrads
+    cpu = scenes.random_tri_scene("detsink", 45, 2000, 0.1, 128, 128, B=2)
+    s = scenes.to_device(cpu, "cuda")
+    gc, gd = [t.cuda() for t in scenes.cotangents(cpu)]
+    base = _tri_grads(s, gc, gd, True)
+    old = pkg.set_deterministic(True)
+    try:
+        assert old is False
+        again = _tri_grads(s, gc, gd, None)          # None -> process default
+        for a, b in zip(base, again):
+            assert torch.equal(a, b)
+        outs = []
+        for _ in range(2):
+            g = PackedSceneGrads(s.verts.clone(), s.verts_color.clone(), s.faces_opacity.clone())
+            r = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
+            with g.direct():
+                c, d = r(g.leaves[0], s.faces, g.leaves[1], g.leaves[2], s.mv_mats, s.proj_mats, s.verts_depth, s.faces_intense)
+                torch.autograd.backward([c, d], [gc, gd])
+            outs.append(g.flat.clone())
+        assert torch.equal(outs[0], outs[1])
+        for a, leaf in zip(base[:3], g.leaves):
+            assert torch.equal(a, leaf.grad)          # 0 + x == x
+    finally:
+        pkg.set_deterministic(old)
