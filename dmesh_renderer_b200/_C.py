@@ -467,12 +467,13 @@ def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, p
 
 def render_tets_backward(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                          inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, grad_color, grad_depth,
-                         pointBuffer, faceBuffer, binningBuffer, imageBuffer, ray_random_seed=None):
+                         pointBuffer, faceBuffer, binningBuffer, imageBuffer, ray_random_seed=None, deterministic=False):
     """RenderFTetsBackwardCUDA (render.cu:338-412).
     Returns (dL_dverts_color[P,3], dL_dfaces_opacity[F]).  `ray_random_seed` is an
     optional trailing argument beyond the reference's 20: the autograd wrapper passes
     the forward's seed so that jittered rays (seed > 0) are re-read from the image
-    buffer; with the reference's 20 arguments pixel-centre rays are used."""
+    buffer; with the reference's 20 arguments pixel-centre rays are used.  `deterministic`: run-to-run reproducible
+    gradients (dmr_tet_backward_deterministic)."""
     lib = _lib.load()
     B, P, F, T = mv_mats.size(0), verts.size(0), faces.size(0), tets.size(0)
     H, W = grad_color.size(2), grad_color.size(3)
@@ -489,8 +490,12 @@ def render_tets_backward(background, verts, faces, verts_color, faces_opacity, m
             imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
             fint = _f32(faces_intense, "faces_intense")
             gc, gd = _f32(grad_color, "grad_color"), _f32(grad_depth, "grad_depth")
-            _lib.check(lib.dmr_tet_backward(B, P, F, T, W, H, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj),
-                                            _ptr(imv), _ptr(ipj), _ptr(fint), _ptr(pointBuffer), _ptr(faceBuffer),
-                                            _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(dL_dverts_color),
-                                            _ptr(dL_dfaces_opacity), _stream()))
+            a = (B, P, F, T, W, H, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj), _ptr(imv), _ptr(ipj), _ptr(fint),
+                 _ptr(pointBuffer), _ptr(faceBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(dL_dverts_color),
+                 _ptr(dL_dfaces_opacity))
+            if deterministic:
+                ws = torch.empty(lib.dmr_tet_backward_deterministic_bytes(P, F), dtype=torch.uint8, device=dev)
+                _lib.check(lib.dmr_tet_backward_deterministic(*a, _ptr(ws), ws.numel(), _stream()))
+            else:
+                _lib.check(lib.dmr_tet_backward(*a, _stream()))
     return dL_dverts_color, dL_dfaces_opacity

@@ -33,10 +33,10 @@ _deterministic_default = False
 
 
 def set_deterministic(flag: bool) -> bool:
-    """Process-wide default for the tri renderer's backward pass (extension): True = run-to-run
+    """Process-wide default for the backward passes of both renderers (extension): True = run-to-run
     reproducible gradients (64-bit fixed-point accumulation instead of fp32 atomics; same values within fp32
     accumulation noise, slower).  `TriRenderer(settings, deterministic=...)` / `render_tri(..., deterministic=...)`
-    override it per renderer / call.  Returns the previous value.  The tet renderer is not covered."""
+    override it per renderer / call (TetRenderer / render_tet likewise).  Returns the previous value."""
     global _deterministic_default
     old, _deterministic_default = _deterministic_default, bool(flag)
     return old
@@ -144,10 +144,11 @@ class TetRenderSettings(NamedTuple):      # reference __init__.py:237-241
 
 
 def render_tet(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
-               face_tets, tet_faces, render_settings: TetRenderSettings):
-    """reference __init__.py:243-275"""
+               face_tets, tet_faces, render_settings: TetRenderSettings, deterministic=None):
+    """reference __init__.py:243-275 (`deterministic`: see set_deterministic)"""
+    det = _deterministic_default if deterministic is None else bool(deterministic)
     return _RenderTet.apply(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense,
-                            tets, face_tets, tet_faces, render_settings)
+                            tets, face_tets, tet_faces, render_settings, det)
 
 
 class _RenderTet(th.autograd.Function):
@@ -155,7 +156,8 @@ class _RenderTet(th.autograd.Function):
 
     @staticmethod
     def forward(ctx, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
-                face_tets, tet_faces, render_settings):
+                face_tets, tet_faces, render_settings, deterministic=False):
+        ctx.deterministic = deterministic
         inv = _C._Inverses(mv_mats, proj_mats)   # th.inverse x2 (reference :298-299): one launch, no device sync
         inv_mv_mats, inv_proj_mats = inv.inv_mv, inv.inv_proj
         mv_mats, proj_mats = inv.mv, inv.proj    # contiguous copies written by the same launch
@@ -184,20 +186,21 @@ class _RenderTet(th.autograd.Function):
                 inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, grad_out_color, grad_out_depth,
                 pointBuffer, faceBuffer, binningBuffer, imgBuffer, render_settings.ray_random_seed)
         try:
-            grad_verts_color, grad_faces_opacity = _C.render_tets_backward(*args)
+            grad_verts_color, grad_faces_opacity = _C.render_tets_backward(*args, deterministic=ctx.deterministic)
         except Exception as ex:
             print("\nAn error occured in backward.\n")
             raise ex
         # gradient positions: reference __init__.py:407-422
-        return (None, None, grad_verts_color, grad_faces_opacity, None, None, None, None, None, None, None, None)
+        return (None, None, grad_verts_color, grad_faces_opacity, None, None, None, None, None, None, None, None, None)
 
 
 class TetRenderer(th.nn.Module):
     """reference __init__.py:426-488"""
 
-    def __init__(self, render_settings: TetRenderSettings):
+    def __init__(self, render_settings: TetRenderSettings, deterministic=None):
         super().__init__()
         self.render_settings = render_settings
+        self.deterministic = deterministic     # None: the process-wide default (set_deterministic)
 
     def forward(self, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth, faces_intense, tets,
                 face_tets, tet_faces):
@@ -212,4 +215,4 @@ class TetRenderer(th.nn.Module):
                           faces_opacity.to(dtype=f32), mv_mats.to(dtype=f32).transpose(1, 2),
                           proj_mats.to(dtype=f32).transpose(1, 2), verts_depth.to(dtype=f32),
                           faces_intense.to(dtype=f32), tets.to(dtype=i32), face_tets.to(dtype=i32),
-                          tet_faces.to(dtype=i32), self.render_settings)
+                          tet_faces.to(dtype=i32), self.render_settings, self.deterministic)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "dmr_tet_forward_bin": (c_int, [c_int] * 6 + [c_void_p] * 12 + [c_void_p]),
     "dmr_tet_forward_render": (c_int, [c_int] * 8 + [c_void_p] * 13 + [c_void_p]),
     "dmr_tet_backward": (c_int, [c_int] * 7 + [c_void_p] * 13 + [c_void_p]),
+    "dmr_tet_backward_deterministic_bytes": (c_size_t, [c_int] * 2),
+    "dmr_tet_backward_deterministic": (c_int, [c_int] * 7 + [c_void_p] * 13 + [c_void_p, c_size_t] + [c_void_p]),
     "dmr_debug_view": (c_int, [c_int] * 8 + [c_size_t, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t)]),
     "dmr_nvls_allreduce_sum_f32": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dmr_nvls_allreduce_sum_f32_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, ctypes.c_uint, c_void_p]),

@@ -148,11 +148,12 @@ int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int 
     return DMR_OK;
 }
 
-int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_seed, const float* background,
-                     const float* mv_mats, const float* proj_mats, const float* inv_mv_mats,
-                     const float* inv_proj_mats, const float* faces_intense, const void* point_buffer,
-                     const void* face_buffer, const void* image_buffer, const float* dL_dcolor, const float* dL_ddepth,
-                     float* dL_dverts_color, float* dL_dfaces_opacity, dmr_stream_t stream_)
+static int tet_backward_impl(int B, int P, int F, int T, int W, int H, int ray_random_seed, const float* background,
+                             const float* mv_mats, const float* proj_mats, const float* inv_mv_mats,
+                             const float* inv_proj_mats, const float* faces_intense, const void* point_buffer,
+                             const void* face_buffer, const void* image_buffer, const float* dL_dcolor,
+                             const float* dL_ddepth, float* dL_dverts_color, float* dL_dfaces_opacity,
+                             void* det_workspace, size_t det_workspace_bytes, bool deterministic, dmr_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
@@ -168,10 +169,54 @@ int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_se
                 faces_intense, face_buffer, image_buffer);
     p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
     p.dL_dverts_color = dL_dverts_color; p.dL_dfaces_opacity = dL_dfaces_opacity;
+    p.det_gmax = nullptr; p.det_vert = nullptr; p.det_fopa = nullptr;
+    if (deterministic) {
+        TetDetLayout DL = TetDetLayout::make((size_t)P, (size_t)F);
+        if (!det_workspace || det_workspace_bytes < DL.total) {
+            set_error("deterministic backward needs a workspace of %zu bytes (dmr_tet_backward_deterministic_bytes)", DL.total);
+            return DMR_EINVAL;
+        }
+        p.det_gmax = at<uint32_t>(det_workspace, DL.gmax);
+        p.det_vert = at<long long>(det_workspace, DL.vert);
+        p.det_fopa = at<long long>(det_workspace, DL.fopa);
+        p.grad_vacc = nullptr;
+        DMR_CUDA(cudaMemsetAsync(det_workspace, 0, DL.total, stream));
+        return tet_march_backward_deterministic(p, stream);
+    }
     TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
     p.grad_vacc = const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc));
     DMR_CUDA(cudaMemsetAsync(p.grad_vacc, 0, sizeof(float4) * (size_t)P, stream));
     return tet_march_backward(p, stream);
+}
+
+int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_seed, const float* background,
+                     const float* mv_mats, const float* proj_mats, const float* inv_mv_mats,
+                     const float* inv_proj_mats, const float* faces_intense, const void* point_buffer,
+                     const void* face_buffer, const void* image_buffer, const float* dL_dcolor, const float* dL_ddepth,
+                     float* dL_dverts_color, float* dL_dfaces_opacity, dmr_stream_t stream)
+{
+    return tet_backward_impl(B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats,
+                             inv_proj_mats, faces_intense, point_buffer, face_buffer, image_buffer, dL_dcolor, dL_ddepth,
+                             dL_dverts_color, dL_dfaces_opacity, nullptr, 0, false, stream);
+}
+
+size_t dmr_tet_backward_deterministic_bytes(int P, int F)
+{
+    if (P < 0 || F < 0) return 0;
+    return TetDetLayout::make((size_t)P, (size_t)F).total;
+}
+
+int dmr_tet_backward_deterministic(int B, int P, int F, int T, int W, int H, int ray_random_seed,
+                                   const float* background, const float* mv_mats, const float* proj_mats,
+                                   const float* inv_mv_mats, const float* inv_proj_mats, const float* faces_intense,
+                                   const void* point_buffer, const void* face_buffer, const void* image_buffer,
+                                   const float* dL_dcolor, const float* dL_ddepth, float* dL_dverts_color,
+                                   float* dL_dfaces_opacity, void* workspace, size_t workspace_bytes,
+                                   dmr_stream_t stream)
+{
+    return tet_backward_impl(B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats,
+                             inv_proj_mats, faces_intense, point_buffer, face_buffer, image_buffer, dL_dcolor, dL_ddepth,
+                             dL_dverts_color, dL_dfaces_opacity, workspace, workspace_bytes, true, stream);
 }
 
 int dmr_debug_set_tet_first_split(int split)

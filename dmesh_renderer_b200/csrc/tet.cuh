@@ -139,6 +139,24 @@ struct TetParams {
     const float* dL_dcolor; const float* dL_ddepth;
     float* dL_dverts_color; float* dL_dfaces_opacity;
     float4* grad_vacc;            // [P] zeroed scratch: per-vertex colour gradient (xyz), summed over views
+    // deterministic mode only (tet_march_backward_deterministic): zeroed 64-bit fixed-point accumulators (det.cuh)
+    const uint32_t* det_gmax;
+    long long* det_vert;          // [P,4]: dL_dverts_color rgb, -
+    long long* det_fopa;          // [F]
+};
+
+struct TetDetLayout {             // workspace of the deterministic backward pass
+    size_t gmax, vert, fopa, total;
+    static TetDetLayout make(size_t P, size_t F)
+    {
+        TetDetLayout L;
+        size_t o = 0;
+        L.gmax = o; o = align_up(o + 4, 256);
+        L.vert = o; o = align_up(o + 8 * 4 * P, 256);
+        L.fopa = o; o = align_up(o + 8 * F, 256);
+        L.total = o;
+        return L;
+    }
 };
 
 int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
@@ -155,5 +173,6 @@ int tet_jitter(int B, int W, int H, int seed, float2* jitter, cudaStream_t strea
 int tet_first_intersect(const TetParams& p, cudaStream_t stream);
 int tet_march_forward(const TetParams& p, cudaStream_t stream);
 int tet_march_backward(const TetParams& p, cudaStream_t stream);
+int tet_march_backward_deterministic(const TetParams& p, cudaStream_t stream);
 
 }  // namespace dmr

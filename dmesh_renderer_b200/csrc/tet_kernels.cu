@@ -12,6 +12,7 @@
 // branch decisions along every ray (hit tests, normal signs); all such
 // expressions keep the reference's operation order.
 #include "tet.cuh"
+#include "det.cuh"
 #include <curand_kernel.h>
 
 namespace dmr {
@@ -664,6 +665,7 @@ struct TetBwdState {
     float prev_log_T, last_alpha, last_depth, accum_recd;
     float last_color[3], accum_rec[3];
     bool first_iter;
+    float det_sv;       // deterministic mode: fixed-point scale (det.cuh)
 };
 
 // Gradient terms of one crossed face (backward.cu:252-360) and their reduction.
@@ -675,6 +677,7 @@ struct TetBwdState {
 // 0.06 ms slower at C3 because the records (152 MB) have to be zeroed, written and read back; and opportunistic
 // warp aggregation of the lanes that hold the same face (match.any + one shuffle round per extra lane): no gain,
 // 779 vs 770 us.)
+template <bool DET>
 __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st, int face, float rt, float iu, float iv,
                                              const float4 s0, const float4 s1, const float4 s2, const float4 s3,
                                              float intense, float3 ro, float3 rd, const float* mv, const float* pj,
@@ -728,6 +731,16 @@ __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st
     const float g10 = i1 * dL_dcol[0] * intense, g11 = i1 * dL_dcol[1] * intense, g12 = i1 * dL_dcol[2] * intense;
     const float g20 = i2 * dL_dcol[0] * intense, g21 = i2 * dL_dcol[1] * intense, g22 = i2 * dL_dcol[2] * intense;
     const int vi0 = __float_as_int(s2.w), vi1 = __float_as_int(s3.x), vi2 = __float_as_int(s3.y);
+    if (DET) {
+        // deterministic mode (det.cuh): 64-bit fixed-point accumulators, any arrival order gives the same bits
+        const float sv = st.det_sv;
+        long long* a0 = p.det_vert + 4 * (size_t)vi0; long long* a1 = p.det_vert + 4 * (size_t)vi1; long long* a2 = p.det_vert + 4 * (size_t)vi2;
+        det_add(a0 + 0, g00, sv); det_add(a0 + 1, g01, sv); det_add(a0 + 2, g02, sv);
+        det_add(a1 + 0, g10, sv); det_add(a1 + 1, g11, sv); det_add(a1 + 2, g12, sv);
+        det_add(a2 + 0, g20, sv); det_add(a2 + 1, g21, sv); det_add(a2 + 2, g22, sv);
+        det_add(p.det_fopa + face, dL_dopa, sv);
+        return;
+    }
     red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi0), g00, g01, g02, 0.0f);
     red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi1), g10, g11, g12, 0.0f);
     red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi2), g20, g21, g22, 0.0f);
@@ -739,7 +752,8 @@ __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st
 // hit test on the same vertices the forward pass used, all loads independent of the previous step and
 // issued one step ahead.  Steps beyond the cap are re-marched through the adjacency records exactly like
 // the reference (backward.cu:382-477) until the recorded part is reached.
-__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams p)
+template <bool DET>
+__device__ __forceinline__ void tet_march_bwd_body(const TetParams& p)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
@@ -779,6 +793,8 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
     float bd_dot = 0; bd_dot += 1.0 * gd;
 
     TetBwdState st;
+    st.det_sv = 0.0f;
+    if (DET) { float sg; det_scales(*p.det_gmax, st.det_sv, sg); }
     st.prev_log_T = fin_prev_log_T;
     st.last_alpha = 0.0f; st.last_depth = 0.0f; st.accum_recd = 0.0f;
 #pragma unroll
@@ -809,7 +825,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
             const float4* sh4 = reinterpret_cast<const float4*>(p.shade + curr_face);
             const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2], s3 = sh4[3];
             const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
-            tet_bwd_face(p, st, curr_face, rt, iu, iv, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
+            tet_bwd_face<DET>(p, st, curr_face, rt, iu, iv, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
                          final_T, final_prev_T);
             k--;
             if (curr_face == first_face) return;         // backward.cu:363-366
@@ -850,7 +866,7 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
 
         float3 tuv = f3(0, 0, 0);
         ray_tri_hit(ro, rd, f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), tuv);
-        tet_bwd_face(p, st, face, tuv.x, tuv.y, tuv.z, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
+        tet_bwd_face<DET>(p, st, face, tuv.x, tuv.y, tuv.z, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
                      final_T, final_prev_T);
 
         if (stop_here) break;
@@ -862,6 +878,33 @@ __global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams 
 }
 
 // Once per vertex: float4 accumulator -> dL_dverts_color[P,3].
+__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams p) { tet_march_bwd_body<false>(p); }
+__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_det_kernel(TetParams p) { tet_march_bwd_body<true>(p); }
+
+// Deterministic mode, last step: fixed-point accumulators -> += into dL_dverts_color[P,3] and dL_dfaces_opacity[F].
+__global__ void __launch_bounds__(256) tet_det_convert_kernel(TetParams p)
+{
+    float sv, sg;
+    det_scales(*p.det_gmax, sv, sg);
+    if (sv == 0.0f) return;
+    const double iv = 1.0 / (double)sv;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < (size_t)p.P) {
+        const long long* a = p.det_vert + 4 * i;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const long long q = a[c];
+            if (q != 0) p.dL_dverts_color[3 * i + c] += (float)((double)q * iv);
+        }
+        return;
+    }
+    i -= (size_t)p.P;
+    if (i < (size_t)p.F) {
+        const long long q = p.det_fopa[i];
+        if (q != 0) p.dL_dfaces_opacity[i] += (float)((double)q * iv);
+    }
+}
+
 __global__ void __launch_bounds__(256) tet_grad_vertex_kernel(TetParams p)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -869,6 +912,26 @@ __global__ void __launch_bounds__(256) tet_grad_vertex_kernel(TetParams p)
     const float4 a = p.grad_vacc[v];
     float* o = p.dL_dverts_color + 3 * (size_t)v;
     o[0] += a.x; o[1] += a.y; o[2] += a.z;
+}
+
+int tet_march_backward_deterministic(const TetParams& p, cudaStream_t stream)
+{
+    dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
+    const size_t HW = (size_t)p.W * p.H;
+    {
+        ProfScope prof(ST_TET_BWD, stream);
+        count_launch(1);   // two kernels under one scope
+        int rc = det_gmax(p.dL_dcolor, 3 * p.B * HW, p.dL_ddepth, p.B * HW, const_cast<uint32_t*>(p.det_gmax), stream);
+        if (rc) return rc;
+        tet_march_bwd_det_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tet_march_bwd_det_kernel");
+    }
+    {
+        ProfScope prof(ST_TET_BWD_FINISH, stream);
+        tet_det_convert_kernel<<<(unsigned)(((size_t)p.P + p.F + 255) / 256), 256, 0, stream>>>(p);
+        DMR_LAUNCH_CHECK("tet_det_convert_kernel");
+    }
+    return 0;
 }
 
 int tet_march_backward(const TetParams& p, cudaStream_t stream)

@@ -24,6 +24,7 @@
 // one statistics record per (view, face) finished by tri_grad_finish_kernel)
 // instead of the reference's 23 atomics per covered pixel.
 #include "tri.cuh"
+#include "det.cuh"
 
 namespace dmr {
 
@@ -325,37 +326,6 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 #ifndef DMR_TRI_BWD_GROUP_LANES
 #define DMR_TRI_BWD_GROUP_LANES 2
 #endif
-// Deterministic mode
-// ----------------------------------
-// Everything up to the gradient accumulation is already run-to-run reproducible (stable sorts, fixed per-pixel
-// compositing order); only the ORDER in which the groups' partial sums reach a (view, face) record, and the faces'
-// contributions reach a vertex, varies -- and fp32 addition is not associative.  The deterministic variant
-// accumulates the same partial sums as 64-bit FIXED-POINT integers (integer addition is associative, so any
-// arrival order gives the same bits): value * 2^k rounded to nearest, added with red.global.add.u64.
-// All gradients are linear in the cotangent, so k is chosen relative to g = max |dL_dout| (found by a max-reduction,
-// itself order-independent): with 2^(e-1) <= g < 2^e,
-//     colour / opacity / intensity / depth terms:  k = 38 - e   (|sum| < 3.4e7 g, resolution 3.6e-12 g)
-//     vertex-position terms (carry 1/det):          k = 28 - e   (|sum| < 3.4e10 g, resolution 3.7e-9 g)
-// A term beyond the range saturates (cvt.rni.s64.f32) instead of wrapping.
-#define DMR_DET_VALUE_BITS 38
-#define DMR_DET_GEOM_BITS 28
-__device__ __forceinline__ void det_scales(uint32_t gmax_bits, float& sv, float& sg)
-{
-    const float g = __uint_as_float(gmax_bits);
-    sv = sg = 0.0f;
-    if (!(g > 0.0f) || !(g <= 3.0e38f)) return;      // zero (all gradients are zero), inf or NaN cotangents
-    int e;
-    frexpf(g, &e);
-    e = max(e, -80);
-    sv = ldexpf(1.0f, DMR_DET_VALUE_BITS - e);
-    sg = ldexpf(1.0f, DMR_DET_GEOM_BITS - e);
-}
-__device__ __forceinline__ void det_add(long long* dst, float v, float scale)
-{
-    const long long q = __float2ll_rn(v * scale);
-    if (q != 0) atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(q));
-}
-
 template <int GL, bool DET>
 __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 {
@@ -673,7 +643,7 @@ __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_det_kern
 
 // Deterministic mode: g = max |dL_dout| over both cotangent images, as float bits (non-negative floats order like
 // unsigned integers; the maximum does not depend on the order of the comparisons).
-__global__ void __launch_bounds__(256) tri_det_gmax_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
+__global__ void __launch_bounds__(256) det_gmax_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
                                                            size_t nb, uint32_t* __restrict__ gmax)
 {
     uint32_t m = 0;
@@ -855,6 +825,13 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
     return 0;
 }
 
+int det_gmax(const float* a, size_t na, const float* b, size_t nb, uint32_t* gmax, cudaStream_t stream)
+{
+    det_gmax_kernel<<<592, 256, 0, stream>>>(a, na, b, nb, gmax);
+    DMR_LAUNCH_CHECK("det_gmax_kernel");
+    return 0;
+}
+
 int tri_render_backward_deterministic(const TriRenderParams& p, cudaStream_t stream)
 {
     if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
@@ -863,9 +840,8 @@ int tri_render_backward_deterministic(const TriRenderParams& p, cudaStream_t str
     {
         ProfScope prof(ST_TRI_BWD, stream);
         count_launch(1);   // two kernels under one scope
-        tri_det_gmax_kernel<<<592, 256, 0, stream>>>(p.dL_dcolor, 3 * p.B * HW, p.dL_ddepth, p.B * HW,
-                                                     const_cast<uint32_t*>(p.det_gmax));
-        DMR_LAUNCH_CHECK("tri_det_gmax_kernel");
+        int rc = det_gmax(p.dL_dcolor, 3 * p.B * HW, p.dL_ddepth, p.B * HW, const_cast<uint32_t*>(p.det_gmax), stream);
+        if (rc) return rc;
         tri_render_bwd_det_kernel<<<grid, 256, 0, stream>>>(p);
         DMR_LAUNCH_CHECK("tri_render_bwd_det_kernel");
     }

@@ -229,6 +229,24 @@ int dmr_tet_backward(
     float* dL_dverts_color,      /* [P,3] */
     float* dL_dfaces_opacity,    /* [F]   */
     dmr_stream_t stream);
+/* The same with run-to-run reproducible gradients (see dmr_tri_backward_deterministic: the reference's 10 scalar */
+/* atomics per crossed face, cuda_renderer/backward.cu:341-360, become 64-bit fixed-point additions with 38       */
+/* fractional bits below max |dL_dout|).  `workspace`: dmr_tet_backward_deterministic_bytes(P, F) bytes of device  */
+/* scratch (zeroed by the call).                                                                                   */
+size_t dmr_tet_backward_deterministic_bytes(int P, int F);
+int dmr_tet_backward_deterministic(
+    int B, int P, int F, int T, int W, int H,
+    int ray_random_seed,
+    const float* background,
+    const float* mv_mats, const float* proj_mats,
+    const float* inv_mv_mats, const float* inv_proj_mats,
+    const float* faces_intense,
+    const void* point_buffer, const void* face_buffer,
+    const void* image_buffer,
+    const float* dL_dcolor, const float* dL_ddepth,
+    float* dL_dverts_color, float* dL_dfaces_opacity,
+    void* workspace, size_t workspace_bytes,
+    dmr_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
 /* Read-only views into the state buffers for the bit-exact parity checks    */
