@@ -19,7 +19,9 @@ def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for s in ["dmr_tri_state_bytes", "dmr_binning_bytes", "dmr_tri_forward_bin", "dmr_tri_forward_render",
               "dmr_tri_backward", "dmr_tet_state_bytes", "dmr_tet_forward_bin", "dmr_tet_forward_render",
-              "dmr_tet_backward", "dmr_debug_view", "dmr_sort_pairs", "dmr_sort_temp_bytes", "dmr_last_error"]:
+              "dmr_tet_backward", "dmr_debug_view", "dmr_sort_pairs", "dmr_sort_temp_bytes", "dmr_last_error",
+              "dmr_camera_inverses", "dmr_tri_backward_deterministic", "dmr_tet_backward_deterministic",
+              "dmr_tri_depth_chain", "dmr_nvls_allreduce_sum_f32_fused"]:
         assert s in syms
 
 
@@ -52,6 +54,14 @@ def test_size_queries_need_no_gpu():
     # negative sizes are rejected with a message, not a crash
     assert lib.dmr_tri_state_bytes(-1, 1, 1, 16, 16, out) != 0
     assert b"size" in lib.dmr_last_error()
+    # deterministic-mode workspaces: 24 statistics per (view, face) + per-vertex / per-face accumulators, 8 bytes each
+    assert lib.dmr_tri_backward_deterministic_bytes(2, 1000, 500) >= 8 * (24 * 2 * 500 + 8 * 1000 + 2 * 1000 + 500)
+    assert lib.dmr_tet_backward_deterministic_bytes(100, 300) >= 8 * (4 * 100 + 300)
+    # argument validation happens before any CUDA call
+    assert lib.dmr_camera_inverses(0, None, 0, 0, 0, None, 0, 0, 0, None, None, None) == 0          # empty batch
+    assert lib.dmr_camera_inverses(-1, None, 0, 0, 0, None, 0, 0, 0, None, None, None) == 1         # DMR_EINVAL
+    assert lib.dmr_camera_inverses(2, None, 16, 4, 1, None, 16, 4, 1, None, None, None) == 1
+    assert b"null" in lib.dmr_last_error()
     assert lib.dmr_profile_stage_count() >= 16
     names = [lib.dmr_profile_stage_name(i).decode() for i in range(lib.dmr_profile_stage_count())]
     assert "tri_render_backward" in names and "sort_pass0" in names
