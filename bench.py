@@ -102,12 +102,20 @@ class L2Flush:
         self.buf.fill_(self.v)
 
 
+CPU_BINDING = None   # cores this rank was bound to (N > 1 only)
+
+
 def dist_setup(gpus):
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if ws > 1:
         torch.cuda.set_device(local)
+        if os.environ.get("DMR_BENCH_NO_CPU_BINDING") != "1":
+            from dmesh_renderer_b200.multiview import bind_to_gpu_cpus
+            cores = bind_to_gpu_cpus(local)     # pinned staging buffers on the GPU's own NUMA node
+            global CPU_BINDING
+            CPU_BINDING = len(cores) if cores else None
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
@@ -373,6 +381,8 @@ def run_ours(args, ws, rank, local):
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                    "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "impl": "dmesh_renderer_b200"}
+    if ws > 1:
+        out["config"]["host_cores_bound_to_gpu_numa_node"] = CPU_BINDING
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out), flush=True)

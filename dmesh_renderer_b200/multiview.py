@@ -17,6 +17,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_cpus(device_index: int, min_cores: int = 2):
+    """Restrict this process (the calling thread and every thread it creates afterwards) to the CPU cores NVML lists
+    as local to GPU `device_index` -- same NUMA node / PCIe root complex -- so that the pinned staging buffers
+    allocated afterwards live in that node's memory and the H2D copies of several ranks do not all cross the
+    socket interconnect.  Call it right after torch.cuda.set_device(local_rank), before allocating pinned memory.
+    Returns the core list, or None when NVML is unavailable or fewer than `min_cores` of those cores are usable
+    (e.g. a container cpuset on the other socket): then nothing is changed."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = getattr(torch.cuda.get_device_properties(device_index), "uuid", None)
+        if uuid is not None:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cores = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        local = sorted(cores & os.sched_getaffinity(0))
+        if len(local) < min_cores:
+            return None
+        os.sched_setaffinity(0, local)
+        return local
+    except Exception:
+        return None
+
+
 def shard_views(num_views: int, rank: int, world_size: int) -> range:
     """Contiguous slice of the cameras owned by `rank` (rank r renders
     views r*B/G .. (r+1)*B/G - 1; remainders go to the first ranks)."""
