@@ -98,3 +98,15 @@ def test_sync_free_inverses_match_torch_inverse_and_raise_on_singular():
     a[1] = 0
     with pytest.raises(RuntimeError, match="singular"):
         _C._Inverses(a, b)
+
+
+def test_cpu_binding_helper_is_a_no_op_without_a_gpu():
+    """multiview.bind_to_gpu_cpus must never fail a job: without NVML / a GPU it returns None and leaves the
+    process's CPU affinity alone."""
+    import os
+    from dmesh_renderer_b200.multiview import bind_to_gpu_cpus
+    before = os.sched_getaffinity(0)
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    assert bind_to_gpu_cpus(0) is None
+    assert os.sched_getaffinity(0) == before
