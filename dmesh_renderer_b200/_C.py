@@ -204,8 +204,8 @@ class _TriPending:
 def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, verts_depth,
                       faces_intense, image_height, image_width):
     """Validate, allocate state, enqueue phase 1 (preprocess + records + scan) on the current stream.
-    Split out of render_tris so that the autograd wrapper can compute torch.inverse (host-bound, ~0.2 ms for
-    two [B,4,4] stacks) while the GPU runs phase 1.  Returns a pending-call object for tri_forward_finish."""
+    Split out of render_tris so that a caller can do host work (allocate the speculative binning buffer, prepare the
+    phase-2 arguments) while the GPU runs phase 1.  Returns a pending-call object for tri_forward_finish."""
     if verts.dim() != 2 or verts.size(1) != 3:
         _err("verts must have dimensions (num_points, 3)")
     if faces.dim() != 2 or faces.size(1) != 3:
