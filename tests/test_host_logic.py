@@ -110,3 +110,33 @@ def test_cpu_binding_helper_is_a_no_op_without_a_gpu():
         pytest.skip("CPU-only check")
     assert bind_to_gpu_cpus(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_gradient_sink_matching_rules():
+    """_C.grad_sink_for: a renderer call is redirected into a PackedSceneGrads buffer only while the sink is active,
+    only for the sink's own leaves with live .grad views, and the sink stack unwinds on exceptions."""
+    from dmesh_renderer_b200 import _C
+    from dmesh_renderer_b200.multiview import PackedSceneGrads
+    v, c, o = torch.randn(5, 3), torch.rand(5, 3), torch.rand(4)
+    g = PackedSceneGrads(v, c, o)
+    assert g.flat.numel() == 34 and all(leaf.grad.data_ptr() >= g.flat.data_ptr() for leaf in g.leaves)
+    assert _C.grad_sink_for(*g.leaves) is None                      # not active
+    with g.direct():
+        assert _C.grad_sink_for(*g.leaves) is g
+        assert _C.grad_sink_for(v.clone(), c, o) is None             # a copy is not the leaf
+        assert _C.grad_sink_for(v * 1.0, c, o) is None               # neither is a function of it
+        assert _C.grad_sink_for(c, v, o) is None                     # order matters
+        other = PackedSceneGrads(v.detach().clone(), c.detach().clone(), o.detach().clone())
+        with other.direct():                                         # innermost matching sink wins, outer one still found
+            assert _C.grad_sink_for(*other.leaves) is other
+            assert _C.grad_sink_for(*g.leaves) is g
+        assert _C.grad_sink_for(*other.leaves) is None
+        saved = v.grad
+        v.grad = None                                                # e.g. optimizer.zero_grad(set_to_none=True)
+        assert _C.grad_sink_for(*g.leaves) is None
+        v.grad = saved
+    assert not _C._grad_sinks
+    with pytest.raises(ValueError):
+        with g.direct():
+            raise ValueError("boom")
+    assert not _C._grad_sinks
