@@ -326,6 +326,12 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 #ifndef DMR_TRI_BWD_GROUP_LANES
 #define DMR_TRI_BWD_GROUP_LANES 2
 #endif
+// Experiment switch, OFF (not yet measured on the GPU, see profiles/README.md section 7): 1 = form 1/(1-alpha) once per
+// staged instance and multiply, instead of the reference's two divisions per covered pixel (backward.cu:244-252,
+// 299-308).  Changes T and the background term by an ulp per step, so it needs the parity run before it ships.
+#ifndef DMR_TRI_BWD_RCP_ALPHA
+#define DMR_TRI_BWD_RCP_ALPHA 0
+#endif
 template <int GL, bool DET>
 __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 {
@@ -336,6 +342,9 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
     __shared__ uint32_t s_gmask[8 * (RB / 32) * (32 / GL)];   // [warp][slice][group]: surviving instances
     __shared__ int s_glast[8 * (32 / GL)];                    // [warp][group]: largest n_contrib of the group's pixels
     __shared__ unsigned char s_cidx[8 * RB];                  // [warp][compacted position] -> position in the chunk
+#if DMR_TRI_BWD_RCP_ALPHA
+    __shared__ float s_rcpa[RB];                              // 1 / (1 - alpha) of the staged instances
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane / GL, l = lane % GL;
     const int b = blockIdx.z;
@@ -406,6 +415,9 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                 uint4* dst = s_rec + tid * 9;
 #pragma unroll
                 for (int q = 0; q < 9; q++) dst[q] = src[q];
+#if DMR_TRI_BWD_RCP_ALPHA
+                s_rcpa[tid] = 1.0f / (1.0f - __uint_as_float(dst[0].w));
+#endif
             }
         }
         __syncthreads();
@@ -512,7 +524,12 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         const float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
 
                         // backward.cu:244-252
+#if DMR_TRI_BWD_RCP_ALPHA
+                        const float rcpa = s_rcpa[j];
+                        if (!T_first) T = T * rcpa;
+#else
                         if (!T_first) T = T / (1.f - alpha);
+#endif
                         T_first = false;
 
                         float dL_dalpha = 0.0f;
@@ -534,7 +551,11 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                             dL_dalpha += (-prev_T_final) * bg_dot;
                             dL_dalpha += (-prev_T_final) * bd_dot;
                         } else {
+#if DMR_TRI_BWD_RCP_ALPHA
+                            const float k = -T_final * rcpa;
+#else
                             const float k = -T_final / (1.f - alpha);
+#endif
                             dL_dalpha += k * bg_dot;
                             dL_dalpha += k * bd_dot;
                         }
