@@ -7,7 +7,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmesh_b200.so")
+# DMESH_B200_LIB: development override -- load another build of the SAME library (e.g. an experiment variant made by
+# tools/build_variant.sh) instead of the in-tree one.  It is not a fallback: a missing file still raises.
+LIB_PATH = os.environ.get("DMESH_B200_LIB") or os.path.join(_HERE, "libdmesh_b200.so")
 
 c_int = ctypes.c_int
 c_size_t = ctypes.c_size_t
