@@ -142,6 +142,17 @@ __device__ __forceinline__ unsigned subblock_cull16(const uint4 e0, const uint4 
     return r;
 }
 
+// Experiment switch, OFF (not yet measured on the GPU, see profiles/README.md section 7): 1 = the thread that stages an
+// instance replaces its three vertex positions, in shared memory, by the per-(view, face) constants of the ray-triangle
+// system -- the camera origin is the same for every pixel of a view, so with T = ro - p0
+//     det = rd . (E2 x E1),   u det = rd . (E2 x T),   v det = rd . (T x E1)
+// and a covered pixel needs three dot products and one reciprocal instead of Moeller-Trumbore's three differences,
+// two cross products and three dots (19 % of the kernel's instructions).  Same real-number result, different
+// roundings (colour and depth move by ~1 ulp; n_contrib / final_T do not depend on it): needs the parity run.
+#ifndef DMR_TRI_FWD_FACE_CONSTANTS
+#define DMR_TRI_FWD_FACE_CONSTANTS 0
+#endif
+
 // Forward: the whole warp walks one survivor list for its 8x4 block.  (A variant in which the four
 // 4x2 sub-blocks walk their own lists, as the backward kernel does, was measured SLOWER here --
 // 234 vs 211 us at C2: the forward shading path is short, so the extra find-loop bookkeeping costs
@@ -179,6 +190,15 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
                 uint4* dst = s_rec + tid * 9;
 #pragma unroll
                 for (int q = 0; q < 9; q++) dst[q] = src[q];
+#if DMR_TRI_FWD_FACE_CONSTANTS
+                float* wv = reinterpret_cast<float*>(dst + 3);
+                const float3 q0 = f3(wv[0], wv[1], wv[2]), q1 = f3(wv[3], wv[4], wv[5]), q2 = f3(wv[6], wv[7], wv[8]);
+                const float3 Tv = ro - q0, E1 = q1 - q0, E2 = q2 - q0;      // ro: the view's camera origin
+                const float3 Nv = cross3(E2, E1), Av = cross3(E2, Tv), Qv = cross3(Tv, E1);
+                wv[0] = Nv.x; wv[1] = Nv.y; wv[2] = Nv.z;
+                wv[3] = Av.x; wv[4] = Av.y; wv[5] = Av.z;
+                wv[6] = Qv.x; wv[7] = Qv.y; wv[8] = Qv.z;
+#endif
             }
         }
         __syncthreads();
@@ -218,9 +238,17 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
                 const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
 
                 const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
-                float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
                 float3 tuv = f3(0, 0, 0);
+#if DMR_TRI_FWD_FACE_CONSTANTS
+                const float det = dot3(rd, f3(w[0], w[1], w[2]));
+                if (det == 0.0f) continue;
+                const float inv_det = 1.0f / det;
+                tuv.y = dot3(rd, f3(w[3], w[4], w[5])) * inv_det;
+                tuv.z = dot3(rd, f3(w[6], w[7], w[8])) * inv_det;
+#else
+                float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
                 if (!ray_tri_tuv(ro, rd, v0, v1, v2, tuv)) continue;
+#endif
                 float uc, vc;
                 int code;
                 clamp_bary(tuv.y, tuv.z, uc, vc, code);
