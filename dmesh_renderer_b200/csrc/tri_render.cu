@@ -360,6 +360,12 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 #ifndef DMR_TRI_BWD_RCP_ALPHA
 #define DMR_TRI_BWD_RCP_ALPHA 0
 #endif
+// Experiment switch, OFF (same status): the backward twin of DMR_TRI_FWD_FACE_CONSTANTS.  The staged copy of a record
+// carries E2 x E1, E2 x T, T x E1 in place of the three vertex positions and E2 . (T x E1) in place of the first
+// vertex id (neither is read from shared memory here; tri_grad_finish_kernel reads the global record).
+#ifndef DMR_TRI_BWD_FACE_CONSTANTS
+#define DMR_TRI_BWD_FACE_CONSTANTS 0
+#endif
 template <int GL, bool DET>
 __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 {
@@ -445,6 +451,16 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                 for (int q = 0; q < 9; q++) dst[q] = src[q];
 #if DMR_TRI_BWD_RCP_ALPHA
                 s_rcpa[tid] = 1.0f / (1.0f - __uint_as_float(dst[0].w));
+#endif
+#if DMR_TRI_BWD_FACE_CONSTANTS
+                float* wv = reinterpret_cast<float*>(dst + 3);
+                const float3 q0 = f3(wv[0], wv[1], wv[2]), q1 = f3(wv[3], wv[4], wv[5]), q2 = f3(wv[6], wv[7], wv[8]);
+                const float3 Tv = ro - q0, E1 = q1 - q0, E2 = q2 - q0;      // ro: the view's camera origin
+                const float3 Nv = cross3(E2, E1), Av = cross3(E2, Tv), Qv = cross3(Tv, E1);
+                wv[0] = Nv.x; wv[1] = Nv.y; wv[2] = Nv.z;
+                wv[3] = Av.x; wv[4] = Av.y; wv[5] = Av.z;
+                wv[6] = Qv.x; wv[7] = Qv.y; wv[8] = Qv.z;
+                wv[21] = dot3(Qv, E2);
 #endif
             }
         }
@@ -535,10 +551,22 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                 if (have && cov) {
                     const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
                     const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
-                    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
                     float3 tuv = f3(0, 0, 0);
                     float inv_denom = 0.0f;
-                    if (ray_tri_tuv(ro, rd, v0, v1, v2, tuv, inv_denom)) {
+#if DMR_TRI_BWD_FACE_CONSTANTS
+                    const float det = dot3(rd, f3(w[0], w[1], w[2]));
+                    const bool hit = det != 0.0f;
+                    if (hit) {
+                        inv_denom = 1.0f / det;
+                        tuv.x = w[21] * inv_denom;
+                        tuv.y = dot3(rd, f3(w[3], w[4], w[5])) * inv_denom;
+                        tuv.z = dot3(rd, f3(w[6], w[7], w[8])) * inv_denom;
+                    }
+#else
+                    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
+                    const bool hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv, inv_denom);
+#endif
+                    if (hit) {
                         float uc, vc;
                         int code;
                         clamp_bary(tuv.y, tuv.z, uc, vc, code);
