@@ -47,18 +47,28 @@ def _require_cuda(*ts):
 
 
 class _Pinned:
-    """One pinned int32 per device for the num_rendered read-back (the single
-    host<->device synchronisation of a forward call, as in
-    rasterizer_impl.cu:287-292)."""
-    _slots = {}
+    """Pinned int32 words for the num_rendered read-back (the single host<->device synchronisation of a forward
+    call, as in rasterizer_impl.cu:287-292).  Every forward call in flight owns ITS OWN word, taken from a small
+    per-device pool and given back when the call has read it: the split API (tri_forward_begin / _finish) allows
+    several calls between their two phases, and ctypes releases the GIL inside dmr_wait_i32, so two Python threads
+    can render on one GPU at the same time -- neither may see the other's count.  list.pop / list.append are
+    atomic under the GIL."""
+    _free = {}
 
     @classmethod
-    def get(cls, device):
-        key = device.index if device.index is not None else torch.cuda.current_device()
-        if key not in cls._slots:
-            t = torch.zeros(1, dtype=torch.int32).pin_memory()
-            cls._slots[key] = (t, t.numpy(), ctypes.c_void_p(t.data_ptr()))   # tensor, numpy view (cheap host reads), pointer
-        return cls._slots[key]
+    def acquire(cls, device, n=1):
+        key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+        pool = cls._free.setdefault(key, [])
+        try:
+            return pool.pop()
+        except IndexError:
+            t = torch.zeros(n, dtype=torch.int32).pin_memory()
+            return (t, t.numpy(), ctypes.c_void_p(t.data_ptr()), key)   # tensor, numpy view (cheap host reads), pointer, pool
+
+    @classmethod
+    def release(cls, slot):
+        if slot is not None:
+            cls._free[slot[3]].append(slot)
 
 
 def _stream():
@@ -104,11 +114,18 @@ def _speculative_binning(lib, key, u8):
     return torch.empty(lib.dmr_binning_bytes(prev + prev // 4 + 1024), **u8)
 
 
+_MAX_R = (1 << 30) - 1          # the sort's descriptors carry 30-bit prefixes (csrc/radix_sort.cu)
+
+
 def _wait_R(lib, pinned, key, spec, u8):
     """The one host<->device synchronisation of a forward call (rasterizer_impl.cu:287-292): wait for
     num_rendered, return (R, binning buffer)."""
     _lib.check(lib.dmr_wait_i32(pinned[2], _SENTINEL, _stream()))
     R = int(pinned[1][0])
+    if R < 0 or R > _MAX_R:         # the scan saturates at 2^32 - 1, which arrives here as a negative int32
+        raise RuntimeError("dmesh_renderer_b200: %s tile instances exceed the supported maximum of 2^30 - 1 "
+                           "(the reference's int limit is 2^31 - 1); render fewer views per call" %
+                           ("more than 2^31" if R < 0 else str(R)))
     _last_R[key] = R
     need = lib.dmr_binning_bytes(R) if R > 0 else 0
     if spec is not None and spec.numel() >= need:
@@ -124,23 +141,20 @@ class _Inverses:
     synchronisation the forward call needs anyway (num_rendered), and a singular matrix raises the same error,
     through torch.inverse itself.  `mv` / `proj` are contiguous copies of the inputs written by the same kernel
     (the API passes transposed views).  Anything but fp32 CUDA [B,4,4] stacks takes torch.linalg.inv_ex."""
-    __slots__ = ("inv_mv", "inv_proj", "mv", "proj", "mats", "host_np")
+    __slots__ = ("inv_mv", "inv_proj", "mv", "proj", "mats", "host_np", "slot")
     _pinned = {}
 
     def __init__(self, mv_mats, proj_mats):
         self.mats = (mv_mats, proj_mats)
         self.mv, self.proj = mv_mats, proj_mats
         self.host_np = None
+        self.slot = None
         native = (mv_mats.is_cuda and proj_mats.is_cuda and mv_mats.device == proj_mats.device and
                   mv_mats.dtype == torch.float32 and proj_mats.dtype == torch.float32 and mv_mats.dim() == 3 and
                   mv_mats.shape == proj_mats.shape and tuple(mv_mats.shape[1:]) == (4, 4) and mv_mats.size(0) > 0)
         if native:
             dev, B = mv_mats.device, mv_mats.size(0)
-            key = (dev.index, B)
-            slot = _Inverses._pinned.get(key)
-            if slot is None:
-                host = torch.zeros(2 * B, dtype=torch.int32).pin_memory()
-                slot = _Inverses._pinned[key] = (host, host.numpy(), ctypes.c_void_p(host.data_ptr()))
+            slot = self.slot = _Pinned.acquire(dev, 2 * B)      # this call's own `info` words (see _Pinned)
             with _on_device(dev):
                 out = torch.empty((4, B, 4, 4), dtype=torch.float32, device=dev)
                 _lib.check(_lib.load().dmr_camera_inverses(B, _ptr(mv_mats), *mv_mats.stride(), _ptr(proj_mats),
@@ -172,6 +186,9 @@ class _Inverses:
             bad = any(bool(i.any()) for i in infos)
         else:
             bad = self.host_np is not None and bool(self.host_np.any())
+        if self.slot is not None:
+            _Pinned.release(self.slot)
+            self.slot = self.host_np = None
         if bad:
             torch.inverse(self.mats[0])   # raises torch's own "singular matrix" error
             torch.inverse(self.mats[1])
@@ -248,7 +265,7 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
         st.bufs = [torch.empty(sizes[0], **u8), torch.empty(sizes[1], **u8), torch.empty(sizes[2], **u8)]
         st.outs = [torch.empty((B, NUM_CHANNELS, H, W), dtype=torch.float32, device=dev),
                    torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)]
-        st.pinned = _Pinned.get(dev)
+        st.pinned = _Pinned.acquire(dev)     # released by tri_forward_finish
         _arm(st.pinned)
         _lib.check(lib.dmr_tri_forward_bin(B, P, F, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa), _ptr(mv),
                                            _ptr(pj), _ptr(vdep), _ptr(fint), _ptr(st.bufs[0]), _ptr(st.bufs[1]),
@@ -290,7 +307,11 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
             inverses.join()
         # (Measured and rejected: one native call that waits for R and launches phase 2 without returning to Python
         # in between -- 1163 vs 1159 views/s at C2: the bubble is the D2H + launch latency, not the interpreter.)
-        R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
+        try:
+            R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
+        finally:
+            _Pinned.release(st.pinned)
+            st.pinned = None
         _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, *a, _ptr(bin_buf), *b2))
         if inverses is not None:
             inverses.check()
@@ -367,11 +388,14 @@ def render_tris_backward(background, verts, faces, verts_color, faces_opacity, m
                 gp[:3] = [ctypes.c_void_p(t.data_ptr()) for t in accumulate_into]
             a = (B, P, F, W, H, int(R), _ptr(bg), _ptr(imv), _ptr(ipj), _ptr(pointBuffer), _ptr(faceBuffer),
                  _ptr(binningBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd), gp[0], gp[1], gp[2], gp[3], gp[4])
+            # scratch of the call (statistics per (view, face), per-vertex accumulators): the state buffers saved for
+            # backward are only read.  The caching allocator reuses the block for later work on the same stream.
             if deterministic:
                 ws = torch.empty(lib.dmr_tri_backward_deterministic_bytes(B, P, F), dtype=torch.uint8, device=dev)
                 _lib.check(lib.dmr_tri_backward_deterministic(*a, _ptr(ws), ws.numel(), _stream()))
             else:
-                _lib.check(lib.dmr_tri_backward(*a, _stream()))
+                ws = torch.empty(lib.dmr_tri_backward_workspace_bytes(B, P, F), dtype=torch.uint8, device=dev)
+                _lib.check(lib.dmr_tri_backward(*a, _ptr(ws), ws.numel(), _stream()))
         if accumulate_into is not None:
             dL_dverts, dL_dvcolor, dL_dfopacity = accumulate_into
         else:
@@ -398,12 +422,45 @@ def tri_depth_chain(verts, mv_mats, proj_mats, dL_dvdepth, dL_dverts):
 # ---------------------------------------------------------------------------
 # tet renderer
 # ---------------------------------------------------------------------------
+class _TetRecordCache:
+    """The view-independent adjacency records of the tet renderer (one 128-byte TetRec per tet, csrc/tet.cuh)
+    depend only on verts / faces / tets / face_tets / tet_faces.  None of them carries a gradient in the tet
+    renderer (reference dmesh_renderer/__init__.py:407-422), so in an optimisation loop they are the same tensors in
+    every step: the records are built once and reused while the caller keeps passing the SAME tensor objects,
+    unmodified (identity + torch's in-place version counter; weak references, so a freed tensor can never match a
+    new one that happens to reuse its memory).  One entry per device."""
+    _entries = {}
+
+    @classmethod
+    def get(cls, lib, tensors, T, dev):
+        import weakref
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        e = cls._entries.get(key)
+        if e is not None:
+            refs, versions, buf = e
+            if len(refs) == len(tensors) and all(r() is t for r, t in zip(refs, tensors)) and \
+                    versions == tuple(t._version for t in tensors):
+                return buf, 1
+        buf = torch.empty(lib.dmr_tet_records_bytes(T), dtype=torch.uint8, device=dev)
+        try:
+            cls._entries[key] = ([weakref.ref(t) for t in tensors], tuple(t._version for t in tensors), buf)
+        except TypeError:
+            cls._entries.pop(key, None)
+        return buf, 0
+
+    @classmethod
+    def clear(cls):
+        cls._entries.clear()
+
+
 def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
                 verts_depth, faces_intense, tets, face_tets, tet_faces, image_height, image_width, ray_random_seed,
                 inverses=None):
     """RenderFTetsCUDA (render.cu:213-336).
     Returns (color[B,3,H,W], depth[B,1,H,W], active_f32[B,H,W], pointBuffer, faceBuffer, binningBuffer, imgBuffer).
-    `inverses` (beyond the reference's 17 arguments): see tri_forward_finish."""
+    `inverses` (beyond the reference's 17 arguments): see tri_forward_finish.
+    The cached adjacency records (_TetRecordCache) travel with the returned face buffer as its attribute
+    `tet_records`, for render_tets_backward."""
     if verts.dim() != 2 or verts.size(1) != 3:
         _err("verts must have dimensions (num_points, 3)")
     if faces.dim() != 2 or faces.size(1) != 3:
@@ -445,35 +502,42 @@ def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, p
         out_depth = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
         out_active = torch.empty((B, H, W), dtype=torch.float32, device=dev)
 
-        pinned = _Pinned.get(dev)
+        tet_rec, rec_valid = _TetRecordCache.get(lib, (verts_c, faces_c, tets_c, ft_c, tf_c), T, dev)
+        pinned = _Pinned.acquire(dev)
         _arm(pinned)
         stream = _stream()
-        _lib.check(lib.dmr_tet_forward_bin(B, P, F, T, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa),
-                                           _ptr(mv), _ptr(pj), _ptr(tets_c), _ptr(ft_c), _ptr(tf_c), _ptr(point_buf),
-                                           _ptr(face_buf), pinned[2], stream))
-        key = ("tet", B, P, F, T, W, H)
-        spec = _speculative_binning(lib, key, u8)
-        if inverses is not None:
-            inverses.join()
-        R, bin_buf = _wait_R(lib, pinned, key, spec, u8)
+        try:
+            _lib.check(lib.dmr_tet_forward_bin(B, P, F, T, W, H, _ptr(verts_c), _ptr(faces_c), _ptr(vcol), _ptr(fopa),
+                                               _ptr(mv), _ptr(pj), _ptr(tets_c), _ptr(ft_c), _ptr(tf_c), _ptr(point_buf),
+                                               _ptr(face_buf), _ptr(tet_rec), rec_valid, pinned[2], stream))
+            key = ("tet", B, P, F, T, W, H)
+            spec = _speculative_binning(lib, key, u8)
+            if inverses is not None:
+                inverses.join()
+            R, bin_buf = _wait_R(lib, pinned, key, spec, u8)
+        finally:
+            _Pinned.release(pinned)
         if inverses is not None:
             inverses.check()
         _lib.check(lib.dmr_tet_forward_render(B, P, F, T, W, H, R, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj),
                                               _ptr(imv), _ptr(ipj), _ptr(fint), _ptr(point_buf), _ptr(face_buf),
-                                              _ptr(bin_buf), _ptr(img_buf), _ptr(out_color), _ptr(out_depth),
-                                              _ptr(out_active), stream))
+                                              _ptr(tet_rec), _ptr(bin_buf), _ptr(img_buf), _ptr(out_color),
+                                              _ptr(out_depth), _ptr(out_active), stream))
+        face_buf.tet_records = tet_rec     # kept alive (and found by render_tets_backward) through the face buffer
     return out_color, out_depth, out_active, point_buf, face_buf, bin_buf, img_buf
 
 
 def render_tets_backward(background, verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats,
                          inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, grad_color, grad_depth,
-                         pointBuffer, faceBuffer, binningBuffer, imageBuffer, ray_random_seed=None, deterministic=False):
+                         pointBuffer, faceBuffer, binningBuffer, imageBuffer, ray_random_seed=None, deterministic=False,
+                         tet_records=None):
     """RenderFTetsBackwardCUDA (render.cu:338-412).
     Returns (dL_dverts_color[P,3], dL_dfaces_opacity[F]).  `ray_random_seed` is an
     optional trailing argument beyond the reference's 20: the autograd wrapper passes
     the forward's seed so that jittered rays (seed > 0) are re-read from the image
     buffer; with the reference's 20 arguments pixel-centre rays are used.  `deterministic`: run-to-run reproducible
-    gradients (dmr_tet_backward_deterministic)."""
+    gradients (dmr_tet_backward_deterministic).  `tet_records`: the adjacency records of the forward call (the
+    autograd wrapper passes them; otherwise they are taken from the face buffer's attribute or rebuilt)."""
     lib = _lib.load()
     B, P, F, T = mv_mats.size(0), verts.size(0), faces.size(0), tets.size(0)
     H, W = grad_color.size(2), grad_color.size(3)
@@ -490,12 +554,21 @@ def render_tets_backward(background, verts, faces, verts_color, faces_opacity, m
             imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
             fint = _f32(faces_intense, "faces_intense")
             gc, gd = _f32(grad_color, "grad_color"), _f32(grad_depth, "grad_depth")
+            tet_rec = tet_records if tet_records is not None else getattr(faceBuffer, "tet_records", None)
+            if tet_rec is None:
+                # the face buffer did not come straight from render_tets (e.g. unpacked from autograd's saved
+                # tensors, which drops Python attributes): rebuild the view-independent records
+                tet_rec = torch.empty(lib.dmr_tet_records_bytes(T), dtype=torch.uint8, device=dev)
+                _lib.check(lib.dmr_tet_build_records(P, F, T, _ptr(_f32(verts, "verts")), _ptr(_i32(faces, "faces")),
+                                                     _ptr(_i32(tets, "tets")), _ptr(_i32(face_tets, "face_tets")),
+                                                     _ptr(_i32(tet_faces, "tet_faces")), _ptr(tet_rec), _stream()))
             a = (B, P, F, T, W, H, int(ray_random_seed), _ptr(bg), _ptr(mv), _ptr(pj), _ptr(imv), _ptr(ipj), _ptr(fint),
-                 _ptr(pointBuffer), _ptr(faceBuffer), _ptr(imageBuffer), _ptr(gc), _ptr(gd), _ptr(dL_dverts_color),
-                 _ptr(dL_dfaces_opacity))
+                 _ptr(pointBuffer), _ptr(faceBuffer), _ptr(tet_rec), _ptr(imageBuffer), _ptr(gc), _ptr(gd),
+                 _ptr(dL_dverts_color), _ptr(dL_dfaces_opacity))
             if deterministic:
                 ws = torch.empty(lib.dmr_tet_backward_deterministic_bytes(P, F), dtype=torch.uint8, device=dev)
                 _lib.check(lib.dmr_tet_backward_deterministic(*a, _ptr(ws), ws.numel(), _stream()))
             else:
-                _lib.check(lib.dmr_tet_backward(*a, _stream()))
+                ws = torch.empty(lib.dmr_tet_backward_workspace_bytes(P), dtype=torch.uint8, device=dev)
+                _lib.check(lib.dmr_tet_backward(*a, _ptr(ws), ws.numel(), _stream()))
     return dL_dverts_color, dL_dfaces_opacity

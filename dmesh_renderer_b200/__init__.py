@@ -91,7 +91,11 @@ class _RenderTri(th.autograd.Function):
                 inv_proj_mats, verts_depth, faces_intense, grad_out_color, grad_out_depth, num_rendered, pointBuffer,
                 faceBuffer, binningBuffer, imgBuffer)
         sink = ctx.grad_sink
-        into = None if sink is None else tuple(leaf.grad for leaf in sink.leaves)
+        into = None
+        if sink is not None and sink.bind() == 0:
+            into = tuple(leaf.grad for leaf in sink.leaves)
+        # (bind() != 0: a leaf's .grad was dropped or replaced between forward and backward -- e.g. zero_grad with
+        # set_to_none=True; the sink has re-attached it and this call hands its gradients to autograd the ordinary way)
         try:
             grad_verts, grad_verts_color, grad_faces_opacity, grad_verts_depth, grad_faces_intense = \
                 _C.render_tris_backward(*args, accumulate_into=into, deterministic=ctx.deterministic)
@@ -171,6 +175,7 @@ class _RenderTet(th.autograd.Function):
             raise ex
         active = (active > 0.5)
         ctx.render_settings = render_settings
+        ctx.tet_records = getattr(faceBuffer, "tet_records", None)   # cached adjacency records (no gradient, not an input)
         ctx.save_for_backward(verts, faces, verts_color, faces_opacity, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
                               verts_depth, faces_intense, tets, face_tets, tet_faces, pointBuffer, faceBuffer,
                               binningBuffer, imgBuffer)
@@ -186,7 +191,8 @@ class _RenderTet(th.autograd.Function):
                 inv_proj_mats, verts_depth, faces_intense, tets, face_tets, tet_faces, grad_out_color, grad_out_depth,
                 pointBuffer, faceBuffer, binningBuffer, imgBuffer, render_settings.ray_random_seed)
         try:
-            grad_verts_color, grad_faces_opacity = _C.render_tets_backward(*args, deterministic=ctx.deterministic)
+            grad_verts_color, grad_faces_opacity = _C.render_tets_backward(*args, deterministic=ctx.deterministic,
+                                                                           tet_records=ctx.tet_records)
         except Exception as ex:
             print("\nAn error occured in backward.\n")
             raise ex

@@ -29,14 +29,18 @@ SIGNATURES = {
     "dmr_tri_forward_bin": (c_int, [c_int] * 5 + [c_void_p] * 11 + [c_void_p]),
     "dmr_tri_depth_chain": (c_int, [c_int, c_int] + [c_void_p] * 5 + [c_void_p]),
     "dmr_tri_forward_render": (c_int, [c_int] * 6 + [c_void_p] * 9 + [c_void_p]),
-    "dmr_tri_backward": (c_int, [c_int] * 6 + [c_void_p] * 14 + [c_void_p]),
+    "dmr_tri_backward_workspace_bytes": (c_size_t, [c_int] * 3),
+    "dmr_tri_backward": (c_int, [c_int] * 6 + [c_void_p] * 14 + [c_void_p, c_size_t] + [c_void_p]),
     "dmr_tri_backward_deterministic_bytes": (c_size_t, [c_int] * 3),
     "dmr_tri_backward_deterministic": (c_int, [c_int] * 6 + [c_void_p] * 14 + [c_void_p, c_size_t] + [c_void_p]),
-    "dmr_tet_forward_bin": (c_int, [c_int] * 6 + [c_void_p] * 12 + [c_void_p]),
-    "dmr_tet_forward_render": (c_int, [c_int] * 8 + [c_void_p] * 13 + [c_void_p]),
-    "dmr_tet_backward": (c_int, [c_int] * 7 + [c_void_p] * 13 + [c_void_p]),
+    "dmr_tet_records_bytes": (c_size_t, [c_int]),
+    "dmr_tet_build_records": (c_int, [c_int] * 3 + [c_void_p] * 6 + [c_void_p]),
+    "dmr_tet_forward_bin": (c_int, [c_int] * 6 + [c_void_p] * 12 + [c_int] + [c_void_p] * 2),
+    "dmr_tet_forward_render": (c_int, [c_int] * 8 + [c_void_p] * 14 + [c_void_p]),
+    "dmr_tet_backward_workspace_bytes": (c_size_t, [c_int]),
+    "dmr_tet_backward": (c_int, [c_int] * 7 + [c_void_p] * 14 + [c_void_p, c_size_t] + [c_void_p]),
     "dmr_tet_backward_deterministic_bytes": (c_size_t, [c_int] * 2),
-    "dmr_tet_backward_deterministic": (c_int, [c_int] * 7 + [c_void_p] * 13 + [c_void_p, c_size_t] + [c_void_p]),
+    "dmr_tet_backward_deterministic": (c_int, [c_int] * 7 + [c_void_p] * 14 + [c_void_p, c_size_t] + [c_void_p]),
     "dmr_debug_view": (c_int, [c_int] * 8 + [c_size_t, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t)]),
     "dmr_nvls_allreduce_sum_f32": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "dmr_nvls_allreduce_sum_f32_fused": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, ctypes.c_uint, c_void_p]),
@@ -51,6 +55,7 @@ SIGNATURES = {
     "dmr_profile_read": (c_int, [ctypes.POINTER(ctypes.c_float)]),
     "dmr_sort_temp_bytes": (c_size_t, [c_size_t]),
     "dmr_sort_pairs": (c_int, [c_void_p] * 4 + [c_size_t, c_int, c_void_p, c_void_p]),
+    "dmr_sort_pairs_u32": (c_int, [c_void_p] * 4 + [c_size_t, c_int, c_void_p, c_void_p]),
 }
 
 

@@ -14,20 +14,35 @@
 namespace dmr {
 
 // ---------------------------------------------------------------------------
-// Single-pass inclusive scan (decoupled look-back), uint32.
-// state[0] = ticket counter, state[1] = grand total, state[32 + t] = tile
-// descriptor { flag:2 | value:30 }.  state must be zero on entry.
+// Single-pass inclusive scan (decoupled look-back), uint32 data, 64-bit running prefix.
+// state[0] = ticket counter, state[1] = grand total (saturated at 2^32 - 1), then from word 32 on one 64-bit
+// tile descriptor { flag:2 | value:62 } per tile.  state must be zero on entry.
 // One read and one write of the data: 8 B per element.
+// The prefix is carried in 64 bits so that a total beyond 2^30 (the sort's limit) or 2^32 is REPORTED -- the host
+// then refuses the call (DMR_ETOOLARGE) -- instead of spilling into the flag bits of a 32-bit descriptor and
+// silently corrupting the offsets and num_rendered (the reference's CUB scan is exact up to 2^31 - 1).
 // ---------------------------------------------------------------------------
-#define SCAN_FLAG_AGG  (1u << 30)
-#define SCAN_FLAG_INCL (2u << 30)
-#define SCAN_VAL_MASK  ((1u << 30) - 1u)
+#define SCAN_FLAG_AGG  (1ull << 62)
+#define SCAN_FLAG_INCL (2ull << 62)
+#define SCAN_VAL_MASK  ((1ull << 62) - 1ull)
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
     const uint32_t* __restrict__ in, const uint32_t* __restrict__ index, uint32_t* __restrict__ out, size_t n,
     uint32_t* __restrict__ state, int32_t* __restrict__ total_mapped)
 {
     __shared__ uint32_t s_warp[DMR_SCAN_THREADS / 32];
+    __shared__ unsigned long long s_warp64[DMR_SCAN_THREADS / 32];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -63,8 +78,9 @@ __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
         for (int i = 0; i < DMR_SCAN_ITEMS; i++) v[i] = (base + i < n) ? in[base + i] : 0u;
     }
     uint32_t sum = 0;
+    unsigned long long sum64 = 0;   // exact, for the tile aggregate: 4096 faces that each cover a huge tile grid can exceed 32 bits
 #pragma unroll
-    for (int i = 0; i < DMR_SCAN_ITEMS; i++) { sum += v[i]; v[i] = sum; }
+    for (int i = 0; i < DMR_SCAN_ITEMS; i++) { sum64 += v[i]; sum += v[i]; v[i] = sum; }
 
     // warp inclusive scan of the thread sums
     uint32_t incl = sum;
@@ -73,47 +89,51 @@ __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum64 += __shfl_xor_sync(0xffffffffu, sum64, o);
+    if (lane == 31) { s_warp[warp] = incl; s_warp64[warp] = sum64; }
     __syncthreads();
-    uint32_t warp_off = 0, tile_total = 0;
+    uint32_t warp_off = 0;
+    unsigned long long tile_total = 0;
 #pragma unroll
     for (int w = 0; w < DMR_SCAN_THREADS / 32; w++) {
-        uint32_t t = s_warp[w];
-        if (w < warp) warp_off += t;
-        tile_total += t;
+        if (w < warp) warp_off += s_warp[w];
+        tile_total += s_warp64[w];
     }
     uint32_t thread_excl = warp_off + incl - sum;
 
     // publish + decoupled look-back (warp 0)
     if (warp == 0) {
-        uint32_t* desc = state + 32;
-        if (lane == 0) st_volatile_u32(&desc[tile], (tile == 0 ? SCAN_FLAG_INCL : SCAN_FLAG_AGG) | tile_total);
-        uint32_t excl = 0;
+        unsigned long long* desc = reinterpret_cast<unsigned long long*>(state + 32);
+        if (lane == 0) st_volatile_u64(&desc[tile], (tile == 0 ? SCAN_FLAG_INCL : SCAN_FLAG_AGG) | tile_total);
+        unsigned long long excl = 0;
         if (tile > 0) {
             long long t = (long long)tile - 1;
             while (true) {
                 long long idx = t - lane;
-                uint32_t d = SCAN_FLAG_INCL;   // virtual predecessor of tile 0: inclusive 0
+                unsigned long long d = SCAN_FLAG_INCL;   // virtual predecessor of tile 0: inclusive 0
                 if (idx >= 0) {
-                    do { d = ld_volatile_u32(&desc[idx]); } while ((d >> 30) == 0);
+                    do { d = ld_volatile_u64(&desc[idx]); } while ((d >> 62) == 0);
                 }
-                unsigned incl_mask = __ballot_sync(0xffffffffu, (d >> 30) == 2u);
+                unsigned incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2u);
                 int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-                uint32_t c = (lane <= first) ? (d & SCAN_VAL_MASK) : 0u;
+                unsigned long long c = (lane <= first) ? (d & SCAN_VAL_MASK) : 0ull;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
                 excl += c;
                 if (incl_mask) break;
                 t -= 32;
             }
-            if (lane == 0) st_volatile_u32(&desc[tile], SCAN_FLAG_INCL | (excl + tile_total));
+            if (lane == 0) st_volatile_u64(&desc[tile], SCAN_FLAG_INCL | (excl + tile_total));
         }
         if (lane == 0) {
-            s_excl = excl;
+            s_excl = (uint32_t)excl;     // offsets are 32-bit; a total beyond 2^32 - 1 is reported below and refused
             size_t ntile = (n + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
             if ((size_t)tile == ntile - 1) {
-                state[1] = excl + tile_total;
-                if (total_mapped) *total_mapped = (int32_t)(excl + tile_total);
+                const unsigned long long tot = excl + tile_total;
+                const uint32_t tot32 = tot > 0xffffffffull ? 0xffffffffu : (uint32_t)tot;
+                state[1] = tot32;
+                if (total_mapped) *total_mapped = (int32_t)tot32;
             }
         }
     }
@@ -187,12 +207,16 @@ template <bool HIST>   // HIST: accumulate the tile sort's histograms as a by-pr
 __global__ void __launch_bounds__(256) duplicate_kernel(
     size_t BF, int F, int tiles_x, int tiles_per_view, const uint32_t* __restrict__ order,
     const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
-    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, SortPre sp, uint2* __restrict__ ranges, size_t n_ranges)
+    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, SortPre sp, uint2* __restrict__ ranges, size_t n_ranges,
+    const uint32_t* __restrict__ total_dev, uint32_t total_host)
 {
     // tiles without instances keep the empty range (0,0): zero the table here (tile_ranges_kernel runs after the
     // sort) instead of with one more memset between the num_rendered read-back and this launch
     for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n_ranges; t += (size_t)gridDim.x * 256)
         ranges[t] = make_uint2(0u, 0u);
+    // The host sized keys / vals from ITS copy of num_rendered.  If that is not the total the scan produced on the
+    // device (a caller mixing up the counts of two calls in flight), emit nothing rather than write out of bounds.
+    if (*total_dev != total_host) return;
     __shared__ uint32_t s_incl[256];
     __shared__ uint2 s_rect[256];
     __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance divisions hoisted)
@@ -379,11 +403,11 @@ int bin_instances(int B, int F, int W, int H, size_t R, const void* fb, const Fa
         if (fused)
             duplicate_kernel<true><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
                                                             at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp,
-                                                            ranges, tiles);
+                                                            ranges, tiles, at<uint32_t>(fb, L.scan_state) + 1, (uint32_t)R);
         else
             duplicate_kernel<false><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
                                                              at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp,
-                                                             ranges, tiles);
+                                                             ranges, tiles, at<uint32_t>(fb, L.scan_state) + 1, (uint32_t)R);
         DMR_LAUNCH_CHECK("duplicate_kernel");
     }
     if ((rc = sort_pairs_u32_pre(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, fused, stream))) return rc;

@@ -8,6 +8,7 @@
 #include "../../include/dmesh_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <sched.h>
 
 namespace dmr {
 
@@ -95,7 +96,7 @@ using namespace dmr;
 
 extern "C" {
 
-int dmr_abi_version(void) { return 1; }
+int dmr_abi_version(void) { return 2; }
 const char* dmr_last_error(void) { return g_err; }
 
 unsigned long long dmr_launch_count(void) { return g_launches; }
@@ -127,13 +128,17 @@ int dmr_profile_read(float* ms_out)
 
 int dmr_wait_i32(volatile int32_t* host_value, int32_t sentinel, dmr_stream_t stream_)
 {
-    // Spin on the pinned word (the D2H copy of num_rendered lands a few microseconds before a
-    // cudaStreamSynchronize would return); after ~2 s fall back to the stream synchronisation, which also
-    // reports a faulted stream instead of spinning forever.
+    // Poll the pinned word (the D2H copy of num_rendered lands a few microseconds before a
+    // cudaStreamSynchronize would return).  The first ~50 us are a tight pause loop (the common case: phase 1 of
+    // a small scene is nearly done when the host gets here); after that the thread yields its core between polls,
+    // so that several ranks sharing a host do not each burn a core for the whole of a long phase 1.  A finished
+    // or faulted stream ends the wait through the stream synchronisation, which also reports the fault.
     if (!host_value) { set_error("host_value is null"); return DMR_EINVAL; }
     for (long long spin = 0; spin < 2000000000LL; spin++) {
         if (*host_value != sentinel) return DMR_OK;
-        if ((spin & 0xffff) == 0xffff && cudaStreamQuery((cudaStream_t)stream_) != cudaErrorNotReady) break;
+        __builtin_ia32_pause();
+        if (spin > 4096) sched_yield();
+        if ((spin & 0x3fff) == 0x3fff && cudaStreamQuery((cudaStream_t)stream_) != cudaErrorNotReady) break;
     }
     DMR_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
     return DMR_OK;
@@ -144,7 +149,7 @@ int dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3])
     if (!out) { set_error("out is null"); return DMR_EINVAL; }
     if (!sizes_ok(B, P, F, W, H)) return DMR_ETOOLARGE;
     out[0] = align_up(sizeof(float4) * (size_t)B * P, 256) + 256;
-    out[1] = TriFaceLayout::make((size_t)B * F, (size_t)P).total;
+    out[1] = TriFaceLayout::make((size_t)B * F).total;
     out[2] = TriImageLayout::make(B, W, H).total;
     return DMR_OK;
 }
@@ -160,6 +165,13 @@ int dmr_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* k
     return sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, (cudaStream_t)stream);
 }
 
+int dmr_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
+                       int end_bit, void* temp, dmr_stream_t stream)
+{
+    if (n && (!keys_in || !keys_out || !vals_out || !temp)) { set_error("null pointer"); return DMR_EINVAL; }
+    return sort_pairs_u32(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, true, (cudaStream_t)stream);
+}
+
 int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, const int* faces,
                         const float* verts_color, const float* faces_opacity, const float* mv_mats,
                         const float* proj_mats, const float* verts_depth, const float* faces_intense,
@@ -173,7 +185,7 @@ int dmr_tri_forward_bin(int B, int P, int F, int W, int H, const float* verts, c
     if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats ||
         !faces_intense || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
     const size_t BF = (size_t)B * F;
-    TriFaceLayout L = TriFaceLayout::make(BF, (size_t)P);
+    TriFaceLayout L = TriFaceLayout::make(BF);
     float4* vimg = static_cast<float4*>(point_buffer);
     int rc;
     SortPre face_sort;
@@ -207,7 +219,7 @@ int dmr_tri_forward_render(int B, int P, int F, int W, int H, int R, const float
     if (!background || !inv_mv_mats || !inv_proj_mats || !image_buffer || !out_color || !out_depth ||
         (R > 0 && (!binning_buffer || !face_buffer))) { set_error("null pointer"); return DMR_EINVAL; }
     (void)point_buffer;
-    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F, (size_t)P);
+    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
     TriImageLayout IL = TriImageLayout::make(B, W, H);
     uint2* ranges = at<uint2>(image_buffer, IL.ranges);
     int rc = bin_instances(B, F, W, H, (size_t)R, face_buffer, FL.bin, binning_buffer, ranges, stream);
@@ -232,7 +244,7 @@ static int tri_backward_impl(int B, int P, int F, int W, int H, int R, const flo
                              const float* inv_proj_mats, const void* point_buffer, const void* face_buffer,
                              const void* binning_buffer, const void* image_buffer, const float* dL_dcolor,
                              const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity,
-                             float* dL_dvdepth, float* dL_dfintense, void* det_workspace, size_t det_workspace_bytes,
+                             float* dL_dvdepth, float* dL_dfintense, void* workspace, size_t workspace_bytes,
                              bool deterministic, dmr_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -244,7 +256,7 @@ static int tri_backward_impl(int B, int P, int F, int W, int H, int R, const flo
         return DMR_EINVAL;
     }
     (void)point_buffer;
-    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F, (size_t)P);
+    TriFaceLayout FL = TriFaceLayout::make((size_t)B * F);
     TriImageLayout IL = TriImageLayout::make(B, W, H);
     BinningLayout BL = BinningLayout::make((size_t)R);
     TriRenderParams p = {};
@@ -261,7 +273,8 @@ static int tri_backward_impl(int B, int P, int F, int W, int H, int R, const flo
     p.dL_dvdepth = dL_dvdepth; p.dL_dfintense = dL_dfintense;
     if (deterministic) {
         TriDetLayout DL = TriDetLayout::make((size_t)B, (size_t)P, (size_t)F);
-        if (!det_workspace || det_workspace_bytes < DL.total) {
+        void* det_workspace = workspace;
+        if (!det_workspace || workspace_bytes < DL.total) {
             set_error("deterministic backward needs a workspace of %zu bytes (dmr_tri_backward_deterministic_bytes)", DL.total);
             return DMR_EINVAL;
         }
@@ -273,12 +286,17 @@ static int tri_backward_impl(int B, int P, int F, int W, int H, int R, const flo
         DMR_CUDA(cudaMemsetAsync(det_workspace, 0, DL.total, stream));
         return tri_render_backward_deterministic(p, stream);
     }
-    // backward scratch lives in the face buffer (opaque state owned by autograd ctx)
-    p.grad_stats = const_cast<float*>(at<float>(face_buffer, FL.grad_stats));
+    // backward scratch: the caller's workspace (the forward's state buffers stay read-only)
+    TriBwdLayout WL = TriBwdLayout::make((size_t)B * F, (size_t)P);
+    if (!workspace || workspace_bytes < WL.total) {
+        set_error("backward needs a workspace of %zu bytes (dmr_tri_backward_workspace_bytes)", WL.total);
+        return DMR_EINVAL;
+    }
+    p.grad_stats = at<float>(workspace, WL.grad_stats);
     // per-vertex vector accumulators only when there are at least two (view, face) records per vertex
     const bool use_vacc = (size_t)B * F >= 2 * (size_t)P;
-    p.grad_vacc = use_vacc ? const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc)) : nullptr;
-    DMR_CUDA(cudaMemsetAsync(p.grad_stats, 0, (use_vacc ? FL.grad_end : FL.grad_vacc) - FL.grad_stats, stream));
+    p.grad_vacc = use_vacc ? at<float4>(workspace, WL.grad_vacc) : nullptr;
+    DMR_CUDA(cudaMemsetAsync(workspace, 0, use_vacc ? WL.total - 256 : WL.stats_end, stream));
     return tri_render_backward(p, stream);
 }
 
@@ -286,11 +304,17 @@ int dmr_tri_backward(int B, int P, int F, int W, int H, int R, const float* back
                      const float* inv_proj_mats, const void* point_buffer, const void* face_buffer,
                      const void* binning_buffer, const void* image_buffer, const float* dL_dcolor,
                      const float* dL_ddepth, float* dL_dverts, float* dL_dvcolor, float* dL_dfopacity,
-                     float* dL_dvdepth, float* dL_dfintense, dmr_stream_t stream)
+                     float* dL_dvdepth, float* dL_dfintense, void* workspace, size_t workspace_bytes, dmr_stream_t stream)
 {
     return tri_backward_impl(B, P, F, W, H, R, background, inv_mv_mats, inv_proj_mats, point_buffer, face_buffer,
                              binning_buffer, image_buffer, dL_dcolor, dL_ddepth, dL_dverts, dL_dvcolor, dL_dfopacity,
-                             dL_dvdepth, dL_dfintense, nullptr, 0, false, stream);
+                             dL_dvdepth, dL_dfintense, workspace, workspace_bytes, false, stream);
+}
+
+size_t dmr_tri_backward_workspace_bytes(int B, int P, int F)
+{
+    if (B < 0 || P < 0 || F < 0) return 0;
+    return TriBwdLayout::make((size_t)B * F, (size_t)P).total;
 }
 
 size_t dmr_tri_backward_deterministic_bytes(int B, int P, int F)
@@ -326,7 +350,7 @@ int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, in
         off = kind == DMR_VIEW_KEYS_UNSORTED ? L.keys_unsorted : kind == DMR_VIEW_VALUES_UNSORTED ? L.vals_unsorted
             : kind == DMR_VIEW_KEYS_SORTED ? L.keys_sorted : L.vals_sorted;
     } else if (renderer == 0) {
-        TriFaceLayout FL = TriFaceLayout::make(BF, (size_t)P);
+        TriFaceLayout FL = TriFaceLayout::make(BF);
         TriImageLayout IL = TriImageLayout::make(B, W, H);
         switch (kind) {
         case DMR_VIEW_TILES_TOUCHED: off = FL.bin.tiles_touched; n = BF; break;
@@ -339,7 +363,7 @@ int dmr_debug_view(int renderer, int kind, int B, int P, int F, int T, int W, in
         default: set_error("unknown view kind %d", kind); return DMR_EINVAL;
         }
     } else {
-        TetFaceLayout FL = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
+        TetFaceLayout FL = TetFaceLayout::make(BF, (size_t)F);
         TetImageLayout IL = TetImageLayout::make(B, W, H);
         switch (kind) {
         case DMR_VIEW_TILES_TOUCHED: off = FL.bin.tiles_touched; n = BF; break;

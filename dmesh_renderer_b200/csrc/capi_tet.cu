@@ -40,7 +40,7 @@ int dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[3])
     if (!out) { set_error("out is null"); return DMR_EINVAL; }
     if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
     out[0] = align_up(sizeof(float4) * (size_t)B * P, 256) + 256;
-    out[1] = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P).total;
+    out[1] = TetFaceLayout::make((size_t)B * F, (size_t)F).total;
     out[2] = TetImageLayout::make(B, W, H).total;
     return DMR_OK;
 }
@@ -48,16 +48,17 @@ int dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[3])
 int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* verts, const int* faces,
                         const float* verts_color, const float* faces_opacity, const float* mv_mats,
                         const float* proj_mats, const int* tets, const int* face_tets, const int* tet_faces,
-                        void* point_buffer, void* face_buffer, int32_t* num_rendered_host, dmr_stream_t stream_)
+                        void* point_buffer, void* face_buffer, void* tet_records, int tet_records_valid,
+                        int32_t* num_rendered_host, dmr_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
     if (!num_rendered_host) { set_error("num_rendered_host is null"); return DMR_EINVAL; }
     if (B == 0 || P == 0 || F == 0) { *num_rendered_host = 0; return DMR_OK; }
     if (!verts || !faces || !verts_color || !faces_opacity || !mv_mats || !proj_mats || !face_tets ||
-        (T > 0 && (!tets || !tet_faces)) || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
+        (T > 0 && (!tets || !tet_faces || !tet_records)) || !point_buffer || !face_buffer) { set_error("null pointer"); return DMR_EINVAL; }
     const size_t BF = (size_t)B * F;
-    TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F, (size_t)T, (size_t)P);
+    TetFaceLayout L = TetFaceLayout::make(BF, (size_t)F);
     float4* vimg = static_cast<float4*>(point_buffer);
     int rc;
     SortPre face_sort;
@@ -72,23 +73,25 @@ int dmr_tet_forward_bin(int B, int P, int F, int T, int W, int H, const float* v
     // building them on a second stream concurrently with the binning chain -- the chain's preprocess and sort
     // kernels are HBM-bound like the record builders, they just slow each other down: C3 forward 1.78 ms both ways.)
     if ((rc = tet_build_records(P, F, T, verts, faces, verts_color, faces_opacity, tets, face_tets, tet_faces,
-                                at<TetRec>(face_buffer, L.tet_rec), at<TetShade>(face_buffer, L.shade), stream)))
+                                tet_records_valid ? nullptr : static_cast<TetRec*>(tet_records),
+                                at<TetShade>(face_buffer, L.shade), stream)))
         return rc;
     return DMR_OK;
 }
 
 static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, int seed, const float* bg,
                         const float* mv, const float* proj, const float* inv_mv, const float* inv_proj,
-                        const float* faces_intense, const void* face_buffer, const void* image_buffer)
+                        const float* faces_intense, const void* face_buffer, const void* tet_records,
+                        const void* image_buffer)
 {
-    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F);
     TetImageLayout IL = TetImageLayout::make(B, W, H);
     p = TetParams{};
     p.B = B; p.P = P; p.F = F; p.T = T; p.W = W; p.H = H;
     p.mv = mv; p.proj = proj; p.inv_mv = inv_mv; p.inv_proj = inv_proj;
     p.faces_intense = faces_intense; p.bg = bg;
     p.face_rec = at<TetFaceRec>(face_buffer, FL.face_rec);
-    p.tet_rec = at<TetRec>(face_buffer, FL.tet_rec);
+    p.tet_rec = static_cast<const TetRec*>(tet_records);
     p.shade = at<TetShade>(face_buffer, FL.shade);
     p.ranges = at<uint2>(image_buffer, IL.ranges);
     p.jitter = seed > 0 ? at<float2>(image_buffer, IL.jitter) : nullptr;
@@ -119,25 +122,26 @@ static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, 
 int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int ray_random_seed,
                            const float* background, const float* mv_mats, const float* proj_mats,
                            const float* inv_mv_mats, const float* inv_proj_mats, const float* faces_intense,
-                           const void* point_buffer, void* face_buffer, void* binning_buffer, void* image_buffer,
-                           float* out_color, float* out_depth, float* out_active, dmr_stream_t stream_)
+                           const void* point_buffer, void* face_buffer, const void* tet_records, void* binning_buffer,
+                           void* image_buffer, float* out_color, float* out_depth, float* out_active, dmr_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!tet_sizes_ok(B, P, F, T, W, H) || R < 0) return DMR_ETOOLARGE;
     if (B == 0) return DMR_OK;
     if (!background || !mv_mats || !proj_mats || !inv_mv_mats || !inv_proj_mats || !face_buffer || !image_buffer ||
-        !out_color || !out_depth || !out_active || (F > 0 && !faces_intense) || (R > 0 && !binning_buffer)) {
+        !out_color || !out_depth || !out_active || (F > 0 && !faces_intense) || (R > 0 && !binning_buffer) ||
+        (T > 0 && !tet_records)) {
         set_error("null pointer");
         return DMR_EINVAL;
     }
     (void)point_buffer;
-    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
+    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F);
     TetImageLayout IL = TetImageLayout::make(B, W, H);
     uint2* ranges = at<uint2>(image_buffer, IL.ranges);
     int rc;
     TetParams p;
     fill_params(p, B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
-                faces_intense, face_buffer, image_buffer);
+                faces_intense, face_buffer, tet_records, image_buffer);
     if (ray_random_seed > 0)
         if ((rc = tet_jitter(B, W, H, ray_random_seed, at<float2>(image_buffer, IL.jitter), stream))) return rc;
     if ((rc = bin_instances(B, F, W, H, (size_t)R, face_buffer, FL.bin, binning_buffer, ranges, stream))) return rc;
@@ -151,22 +155,25 @@ int dmr_tet_forward_render(int B, int P, int F, int T, int W, int H, int R, int 
 static int tet_backward_impl(int B, int P, int F, int T, int W, int H, int ray_random_seed, const float* background,
                              const float* mv_mats, const float* proj_mats, const float* inv_mv_mats,
                              const float* inv_proj_mats, const float* faces_intense, const void* point_buffer,
-                             const void* face_buffer, const void* image_buffer, const float* dL_dcolor,
-                             const float* dL_ddepth, float* dL_dverts_color, float* dL_dfaces_opacity,
-                             void* det_workspace, size_t det_workspace_bytes, bool deterministic, dmr_stream_t stream_)
+                             const void* face_buffer, const void* tet_records, const void* image_buffer,
+                             const float* dL_dcolor, const float* dL_ddepth, float* dL_dverts_color,
+                             float* dL_dfaces_opacity, void* workspace, size_t workspace_bytes, bool deterministic,
+                             dmr_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!tet_sizes_ok(B, P, F, T, W, H)) return DMR_ETOOLARGE;
     if (B == 0 || F == 0 || T == 0) return DMR_OK;
     if (!background || !mv_mats || !proj_mats || !inv_mv_mats || !inv_proj_mats || !faces_intense || !face_buffer ||
-        !image_buffer || !dL_dcolor || !dL_ddepth || !dL_dverts_color || !dL_dfaces_opacity) {
+        !tet_records || !image_buffer || !dL_dcolor || !dL_ddepth || !dL_dverts_color || !dL_dfaces_opacity) {
         set_error("null pointer");
         return DMR_EINVAL;
     }
     (void)point_buffer;
+    void* det_workspace = workspace;
+    const size_t det_workspace_bytes = workspace_bytes;
     TetParams p;
     fill_params(p, B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats, inv_proj_mats,
-                faces_intense, face_buffer, image_buffer);
+                faces_intense, face_buffer, tet_records, image_buffer);
     p.dL_dcolor = dL_dcolor; p.dL_ddepth = dL_ddepth;
     p.dL_dverts_color = dL_dverts_color; p.dL_dfaces_opacity = dL_dfaces_opacity;
     p.det_gmax = nullptr; p.det_vert = nullptr; p.det_fopa = nullptr;
@@ -183,8 +190,12 @@ static int tet_backward_impl(int B, int P, int F, int T, int W, int H, int ray_r
         DMR_CUDA(cudaMemsetAsync(det_workspace, 0, DL.total, stream));
         return tet_march_backward_deterministic(p, stream);
     }
-    TetFaceLayout FL = TetFaceLayout::make((size_t)B * F, (size_t)F, (size_t)T, (size_t)P);
-    p.grad_vacc = const_cast<float4*>(at<float4>(face_buffer, FL.grad_vacc));
+    // backward scratch: float4 per vertex (colour gradient, 16-byte aligned for red.v4) in the caller's workspace
+    if (!workspace || workspace_bytes < sizeof(float4) * (size_t)P) {
+        set_error("backward needs a workspace of %zu bytes (dmr_tet_backward_workspace_bytes)", sizeof(float4) * (size_t)P);
+        return DMR_EINVAL;
+    }
+    p.grad_vacc = static_cast<float4*>(workspace);
     DMR_CUDA(cudaMemsetAsync(p.grad_vacc, 0, sizeof(float4) * (size_t)P, stream));
     return tet_march_backward(p, stream);
 }
@@ -192,13 +203,28 @@ static int tet_backward_impl(int B, int P, int F, int T, int W, int H, int ray_r
 int dmr_tet_backward(int B, int P, int F, int T, int W, int H, int ray_random_seed, const float* background,
                      const float* mv_mats, const float* proj_mats, const float* inv_mv_mats,
                      const float* inv_proj_mats, const float* faces_intense, const void* point_buffer,
-                     const void* face_buffer, const void* image_buffer, const float* dL_dcolor, const float* dL_ddepth,
-                     float* dL_dverts_color, float* dL_dfaces_opacity, dmr_stream_t stream)
+                     const void* face_buffer, const void* tet_records, const void* image_buffer, const float* dL_dcolor,
+                     const float* dL_ddepth, float* dL_dverts_color, float* dL_dfaces_opacity, void* workspace,
+                     size_t workspace_bytes, dmr_stream_t stream)
 {
     return tet_backward_impl(B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats,
-                             inv_proj_mats, faces_intense, point_buffer, face_buffer, image_buffer, dL_dcolor, dL_ddepth,
-                             dL_dverts_color, dL_dfaces_opacity, nullptr, 0, false, stream);
+                             inv_proj_mats, faces_intense, point_buffer, face_buffer, tet_records, image_buffer, dL_dcolor,
+                             dL_ddepth, dL_dverts_color, dL_dfaces_opacity, workspace, workspace_bytes, false, stream);
 }
+
+size_t dmr_tet_backward_workspace_bytes(int P) { return P < 0 ? 0 : sizeof(float4) * (size_t)P + 256; }
+
+int dmr_tet_build_records(int P, int F, int T, const float* verts, const int* faces, const int* tets,
+                          const int* face_tets, const int* tet_faces, void* tet_records, dmr_stream_t stream)
+{
+    if (P < 0 || F < 0 || T < 0 || T > DMR_TET_MAX_TETS) { set_error("bad size"); return DMR_EINVAL; }
+    if (T == 0) return DMR_OK;
+    if (!verts || !faces || !tets || !face_tets || !tet_faces || !tet_records) { set_error("null pointer"); return DMR_EINVAL; }
+    return tet_build_records(P, F, T, verts, faces, nullptr, nullptr, tets, face_tets, tet_faces,
+                             static_cast<TetRec*>(tet_records), nullptr, (cudaStream_t)stream);
+}
+
+size_t dmr_tet_records_bytes(int T) { return T < 0 ? 0 : align_up(sizeof(TetRec) * (size_t)T, 256) + 256; }
 
 size_t dmr_tet_backward_deterministic_bytes(int P, int F)
 {
@@ -209,14 +235,14 @@ size_t dmr_tet_backward_deterministic_bytes(int P, int F)
 int dmr_tet_backward_deterministic(int B, int P, int F, int T, int W, int H, int ray_random_seed,
                                    const float* background, const float* mv_mats, const float* proj_mats,
                                    const float* inv_mv_mats, const float* inv_proj_mats, const float* faces_intense,
-                                   const void* point_buffer, const void* face_buffer, const void* image_buffer,
-                                   const float* dL_dcolor, const float* dL_ddepth, float* dL_dverts_color,
-                                   float* dL_dfaces_opacity, void* workspace, size_t workspace_bytes,
-                                   dmr_stream_t stream)
+                                   const void* point_buffer, const void* face_buffer, const void* tet_records,
+                                   const void* image_buffer, const float* dL_dcolor, const float* dL_ddepth,
+                                   float* dL_dverts_color, float* dL_dfaces_opacity, void* workspace,
+                                   size_t workspace_bytes, dmr_stream_t stream)
 {
     return tet_backward_impl(B, P, F, T, W, H, ray_random_seed, background, mv_mats, proj_mats, inv_mv_mats,
-                             inv_proj_mats, faces_intense, point_buffer, face_buffer, image_buffer, dL_dcolor, dL_ddepth,
-                             dL_dverts_color, dL_dfaces_opacity, workspace, workspace_bytes, true, stream);
+                             inv_proj_mats, faces_intense, point_buffer, face_buffer, tet_records, image_buffer, dL_dcolor,
+                             dL_ddepth, dL_dverts_color, dL_dfaces_opacity, workspace, workspace_bytes, true, stream);
 }
 
 int dmr_debug_set_tet_first_split(int split)

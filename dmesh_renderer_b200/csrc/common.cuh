@@ -208,7 +208,7 @@ struct FaceBinLayout {
         L.depth_sorted = o;  o = align_up(o + 4 * BF, 256);
         L.offsets = o;       o = align_up(o + 4 * BF, 256);
         size_t ntile = (BF + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
-        L.scan_state = o;    o = align_up(o + 4 * (ntile + 64), 256);   // [0]=ticket, [1]=total, [32..]=descriptors
+        L.scan_state = o;    o = align_up(o + 8 * ntile + 256, 256);    // [0]=ticket, [1]=total, from word 32: 64-bit descriptors
         L.fsort_temp = o;    o = align_up(o + sort_temp_bytes_u32(BF), 256);
         L.end = o;
         return L;
@@ -217,17 +217,29 @@ struct FaceBinLayout {
 
 struct TriFaceLayout {
     FaceBinLayout bin;
-    size_t records, grad_stats, grad_vacc, grad_end, total;
-    __host__ static TriFaceLayout make(size_t BF, size_t P)
+    size_t records, total;
+    __host__ static TriFaceLayout make(size_t BF)
     {
         TriFaceLayout L;
         L.bin = FaceBinLayout::make(BF);
         size_t o = L.bin.end;
         L.records = o;       o = align_up(o + sizeof(TriRecord) * BF, 256);
-        // backward scratch, zeroed per call as one range [grad_stats, grad_end)
+        L.total = o + 256;
+        return L;
+    }
+};
+
+// Backward scratch of the tri renderer (dmr_tri_backward's `workspace`), zeroed per call.  Not part of the face
+// buffer: that one is saved for backward by autograd and must stay read-only.
+struct TriBwdLayout {
+    size_t grad_stats, grad_vacc, stats_end, total;
+    __host__ static TriBwdLayout make(size_t BF, size_t P)
+    {
+        TriBwdLayout L;
+        size_t o = 0;
         L.grad_stats = o;    o = align_up(o + 96 * BF, 256);   // 24 floats per (view, face)
+        L.stats_end = o;
         L.grad_vacc = o;     o = align_up(o + 32 * P, 256);    // float4[2][P]: dL_dverts, dL_dvcolor (16-byte aligned for red.v4)
-        L.grad_end = o;
         L.total = o + 256;
         return L;
     }
@@ -271,7 +283,7 @@ int sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* k
 
 // inclusive scan of in[index ? index[i] : i]
 int inclusive_scan_u32(const uint32_t* in, const uint32_t* index, uint32_t* out, size_t n,
-                       uint32_t* state /* zeroed, ntile+64 words */, int32_t* total_host /* pinned, may be null */,
+                       uint32_t* state /* zeroed, 8*ntile + 256 bytes */, int32_t* total_host /* pinned, may be null */,
                        cudaStream_t stream);
 
 // Two-level binning (replaces InclusiveSum + duplicateWithKeys + the 64-bit SortPairs + identifyTileRanges,

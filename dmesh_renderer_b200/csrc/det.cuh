@@ -29,6 +29,10 @@ __device__ __forceinline__ void det_scales(uint32_t gmax_bits, float& sv, float&
     sv = ldexpf(1.0f, DMR_DET_VALUE_BITS - e);
     sg = ldexpf(1.0f, DMR_DET_GEOM_BITS - e);
 }
+// Non-finite cotangents (inf / NaN bit patterns order above every finite float): the fixed-point format has no
+// representation for them, so the convert kernels POISON the gradients with NaN -- as the fp32-atomic path and the
+// reference would propagate it -- instead of returning all zeros, which would look like a clean step.
+__device__ __forceinline__ bool det_nonfinite(uint32_t gmax_bits) { return gmax_bits >= 0x7f800000u; }
 __device__ __forceinline__ void det_add(long long* dst, float v, float scale)
 {
     const long long q = __float2ll_rn(v * scale);

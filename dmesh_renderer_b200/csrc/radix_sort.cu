@@ -123,6 +123,24 @@ struct RsBuffers {
     KeyT* ktmp; uint32_t* vtmp;
 };
 
+// Lanes of the warp whose digit equals this lane's: one ballot per digit bit.  Written in PTX so that every bit
+// costs four instructions (test, vote, conditional complement, and); the C++ form `bit ? m : ~m` compiled to
+// seven (shift, mask, compare, vote, test, select, and-merge), and the ranking loop was 54 % of the pass.
+template <int NBITS>
+__device__ __forceinline__ unsigned digit_peers(uint32_t d, unsigned peers)
+{
+#pragma unroll
+    for (int bit = 0; bit < NBITS; bit++) {
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 m;\n\t"
+            "setp.ne.u32 p, %1, 0;\n\t"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+            "@!p not.b32 m, m;\n\t"
+            "and.b32 %0, %0, m;\n\t}"
+            : "+r"(peers) : "r"(d & (1u << bit)));
+    }
+    return peers;
+}
+
 // Phase order per tile (4096 keys, 512 threads x 8 keys):
 //   load -> per-warp digit COUNTS (shared atomics) -> publish the tile aggregate EARLY -> stable
 //   ranking (ballot multi-split) -> scatter into shared memory -> look-back -> coalesced write-out.
@@ -134,22 +152,20 @@ struct RsBuffers {
 // L2 round trip per RS_LB tiles.
 // NBITS = digit bits of this pass (8 except for the top pass of a sort): a compile-time constant so that the
 // ranking loop is exactly NBITS ballots with no run-time tests.
-template <typename KeyT, int RS_THREADS, int RS_KPT, int RS_MINB, int NBITS>
-__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n, int pass,
-                                                                          const uint32_t* __restrict__ hist_excl,
-                                                                          SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
+// FULL = every key slot of the tile is valid (all tiles of a pass but the last): no bounds tests, no padding class.
+template <typename KeyT, int RS_THREADS, int RS_KPT, int NBITS, bool FULL>
+__device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, size_t n, int pass,
+                                                 const uint32_t* __restrict__ hist_excl, SortCtl* __restrict__ ctl,
+                                                 uint32_t* __restrict__ desc, unsigned char* rs_smem, uint32_t tile,
+                                                 uint32_t* s_wsum)
 {
     constexpr int RS_TILE = RS_THREADS * RS_KPT;
     constexpr int RS_WARPS = RS_THREADS / 32;
-    if (!ctl->exec[pass]) return;
-    extern __shared__ __align__(16) unsigned char rs_smem[];
     KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                               // RS_TILE
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE);   // RS_TILE
     uint32_t* s_whist = s_vals + RS_TILE;                                          // RS_WARPS * 256
     uint32_t* s_dbase = s_whist + RS_WARPS * 256;                                  // 256: local exclusive digit base
     int32_t*  s_gbase = reinterpret_cast<int32_t*>(s_dbase + 256);                 // 256: global pos - local pos (wrapping)
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_wsum[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t s = ctl->src[pass], d_sel = ctl->dst[pass];
@@ -158,12 +174,8 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     KeyT* kout = (d_sel == 1) ? buf.kout : buf.ktmp;
     uint32_t* vout = (d_sel == 1) ? buf.vout : buf.vtmp;
 
-    if (tid == 0) s_tile = atomicAdd(&ctl->ticket[pass], 1u);
-    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) s_whist[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
     const size_t tile_base = (size_t)tile * RS_TILE;
-    const uint32_t nvalid = (uint32_t)((n - tile_base < RS_TILE) ? (n - tile_base) : RS_TILE);
+    const uint32_t nvalid = FULL ? (uint32_t)RS_TILE : (uint32_t)(n - tile_base);
 
     const int shift = 8 * pass;
     constexpr uint32_t dmask = (1u << NBITS) - 1u;
@@ -176,20 +188,27 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
         uint32_t loc = wbase + i * 32 + lane;
-        key[i] = (loc < nvalid) ? kin[tile_base + loc] : (KeyT)~(KeyT)0;
+        key[i] = (FULL || loc < nvalid) ? kin[tile_base + loc] : (KeyT)~(KeyT)0;
     }
+    if (vin) {
 #pragma unroll
-    for (int i = 0; i < RS_KPT; i++) {
-        uint32_t loc = wbase + i * 32 + lane;
-        val[i] = (loc < nvalid) ? (vin ? vin[tile_base + loc] : (uint32_t)(tile_base + loc)) : 0u;   // null = identity
+        for (int i = 0; i < RS_KPT; i++) {
+            uint32_t loc = wbase + i * 32 + lane;
+            val[i] = (FULL || loc < nvalid) ? vin[tile_base + loc] : 0u;
+        }
+    } else {   // null = identity
+#pragma unroll
+        for (int i = 0; i < RS_KPT; i++) val[i] = (uint32_t)(tile_base + wbase + i * 32 + lane);
     }
 
     // ---- per-warp digit counts
     uint32_t* wh = s_whist + warp * 256;
+    uint32_t dig[RS_KPT];
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
         uint32_t loc = wbase + i * 32 + lane;
-        if (loc < nvalid) atomicAdd(&wh[(uint32_t)(key[i] >> shift) & dmask], 1u);
+        dig[i] = (uint32_t)(key[i] >> shift) & dmask;
+        if (FULL || loc < nvalid) atomicAdd(&wh[dig[i]], 1u);
     }
     __syncthreads();
 
@@ -225,28 +244,33 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     __syncthreads();
 
     // ---- stable rank inside the warp (running per-warp offsets), scatter into shared memory.
+    //      The peer masks of all RS_KPT rounds are formed first (independent ballots, no memory traffic in between);
+    //      only the running-offset update is serial.
     //      (Measured and rejected: packed per-round counters -- 8 x 8-bit counts per (warp, digit) filled by the
     //      leader of every digit run, ranks from byte prefixes -- which make the 8 rounds independent of each
-    //      other: 306 vs 282 us per pass at C5; the extra shared-memory traffic costs more than the chain.)
+    //      other: 306 vs 282 us per pass at C5; the extra shared-memory traffic costs more than the chain.
+    //      A single match.any.sync per key instead of the ballots: 9 % slower, its issue rate is far lower.)
     const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned peers[RS_KPT];
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
-        uint32_t loc = wbase + i * 32 + lane;
-        const bool ok = loc < nvalid;
-        uint32_t d = ok ? ((uint32_t)(key[i] >> shift) & dmask) : 256u;   // padding: own class
-        // peers = lanes holding the same digit.  Built from one ballot per digit bit (8 VOTE + 8 LOP3):
-        // measured 9% faster per pass than a single match.any.sync, whose issue rate is far lower.
-        unsigned peers = __ballot_sync(0xffffffffu, ok);
-        if (!ok) peers = ~peers;
-#pragma unroll
-        for (int bit = 0; bit < NBITS; bit++) {
-            const unsigned m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
-            peers &= ((d >> bit) & 1u) ? m : ~m;
+        if (FULL) {
+            peers[i] = digit_peers<NBITS>(dig[i], 0xffffffffu);
+        } else {
+            const bool ok = wbase + i * 32 + lane < nvalid;
+            unsigned pm = __ballot_sync(0xffffffffu, ok);
+            if (!ok) pm = ~pm;                               // padding: own class
+            peers[i] = digit_peers<NBITS>(dig[i], pm);
         }
-        int leader = __ffs(peers) - 1;
-        uint32_t before = __popc(peers & lt_mask);
+    }
+#pragma unroll
+    for (int i = 0; i < RS_KPT; i++) {
+        const bool ok = FULL || wbase + i * 32 + lane < nvalid;
+        const uint32_t d = dig[i];
+        const int leader = __ffs(peers[i]) - 1;
+        const uint32_t before = __popc(peers[i] & lt_mask);
         uint32_t old = 0;
-        if (ok && lane == leader) { old = wh[d]; wh[d] = old + __popc(peers); }
+        if (ok && lane == leader) { old = wh[d]; wh[d] = old + __popc(peers[i]); }
         old = __shfl_sync(0xffffffffu, old, leader);
         if (ok) {
             uint32_t pos = s_dbase[d] + old + before;
@@ -284,13 +308,48 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     __syncthreads();
 
     // ---- coalesced write-out
-    for (uint32_t p = tid; p < nvalid; p += RS_THREADS) {
-        KeyT k = s_keys[p];
-        uint32_t d = (uint32_t)(k >> shift) & dmask;
-        size_t g = (size_t)(uint32_t)(s_gbase[d] + (int32_t)p);
-        kout[g] = k;
-        vout[g] = s_vals[p];
+    if (FULL) {
+#pragma unroll
+        for (int i = 0; i < RS_KPT; i++) {
+            const uint32_t p = i * RS_THREADS + tid;
+            KeyT k = s_keys[p];
+            uint32_t d = (uint32_t)(k >> shift) & dmask;
+            size_t g = (size_t)(uint32_t)(s_gbase[d] + (int32_t)p);
+            kout[g] = k;
+            vout[g] = s_vals[p];
+        }
+    } else {
+        for (uint32_t p = tid; p < nvalid; p += RS_THREADS) {
+            KeyT k = s_keys[p];
+            uint32_t d = (uint32_t)(k >> shift) & dmask;
+            size_t g = (size_t)(uint32_t)(s_gbase[d] + (int32_t)p);
+            kout[g] = k;
+            vout[g] = s_vals[p];
+        }
     }
+}
+
+template <typename KeyT, int RS_THREADS, int RS_KPT, int RS_MINB, int NBITS>
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n, int pass,
+                                                                          const uint32_t* __restrict__ hist_excl,
+                                                                          SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
+{
+    constexpr int RS_TILE = RS_THREADS * RS_KPT;
+    constexpr int RS_WARPS = RS_THREADS / 32;
+    if (!ctl->exec[pass]) return;
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_wsum[8];
+    uint32_t* s_whist = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * RS_TILE) + RS_TILE;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(&ctl->ticket[pass], 1u);
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) s_whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if ((size_t)(tile + 1) * RS_TILE <= n)
+        rs_onesweep_tile<KeyT, RS_THREADS, RS_KPT, NBITS, true>(buf, n, pass, hist_excl, ctl, desc, rs_smem, tile, s_wsum);
+    else
+        rs_onesweep_tile<KeyT, RS_THREADS, RS_KPT, NBITS, false>(buf, n, pass, hist_excl, ctl, desc, rs_smem, tile, s_wsum);
 }
 
 template <typename KeyT, int THREADS, int KPT, int MINB>

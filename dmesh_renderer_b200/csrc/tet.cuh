@@ -53,19 +53,21 @@ struct __align__(16) TetShade {
 };
 static_assert(sizeof(TetShade) == 64, "TetShade must be 4 x 16 bytes");
 
+// Face buffer of the tet renderer.  The view-independent adjacency records (TetRec[T]) are NOT part of it: they
+// depend only on the geometry tables, which carry no gradient and are the same in every optimisation step, so they
+// live in a separate `tet_records` buffer the caller may keep across calls (dmr_tet_records_bytes,
+// dmr_tet_forward_bin's tet_records_valid).  The backward scratch is the caller's workspace (the state buffers of
+// the forward call stay read-only).
 struct TetFaceLayout {
     FaceBinLayout bin;
-    size_t face_rec, tet_rec, shade, grad_vacc, total;
-    __host__ static TetFaceLayout make(size_t BF, size_t F, size_t T, size_t P)
+    size_t face_rec, shade, total;
+    __host__ static TetFaceLayout make(size_t BF, size_t F)
     {
         TetFaceLayout L;
         L.bin = FaceBinLayout::make(BF);
         size_t o = L.bin.end;
         L.face_rec = o;      o = align_up(o + sizeof(TetFaceRec) * BF, 256);
-        L.tet_rec = o;       o = align_up(o + sizeof(TetRec) * T, 256);
         L.shade = o;         o = align_up(o + sizeof(TetShade) * F, 256);
-        // backward scratch, zeroed per call: float4 per vertex (colour gradient, 16-byte aligned for red.v4)
-        L.grad_vacc = o;     o = align_up(o + 16 * P, 256);
         L.total = o + 256;
         return L;
     }
@@ -166,6 +168,8 @@ int depth_chain(int B, int P, const float* verts, const float* mv, const float* 
 int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
                          uint32_t* tiles_touched, uint32_t* depth_key, uint2* rect, TetFaceRec* rec,
                          const SortPre& face_sort, cudaStream_t stream);
+// tet_rec == nullptr: the adjacency records are valid already (cached by the caller), only the shading records
+// (colour / opacity change every step) are rebuilt
 int tet_build_records(int P, int F, int T, const float* verts, const int* faces, const float* verts_color,
                       const float* faces_opacity, const int* tets, const int* face_tets, const int* tet_faces,
                       TetRec* tet_rec, TetShade* shade, cudaStream_t stream);

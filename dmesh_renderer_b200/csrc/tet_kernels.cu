@@ -188,12 +188,12 @@ int tet_build_records(int P, int F, int T, const float* verts, const int* faces,
 {
     (void)P;
     ProfScope prof(ST_TET_RECORDS, stream);
-    if (T > 0 && F > 0) count_launch(1);   // two kernels under one scope
-    if (T > 0) {
+    if (T > 0 && F > 0 && tet_rec && shade) count_launch(1);   // two kernels under one scope
+    if (T > 0 && tet_rec) {
         tet_build_tetrec_kernel<<<(T + 127) / 128, 128, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
         DMR_LAUNCH_CHECK("tet_build_tetrec_kernel");
     }
-    if (F > 0) {
+    if (F > 0 && shade) {
         tet_build_shade_kernel<<<(F + 255) / 256, 256, 0, stream>>>(F, faces, verts_color, faces_opacity, face_tets, shade);
         DMR_LAUNCH_CHECK("tet_build_shade_kernel");
     }
@@ -886,9 +886,15 @@ __global__ void __launch_bounds__(256) tet_det_convert_kernel(TetParams p)
 {
     float sv, sg;
     det_scales(*p.det_gmax, sv, sg);
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (det_nonfinite(*p.det_gmax)) {
+        const float nan = __int_as_float(0x7fc00000);
+        if (i < (size_t)p.P) { for (int c = 0; c < 3; c++) p.dL_dverts_color[3 * i + c] = nan; }
+        else if (i - (size_t)p.P < (size_t)p.F) p.dL_dfaces_opacity[i - (size_t)p.P] = nan;
+        return;
+    }
     if (sv == 0.0f) return;
     const double iv = 1.0 / (double)sv;
-    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i < (size_t)p.P) {
         const long long* a = p.det_vert + 4 * i;
 #pragma unroll

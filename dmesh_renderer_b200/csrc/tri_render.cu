@@ -80,86 +80,93 @@ __device__ __forceinline__ bool block_may_cover(const uint4 e0, const uint4 e1, 
     return (m0 & m1 & m2) < 0;   // every edge can still be negative somewhere in the block
 }
 
-// Exact conservative cull of one instance against the four 4x2 sub-blocks of a warp's 8x4 block:
-// bit s of the result is set when sub-block s (x half = s&1, y half = s>>1) may contain a covered pixel.
-__device__ __forceinline__ unsigned subblock_cull(const uint4 e0, const uint4 e1, const uint4 e2, int bx0, int by0)
+// Exact coverage of one instance over the warp's whole 8x4 pixel block, evaluated by ONE lane: bit p of the
+// result <-> pixel (bx0 + (p & 7), by0 + (p >> 3)) is covered (in_tri true).  The three edge functions are
+// stepped incrementally (ring operations mod 2^32, so the result is bit-identical to evaluating
+// ea*x + eb*y + ec per pixel, overflow behaviour included); the pixels are visited from 31 down to 0 and
+// every sign bit is shifted in with one funnel shift: 5 instructions per pixel.
+__device__ __forceinline__ uint32_t block_coverage(const uint4 e0, const uint4 e1, const uint4 e2, int bx0, int by0)
 {
-    if (!(e2.w & DMR_REC_SAFE)) return 0xfu;
-    const int a[3] = { (int)e0.x, (int)e1.x, (int)e2.x }, bb[3] = { (int)e0.y, (int)e1.y, (int)e2.y };
-    const int cc[3] = { (int)e0.z, (int)e1.z, (int)e2.z };
-    int m[4] = { -1, -1, -1, -1 };
+    uint32_t r0 = e0.x * (uint32_t)(bx0 + 7) + e0.y * (uint32_t)(by0 + 3) + e0.z;
+    uint32_t r1 = e1.x * (uint32_t)(bx0 + 7) + e1.y * (uint32_t)(by0 + 3) + e1.z;
+    uint32_t r2 = e2.x * (uint32_t)(bx0 + 7) + e2.y * (uint32_t)(by0 + 3) + e2.z;
+    uint32_t cov = 0;
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int xl = a[k] * (a[k] < 0 ? bx0 + 3 : bx0), xh = a[k] * (a[k] < 0 ? bx0 + 7 : bx0 + 4);
-        const int yl = cc[k] + bb[k] * (bb[k] < 0 ? by0 + 1 : by0), yh = cc[k] + bb[k] * (bb[k] < 0 ? by0 + 3 : by0 + 2);
-        m[0] &= xl + yl; m[1] &= xh + yl; m[2] &= xl + yh; m[3] &= xh + yh;
+    for (int y = 3; y >= 0; y--) {
+        uint32_t s0 = r0, s1 = r1, s2 = r2;
+#pragma unroll
+        for (int x = 7; x >= 0; x--) {
+            cov = __funnelshift_l(s0 & s1 & s2, cov, 1);   // (cov << 1) | sign(s0 & s1 & s2)
+            if (x > 0) { s0 -= e0.x; s1 -= e1.x; s2 -= e2.x; }
+        }
+        if (y > 0) { r0 -= e0.y; r1 -= e1.y; r2 -= e2.y; }
     }
-    return (m[0] < 0 ? 1u : 0u) | (m[1] < 0 ? 2u : 0u) | (m[2] < 0 ? 4u : 0u) | (m[3] < 0 ? 8u : 0u);
+    return cov;
 }
 
-// The same against the eight 2x2 sub-blocks: bit s <-> x quarter = s&3, y half = s>>2.
-__device__ __forceinline__ unsigned subblock_cull8(const uint4 e0, const uint4 e1, const uint4 e2, int bx0, int by0)
+// 32x32 bit-matrix transpose across the lanes of a warp: lane i enters with row i (bit p = element (i, p)),
+// lane p leaves with column p (bit i = element (i, p)).  Five butterfly steps; step j swaps the off-diagonal
+// j x j blocks between lanes l and l ^ j.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 {
-    if (!(e2.w & DMR_REC_SAFE)) return 0xffu;
-    const int a[3] = { (int)e0.x, (int)e1.x, (int)e2.x }, bb[3] = { (int)e0.y, (int)e1.y, (int)e2.y };
-    const int cc[3] = { (int)e0.z, (int)e1.z, (int)e2.z };
-    int m[8] = { -1, -1, -1, -1, -1, -1, -1, -1 };
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int xo = a[k] < 0 ? 1 : 0, yo = bb[k] < 0 ? 1 : 0;
-        const int x0 = a[k] * (bx0 + xo), dx = 2 * a[k];                 // minimum over x in {bx0+2i, bx0+2i+1}
-        const int y0 = cc[k] + bb[k] * (by0 + yo), y1 = y0 + 2 * bb[k];  // minimum over y in {by0+2j, by0+2j+1}
-#pragma unroll
-        for (int i = 0; i < 4; i++) { m[i] &= x0 + i * dx + y0; m[4 + i] &= x0 + i * dx + y1; }
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
     }
-    unsigned r = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r |= m[i] < 0 ? (1u << i) : 0u;
-    return r;
+    return x;
 }
 
-// The same against the sixteen 2x1 sub-blocks: bit s <-> x quarter = s&3, row = s>>2.
-__device__ __forceinline__ unsigned subblock_cull16(const uint4 e0, const uint4 e1, const uint4 e2, int bx0, int by0)
-{
-    if (!(e2.w & DMR_REC_SAFE)) return 0xffffu;
-    const int a[3] = { (int)e0.x, (int)e1.x, (int)e2.x }, bb[3] = { (int)e0.y, (int)e1.y, (int)e2.y };
-    const int cc[3] = { (int)e0.z, (int)e1.z, (int)e2.z };
-    int m[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) m[i] = -1;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int x0 = a[k] * (bx0 + (a[k] < 0 ? 1 : 0)), dx = 2 * a[k];
-        const int y0 = cc[k] + bb[k] * by0;
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) m[4 * j + i] &= x0 + i * dx + y0 + j * bb[k];
-    }
-    unsigned r = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) r |= m[i] < 0 ? (1u << i) : 0u;
-    return r;
-}
+#define HB 128           // staged instances a warp culls / compacts / rasterises in one go
+#define HS (HB / 32)     // 32-entry slices of the compacted list of such a pass
 
-// Experiment switch, OFF (not yet measured on the GPU, see profiles/README.md section 7): 1 = the thread that stages an
-// instance replaces its three vertex positions, in shared memory, by the per-(view, face) constants of the ray-triangle
-// system -- the camera origin is the same for every pixel of a view, so with T = ro - p0
-//     det = rd . (E2 x E1),   u det = rd . (E2 x T),   v det = rd . (T x E1)
+// Per-(view, face) constants of the ray-triangle system, formed by the thread that stages an instance IN THE
+// STAGED COPY of its record (the record in HBM does not grow): the camera origin is the same for every pixel of a
+// view, so with T = ro - p0
+//     det = rd . (E2 x E1),   u det = rd . (E2 x T),   v det = rd . (T x E1),   t det = E2 . (T x E1)
 // and a covered pixel needs three dot products and one reciprocal instead of Moeller-Trumbore's three differences,
-// two cross products and three dots (19 % of the kernel's instructions).  Same real-number result, different
-// roundings (colour and depth move by ~1 ulp; n_contrib / final_T do not depend on it): needs the parity run.
+// two cross products and four dots.  Same real-number result as ray_tri_tuv, different roundings (colour and depth
+// move by ~1 ulp; n_contrib / final_T do not depend on it).  0 = evaluate ray_tri_tuv per covered pixel.
 #ifndef DMR_TRI_FWD_FACE_CONSTANTS
-#define DMR_TRI_FWD_FACE_CONSTANTS 0
+#define DMR_TRI_FWD_FACE_CONSTANTS 1
 #endif
 
-// Forward: the whole warp walks one survivor list for its 8x4 block.  (A variant in which the four
-// 4x2 sub-blocks walk their own lists, as the backward kernel does, was measured SLOWER here --
-// 234 vs 211 us at C2: the forward shading path is short, so the extra find-loop bookkeeping costs
-// more than the better lane utilisation saves.)
-__global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
+__device__ __forceinline__ void stage_face_constants(uint4* dst, const float3 ro, bool with_t)
+{
+    float* wv = reinterpret_cast<float*>(dst + 3);
+    const float3 q0 = f3(wv[0], wv[1], wv[2]), q1 = f3(wv[3], wv[4], wv[5]), q2 = f3(wv[6], wv[7], wv[8]);
+    const float3 Tv = ro - q0, E1 = q1 - q0, E2 = q2 - q0;
+    const float3 Nv = cross3(E2, E1), Av = cross3(E2, Tv), Qv = cross3(Tv, E1);
+    wv[0] = Nv.x; wv[1] = Nv.y; wv[2] = Nv.z;
+    wv[3] = Av.x; wv[4] = Av.y; wv[5] = Av.z;
+    wv[6] = Qv.x; wv[7] = Qv.y; wv[8] = Qv.z;
+    if (with_t) wv[21] = dot3(Qv, E2);
+}
+
+// Forward.  Per round of RB staged instances every warp works through its 8x4 pixel block in passes of HB
+// instances:
+//   (1) cull + compact: one lane per instance tests the instance against the whole block (minimum of each edge
+//       function over the block, exact for overflow-free records); the survivors' positions are compacted, in list
+//       order, into a per-warp index list -- a tile's list holds every face that touches the 16x16 tile, only
+//       ~1/3 of them reach a given 8x4 block;
+//   (2) rasterise: one lane per SURVIVOR evaluates the exact coverage of all 32 pixels (block_coverage, 5
+//       instructions per pixel) and a 32x32 bit transpose turns the 32 instance rows into one mask per pixel.
+//       (The previous version let all 32 lanes test their own pixel against one survivor at a time: 25 warp
+//       instructions per survivor and 28 % of the kernel at C2; this is ~7 per survivor.)
+//   (3) shade: every lane pops ITS next covered instance from its masks, so the lanes of a warp shade different
+//       faces in the same SIMD pass and per pixel the list order (front to back) is unchanged.  The masks of a
+//       whole pass are known up front, so a lane with few hits in one 32-instance slice moves straight on to the
+//       next one: the number of SIMD passes is the largest per-pixel hit count over HB instances, not the sum of
+//       the per-slice maxima (the shading path ran at 15 of 32 lanes before).
+#ifndef DMR_TRI_FWD_MINB
+#define DMR_TRI_FWD_MINB 4
+#endif
+__global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(TriRenderParams p)
 {
     __shared__ uint4 s_rec[RB * 9];
+    __shared__ unsigned char s_cidx[8 * HB];      // [warp][compacted position] -> position in the staged round
+    __shared__ uint32_t s_pmask[8 * HS * 32];     // [warp][slice][lane]: covered compacted instances of the lane's pixel
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
@@ -168,6 +175,9 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
     const uint32_t py = by0 + (lane >> 3);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
     bool done = !inside;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned char* const cidx = s_cidx + warp * HB;
+    uint32_t* const pmask = s_pmask + warp * HS * 32;
 
     float3 ro, rd;
     pixel_ray<false>(p.inv_mv + 16 * b, p.inv_proj + 16 * b, px + 0.5f, py + 0.5f, p.W, p.H, ro, rd);
@@ -191,85 +201,88 @@ __global__ void __launch_bounds__(256) tri_render_fwd_kernel(TriRenderParams p)
 #pragma unroll
                 for (int q = 0; q < 9; q++) dst[q] = src[q];
 #if DMR_TRI_FWD_FACE_CONSTANTS
-                float* wv = reinterpret_cast<float*>(dst + 3);
-                const float3 q0 = f3(wv[0], wv[1], wv[2]), q1 = f3(wv[3], wv[4], wv[5]), q2 = f3(wv[6], wv[7], wv[8]);
-                const float3 Tv = ro - q0, E1 = q1 - q0, E2 = q2 - q0;      // ro: the view's camera origin
-                const float3 Nv = cross3(E2, E1), Av = cross3(E2, Tv), Qv = cross3(Tv, E1);
-                wv[0] = Nv.x; wv[1] = Nv.y; wv[2] = Nv.z;
-                wv[3] = Av.x; wv[4] = Av.y; wv[5] = Av.z;
-                wv[6] = Qv.x; wv[7] = Qv.y; wv[8] = Qv.z;
+                stage_face_constants(dst, ro, false);      // ro: the view's camera origin
 #endif
             }
         }
         __syncthreads();
         const int cnt = min(RB, total - r * RB);
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
+        for (int h0 = 0; h0 < cnt; h0 += HB) {
             if (__all_sync(0xffffffffu, done)) break;
-            const int jl = c0 + lane;
-            bool keep = false;
-            if (jl < cnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
-            unsigned mask = __ballot_sync(0xffffffffu, keep);
-            // (1) coverage: every lane tests its pixel against every survivor (3 broadcast 16-byte reads,
-            //     6 IMAD + 2 LOP3 each) and keeps the result as a bit mask
-            unsigned mine = 0;
-            while (mask) {
-                const int bit = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const int j = c0 + bit;
-                const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1], e2 = s_rec[j * 9 + 2];
-                uint32_t s0 = e0.x * px + e0.y * py + e0.z;
-                uint32_t s1 = e1.x * px + e1.y * py + e1.z;
-                uint32_t s2 = e2.x * px + e2.y * py + e2.z;
-                if ((int)(s0 & s1 & s2) < 0) mine |= 1u << bit;   // covered (in_tri true)
+            const int hcnt = min(HB, cnt - h0);
+            // (1) cull + compact
+            int ncomp = 0;
+            for (int c0 = 0; c0 < hcnt; c0 += 32) {
+                const int jl = h0 + c0 + lane;
+                bool keep = false;
+                if (c0 + lane < hcnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) cidx[ncomp + __popc(m & lt_mask)] = (unsigned char)jl;
+                ncomp += __popc(m);
             }
-            if (done) mine = 0;
-            // (2) shading: every lane pops ITS next covered instance, so the lanes of a warp shade different
-            //     faces in the same SIMD pass; per pixel the list order (front to back) is unchanged.
-            //     The triangles of these scenes cover ~5 of a block's 32 pixels: walking the survivors one
-            //     at a time left the (long) shading path at 17 of 32 lanes (ncu) with one pass per survivor;
-            //     now the number of passes is the largest per-pixel hit count of the group.
-            //     (Measured and rejected: building the masks of 2/4/8 slices before shading, as the backward
-            //     kernel does per group -- 180/181/177 us against 175 us at C2, 496-619 against 457 us at C5:
-            //     the extra shared-memory traffic and the later early-out cost more than the smoother load.)
-            while (__any_sync(0xffffffffu, mine != 0u)) {
-                if (mine == 0u) continue;
-                const int j = c0 + __ffs(mine) - 1;
-                mine &= mine - 1;
-                const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
-
-                const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
-                float3 tuv = f3(0, 0, 0);
+            __syncwarp();
+            const int nsl = (ncomp + 31) >> 5;
+            // (2) rasterise the survivors, one lane per instance, and transpose to one mask per pixel
+            for (int sl = 0; sl < nsl; sl++) {
+                const int jc = (sl << 5) + lane;
+                uint32_t cov = 0;
+                if (jc < ncomp) {
+                    const int jl = cidx[jc];
+                    cov = block_coverage(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
+                }
+                const uint32_t col = transpose32(cov, lane);
+                pmask[(sl << 5) + lane] = done ? 0u : col;      // read back by this lane only
+            }
+            // (3) shade
+            int sl = 0;
+            uint32_t mine = nsl > 0 ? pmask[lane] : 0u;
+            for (;;) {
+                while (mine == 0u && sl + 1 < nsl) { sl++; mine = pmask[(sl << 5) + lane]; }
+                if (!__any_sync(0xffffffffu, mine != 0u)) break;
+                if (mine != 0u) {
+                    const int bit = __ffs(mine) - 1;
+                    mine &= mine - 1;
+                    const int j = cidx[(sl << 5) + bit];
+                    const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
+                    const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
+                    float3 tuv = f3(0, 0, 0);
 #if DMR_TRI_FWD_FACE_CONSTANTS
-                const float det = dot3(rd, f3(w[0], w[1], w[2]));
-                if (det == 0.0f) continue;
-                const float inv_det = 1.0f / det;
-                tuv.y = dot3(rd, f3(w[3], w[4], w[5])) * inv_det;
-                tuv.z = dot3(rd, f3(w[6], w[7], w[8])) * inv_det;
+                    const float det = dot3(rd, f3(w[0], w[1], w[2]));
+                    const bool hit = det != 0.0f;
+                    if (hit) {
+                        const float inv_det = 1.0f / det;
+                        tuv.y = dot3(rd, f3(w[3], w[4], w[5])) * inv_det;
+                        tuv.z = dot3(rd, f3(w[6], w[7], w[8])) * inv_det;
+                    }
 #else
-                float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
-                if (!ray_tri_tuv(ro, rd, v0, v1, v2, tuv)) continue;
+                    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
+                    const bool hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv);
 #endif
-                float uc, vc;
-                int code;
-                clamp_bary(tuv.y, tuv.z, uc, vc, code);
-                float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
-                const float intense = __uint_as_float(e1.w);
-                // forward.cu:442-451
-                float c0_ = i0 * w[9] + i1 * w[12] + i2 * w[15];  c0_ = c0_ * intense;
-                float c1_ = i0 * w[10] + i1 * w[13] + i2 * w[16]; c1_ = c1_ * intense;
-                float c2_ = i0 * w[11] + i1 * w[14] + i2 * w[17]; c2_ = c2_ * intense;
-                float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
-                const float alpha = __uint_as_float(e0.w);
-                float test_T = T * (1 - alpha);
-                C0 += c0_ * alpha * T;
-                C1 += c1_ * alpha * T;
-                C2 += c2_ * alpha * T;
-                D += iD * alpha * T;
-                pT = T;
-                T = test_T;
-                last_contributor = (uint32_t)(r * RB + j + 1);
-                if (T < DMR_T_EPS) { done = true; mine = 0; }
+                    if (hit) {
+                        float uc, vc;
+                        int code;
+                        clamp_bary(tuv.y, tuv.z, uc, vc, code);
+                        float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
+                        const float intense = __uint_as_float(e1.w);
+                        // forward.cu:442-451
+                        float c0_ = i0 * w[9] + i1 * w[12] + i2 * w[15];  c0_ = c0_ * intense;
+                        float c1_ = i0 * w[10] + i1 * w[13] + i2 * w[16]; c1_ = c1_ * intense;
+                        float c2_ = i0 * w[11] + i1 * w[14] + i2 * w[17]; c2_ = c2_ * intense;
+                        float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
+                        const float alpha = __uint_as_float(e0.w);
+                        float test_T = T * (1 - alpha);
+                        C0 += c0_ * alpha * T;
+                        C1 += c1_ * alpha * T;
+                        C2 += c2_ * alpha * T;
+                        D += iD * alpha * T;
+                        pT = T;
+                        T = test_T;
+                        last_contributor = (uint32_t)(r * RB + j + 1);
+                        if (T < DMR_T_EPS) { done = true; mine = 0u; sl = nsl; }
+                    }
+                }
             }
+            __syncwarp();   // the next pass overwrites the index list
         }
     }
 
@@ -323,11 +336,13 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 
 // Backward design
 // ---------------
-// * A warp owns an 8x4 pixel block, split into GROUPS of GL lanes (sub-blocks of 4x2, 2x2 or 2x1 pixels;
-//   2x1 is the default, table below).  Each group walks ITS OWN list of surviving instances (exact
-//   edge-function cull per sub-block), so the groups shade different faces in the same SIMD pass: for the
-//   small triangles that dominate real scenes this multiplies the lane utilisation of the (long)
-//   gradient path.
+// * A warp owns an 8x4 pixel block (pixel of lane p: x = p & 7, y = p >> 3), split into 16 GROUPS of 2
+//   horizontally adjacent pixels.  Cull, compaction and exact per-pixel coverage masks are built exactly as in
+//   the forward kernel (one lane per surviving instance + 32x32 bit transpose); a group's candidate list is the
+//   OR of its two pixel masks, so finding a group's next instance is one count-leading-zeros -- no edge
+//   functions and no votes inside the walk (the previous version popped candidates of a conservative 2x1
+//   sub-block cull and re-tested them per pixel: 20 % of the kernel's instructions at C2, plus 8 % for the cull).
+//   Each group walks ITS OWN list, back to front, so the groups shade different faces in the same SIMD pass.
 // * Vertex-position gradients are not formed per pixel.  With u = A/D, A = rd.(E2xT), D = rd.(E2xE1) and
 //   the reference's "v" derivative (ray_tri_intersection_grad, auxiliary.h:288-333, actually the derivative
 //   of t = Nt/D, Nt = (TxE1).E2), the per-face sums only need
@@ -335,61 +350,53 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 //   (7 floats); tri_grad_finish_kernel turns them into dL_dp0..2 once per (view, face):
 //       g_E1 = S3 (E2xT) - S24xE2,  g_E2 = TxS1 - E1xS24 + S3 (TxE1),  g_T = S1xE2 + S3 (E1xE2).
 //   This is the same derivative the reference evaluates per covered pixel with ~150 instructions.
-// * All 21 per-hit terms of a group are reduced over its lanes with a transpose-reduction
-//   (GL = 8: 12+6+4 = 22 shuffles, GL = 2: 12) and added to ONE contiguous 96-byte statistics record per
-//   (view, face) with vector reductions (red.v4 / red.v2) instead of 21 scalar reductions per lane.
+// * All 21 per-hit terms of a group are reduced over its two lanes with a transpose-reduction (12 shuffles)
+//   and added to ONE contiguous 96-byte statistics record per (view, face) with vector reductions (red.v4)
+//   instead of 21 scalar reductions per lane.
 // Statistics (logical order, 24 floats; memory position = stat_slot(i)):
 //   S1[3] S24[3] S3 dL_dopacity dL_dintense dL_ddepth[3] dL_dcolor[3][3] pad[3]
-// GL = lanes per group: 8 (four 4x2 sub-blocks per warp), 4 (eight 2x2) or 2 (sixteen 2x1).
-// Measured tri_render_bwd_kernel, us (B200):      C2      C5     C4 (8 views)
-//                                       GL = 8    537    1172    7808
-//                                       GL = 4    476    1079    6752
-//                                       GL = 2    459    1057    6532
-// Smaller groups shade more different faces per SIMD pass (the triangles of these scenes cover a few
-// pixels of a 4x2 block) and need fewer shuffle steps; GL = 1 would need no shuffles at all but
-// 6 vector reductions per covered pixel, which the LSU/L2 cannot sustain (tools/ubench_red.cu).
+// History of the group size, measured on B200 with the earlier find loop (us, C2 / C5 / C4 with 8 views):
+// 8 lanes 537 / 1172 / 7808, 4 lanes 476 / 1079 / 6752, 2 lanes 459 / 1057 / 6532.  One lane per group would need
+// no shuffles at all but 6 vector reductions per covered pixel, which the LSU/L2 cannot sustain
+// (tools/ubench_red.cu).
 #ifndef DMR_TRI_BWD_MINB
 #define DMR_TRI_BWD_MINB 3
 #endif
-#ifndef DMR_TRI_BWD_GROUP_LANES
-#define DMR_TRI_BWD_GROUP_LANES 2
-#endif
-// Experiment switch, OFF (not yet measured on the GPU, see profiles/README.md section 7): 1 = form 1/(1-alpha) once per
-// staged instance and multiply, instead of the reference's two divisions per covered pixel (backward.cu:244-252,
-// 299-308).  Changes T and the background term by an ulp per step, so it needs the parity run before it ships.
+// 1 = form 1/(1-alpha) once per staged instance and multiply, instead of the reference's two divisions per covered
+// pixel (backward.cu:244-252, 299-308).  Changes T and the background term by an ulp per step.
 #ifndef DMR_TRI_BWD_RCP_ALPHA
-#define DMR_TRI_BWD_RCP_ALPHA 0
+#define DMR_TRI_BWD_RCP_ALPHA 1
 #endif
-// Experiment switch, OFF (same status): the backward twin of DMR_TRI_FWD_FACE_CONSTANTS.  The staged copy of a record
-// carries E2 x E1, E2 x T, T x E1 in place of the three vertex positions and E2 . (T x E1) in place of the first
-// vertex id (neither is read from shared memory here; tri_grad_finish_kernel reads the global record).
+// The backward twin of DMR_TRI_FWD_FACE_CONSTANTS: the staged copy of a record carries E2 x E1, E2 x T, T x E1 in
+// place of the three vertex positions and E2 . (T x E1) in place of the first vertex id (neither is read from
+// shared memory here; tri_grad_finish_kernel reads the global record).
 #ifndef DMR_TRI_BWD_FACE_CONSTANTS
-#define DMR_TRI_BWD_FACE_CONSTANTS 0
+#define DMR_TRI_BWD_FACE_CONSTANTS 1
 #endif
-template <int GL, bool DET>
+template <bool DET>
 __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 {
-    static_assert(!DET || GL == 2, "the deterministic variant exists for 2-lane groups only");
     __shared__ uint4 s_rec[RB * 9];
     __shared__ uint32_t s_face[RB];
     __shared__ int s_max[8];
-    __shared__ uint32_t s_gmask[8 * (RB / 32) * (32 / GL)];   // [warp][slice][group]: surviving instances
-    __shared__ int s_glast[8 * (32 / GL)];                    // [warp][group]: largest n_contrib of the group's pixels
-    __shared__ unsigned char s_cidx[8 * RB];                  // [warp][compacted position] -> position in the chunk
+    __shared__ unsigned char s_cidx[8 * HB];      // [warp][compacted position] -> position in the chunk
+    __shared__ uint32_t s_pmask[8 * HS * 32];     // [warp][slice][lane]: covered compacted instances of the lane's pixel
 #if DMR_TRI_BWD_RCP_ALPHA
-    __shared__ float s_rcpa[RB];                              // 1 / (1 - alpha) of the staged instances
+    __shared__ float s_rcpa[RB];                  // 1 / (1 - alpha) of the staged instances
 #endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane / GL, l = lane % GL;
     const int b = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int bx0 = blockIdx.x * DMR_TILE + (warp & 1) * 8, by0 = blockIdx.y * DMR_TILE + (warp >> 1) * 4;
-    const uint32_t px = GL == 8 ? bx0 + (g & 1) * 4 + (l & 3) : bx0 + (g & 3) * 2 + (l & 1);
-    const uint32_t py = GL == 8 ? by0 + (g >> 1) * 2 + (l >> 2) : GL == 4 ? by0 + (g >> 2) * 2 + (l >> 1) : by0 + (g >> 2);
+    const uint32_t px = bx0 + (lane & 7);
+    const uint32_t py = by0 + (lane >> 3);
     const bool inside = px < (uint32_t)p.W && py < (uint32_t)p.H;
     const size_t HW = (size_t)p.W * p.H;
     const size_t pix = (size_t)py * p.W + px;
     const size_t bpix = (size_t)b * HW + pix;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned char* const cidx = s_cidx + warp * HB;
+    uint32_t* const pmask = s_pmask + warp * HS * 32;
 
     float3 ro, rd;
     pixel_ray<false>(p.inv_mv + 16 * b, p.inv_proj + 16 * b, px + 0.5f, py + 0.5f, p.W, p.H, ro, rd);
@@ -417,23 +424,18 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
     float acc0 = 0, acc1 = 0, acc2 = 0, accd = 0;
     float last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, ld = 0;
 
-    // The tile walks only the prefix some pixel of it composited; a warp / a group only its own.
-    int group_last = last_contributor;
+    // The tile walks only the prefix some pixel of it composited; a warp only its own.
+    int warp_last = last_contributor;
 #pragma unroll
-    for (int o = GL / 2; o > 0; o >>= 1) group_last = max(group_last, __shfl_xor_sync(0xffffffffu, group_last, o));
-    int warp_last = group_last;
-#pragma unroll
-    for (int o = 16; o >= GL; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xffffffffu, warp_last, o));
     if (lane == 0) s_max[warp] = warp_last;
-    if (l == 0) s_glast[warp * (32 / GL) + g] = group_last;
     __syncthreads();
     int tile_last = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) tile_last = max(tile_last, s_max[w]);
     const int nchunk = (tile_last + RB - 1) / RB;   // chunk c covers list positions [c*RB, c*RB+RB)
 
-    // pixel ranges of the four sub-blocks: x in {bx0..bx0+3, bx0+4..bx0+7}, y in {by0..by0+1, by0+2..by0+3}
-    const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+    const bool h1 = lane & 1;
     float* const stats = p.grad_stats;
     float det_sv = 0.0f, det_sg = 0.0f;
     if (DET) det_scales(*p.det_gmax, det_sv, det_sg);
@@ -453,102 +455,79 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                 s_rcpa[tid] = 1.0f / (1.0f - __uint_as_float(dst[0].w));
 #endif
 #if DMR_TRI_BWD_FACE_CONSTANTS
-                float* wv = reinterpret_cast<float*>(dst + 3);
-                const float3 q0 = f3(wv[0], wv[1], wv[2]), q1 = f3(wv[3], wv[4], wv[5]), q2 = f3(wv[6], wv[7], wv[8]);
-                const float3 Tv = ro - q0, E1 = q1 - q0, E2 = q2 - q0;      // ro: the view's camera origin
-                const float3 Nv = cross3(E2, E1), Av = cross3(E2, Tv), Qv = cross3(Tv, E1);
-                wv[0] = Nv.x; wv[1] = Nv.y; wv[2] = Nv.z;
-                wv[3] = Av.x; wv[4] = Av.y; wv[5] = Av.z;
-                wv[6] = Qv.x; wv[7] = Qv.y; wv[8] = Qv.z;
-                wv[21] = dot3(Qv, E2);
+                stage_face_constants(dst, ro, true);       // ro: the view's camera origin
 #endif
             }
         }
         __syncthreads();
         const int cnt = min(RB, warp_last - c * RB);       // this warp's share of the chunk
+        // reference: skip when contributor >= last_contributor (backward.cu:192-194); in chunk-relative positions
+        const int limit = last_contributor - c * RB;
 
-        // ---- cull, step 1: instances that can touch the warp's 8x4 block at all (3 edge minima per instance,
-        //      one lane per instance) are COMPACTED, in list order, into a per-warp index list.  A tile's
-        //      list holds every face that touches the 16x16 tile; ~1/3 of them reach a given 8x4 block, and
-        //      the exact 16-way sub-block test below (270 instructions per 32 instances) only runs on those.
-        int ncomp = 0;
-        for (int c0 = 0; c0 < cnt; c0 += 32) {
-            const int jl = c0 + lane;
-            bool keep = false;
-            if (jl < cnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) s_cidx[warp * RB + ncomp + __popc(m & ((1u << lane) - 1u))] = (unsigned char)jl;
-            ncomp += __popc(m);
-        }
-        __syncwarp();
-        const int nch = (ncomp + 31) >> 5;      // 32-entry slices of the compacted list
-
-        // ---- cull, step 2: lane tests one compacted instance against the sub-blocks; the survivors of every
-        //      sub-block go to shared memory as one bit mask per (slice, group).  Groups then walk the WHOLE
-        //      staged chunk at their own pace: when every group had to finish a 32-instance slice before any
-        //      could start the next, only ~55% of the groups had work in a SIMD pass (ncu: 14 of 32 lanes in
-        //      the shading path).
-        for (int ch = 0; ch < nch; ch++) {
-            unsigned k4 = 0;   // bit s: instance may cover sub-block s
-            {
-                const int jc = (ch << 5) + lane;
+        for (int h0 = cnt > 0 ? ((cnt - 1) / HB) * HB : -1; h0 >= 0; h0 -= HB) {
+            const int hcnt = min(HB, cnt - h0);
+            // (1) cull + compact, in list order
+            int ncomp = 0;
+            for (int c0 = 0; c0 < hcnt; c0 += 32) {
+                const int jl = h0 + c0 + lane;
+                bool keep = false;
+                if (c0 + lane < hcnt) keep = block_may_cover(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, bx0 + 7, by0, by0 + 3);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) cidx[ncomp + __popc(m & lt_mask)] = (unsigned char)jl;
+                ncomp += __popc(m);
+            }
+            __syncwarp();
+            const int nsl = (ncomp + 31) >> 5;
+            // (2) exact coverage masks per pixel; instances at or behind the pixel's last contributor are dropped
+            for (int sl = 0; sl < nsl; sl++) {
+                const int jc = (sl << 5) + lane;
+                uint32_t cov = 0;
                 if (jc < ncomp) {
-                    const int jl = s_cidx[warp * RB + jc];
-                    if (GL == 8) k4 = subblock_cull(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
-                    else if (GL == 4) k4 = subblock_cull8(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
-                    else k4 = subblock_cull16(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
-                    // drop the sub-blocks whose pixels all stopped compositing before this list position
-                    const int pos = c * RB + jl;
-                    unsigned alive = 0;
-#pragma unroll
-                    for (int sb = 0; sb < 32 / GL; sb++) alive |= (s_glast[warp * (32 / GL) + sb] > pos ? 1u : 0u) << sb;
-                    k4 &= alive;
+                    const int jl = cidx[jc];
+                    cov = block_coverage(s_rec[jl * 9 + 0], s_rec[jl * 9 + 1], s_rec[jl * 9 + 2], bx0, by0);
                 }
-            }
-            unsigned mymask = 0;
-#pragma unroll
-            for (int sb = 0; sb < 32 / GL; sb++) {
-                const unsigned msb = __ballot_sync(0xffffffffu, k4 & (1u << sb));
-                if (g == sb) mymask = msb;
-            }
-            if (l == 0) s_gmask[(warp * (RB / 32) + ch) * (32 / GL) + g] = mymask;
-        }
-        __syncwarp();
-
-        int gch = nch - 1;                                                         // slice the group is working on
-        unsigned gm = nch > 0 ? s_gmask[(warp * (RB / 32) + gch) * (32 / GL) + g] : 0u;   // its remaining candidates
-        if (nch > 0) {
-            for (;;) {
-                // ---- find: advance every group to its next instance with at least one covered pixel
-                bool have = false, cov = false;
-                int j = 0;
-                for (;;) {
-                    while (!have && gm == 0u && gch > 0) { gch--; gm = s_gmask[(warp * (RB / 32) + gch) * (32 / GL) + g]; }
-                    const bool searching = !have && gm != 0u;
-                    bool cj = false;
-                    int jj = 0;
-                    if (searching) {
-                        const int bit = 31 - __clz(gm);
-                        gm &= ~(1u << bit);
-                        jj = s_cidx[warp * RB + (gch << 5) + bit];   // compacted position -> position in the chunk
-                        const uint4 e0 = s_rec[jj * 9 + 0], e1 = s_rec[jj * 9 + 1], e2 = s_rec[jj * 9 + 2];
-                        const uint32_t s0 = e0.x * px + e0.y * py + e0.z;
-                        const uint32_t s1 = e1.x * px + e1.y * py + e1.z;
-                        const uint32_t s2 = e2.x * px + e2.y * py + e2.z;
-                        // reference: skip when contributor >= last_contributor (backward.cu:192-194)
-                        cj = (c * RB + jj) < last_contributor && (int)(s0 & s1 & s2) < 0;
+                uint32_t col = transpose32(cov, lane);
+                if (col != 0u) {
+                    const int n_here = min(32, ncomp - (sl << 5));
+                    if ((int)cidx[(sl << 5) + n_here - 1] >= limit) {
+                        int lo = 0, hi = n_here;           // first entry of the slice at or behind the limit
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((int)cidx[(sl << 5) + mid] < limit) lo = mid + 1; else hi = mid;
+                        }
+                        if (lo < 32) col &= (1u << lo) - 1u;
                     }
-                    const unsigned bal = __ballot_sync(0xffffffffu, cj);
-                    if (searching && ((bal >> (lane & (32 - GL))) & ((1u << GL) - 1u))) { have = true; j = jj; cov = cj; }
-                    if (!__any_sync(0xffffffffu, !have && (gm != 0u || gch > 0))) break;
                 }
+                pmask[(sl << 5) + lane] = col;
+            }
+            __syncwarp();
+
+            // (3) walk, back to front: both lanes of a group hold the group's candidate mask `gm` and its own
+            //     pixel's mask `mine` of the slice the group is working on
+            int sl = nsl;
+            uint32_t mine = 0u, gm = 0u;
+            for (;;) {
+                while (gm == 0u && sl > 0) {
+                    sl--;
+                    mine = pmask[(sl << 5) + lane];
+                    gm = mine | pmask[(sl << 5) + (lane ^ 1)];
+                }
+                const bool have = gm != 0u;
                 if (!__any_sync(0xffffffffu, have)) break;
+                bool cov = false;
+                int j = 0;
+                if (have) {
+                    const int bit = 31 - __clz(gm);
+                    gm &= ~(1u << bit);
+                    cov = (mine >> bit) & 1u;
+                    j = cidx[(sl << 5) + bit];
+                }
 
                 // ---- shade: lanes with a covered pixel evaluate the gradient terms of their group's face
                 float v[24];
 #pragma unroll
                 for (int k = 0; k < 24; k++) v[k] = 0.0f;
-                if (have && cov) {
+                if (cov) {
                     const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
                     const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
                     float3 tuv = f3(0, 0, 0);
@@ -647,75 +626,43 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                     }
                 }
 
-                // ---- reduce over the lanes of each group
-                if (GL == 8) {
-                    // 24 -> 12 -> 6 values per lane, then the even lane of each pair completes sums 0..3 and the
-                    // odd lane sums 4..5 of its class
-                    xreduce_step<12, 4>(v, h4);
-                    xreduce_step<6, 2>(v, h2);
-                    const float r0 = __shfl_xor_sync(0xffffffffu, h1 ? v[0] : v[4], 1);
-                    const float r1 = __shfl_xor_sync(0xffffffffu, h1 ? v[1] : v[5], 1);
-                    const float r2 = __shfl_xor_sync(0xffffffffu, v[2], 1);
-                    const float r3 = __shfl_xor_sync(0xffffffffu, v[3], 1);
+                // ---- reduce over the two lanes of each group: 24 -> 12 values per lane; lane class c = lane & 1
+                //      owns logical 12c..12c+11 = quads 2c, 2c+1 and the two adjacent pairs 2c, 2c+1 (one more
+                //      16-byte vector)
+                xreduce_step<12, 1>(v, h1);
+                if (DET) {
                     if (have) {
-                        float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
-                        const int cls = (lane >> 1) & 3;
-                        if (!h1) {
-                            const float a0 = v[0] + r0, a1 = v[1] + r1, a2 = v[2] + r2, a3 = v[3] + r3;
-                            if (a0 != 0.0f || a1 != 0.0f || a2 != 0.0f || a3 != 0.0f) red_add_v4(rec + 4 * cls, a0, a1, a2, a3);
-                        } else if (cls < 3) {   // class 3's odd lane owns logical 22..23 = padding
-                            const float a4 = v[4] + r0, a5 = v[5] + r1;
-                            if (a4 != 0.0f || a5 != 0.0f) red_add_v2(rec + 16 + 2 * cls, a4, a5);
-                        }
-                    }
-                } else if (GL == 2) {
-                    // 2 lanes: 24 -> 12 values per lane; lane class c = lane & 1 owns logical 12c..12c+11 =
-                    // quads 2c, 2c+1 and the two adjacent pairs 2c, 2c+1 (one more 16-byte vector)
-                    xreduce_step<12, 1>(v, h1);
-                    if (DET) {
-                        if (have) {
-                            // fixed-point record in LOGICAL order: this lane holds sums 12*cls .. 12*cls+11
-                            const int cls = lane & 1;
-                            long long* rec = p.det_stats + ((size_t)b * p.F + s_face[j]) * 24 + 12 * cls;
-#pragma unroll
-                            for (int k = 0; k < 12; k++) {
-                                if (cls == 1 && k >= 9) break;                       // logical 21..23: padding
-                                det_add(rec + k, v[k], (cls == 0 && k < 7) ? det_sg : det_sv);
-                            }
-                        }
-                    } else if (have) {
-                        float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
+                        // fixed-point record in LOGICAL order: this lane holds sums 12*cls .. 12*cls+11
                         const int cls = lane & 1;
-                        // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
-                        red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
-                        red_add_v4(rec + 8 * cls + 4, v[6], v[7], v[8], v[9]);
-                        red_add_v4(rec + 16 + 4 * cls, v[4], v[5], v[10], v[11]);
+                        long long* rec = p.det_stats + ((size_t)b * p.F + s_face[j]) * 24 + 12 * cls;
+#pragma unroll
+                        for (int k = 0; k < 12; k++) {
+                            if (cls == 1 && k >= 9) break;                       // logical 21..23: padding
+                            det_add(rec + k, v[k], (cls == 0 && k < 7) ? det_sg : det_sv);
+                        }
                     }
-                } else {
-                    // 4 lanes: 24 -> 12 -> 6 values per lane; lane class = lane & 3 owns logical 6c..6c+5
-                    xreduce_step<12, 2>(v, h2);
-                    xreduce_step<6, 1>(v, h1);
-                    if (have) {
-                        float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
-                        const int cls = lane & 3;
-                        if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f) red_add_v4(rec + 4 * cls, v[0], v[1], v[2], v[3]);
-                        if (cls < 3 && (v[4] != 0.0f || v[5] != 0.0f)) red_add_v2(rec + 16 + 2 * cls, v[4], v[5]);
-                    }
+                } else if (have) {
+                    float* rec = stats + ((size_t)b * p.F + s_face[j]) * 24;
+                    const int cls = lane & 1;
+                    // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
+                    red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
+                    red_add_v4(rec + 8 * cls + 4, v[6], v[7], v[8], v[9]);
+                    red_add_v4(rec + 16 + 4 * cls, v[4], v[5], v[10], v[11]);
                 }
             }
+            __syncwarp();   // the next pass overwrites the index list and the masks
         }
     }
 }
 
-template <int GL>
 __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(TriRenderParams p)
 {
-    tri_render_bwd_body<GL, false>(p);
+    tri_render_bwd_body<false>(p);
 }
 
 __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_det_kernel(TriRenderParams p)
 {
-    tri_render_bwd_body<2, true>(p);
+    tri_render_bwd_body<true>(p);
 }
 
 // Deterministic mode: g = max |dL_dout| over both cotangent images, as float bits (non-negative floats order like
@@ -745,6 +692,7 @@ __device__ __forceinline__ void tri_grad_finish_body(const TriRenderParams& p)
     float det_sv = 0.0f, det_sg = 0.0f;
     if (DET) {
         det_scales(*p.det_gmax, det_sv, det_sg);
+        if (det_nonfinite(*p.det_gmax)) { p.dL_dfintense[idx] = __int_as_float(0x7fc00000); return; }
         if (det_sv == 0.0f) return;
         const double iv = 1.0 / (double)det_sv, ig = 1.0 / (double)det_sg;
         const long long* r = p.det_stats + idx * 24;
@@ -830,10 +778,17 @@ __global__ void __launch_bounds__(256) tri_det_convert_kernel(TriRenderParams p)
 {
     float sv, sg;
     det_scales(*p.det_gmax, sv, sg);
-    if (sv == 0.0f) return;
-    const double iv = 1.0 / (double)sv, ig = 1.0 / (double)sg;
     const size_t P = (size_t)p.P, BP = (size_t)p.B * p.P, F = (size_t)p.F;
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (det_nonfinite(*p.det_gmax)) {
+        const float nan = __int_as_float(0x7fc00000);
+        if (i < P) { for (int c = 0; c < 3; c++) { p.dL_dverts[3 * i + c] = nan; p.dL_dvcolor[3 * i + c] = nan; } }
+        else if (i - P < BP) p.dL_dvdepth[i - P] = nan;
+        else if (i - P - BP < F) p.dL_dfopacity[i - P - BP] = nan;
+        return;
+    }
+    if (sv == 0.0f) return;
+    const double iv = 1.0 / (double)sv, ig = 1.0 / (double)sg;
     if (i < P) {
         const long long* a = p.det_vert + 8 * i;
 #pragma unroll
@@ -885,7 +840,7 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
     {
         ProfScope prof(ST_TRI_BWD, stream);
-        tri_render_bwd_kernel<DMR_TRI_BWD_GROUP_LANES><<<grid, 256, 0, stream>>>(p);
+        tri_render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
         DMR_LAUNCH_CHECK("tri_render_bwd_kernel");
     }
     {

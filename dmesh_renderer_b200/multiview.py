@@ -71,6 +71,8 @@ class PackedSceneGrads:
         self._fused = True             # barriers inside the all-reduce kernel (False: separate signal-pad barriers)
         n = sum(t.numel() for t in self.leaves)
         self._nvls = None
+        # which collective all_reduce() runs and, for the fallback, why: "nvls" | "nccl: <reason>" | "none: <reason>"
+        self.collective = "nccl: use_nvls=False" if use_nvls is False else "none: single process"
         full = None
         if use_nvls is not False:
             full = self._try_symmetric(n, verts.device, group)
@@ -78,20 +80,39 @@ class PackedSceneGrads:
             full = torch.zeros(n, dtype=torch.float32, device=verts.device)
         self._full = full              # padded to a multiple of 4 * world_size floats in the NVLS case
         self.flat = full[:n]
-        o = 0
         for t in self.leaves:
             if not t.requires_grad:
                 t.requires_grad_(True)
-            t.grad = self.flat[o:o + t.numel()].view_as(t)
+        self.bind()
+
+    def bind(self):
+        """(Re-)attach the leaves' .grad tensors to the packed buffer.  Anything that REPLACES .grad --
+        optimizer.zero_grad() with its default set_to_none=True, `leaf.grad = None` -- silently disconnects a leaf:
+        autograd would then accumulate into a fresh tensor and all_reduce() would exchange a stale buffer.  zero_(),
+        direct() and all_reduce() therefore call this first; a gradient found in a foreign tensor is moved into the
+        packed buffer so that nothing is lost.  Returns the number of leaves that had to be re-attached."""
+        o, fixed = 0, 0
+        for t in self.leaves:
+            view = self.flat[o:o + t.numel()].view_as(t)
+            g = t.grad
+            if g is None or g.data_ptr() != view.data_ptr() or g.shape != view.shape or g.dtype != view.dtype:
+                if g is not None:
+                    view.copy_(g)
+                t.grad = view
+                fixed += 1
             o += t.numel()
+        return fixed
 
     def _try_symmetric(self, n, device, group):
         if not (device.type == "cuda" and dist.is_available() and dist.is_initialized()):
+            self.collective = "none: single process" if not (dist.is_available() and dist.is_initialized()) \
+                else "%s: tensors on %s" % (dist.get_backend(group), device.type)
             return None
         ws = dist.get_world_size(group)
         if ws <= 1 or dist.get_backend(group) != "nccl":
+            self.collective = "none: world size 1" if ws <= 1 else "%s: not an NCCL group" % dist.get_backend(group)
             return None
-        ok, full, hdl = 1, None, None
+        ok, full, hdl, why = 1, None, None, ""
         try:
             import torch.distributed._symmetric_memory as symm_mem
             pg = group if group is not None else dist.group.WORLD
@@ -105,28 +126,31 @@ class PackedSceneGrads:
             full.zero_()
             hdl = symm_mem.rendezvous(full, pg)
             if not hdl.multicast_ptr:     # no NVLS multicast object behind the allocation (no NVSwitch / disabled)
-                ok = 0
+                ok, why = 0, "symmetric allocation has no multicast address (no NVSwitch multicast on this node)"
             # flag words for the in-kernel cross-GPU barriers (symmetric, zeroed) + this GPU's control words
             flags = symm_mem.empty(256, dtype=torch.int32, device=device)
             flags.zero_()
             fh = symm_mem.rendezvous(flags, pg)
             ctl = torch.zeros(4, dtype=torch.int32, device=device)
-        except Exception:
-            ok = 0
+        except Exception as ex:           # symmetric memory unavailable in this build / on this node
+            ok, why = 0, "symmetric memory setup failed: %s: %s" % (type(ex).__name__, str(ex).splitlines()[0][:200] if str(ex) else "")
         # all ranks must take the same path
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag.item()) != 1:
+            self.collective = "nccl: " + (why or "another rank could not set up symmetric memory")
             return None
         torch.cuda.synchronize(device)
         dist.barrier(group)            # every rank's flag words are zero before anybody signals
         self._nvls = (hdl, int(hdl.multicast_ptr) + int(getattr(hdl, "offset", 0) or 0), full.numel(), dist.get_rank(group), ws)
         self._flags = (flags, fh, int(fh.buffer_ptrs_dev), ctl)
         self._epoch = 0
+        self.collective = "nvls"
         return full
 
     def zero_(self):
         self._full.zero_()
+        self.bind()
 
     @contextlib.contextmanager
     def direct(self):
@@ -135,6 +159,7 @@ class PackedSceneGrads:
         The leaves must be passed to the renderer themselves (not views or functions of them); gradient hooks on
         them do not see this contribution.  The choice is made at forward time, so backward may run later."""
         from . import _C
+        self.bind()
         _C._grad_sinks.append(self)
         try:
             yield self
@@ -142,6 +167,7 @@ class PackedSceneGrads:
             _C._grad_sinks.remove(self)
 
     def all_reduce(self, group=None, async_op=False):
+        self.bind()
         if self._nvls is not None:
             import ctypes
             from . import _lib

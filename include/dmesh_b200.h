@@ -13,8 +13,11 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`
  *   - all work is enqueued on `stream` (a cudaStream_t); the library never
- *     synchronises the device except where stated, never allocates device
- *     memory, and keeps no global state (re-entrant per stream)
+ *     synchronises the device except where stated and never allocates device
+ *     memory.  Rendering state lives entirely in the caller's buffers (calls on
+ *     different streams / threads are independent); the only process-wide state
+ *     is diagnostic: the launch counter, the dmr_profile_* stage timers and the
+ *     dmr_debug_set_* test hooks (not thread-safe, off by default)
  *   - return value: 0 on success, non-zero DMR_E* code otherwise; the message
  *     is available through dmr_last_error() (thread-local)
  *   - matrices are the 16 floats of the reference's column-major convention
@@ -51,6 +54,14 @@ const char* dmr_last_error(void);
 /* ------------------------------------------------------------------------ */
 int    dmr_tri_state_bytes(int B, int P, int F, int W, int H, size_t out[3]);
 int    dmr_tet_state_bytes(int B, int P, int F, int T, int W, int H, size_t out[3]);
+/* The tet renderer's view-independent adjacency records (one 128-byte record per tet, replacing the per-step   */
+/* gathers of cuda_renderer/forward.cu:672-768).  They depend only on verts / faces / tets / face_tets /         */
+/* tet_faces -- none of which carries a gradient -- so a caller may build them once and reuse the buffer for      */
+/* every later call on the same geometry (dmr_tet_forward_bin: tet_records_valid).                                */
+size_t dmr_tet_records_bytes(int T);
+/* Builds them stand-alone (dmr_tet_forward_bin does the same when tet_records_valid == 0). */
+int    dmr_tet_build_records(int P, int F, int T, const float* verts, const int* faces, const int* tets,
+                             const int* face_tets, const int* tet_faces, void* tet_records, dmr_stream_t stream);
 /* Replaces required<BinningState>(R): rasterizer_impl.cu:297-299.           */
 size_t dmr_binning_bytes(size_t R);
 
@@ -134,8 +145,15 @@ int dmr_tri_forward_render(
 /* (rasterizer_impl.cu:387-467) -> TRI_BACKWARD::renderCUDA                   */
 /* (cuda_rasterizer/backward.cu:9-421).  The five gradient buffers must be   */
 /* zero-initialised by the caller (the reference does torch::zeros,          */
-/* render.cu:166-171); gradients are accumulated into them.                  */
+/* render.cu:166-171); gradients are accumulated into them.  The four state  */
+/* buffers of the forward call are only READ (a saved-for-backward tensor is */
+/* never modified, so several backward passes of one forward may run         */
+/* concurrently); the per-(view, face) gradient statistics and per-vertex    */
+/* accumulators live in `workspace`: device scratch of                       */
+/* dmr_tri_backward_workspace_bytes(B, P, F) bytes, zeroed by the call, free  */
+/* again once the work enqueued by the call has completed.                   */
 /* ------------------------------------------------------------------------ */
+size_t dmr_tri_backward_workspace_bytes(int B, int P, int F);
 int dmr_tri_backward(
     int B, int P, int F, int W, int H, int R,
     const float* background,
@@ -149,6 +167,7 @@ int dmr_tri_backward(
     float* dL_dfopacity,         /* [F]    summed over views */
     float* dL_dvdepth,           /* [B,P]  */
     float* dL_dfintense,         /* [B,F]  */
+    void* workspace, size_t workspace_bytes,
     dmr_stream_t stream);
 
 /* The same with run-to-run REPRODUCIBLE gradients (the reference's scalar atomics,             */
@@ -187,6 +206,8 @@ int dmr_tet_forward_bin(
     const int* face_tets,        /* [F,2], -1 = none */
     const int* tet_faces,        /* [T,4] */
     void* point_buffer, void* face_buffer,
+    void* tet_records,           /* dmr_tet_records_bytes(T) bytes */
+    int tet_records_valid,       /* 0: build the records; 1: `tet_records` already holds them for exactly this geometry */
     int32_t* num_rendered_host,
     dmr_stream_t stream);
 
@@ -207,6 +228,7 @@ int dmr_tet_forward_render(
     const float* inv_mv_mats, const float* inv_proj_mats,
     const float* faces_intense,  /* [B,F] */
     const void* point_buffer, void* face_buffer,
+    const void* tet_records,
     void* binning_buffer, void* image_buffer,
     float* out_color, float* out_depth, float* out_active,
     dmr_stream_t stream);
@@ -215,7 +237,10 @@ int dmr_tet_forward_render(
 /* Tet renderer, backward.  Replaces CudaRenderer::Renderer::backward        */
 /* (renderer_impl.cu:413-498) -> TET_BACKWARD::renderCUDA                    */
 /* (cuda_renderer/backward.cu:86-487).  Gradient buffers zeroed by caller.   */
+/* The forward call's state buffers are only read; `workspace`: device       */
+/* scratch of dmr_tet_backward_workspace_bytes(P) bytes, zeroed by the call. */
 /* ------------------------------------------------------------------------ */
+size_t dmr_tet_backward_workspace_bytes(int P);
 int dmr_tet_backward(
     int B, int P, int F, int T, int W, int H,
     int ray_random_seed,         /* same value as in the forward call */
@@ -224,10 +249,12 @@ int dmr_tet_backward(
     const float* inv_mv_mats, const float* inv_proj_mats,
     const float* faces_intense,
     const void* point_buffer, const void* face_buffer,
+    const void* tet_records,
     const void* image_buffer,
     const float* dL_dcolor, const float* dL_ddepth,
     float* dL_dverts_color,      /* [P,3] */
     float* dL_dfaces_opacity,    /* [F]   */
+    void* workspace, size_t workspace_bytes,
     dmr_stream_t stream);
 /* The same with run-to-run reproducible gradients (see dmr_tri_backward_deterministic: the reference's 10 scalar */
 /* atomics per crossed face, cuda_renderer/backward.cu:341-360, become 64-bit fixed-point additions with 38       */
@@ -242,6 +269,7 @@ int dmr_tet_backward_deterministic(
     const float* inv_mv_mats, const float* inv_proj_mats,
     const float* faces_intense,
     const void* point_buffer, const void* face_buffer,
+    const void* tet_records,
     const void* image_buffer,
     const float* dL_dcolor, const float* dL_ddepth,
     float* dL_dverts_color, float* dL_dfaces_opacity,
@@ -295,6 +323,12 @@ size_t dmr_sort_temp_bytes(size_t n);
 int    dmr_sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in,
                       uint64_t* keys_out, uint32_t* vals_out,
                       size_t n, int end_bit, void* temp, dmr_stream_t stream);
+/* The same sort on 32-bit keys -- the form the renderers use (tile ids of the */
+/* instances, depth keys of the faces; two-level binning).      */
+/* vals_in == NULL stands for the identity (0, 1, 2, ...).  `temp` as above.   */
+int    dmr_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in,
+                          uint32_t* keys_out, uint32_t* vals_out,
+                          size_t n, int end_bit, void* temp, dmr_stream_t stream);
 
 /* ------------------------------------------------------------------------ */
 /* All-reduce(SUM) of an fp32 buffer that lives in symmetric memory, with the */

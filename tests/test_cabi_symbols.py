@@ -38,7 +38,7 @@ def test_python_binding_covers_the_header():
     from dmesh_renderer_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.dmr_abi_version() == 1
+    assert lib.dmr_abi_version() == 2
 
 
 def test_size_queries_need_no_gpu():

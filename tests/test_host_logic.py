@@ -140,3 +140,56 @@ def test_gradient_sink_matching_rules():
         with g.direct():
             raise ValueError("boom")
     assert not _C._grad_sinks
+
+
+def test_packed_scene_grads_rebinds_dropped_grads():
+    """optimizer.zero_grad(set_to_none=True) (or any code that replaces .grad) must not silently
+    disconnect a leaf from the packed buffer that all_reduce() exchanges."""
+    from dmesh_renderer_b200.multiview import PackedSceneGrads
+    g = PackedSceneGrads(torch.zeros(5, 3), torch.zeros(5, 3), torch.zeros(7))
+    assert g.bind() == 0
+    opt = torch.optim.SGD(g.leaves, lr=0.1)
+    g.leaves[0].grad.fill_(1.0)
+    opt.zero_grad()                                   # set_to_none=True: all three .grad become None
+    assert all(leaf.grad is None for leaf in g.leaves)
+    g.zero_()                                         # re-attaches
+    for leaf in g.leaves:
+        assert leaf.grad is not None and g.flat.data_ptr() <= leaf.grad.data_ptr() < g.flat.data_ptr() + 4 * g.flat.numel()
+    # a gradient that autograd put into a foreign tensor is moved into the packed buffer, not lost
+    g.leaves[2].grad = torch.full((7,), 2.5)
+    assert g.bind() == 1
+    assert torch.equal(g.flat[30:], torch.full((7,), 2.5)) and g.leaves[2].grad.data_ptr() == g.flat[30:].data_ptr()
+    g.all_reduce()                                    # single process: no collective, still binds
+    assert g.collective.startswith("none")
+
+
+def test_alias_package_exposes_the_reference_names():
+    import dmesh_renderer
+    import dmesh_renderer_b200
+    for n in ("TriRenderSettings", "render_tri", "TriRenderer", "TetRenderSettings", "render_tet", "TetRenderer"):
+        assert getattr(dmesh_renderer, n) is getattr(dmesh_renderer_b200, n)
+    assert dmesh_renderer._C is dmesh_renderer_b200._C
+
+
+def test_tet_record_cache_keys_on_identity_and_version():
+    from dmesh_renderer_b200._C import _TetRecordCache
+
+    class Lib:
+        @staticmethod
+        def dmr_tet_records_bytes(T):
+            return 128 * T + 256
+    _TetRecordCache.clear()
+    dev = torch.device("cpu")
+    _TetRecordCache._entries.clear()
+    ts = tuple(torch.zeros(4, 3) for _ in range(5))
+    import unittest.mock as mock
+    with mock.patch("torch.cuda.current_device", return_value=0):
+        b0, valid0 = _TetRecordCache.get(Lib, ts, 10, dev)
+        b1, valid1 = _TetRecordCache.get(Lib, ts, 10, dev)
+        assert (valid0, valid1) == (0, 1) and b1 is b0
+        ts[0].add_(1.0)                               # in-place edit of the geometry: version bump -> rebuild
+        b2, valid2 = _TetRecordCache.get(Lib, ts, 10, dev)
+        assert valid2 == 0 and b2 is not b0
+        other = tuple(t.clone() for t in ts)          # equal values, different tensors -> no hit
+        assert _TetRecordCache.get(Lib, other, 10, dev)[1] == 0
+    _TetRecordCache.clear()

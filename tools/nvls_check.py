@@ -19,7 +19,7 @@ dist.init_process_group("nccl", device_id=dev)
 P, F = 600_000, 200_000    # C2
 g = PackedSceneGrads(torch.zeros(P, 3, device=dev), torch.zeros(P, 3, device=dev), torch.zeros(F, device=dev))
 if rank == 0:
-    print("NVLS path:", g._nvls is not None, "floats", g.flat.numel(), "padded", g._full.numel(), flush=True)
+    print("NVLS path:", g._nvls is not None, "| collective:", g.collective, "| floats", g.flat.numel(), "padded", g._full.numel(), flush=True)
 gen = torch.Generator(device=dev).manual_seed(100 + rank)
 for trial in range(3):
     x = torch.randn(g.flat.numel(), device=dev, generator=gen)
@@ -34,6 +34,8 @@ for trial in range(3):
     if rank == 0:
         print("trial %d: max abs diff vs NCCL %.3e, rel L2 %.3e, padding zero %s" % (trial, err, rel, pad_ok), flush=True)
     assert rel < 1e-6 and pad_ok
+    if g._nvls is not None and rank == 0:
+        print("trial %d bit-identical to NCCL: %s" % (trial, bool(torch.equal(g.flat, ref))), flush=True)
 
 
 def timeit(fn, n=50):

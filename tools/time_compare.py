@@ -29,7 +29,9 @@ def timeit(fn, n=20, warm=5):
 
 
 def main():
-    for name in sys.argv[1:]:
+    names = [a for a in sys.argv[1:] if not a.startswith("--")]
+    no_ref = "--no-ref" in sys.argv
+    for name in names:
         views = None
         if ":" in name:
             name, views = name.split(":")
@@ -38,7 +40,7 @@ def main():
         gc, gd = [t.cuda() for t in scenes.cotangents(s)]
         mv, pj = s.mv_mats.transpose(1, 2).contiguous(), s.proj_mats.transpose(1, 2).contiguous()
         imv, ipj = torch.inverse(mv), torch.inverse(pj)
-        ref = ref_harness.ref_module()
+        ref = None if no_ref else ref_harness.ref_module()
         if s.kind == "tri":
             fargs = (s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth,
                      s.faces_intense, s.H, s.W)
