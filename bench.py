@@ -1,27 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the DMesh tile rasterizer hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C2|C1|C4|C5|C3]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4|C2|C1|C5]
+                    [--views-per-call V] [--no-per-config]
 
-Metric (BASELINE.json): fwd+bwd throughput in views/s (and ms per view) of the
-tri renderer.  A "step" = one optimisation step of the hot path: forward +
-backward of this rank's view(s) of the seeded synthetic scene through the PUBLIC
-API (TriRenderer -> autograd -> _C shim -> C ABI -> sm_100a kernels), followed,
-when N > 1, by the single all-reduce of the packed scene gradients
-(dmesh_renderer_b200/multiview.py).
+Metric (BASELINE.json): fwd+bwd throughput in views/s (and ms per 1024x1024 view) of the tri renderer, at
+1/2/4/8 B200, next to the reference CUDA extension on the same box.
 
-Default workload = BASELINE.json configs[1] ("C2": 200k triangles, 1024x1024,
-one view per rank and step; weak scaling: rank r renders camera r of the same
-replicated scene).  `value` is measured with the step inputs resident in HBM,
-`e2e` with the per-view inputs (cameras, verts_depth, faces_intense, target
-images) in pinned HOST memory, copied H2D inside the timed region, and the scalar
-loss read back D2H.
+Default workload = BASELINE.json configs[3] ("C4"): the multi-view DMesh optimisation step -- 1 M triangles,
+64 views at 1024x1024, cameras sharded over the N ranks (STRONG scaling: the job is always the same 64 views; rank r
+renders views r*64/N .. (r+1)*64/N - 1 in calls of --views-per-call views), followed by ONE all-reduce of the packed
+per-triangle / per-vertex scene gradients.  A "step" = that whole optimisation step through the PUBLIC API
+(TriRenderer -> autograd -> _C shim -> C ABI -> sm_100a kernels; dmesh_renderer_b200/multiview.py for the sharding
+and the collective).  `value` = 64 views / step time with the step inputs resident in HBM; `e2e` = the same step
+with the per-step host inputs (cameras and target images, pinned host memory) copied H2D inside the timed region and
+the scalar loss read back D2H.
 
-The reference arm (--impl reference) runs the UNMODIFIED reference CUDA extension
-(oracle/_ref, built from /root/reference by oracle/build_ref.py) on the same
-workload with the same protocol.  The reference has no CPU implementation; the
-CPU oracle (oracle/oracle.cpp) is timed as `cpu_baseline` on our arm's line and is
-the fallback of the reference arm when oracle/_ref cannot be loaded.
+--impl reference: the UNMODIFIED reference CUDA extension (oracle/_ref, built from /root/reference by
+oracle/build_ref.py) runs the same job with the same protocol: every rank renders its 64/N views through
+_C.render_tris / render_tris_backward exactly as the reference's Python wrapper calls them, then torch.distributed
+all-reduces the three view-summed gradient tensors.  The reference has no CPU
+implementation; the CPU oracle (oracle/oracle.cpp) is timed as `cpu_baseline` on our arm's line and is the fallback
+of the reference arm when oracle/_ref cannot be loaded.
+
+At N = 1 both arms also time the other BASELINE configs at the `_C` level (`per_config`: C1, C2, C5 tri; C3 tet),
+so that every ours-vs-reference ratio quoted in README.md is a driver-run number.
 """
 import argparse
 import ctypes
@@ -40,6 +43,7 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "tri_fwd_bwd_views_per_sec_1024x1024"
 UNIT = "views/s"
+TOTAL_VIEWS_C4 = 64
 
 
 # --------------------------------------------------------------------------- helpers
@@ -136,49 +140,60 @@ def max_over_ranks(x, ws, dev):
     return float(t.item())
 
 
+def bit_length(n):
+    return max(int(n).bit_length(), 1)
+
+
 # --------------------------------------------------------------------------- workload
-def make_workload(name, rank, ws, dev):
-    """Scene replicated on every rank; rank r owns its camera(s).  Returns device scene + pinned host copies of the
-    per-step inputs."""
-    from dmesh_renderer_b200 import scenes
-    if name in ("C1", "C2", "C5"):
-        base = scenes.config(name)
-        views_per_rank = 1
-        if ws > 1:   # weak scaling: camera r of a seeded ring around the same scene
-            g = torch.Generator().manual_seed(99)
-            dirs = scenes.fibonacci_dirs(max(ws, 2), g)
-            mv, pj = scenes.cameras(dirs[rank:rank + 1], 3.0, base.W, base.H, 0.5, 6.0)
-            base = base._replace(mv_mats=mv, proj_mats=pj, verts_depth=scenes.ndc_depth(base.verts, mv, pj))
-        total_views = ws
-    elif name == "C4":   # 64 views sharded over the ranks (strong scaling)
+class Workload:
+    """Scene replicated on every rank (device) + this rank's views split into calls + pinned host copies of the
+    per-step host inputs (cameras, target images)."""
+
+    def __init__(self, name, rank, ws, dev, views_per_call):
+        from dmesh_renderer_b200 import scenes
         from dmesh_renderer_b200.multiview import shard_views
-        full = scenes.config("C4", views=64)
-        mine = shard_views(64, rank, ws)
-        sl = slice(mine.start, mine.stop)
-        base = full._replace(mv_mats=full.mv_mats[sl].contiguous(), proj_mats=full.proj_mats[sl].contiguous(),
-                             verts_depth=full.verts_depth[sl].contiguous(), faces_intense=full.faces_intense[sl].contiguous())
-        views_per_rank = len(mine)
-        total_views = 64
-    else:
-        raise SystemExit("unknown workload " + name)
-    s = scenes.to_device(base, dev)
-    gen = torch.Generator().manual_seed(1234 + rank)
-    B = base.mv_mats.shape[0]
-    host = dict(mv=base.mv_mats, proj=base.proj_mats, verts_depth=base.verts_depth, faces_intense=base.faces_intense,
-                target_color=torch.rand(B, 3, base.H, base.W, generator=gen),
-                target_depth=torch.rand(B, 1, base.H, base.W, generator=gen))
-    host = {k: v.contiguous().pin_memory() for k, v in host.items()}
-    return s, host, views_per_rank, total_views
+        self.name = name
+        if name == "C4":     # 64 views sharded over the ranks (strong scaling)
+            mine = shard_views(TOTAL_VIEWS_C4, rank, ws)
+            base = scenes.config("C4", views=TOTAL_VIEWS_C4, view_slice=slice(mine.start, mine.stop))
+            self.total_views, self.scaling = TOTAL_VIEWS_C4, "strong"
+        elif name in ("C1", "C2", "C5"):   # one view per rank (weak scaling): camera r of a seeded ring around the scene
+            base = scenes.config(name)
+            if ws > 1:
+                g = torch.Generator().manual_seed(99)
+                dirs = scenes.fibonacci_dirs(max(ws, 2), g)
+                mv, pj = scenes.cameras(dirs[rank:rank + 1], 3.0, base.W, base.H, 0.5, 6.0)
+                base = base._replace(mv_mats=mv, proj_mats=pj, verts_depth=scenes.ndc_depth(base.verts, mv, pj))
+            self.total_views, self.scaling = ws, "weak"
+        else:
+            raise SystemExit("unknown workload " + name)
+        self.local_views = base.mv_mats.shape[0]
+        self.vpc = max(1, min(views_per_call or self.local_views, self.local_views))
+        self.s = scenes.to_device(base, dev)
+        self.H, self.W = base.H, base.W
+        gen = torch.Generator().manual_seed(1234 + rank)
+        B = self.local_views
+        self.host = {"mv": base.mv_mats.contiguous().pin_memory(), "proj": base.proj_mats.contiguous().pin_memory(),
+                     "target_color": torch.rand(B, 3, base.H, base.W, generator=gen).pin_memory(),
+                     "target_depth": torch.rand(B, 1, base.H, base.W, generator=gen).pin_memory()}
+        self.calls = [(a, min(B, a + self.vpc)) for a in range(0, B, self.vpc)]
 
-
-def describe(name, s, ws, views_per_rank, total_views):
-    return {
-        "workload": {"C1": "configs[0]", "C2": "configs[1]", "C4": "configs[3]", "C5": "configs[4]"}[name] +
-        ": tri renderer fwd+bwd, %d triangles, %dx%d, %d view(s) per rank and step" % (s.faces.shape[0], s.W, s.H, views_per_rank),
-        "triangles": int(s.faces.shape[0]), "vertices": int(s.verts.shape[0]), "image": [s.H, s.W],
-        "views_per_step_total": total_views, "parallelism": "camera-sharded x%d, 1 all-reduce of (6P+F) fp32 (NVLS multimem kernel over symmetric memory, NCCL fallback)" % ws if ws > 1 else "single GPU",
-        "l2_flush": "256 MB device fill between timed steps, outside the timed events",
-    }
+    def describe(self, ws):
+        s = self.s
+        cfgname = {"C1": "configs[0]", "C2": "configs[1]", "C4": "configs[3]", "C5": "configs[4]"}[self.name]
+        if self.name == "C4":
+            what = ("%s: multi-view DMesh optimisation step, tri renderer fwd+bwd, %d triangles, %d views at %dx%d sharded "
+                    "over %d GPU(s) = %d views per rank in calls of %d, one all-reduce of the (6P+F) fp32 scene gradients"
+                    % (cfgname, s.faces.shape[0], self.total_views, s.W, s.H, ws, self.local_views, self.vpc))
+        else:
+            what = "%s: tri renderer fwd+bwd, %d triangles, %dx%d, 1 view per rank and step" % (cfgname, s.faces.shape[0], s.W, s.H)
+        return {"workload": what, "triangles": int(s.faces.shape[0]), "vertices": int(s.verts.shape[0]), "image": [s.H, s.W],
+                "views_per_step_total": self.total_views, "views_per_rank": self.local_views, "views_per_call": self.vpc,
+                "parallelism": ("cameras sharded x%d, scene replicated" % ws) if ws > 1 else "single GPU",
+                "l2_flush": "256 MB device fill between timed steps, outside the timed events",
+                "e2e_host_inputs": "cameras + target colour/depth images of this rank's views (pinned host memory, copied per "
+                                   "call on a copy stream that runs one call ahead); verts_depth / faces_intense are scene-derived "
+                                   "device tensors (DMesh computes them from the scene on the GPU), the scene is resident"}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -186,77 +201,82 @@ def run_ours(args, ws, rank, local):
     from dmesh_renderer_b200 import TriRenderer, TriRenderSettings, _lib
     from dmesh_renderer_b200.multiview import PackedSceneGrads
     dev = torch.device("cuda", local)
-    s, host, vpr, total_views = make_workload(args.workload, rank, ws, dev)
+    wl = Workload(args.workload, rank, ws, dev, args.views_per_call)
+    s = wl.s
     lib = _lib.load()
     renderer = TriRenderer(TriRenderSettings(s.H, s.W, s.bg))
     leaves = PackedSceneGrads(s.verts.clone(), s.verts_color.clone(), s.faces_opacity.clone())
     verts, vcol, fopa = leaves.leaves
-    vdep = s.verts_depth.clone().requires_grad_()
-    fint = s.faces_intense.clone().requires_grad_()
-    tgt_c, tgt_d = host["target_color"].to(dev), host["target_depth"].to(dev)
+    # per-call leaf tensors of the per-view inputs (their gradients stay rank-local)
+    vdep = [s.verts_depth[a:b].clone().requires_grad_() for a, b in wl.calls]
+    fint = [s.faces_intense[a:b].clone().requires_grad_() for a, b in wl.calls]
+    mvs = [s.mv_mats[a:b].contiguous() for a, b in wl.calls]
+    pjs = [s.proj_mats[a:b].contiguous() for a, b in wl.calls]
+    tgt_c = [wl.host["target_color"][a:b].to(dev) for a, b in wl.calls]
+    tgt_d = [wl.host["target_depth"][a:b].to(dev) for a, b in wl.calls]
     flush = L2Flush(dev)
 
     def step_device():
         leaves.zero_()
-        vdep.grad = None
-        fint.grad = None
         with leaves.direct():   # backward kernels accumulate straight into the packed gradient buffer
-            color, depth = renderer(verts, s.faces, vcol, fopa, s.mv_mats, s.proj_mats, vdep, fint)
-            # image loss gradient as cotangent (device resident targets)
-            torch.autograd.backward([color, depth], [color.detach() - tgt_c, depth.detach() - tgt_d])
+            for i in range(len(wl.calls)):
+                vdep[i].grad = None
+                fint[i].grad = None
+                color, depth = renderer(verts, s.faces, vcol, fopa, mvs[i], pjs[i], vdep[i], fint[i])
+                # gradient of the image loss 0.5 * ||render - target||^2 as cotangent (device resident targets)
+                torch.autograd.backward([color, depth], [color.detach() - tgt_c[i], depth.detach() - tgt_d[i]])
         leaves.all_reduce()
 
-    # the per-view render inputs (cameras, verts_depth, faces_intense) live in ONE pinned staging buffer and travel
-    # as one copy; the device tensors handed to the renderer are views of its device twin
-    rkeys = ("mv", "proj", "verts_depth", "faces_intense")
-    n_in = sum(host[k].numel() for k in rkeys)
-    stage_host = torch.empty(n_in, dtype=torch.float32).pin_memory()
-    stage_dev = torch.empty(n_in, dtype=torch.float32, device=dev)
-    dbuf, o = {}, 0
-    for k in rkeys:
-        n = host[k].numel()
-        stage_host[o:o + n].copy_(host[k].reshape(-1))
-        dbuf[k] = stage_dev[o:o + n].view(host[k].shape)
-        o += n
-    for k in ("target_color", "target_depth"):
-        dbuf[k] = torch.empty_like(host[k], device=dev)
-    n_c, n_d = host["target_color"].numel(), host["target_depth"].numel()
-    diff = torch.empty(n_c + n_d, dtype=torch.float32, device=dev)     # [color - target | depth - target]
-    diff_c, diff_d = diff[:n_c].view(host["target_color"].shape), diff[n_c:].view(host["target_depth"].shape)
-    loss_host = torch.zeros(1).pin_memory()
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-
+    # ---- e2e: cameras + targets of call i+1 travel H2D on a copy stream while call i renders (two staging slots)
     copy_stream = torch.cuda.Stream(device=dev)
+    nslot = 2
+    stage = [{"mv": torch.empty_like(mvs[0]), "proj": torch.empty_like(pjs[0]), "tc": torch.empty_like(tgt_c[0]),
+              "td": torch.empty_like(tgt_d[0]), "ready": None, "free": None} for _ in range(nslot)]
+    loss_acc = torch.zeros(1, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in wl.host.values())
+
+    def enqueue_copy(i):
+        a, b = wl.calls[i]
+        st = stage[i % nslot]
+        n = b - a
+        if st["free"] is not None:
+            copy_stream.wait_event(st["free"])      # the call that last used this slot has consumed it
+        with torch.cuda.stream(copy_stream):
+            st["mv"][:n].copy_(wl.host["mv"][a:b], non_blocking=True)
+            st["proj"][:n].copy_(wl.host["proj"][a:b], non_blocking=True)
+            st["tc"][:n].copy_(wl.host["target_color"][a:b], non_blocking=True)
+            st["td"][:n].copy_(wl.host["target_depth"][a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            st["ready"] = ev
 
     def step_e2e():
-        # H2D of this step's inputs from pinned host memory, inside the timed region.  The per-view render inputs
-        # (cameras, verts_depth, faces_intense: 3.2 MB) are submitted first, on the compute stream; the target
-        # images (16.8 MB, ~0.31 ms of PCIe time), which only the loss needs, follow on a copy stream and travel
-        # while the forward pass runs (the H2D engine serves copies in submission order).
         main = torch.cuda.current_stream()
-        stage_dev.copy_(stage_host, non_blocking=True)
-        copy_stream.wait_stream(main)           # the previous step's readers of the target buffers are done
-        with torch.cuda.stream(copy_stream):
-            for k in ("target_color", "target_depth"):
-                dbuf[k].copy_(host[k], non_blocking=True)
-            targets_ready = torch.cuda.Event()
-            targets_ready.record(copy_stream)
+        for st in stage:
+            st["free"] = None
+        copy_stream.wait_stream(main)               # the previous step's readers of the staging slots are done
+        enqueue_copy(0)
         leaves.zero_()
-        vd = dbuf["verts_depth"].requires_grad_()
-        fi = dbuf["faces_intense"].requires_grad_()
+        loss_acc.zero_()
         with leaves.direct():
-            color, depth = renderer(verts, s.faces, vcol, fopa, dbuf["mv"], dbuf["proj"], vd, fi)
-            main.wait_event(targets_ready)
-            # image loss 0.5 * ||render - target||^2; its gradient is the cotangent
-            torch.sub(color.detach(), dbuf["target_color"], out=diff_c)
-            torch.sub(depth.detach(), dbuf["target_depth"], out=diff_d)
-            torch.autograd.backward([color, depth], [diff_c, diff_d])
-            loss = torch.linalg.vector_norm(diff).square() * 0.5
+            for i, (a, b) in enumerate(wl.calls):
+                if i + 1 < len(wl.calls):
+                    enqueue_copy(i + 1)
+                st, n = stage[i % nslot], b - a
+                main.wait_event(st["ready"])
+                vdep[i].grad = None
+                fint[i].grad = None
+                color, depth = renderer(verts, s.faces, vcol, fopa, st["mv"][:n], st["proj"][:n], vdep[i], fint[i])
+                dc, dd = color.detach() - st["tc"][:n], depth.detach() - st["td"][:n]
+                torch.autograd.backward([color, depth], [dc, dd])
+                loss_acc.add_(0.5 * (dc.square().sum() + dd.square().sum()))
+                ev = torch.cuda.Event()
+                ev.record(main)
+                st["free"] = ev
         leaves.all_reduce()
-        loss_host.copy_(loss.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        dbuf["verts_depth"].requires_grad_(False)
-        dbuf["faces_intense"].requires_grad_(False)
+        loss_host.copy_(loss_acc, non_blocking=True)
+        main.synchronize()
         return float(loss_host[0])
 
     # ---- warm-up
@@ -264,11 +284,30 @@ def run_ours(args, ws, rank, local):
         step_device()
     barrier(ws)
 
+    # ---- which collective runs, and is it right?  (outside the timed regions)
+    collective = None
+    if ws > 1:
+        g = torch.Generator(device=dev).manual_seed(77 + rank)
+        x = torch.randn(leaves.flat.numel(), device=dev, generator=g)
+        ref = x.clone()
+        dist.all_reduce(ref)
+        leaves.flat.copy_(x)
+        leaves.all_reduce()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(leaves.flat, ref))
+        rel = float(((leaves.flat - ref).norm() / ref.norm()).item())
+        ok = torch.tensor([1 if same else 0, 1 if rel < 1e-6 else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        collective = {"path": "nvls" if leaves.collective == "nvls" else "nccl", "detail": leaves.collective,
+                      "check": "bit-identical to torch.distributed.all_reduce (NCCL) on every rank" if int(ok[0]) else
+                               ("rel L2 %.2e vs NCCL" % rel if int(ok[1]) else "MISMATCH vs NCCL: rel L2 %.2e" % rel),
+                      "floats": int(leaves.flat.numel())}
+        leaves.zero_()
+
     # ---- timed region 1: device-resident inputs, CUDA events per step, L2 flushed between steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.dmr_launch_count.restype = ctypes.c_ulonglong
     launches0 = lib.dmr_launch_count()
     total_ms = 0.0
     for _ in range(args.steps):
@@ -284,33 +323,37 @@ def run_ours(args, ws, rank, local):
     total_ms = max_over_ranks(total_ms, ws, dev)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = total_views / (ms_per_step / 1e3)
+    value = wl.total_views / (ms_per_step / 1e3)
 
-    # ---- timed region 2: per-kernel durations (stage events inside the library) for the roofline
+    # ---- timed region 2: per-kernel durations (stage events inside the library, on the launching stream) for the
+    #      roofline: one step, read after every call (a stage's events are overwritten by the next call)
     nst = lib.dmr_profile_stage_count()
     names = [lib.dmr_profile_stage_name(i).decode() for i in range(nst)]
-    acc = [0.0] * nst
-    cnt = [0] * nst
-    lib.dmr_profile_enable(1)
+    acc, cnt = [0.0] * nst, [0] * nst
     buf = (ctypes.c_float * nst)()
-    for _ in range(args.steps):
+
+    def read_stages():
+        lib.dmr_profile_read(buf)
+        for i in range(nst):
+            if buf[i] >= 0:
+                acc[i] += buf[i]
+                cnt[i] += 1
+    lib.dmr_profile_enable(1)
+    nprof = min(args.steps, 5)
+    for _ in range(nprof):
         flush()
         torch.cuda.synchronize()
-        # forward and backward are read separately: a stage's events are overwritten by the next call
         leaves.zero_()
-        color, depth = renderer(verts, s.faces, vcol, fopa, s.mv_mats, s.proj_mats, vdep, fint)
-        lib.dmr_profile_read(buf)
-        for i in range(nst):
-            if buf[i] >= 0:
-                acc[i] += buf[i]; cnt[i] += 1
-        torch.autograd.backward([color, depth], [color.detach() - tgt_c, depth.detach() - tgt_d])
-        lib.dmr_profile_read(buf)
-        for i in range(nst):
-            if buf[i] >= 0:
-                acc[i] += buf[i]; cnt[i] += 1
+        for i in range(len(wl.calls)):
+            vdep[i].grad = None
+            fint[i].grad = None
+            color, depth = renderer(verts, s.faces, vcol, fopa, mvs[i], pjs[i], vdep[i], fint[i])
+            read_stages()
+            torch.autograd.backward([color, depth], [color.detach() - tgt_c[i], depth.detach() - tgt_d[i]])
+            read_stages()
     lib.dmr_profile_enable(0)
-    stage_ms = {names[i]: acc[i] / cnt[i] for i in range(nst) if cnt[i]}
-    R = int(renderer_last_R(s, renderer))
+    stage_ms = {names[i]: acc[i] / cnt[i] for i in range(nst) if cnt[i]}      # per launch (= per call of vpc views)
+    stats = scene_stats(s, mvs[0], pjs[0], vdep[0].detach(), fint[0].detach())
 
     # ---- timed region 3: end to end (host inputs, H2D + D2H inside), wall clock
     for _ in range(2):
@@ -324,79 +367,124 @@ def run_ours(args, ws, rank, local):
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
     e2e_s = max_over_ranks(e2e_s, ws, dev)
-    e2e_value = total_views / (e2e_s / args.steps)
+    e2e_value = wl.total_views / (e2e_s / args.steps)
+
+    per_config = None
+    if ws == 1 and not args.no_per_config:
+        del tgt_c, tgt_d, stage
+        torch.cuda.empty_cache()
+        per_config = per_config_times("ours", dev)
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel
-    P, F, px = int(s.verts.shape[0]), int(s.faces.shape[0]), s.H * s.W
-    tiles = vpr * ((s.W + 15) // 16) * ((s.H + 15) // 16)
+    # ---- roofline of the dominant kernel.  Algorithmic bytes per LAUNCH (one call = vpc views of this rank):
+    #      SURVEY.md 8d / DESIGN.md 3 per-unit figures x the units of one launch.
+    P, F, px, vpc = int(s.verts.shape[0]), int(s.faces.shape[0]), s.H * s.W, wl.vpc
+    R = stats["instances_R_per_call"]
+    tiles = vpc * ((s.W + 15) // 16) * ((s.H + 15) // 16)
     npass = (bit_length(tiles) + 7) // 8          # instance sort: tile bits only (two-level binning)
-    BF = F * vpr
-    alg = {   # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md 3), per rank (vpr views)
-        "preprocess_points": 32 * P * vpr, "preprocess_faces": (12 + 48 + 72 + 8 + 16 + 144) * BF,
+    BF = F * vpc
+    alg = {
+        "preprocess_points": 32 * P * vpc, "preprocess_faces": (12 + 48 + 72 + 8 + 16 + 144) * BF,
         "face_depth_sort": (4 + 4 * 16) * BF,      # histogram read + 4 eight-bit passes over (u32 key, u32 index) pairs
         "scan": 12 * BF,                           # order + gathered tiles_touched read, offsets written
         "duplicate_with_keys": 16 * BF + 8 * R,    # order, offsets, rect read; (u32 tile, u32 face) written
         "sort_histogram": 4 * R,
         "tile_ranges": 4 * R + 8 * tiles,
-        "tri_render_forward": 132 * R + 28 * px * vpr,
-        "tri_render_backward": 132 * R + 28 * px * vpr + 4 * (6 * P + F) + 4 * (P + F) * vpr,
-        "tri_grad_finish": (96 + 144) * BF + 4 * (6 * P + F) + 4 * (P + F) * vpr,
+        "tri_render_forward": 132 * R + 28 * px * vpc,
+        "tri_render_backward": 132 * R + 28 * px * vpc + 4 * (6 * P + F) + 4 * (P + F) * vpc,
+        "tri_grad_finish": (96 + 144) * BF + 4 * (6 * P + F) + 4 * (P + F) * vpc,
     }
     for i in range(8):
         alg["sort_pass%d" % i] = 16 * R
     dom = max(stage_ms, key=stage_ms.get)
     peak, peak_src = peaks()
     achieved = alg.get(dom, 0) / (stage_ms[dom] * 1e-3) / 1e9
-    traffic, winst = None, None
+    traffic, winst, tsrc = None, None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        traffic = tj.get(args.workload, {}).get(dom)
-        winst = tj.get(args.workload + "_warp_instructions", {}).get(dom)
+        ent = tj.get(args.workload, {}).get(dom)
+        if ent:
+            # per launch of the captured configuration, scaled to this launch's views where the capture had fewer
+            scale = vpc / float(ent.get("views", vpc))
+            traffic = int(ent["dram_bytes"] * scale)
+            winst = int(ent["warp_instructions"] * scale)
+            tsrc = ent.get("source")
+    hbm_stages = {k: round(alg[k] / (v * 1e-3) / 1e9 / peak, 3) for k, v in stage_ms.items()
+                  if k in alg and not k.startswith("tri_render")}
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                 "kernel_ms": round(stage_ms[dom], 4), "algorithmic_bytes": alg.get(dom, 0),
+                "per_launch": "one call = %d view(s) of this rank" % vpc,
                 "note": "render kernels are issue-bound (coverage tests + shading), not HBM-bound; see DESIGN.md",
-                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "instances_R": R, "sort_passes": npass}
+                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "instances_R_per_call": R, "sort_passes": npass,
+                "hbm_frac_of_streaming_stages": hbm_stages}
     if winst:
         # the bound that actually limits the dominant kernel: warp-instruction issue (148 SMs x 4 schedulers x SM clock);
-        # instruction count from the committed ncu capture, duration measured live above
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        # instruction count from the tracked ncu capture named in traffic_source, duration measured live above
         peak_issue = 148 * 4 * sm_mhz * 1e6
         roofline["issue_bound"] = {"warp_instructions": winst, "achieved_ginst_per_s": round(winst / (stage_ms[dom] * 1e-3) / 1e9, 1),
                                    "peak_ginst_per_s": round(peak_issue / 1e9, 1),
                                    "frac": round(winst / (stage_ms[dom] * 1e-3) / peak_issue, 3)}
+    # compute-side figure of the render kernels: pixel x instance pair tests against the ~4.6 T tests/s
+    # bound (148 SMs x 128 lanes x SM clock / ~8 lane-ops per test)
+    if stats.get("pair_tests_per_view") and "tri_render_forward" in stage_ms:
+        bound = 148 * 128 * sm_mhz * 1e6 / 8.0
+        pt = stats["pair_tests_per_view"] * vpc
+        roofline["pair_tests"] = {"per_view": stats["pair_tests_per_view"], "definition": "sum over tiles of 256 x instances traversed before tile-wide termination",
+                                  "forward_tests_per_s": round(pt / (stage_ms["tri_render_forward"] * 1e-3), 0),
+                                  "bound_tests_per_s": round(bound, 0),
+                                  "forward_frac": round(pt / (stage_ms["tri_render_forward"] * 1e-3) / bound, 4)}
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample
     cpu = cpu_baseline(args.workload) if ws == 1 else None
-
     out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": ws, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-           "scaling": "strong" if args.workload == "C4" else "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic (seeded, SURVEY.md App. E)", "config": describe(args.workload, s, ws, vpr, total_views),
-           "ms_per_view": round(ms_per_step * ws / total_views if args.workload != "C4" else ms_per_step / vpr, 4),
+           "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic (seeded, SURVEY.md App. E)", "config": wl.describe(ws),
+           "ms_per_view": round(ms_per_step / wl.local_views, 4),
            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                    "d2h_bytes_per_step": 4, "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
-           "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "impl": "dmesh_renderer_b200"}
+           "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "impl": "dmesh_renderer_b200",
+           "scene_stats": stats}
+    if collective:
+        out["collective"] = collective
     if ws > 1:
         out["config"]["host_cores_bound_to_gpu_numa_node"] = CPU_BINDING
+    if per_config:
+        out["per_config"] = per_config
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out), flush=True)
 
 
-def bit_length(n):
-    return max(int(n).bit_length(), 1)
-
-
-def renderer_last_R(s, renderer):
-    from dmesh_renderer_b200 import _C
-    mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
-    return _C.render_tris(s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, torch.inverse(mv),
-                          torch.inverse(pj), s.verts_depth, s.faces_intense, s.H, s.W)[0]
+def scene_stats(s, mv, pj, vdep, fint):
+    """R and the pair-test count of one call of the workload (SURVEY.md 8d 'compute-side figure for render')."""
+    from dmesh_renderer_b200 import _C, debug
+    mvt, pjt = mv.transpose(1, 2), pj.transpose(1, 2)
+    R, _, _, pb, fb, bb, ib = _C.render_tris(s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mvt, pjt,
+                                             torch.inverse(mvt), torch.inverse(pjt), vdep, fint, s.H, s.W)
+    B, P, F = mv.shape[0], s.verts.shape[0], s.faces.shape[0]
+    out = {"instances_R_per_call": int(R), "views_in_call": int(B)}
+    try:
+        dims = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=R)
+        ranges = debug.view_torch("tri", "ranges", ib, **dims).to(torch.int64)
+        ncon = debug.view_torch("tri", "n_contrib", ib, **dims).to(torch.int64).view(B, s.H, s.W)
+        fT = debug.view_torch("tri", "final_T", ib, **dims).view(B, s.H, s.W)
+        tx, ty = (s.W + 15) // 16, (s.H + 15) // 16
+        if s.W % 16 == 0 and s.H % 16 == 0:
+            total = (ranges[:, 1] - ranges[:, 0]).view(B, ty, tx)
+            nc = ncon.view(B, ty, 16, tx, 16).amax(dim=(2, 4))
+            alive = (fT >= 1e-4).view(B, ty, 16, tx, 16).any(dim=4).any(dim=2)   # some pixel never terminated: whole list walked
+            trav = torch.where(alive, total, nc)
+            out["pair_tests_per_view"] = int((trav.sum() * 256 // B).item())
+            out["instances_traversed_per_view"] = int((trav.sum() // B).item())
+            out["hits_per_pixel_mean"] = None
+    except Exception as ex:   # statistics only
+        out["pair_tests_error"] = repr(ex)
+    return out
 
 
 def cpu_baseline(workload):
@@ -405,8 +493,11 @@ def cpu_baseline(workload):
     try:
         import oracle
         from dmesh_renderer_b200 import scenes
-        name = workload if workload in ("C1", "C2") else "C2"
-        s = scenes.config(name)
+        if workload == "C4":
+            s, name = scenes.config("C4", views=1), "C4 (1 of its 64 views)"
+        else:
+            name = workload if workload in ("C1", "C2") else "C2"
+            s = scenes.config(name)
         gc, gd = scenes.cotangents(s)
         t0 = time.perf_counter()
         o = oracle.TriOracle(s)
@@ -419,78 +510,183 @@ def cpu_baseline(workload):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "unavailable: %r" % (ex,)}
 
 
+# --------------------------------------------------------------------------- the other BASELINE configs, _C level
+def per_config_times(impl, dev, n=15, warm=4):
+    """fwd / bwd / fwd+bwd ms (median, CUDA events) of C1, C2, C5 (tri) and C3 (tet) through the four `_C` entry
+    points -- the same calls, same seeded scenes and same protocol in both arms (tools/time_compare.py)."""
+    from dmesh_renderer_b200 import scenes
+    if impl == "ours":
+        from dmesh_renderer_b200 import _C as C
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import build_ref
+        C = build_ref.load()
+
+    def timeit(fn):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return round(ts[len(ts) // 2], 4)
+
+    out = {}
+    for name in ("C1", "C2", "C5", "C3"):
+        try:
+            cpu = scenes.config(name)
+            s = scenes.to_device(cpu, dev)
+            gc, gd = [t.to(dev) for t in scenes.cotangents(cpu)]
+            mv, pj = s.mv_mats.transpose(1, 2).contiguous(), s.proj_mats.transpose(1, 2).contiguous()
+            imv, ipj = torch.inverse(mv), torch.inverse(pj)
+            st = {}
+            if s.kind == "tri":
+                fa = (s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth, s.faces_intense)
+
+                def fwd():
+                    st["o"] = C.render_tris(*fa, s.H, s.W)
+
+                def bwd():
+                    o = st["o"]
+                    C.render_tris_backward(*fa, gc, gd, o[0], o[3], o[4], o[5], o[6])
+            else:
+                fa = (s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth,
+                      s.faces_intense, s.tets, s.face_tets, s.tet_faces)
+
+                def fwd():
+                    st["o"] = C.render_tets(*fa, s.H, s.W, 0)
+
+                def bwd():
+                    o = st["o"]
+                    C.render_tets_backward(*fa, gc, gd, o[3], o[4], o[5], o[6])
+
+            def both():
+                fwd()
+                bwd()
+            e = {"ms_fwd": timeit(fwd), "ms_bwd": timeit(bwd), "ms_fwd_bwd": timeit(both),
+                 "image": [s.H, s.W], "faces": int(s.faces.shape[0])}
+            if s.kind == "tri":
+                e["R"] = int(st["o"][0])
+            e["ms_fwd_bwd_per_1024x1024"] = round(e["ms_fwd_bwd"] * 1024 * 1024 / (s.H * s.W), 4)
+            out[name] = e
+            del s, gc, gd, st
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out[name] = {"error": repr(ex)}
+    out["protocol"] = "median of %d after %d warm-ups, CUDA events, `_C` entry points (no autograd), seeded scenes of SURVEY.md App. E" % (n, warm)
+    return out
+
+
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, ws, rank, local):
-    if rank != 0:
-        return   # rank 0 alone runs the reference arm
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", local)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_ref
-    s, host, vpr, total_views = make_workload(args.workload, 0, 1, dev)
     ref = None
     try:
         ref = build_ref.load()
     except Exception as ex:
         sys.stderr.write("reference extension failed to load: %r\n" % (ex,))
-    cfg = describe(args.workload, s, 1, vpr, total_views)
     if ref is None:
+        if rank != 0:
+            return
+        wl = Workload(args.workload, 0, 1, dev, args.views_per_call)
         cpu = cpu_baseline(args.workload)
-        out = {"metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": 1, "steps": 1, "warmup": 0,
+        out = {"metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": ws, "steps": 1, "warmup": 0,
                "ms_per_step": round(1e3 / cpu["value"], 3) if cpu["value"] else None, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+               "scaling": wl.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.describe(1),
                "impl": "reference", "cpu_baseline": cpu,
                "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "note": "oracle/_ref (the reference CUDA extension) could not be loaded; CPU oracle port timed instead"}
         print(json.dumps(out), flush=True)
         return
-    mv, pj = s.mv_mats.transpose(1, 2).contiguous(), s.proj_mats.transpose(1, 2).contiguous()
-    tgt_c, tgt_d = host["target_color"].to(dev), host["target_depth"].to(dev)
+    wl = Workload(args.workload, rank, ws, dev, args.views_per_call)
+    s = wl.s
+    mvs = [s.mv_mats[a:b].transpose(1, 2).contiguous() for a, b in wl.calls]
+    pjs = [s.proj_mats[a:b].transpose(1, 2).contiguous() for a, b in wl.calls]
+    vdep = [s.verts_depth[a:b].contiguous() for a, b in wl.calls]
+    fint = [s.faces_intense[a:b].contiguous() for a, b in wl.calls]
+    tgt_c = [wl.host["target_color"][a:b].to(dev) for a, b in wl.calls]
+    tgt_d = [wl.host["target_depth"][a:b].to(dev) for a, b in wl.calls]
     flush = L2Flush(dev)
+    P, F = s.verts.shape[0], s.faces.shape[0]
+    packed = torch.zeros(6 * P + F, device=dev)       # [dL_dverts | dL_dvcolor | dL_dfopacity], one all-reduce
+    gv, gcol, gop = packed[:3 * P].view(P, 3), packed[3 * P:6 * P].view(P, 3), packed[6 * P:]
 
     def step():
-        # exactly what the reference's Python wrapper does (reference __init__.py:62-88, 124-149)
-        imv, ipj = torch.inverse(mv), torch.inverse(pj)
-        a = (s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj, imv, ipj, s.verts_depth, s.faces_intense)
-        R, color, depth, pb, fb, bb, ib = ref.render_tris(*a, s.H, s.W)
-        ref.render_tris_backward(*a, color - tgt_c, depth - tgt_d, R, pb, fb, bb, ib)
+        packed.zero_()
+        for i in range(len(wl.calls)):
+            # exactly what the reference's Python wrapper does per call (reference __init__.py:62-88, 124-149)
+            imv, ipj = torch.inverse(mvs[i]), torch.inverse(pjs[i])
+            a = (s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mvs[i], pjs[i], imv, ipj, vdep[i], fint[i])
+            R, color, depth, pb, fb, bb, ib = ref.render_tris(*a, s.H, s.W)
+            g = ref.render_tris_backward(*a, color - tgt_c[i], depth - tgt_d[i], R, pb, fb, bb, ib)
+            if len(wl.calls) == 1 and ws == 1:
+                continue                                  # single call, single GPU: the returned tensors ARE the result
+            gv.add_(g[0])
+            gcol.add_(g[1])
+            gop.add_(g[2])
+        if ws > 1:
+            dist.all_reduce(packed)                       # BASELINE.md 3a: torch NCCL all-reduce of the view-summed grads
 
     for _ in range(max(args.warmup, 3)):
         step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+    barrier(ws)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     total_ms = 0.0
     for _ in range(args.steps):
         flush()
-        torch.cuda.synchronize()
+        barrier(ws)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         step()
         b.record()
-        torch.cuda.synchronize()
+        barrier(ws)
         total_ms += a.elapsed_time(b)
-    clocks = sampler.stop()
+    total_ms = max_over_ranks(total_ms, ws, dev)
+    clocks = sampler.stop() if rank == 0 else None
     ms = total_ms / args.steps
-    value = vpr / (ms / 1e3)
-    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": ws, "ranks_used": 1, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, SURVEY.md App. E)", "config": cfg,
-           "impl": "reference", "clocks": clocks,
-           "note": "the reference has no multi-GPU path: rank 0 alone runs it on one B200 (launched with %d rank(s))" % ws,
+    value = wl.total_views / (ms / 1e3)
+    per_config = None
+    if ws == 1 and not args.no_per_config:
+        del tgt_c, tgt_d
+        torch.cuda.empty_cache()
+        per_config = per_config_times("reference", dev)
+    if rank != 0:
+        return
+    out = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": ws, "ranks_used": ws, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": wl.scaling,
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded, SURVEY.md App. E)", "config": wl.describe(ws),
+           "ms_per_view": round(ms / wl.local_views, 4), "impl": "reference", "clocks": clocks,
+           "note": "the reference has no multi-GPU path: every rank runs its unmodified CUDA extension on its share of the views "
+                   "and torch.distributed all-reduces the three view-summed gradient tensors (BASELINE.md 3a)",
            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": 1, "kind": "reference",
                             "sample": "the reference has no CPU path: its unmodified CUDA extension (oracle/_ref) ran the full "
-                                      "workload on one B200, driven by 1 host thread"},
+                                      "workload on %d B200(s), each driven by 1 host thread" % ws},
            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if per_config:
+        out["per_config"] = per_config
     print(json.dumps(out), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4", "C5"])
+    ap.add_argument("--workload", default="C4", choices=["C1", "C2", "C4", "C5"])
+    ap.add_argument("--views-per-call", type=int, default=8,
+                    help="views rendered per renderer call (both arms; C4 only -- the other workloads have one view per rank)")
+    ap.add_argument("--no-per-config", action="store_true", help="skip the C1/C2/C3/C5 `_C`-level timings (N = 1 only)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")

@@ -121,28 +121,12 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 #define HB 128           // staged instances a warp culls / compacts / rasterises in one go
 #define HS (HB / 32)     // 32-entry slices of the compacted list of such a pass
 
-// Per-(view, face) constants of the ray-triangle system, formed by the thread that stages an instance IN THE
-// STAGED COPY of its record (the record in HBM does not grow): the camera origin is the same for every pixel of a
-// view, so with T = ro - p0
-//     det = rd . (E2 x E1),   u det = rd . (E2 x T),   v det = rd . (T x E1),   t det = E2 . (T x E1)
-// and a covered pixel needs three dot products and one reciprocal instead of Moeller-Trumbore's three differences,
-// two cross products and four dots.  Same real-number result as ray_tri_tuv, different roundings (colour and depth
-// move by ~1 ulp; n_contrib / final_T do not depend on it).  0 = evaluate ray_tri_tuv per covered pixel.
-#ifndef DMR_TRI_FWD_FACE_CONSTANTS
-#define DMR_TRI_FWD_FACE_CONSTANTS 1
-#endif
-
-__device__ __forceinline__ void stage_face_constants(uint4* dst, const float3 ro, bool with_t)
-{
-    float* wv = reinterpret_cast<float*>(dst + 3);
-    const float3 q0 = f3(wv[0], wv[1], wv[2]), q1 = f3(wv[3], wv[4], wv[5]), q2 = f3(wv[6], wv[7], wv[8]);
-    const float3 Tv = ro - q0, E1 = q1 - q0, E2 = q2 - q0;
-    const float3 Nv = cross3(E2, E1), Av = cross3(E2, Tv), Qv = cross3(Tv, E1);
-    wv[0] = Nv.x; wv[1] = Nv.y; wv[2] = Nv.z;
-    wv[3] = Av.x; wv[4] = Av.y; wv[5] = Av.z;
-    wv[6] = Qv.x; wv[7] = Qv.y; wv[8] = Qv.z;
-    if (with_t) wv[21] = dot3(Qv, E2);
-}
+// (Measured and rejected, round 2: per-(view, face) constants of the ray-triangle system -- E2 x E1, E2 x T, T x E1 formed
+// once per staged instance, so that a covered pixel needs three dot products instead of Moeller-Trumbore's two cross
+// products and four dots.  -4 % forward, -3 % backward at C4, but it is the same real number with DIFFERENT roundings:
+// for triangles seen edge-on (det tiny against |E1||E2|) the reference's own (u, v) carry a large relative error, and
+// only the reference's exact operation order reproduces it.  C1, C2 and C4 stayed within 1e-5; C5 (4 M triangles,
+// thousands of slivers per image) differed by up to 7e-4 in colour.  Parity wins: ray_tri_tuv stays.)
 
 // Forward.  Per round of RB staged instances every warp works through its 8x4 pixel block in passes of HB
 // instances:
@@ -200,9 +184,6 @@ __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(T
                 uint4* dst = s_rec + tid * 9;
 #pragma unroll
                 for (int q = 0; q < 9; q++) dst[q] = src[q];
-#if DMR_TRI_FWD_FACE_CONSTANTS
-                stage_face_constants(dst, ro, false);      // ro: the view's camera origin
-#endif
             }
         }
         __syncthreads();
@@ -246,18 +227,8 @@ __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(T
                     const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
                     const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
                     float3 tuv = f3(0, 0, 0);
-#if DMR_TRI_FWD_FACE_CONSTANTS
-                    const float det = dot3(rd, f3(w[0], w[1], w[2]));
-                    const bool hit = det != 0.0f;
-                    if (hit) {
-                        const float inv_det = 1.0f / det;
-                        tuv.y = dot3(rd, f3(w[3], w[4], w[5])) * inv_det;
-                        tuv.z = dot3(rd, f3(w[6], w[7], w[8])) * inv_det;
-                    }
-#else
                     const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
                     const bool hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv);
-#endif
                     if (hit) {
                         float uc, vc;
                         int code;
@@ -367,12 +338,6 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 #ifndef DMR_TRI_BWD_RCP_ALPHA
 #define DMR_TRI_BWD_RCP_ALPHA 1
 #endif
-// The backward twin of DMR_TRI_FWD_FACE_CONSTANTS: the staged copy of a record carries E2 x E1, E2 x T, T x E1 in
-// place of the three vertex positions and E2 . (T x E1) in place of the first vertex id (neither is read from
-// shared memory here; tri_grad_finish_kernel reads the global record).
-#ifndef DMR_TRI_BWD_FACE_CONSTANTS
-#define DMR_TRI_BWD_FACE_CONSTANTS 1
-#endif
 template <bool DET>
 __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 {
@@ -454,9 +419,6 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 #if DMR_TRI_BWD_RCP_ALPHA
                 s_rcpa[tid] = 1.0f / (1.0f - __uint_as_float(dst[0].w));
 #endif
-#if DMR_TRI_BWD_FACE_CONSTANTS
-                stage_face_constants(dst, ro, true);       // ro: the view's camera origin
-#endif
             }
         }
         __syncthreads();
@@ -532,19 +494,8 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                     const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
                     float3 tuv = f3(0, 0, 0);
                     float inv_denom = 0.0f;
-#if DMR_TRI_BWD_FACE_CONSTANTS
-                    const float det = dot3(rd, f3(w[0], w[1], w[2]));
-                    const bool hit = det != 0.0f;
-                    if (hit) {
-                        inv_denom = 1.0f / det;
-                        tuv.x = w[21] * inv_denom;
-                        tuv.y = dot3(rd, f3(w[3], w[4], w[5])) * inv_denom;
-                        tuv.z = dot3(rd, f3(w[6], w[7], w[8])) * inv_denom;
-                    }
-#else
                     const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
                     const bool hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv, inv_denom);
-#endif
                     if (hit) {
                         float uc, vc;
                         int code;

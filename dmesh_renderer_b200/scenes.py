@@ -85,7 +85,10 @@ def cameras(dirs, dist, W, H, near, far):
 DEFAULT_DIR = torch.tensor([[0.3, 0.2, 1.0]], dtype=torch.float64) / math.sqrt(0.3 ** 2 + 0.2 ** 2 + 1.0)
 
 
-def random_tri_scene(name, seed, F, sigma, H, W, B=1, opacity=(0.1, 0.7), dist=3.0, near=0.5, far=6.0):
+def random_tri_scene(name, seed, F, sigma, H, W, B=1, opacity=(0.1, 0.7), dist=3.0, near=0.5, far=6.0, view_slice=None):
+    """`view_slice`: keep only these views of the B-view scene (same random stream, so view b is the same camera and
+    the same intensities whether or not the other views are kept; the per-view tensors of the dropped views --
+    verts_depth is [B,P] -- are never built)."""
     g = torch.Generator().manual_seed(seed)
     centres = torch.rand(F, 1, 3, generator=g) * 1.8 - 0.9
     verts = (centres + sigma * torch.randn(F, 3, 3, generator=g)).reshape(3 * F, 3).contiguous()
@@ -94,6 +97,8 @@ def random_tri_scene(name, seed, F, sigma, H, W, B=1, opacity=(0.1, 0.7), dist=3
     faces_opacity = torch.rand(F, generator=g) * (opacity[1] - opacity[0]) + opacity[0]
     faces_intense = torch.rand(B, F, generator=g) * 0.5 + 0.5
     dirs = DEFAULT_DIR if B == 1 else fibonacci_dirs(B, g)
+    if view_slice is not None:
+        dirs, faces_intense = dirs[view_slice], faces_intense[view_slice].contiguous()
     mv, pj = cameras(dirs, dist, W, H, near, far)
     verts_depth = ndc_depth(verts, mv, pj)
     bg = torch.ones(3)
@@ -173,9 +178,9 @@ def tet_grid_scene(name, seed, n, H, W, B=1, opacity=(0.0, 0.1), dist=4.0, near=
 # ---------------------------------------------------------------------------
 # BASELINE.json configs
 # ---------------------------------------------------------------------------
-def config(name, views=None):
-    """C1..C5 of SURVEY.md section 8.  `views` overrides the number of cameras of C4
-    (a rank renders 64/G of them)."""
+def config(name, views=None, view_slice=None):
+    """C1..C5 of SURVEY.md section 8.  `views` overrides the number of cameras of C4; `view_slice` keeps a rank's
+    share of them (a rank renders 64/G views of the 64-view scene)."""
     if name == "C1":
         return random_tri_scene("C1", 0, 10_000, 0.08, 256, 256)
     if name == "C2":
@@ -183,7 +188,7 @@ def config(name, views=None):
     if name == "C3":
         return tet_grid_scene("C3", 2, 64, 512, 512)
     if name == "C4":
-        return random_tri_scene("C4", 3, 1_000_000, 0.01, 1024, 1024, B=views or 64)
+        return random_tri_scene("C4", 3, 1_000_000, 0.01, 1024, 1024, B=views or 64, view_slice=view_slice)
     if name == "C5":
         return random_tri_scene("C5", 4, 4_000_000, 0.02, 2048, 2048, opacity=(0.3, 0.9))
     # small variants for tests
