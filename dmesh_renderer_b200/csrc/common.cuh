@@ -170,7 +170,7 @@ struct __align__(16) TriRecord {
     // q0..q2: hot part (coverage test)
     uint32_t ea0, eb0, ec0; float opacity;
     uint32_t ea1, eb1, ec1; float intense;
-    uint32_t ea2, eb2, ec2; uint32_t flags;   // bit0: edge values cannot overflow on screen
+    uint32_t ea2, eb2, ec2; uint32_t flags;   // bit 0: edge values cannot overflow on screen; bits 1..27: block bbox (below)
     // q3..q8: shading part
     float v0[3], v1[3], v2[3];                // world positions
     float c0[3], c1[3], c2[3];                // vertex colours
@@ -180,6 +180,18 @@ struct __align__(16) TriRecord {
 static_assert(sizeof(TriRecord) == 144, "TriRecord must be 9 x 16 bytes");
 #define DMR_REC_WORDS 36
 #define DMR_REC_SAFE 1u
+// Conservative bounding box of the pixels the (snapped) triangle can cover, in units of the render kernels' warp
+// blocks (8 x 4 pixels), packed into `flags`:
+//   bits 1..9   first block column (pixel x >> 3)      bits 20..23  number of block columns, 15 = unbounded
+//   bits 10..19 first block row    (pixel y >> 2)      bits 24..27  number of block rows,    15 = unbounded
+// The three edge-function minima alone keep ~2.5x more instances per block than really touch it (a small triangle
+// near a block is rarely separated from it by one of ITS OWN edge lines); the box removes those.  A triangle whose
+// box holds no pixel centre at all is stored as degenerate (never covered), which is what in_tri would find.
+#define DMR_REC_BX0_SHIFT 1
+#define DMR_REC_BY0_SHIFT 10
+#define DMR_REC_NBX_SHIFT 20
+#define DMR_REC_NBY_SHIFT 24
+#define DMR_REC_NB_UNBOUNDED 15u
 
 // ---------------------------------------------------------------------------
 // workspace layouts (all offsets 256-byte aligned)

@@ -146,7 +146,7 @@ __device__ __forceinline__ void edge_setup(float2 p1, float2 p2, float2 p3, int 
     flags = 0;
     if (area == 0) {
         for (int k = 0; k < 3; k++) { ea[k] = 0; eb[k] = 0; ec[k] = 0; }
-        flags = DMR_REC_SAFE;
+        flags = DMR_REC_SAFE | (DMR_REC_NB_UNBOUNDED << DMR_REC_NBX_SHIFT) | (DMR_REC_NB_UNBOUNDED << DMR_REC_NBY_SHIFT);
         return;
     }
     if (area < 0) {   // make CCW: swap vertices 2 and 3
@@ -178,11 +178,32 @@ __device__ __forceinline__ void edge_setup(float2 p1, float2 p2, float2 p3, int 
             long long lcy = (long long)(int)vy[k] - (long long)(int)vy[kn];
             long long A = -16 * lcy, Bc = 16 * lcx;
             long long C = 8 * lcx - 8 * lcy + lcy * (long long)(int)vx[k] - lcx * (long long)(int)vy[k] - (long long)bias;
-            long long bound = llabs(A) * (long long)W + llabs(Bc) * (long long)H + llabs(C);
+            // (tiles at the right / bottom border extend up to 15 pixels beyond the image; the block tests evaluate there)
+            long long bound = llabs(A) * (long long)(W + 16) + llabs(Bc) * (long long)(H + 16) + llabs(C);
             if (llabs(lcx) > 0x7ffffffLL || llabs(lcy) > 0x7ffffffLL || bound > 0x7fffffffLL) safe = false;
         }
     }
-    flags = safe ? DMR_REC_SAFE : 0u;
+    // block bbox of the pixels whose centre (16 px + 8 in 1/16-pixel units) lies inside the snapped triangle's
+    // bounding rectangle (closed: conservative for the strict edge tests and the fill rule)
+    uint32_t bx0 = 0, by0 = 0, nbx = DMR_REC_NB_UNBOUNDED, nby = DMR_REC_NB_UNBOUNDED;
+    if (safe && W <= 4096 && H <= 4096) {
+        const int mnx = min(min(x1, x2), x3), mxx = max(max(x1, x2), x3);
+        const int mny = min(min(y1, y2), y3), mxy = max(max(y1, y2), y3);
+        int px0 = (mnx + 7) >> 4, px1 = (mxx - 8) >> 4;      // ceil((min - 8) / 16), floor((max - 8) / 16)
+        int py0 = (mny + 7) >> 4, py1 = (mxy - 8) >> 4;
+        px0 = max(px0, 0); py0 = max(py0, 0);
+        px1 = min(px1, W - 1); py1 = min(py1, H - 1);
+        if (px1 < px0 || py1 < py0) {                          // no pixel centre inside: never covered
+            for (int k = 0; k < 3; k++) { ea[k] = 0; eb[k] = 0; ec[k] = 0; }
+            flags = DMR_REC_SAFE | (DMR_REC_NB_UNBOUNDED << DMR_REC_NBX_SHIFT) | (DMR_REC_NB_UNBOUNDED << DMR_REC_NBY_SHIFT);
+            return;
+        }
+        const uint32_t cx = (uint32_t)(px1 >> 3) - (uint32_t)(px0 >> 3) + 1u, cy = (uint32_t)(py1 >> 2) - (uint32_t)(py0 >> 2) + 1u;
+        if (cx < DMR_REC_NB_UNBOUNDED) { bx0 = (uint32_t)(px0 >> 3); nbx = cx; }
+        if (cy < DMR_REC_NB_UNBOUNDED) { by0 = (uint32_t)(py0 >> 2); nby = cy; }
+    }
+    flags = (safe ? DMR_REC_SAFE : 0u) | (bx0 << DMR_REC_BX0_SHIFT) | (by0 << DMR_REC_BY0_SHIFT) |
+            (nbx << DMR_REC_NBX_SHIFT) | (nby << DMR_REC_NBY_SHIFT);
 }
 
 // ---------------------------------------------------------------------------

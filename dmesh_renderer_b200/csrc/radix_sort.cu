@@ -19,7 +19,22 @@
 
 namespace dmr {
 
+// Tile shape of a onesweep pass: threads per CTA, keys per thread, resident CTAs per SM (register cap).
+#ifndef DMR_RS_THREADS
+#define DMR_RS_THREADS 512
+#endif
+#ifndef DMR_RS_KPT
+#define DMR_RS_KPT 8
+#endif
+#ifndef DMR_RS_MINB
+#define DMR_RS_MINB 2
+#endif
+#ifndef DMR_RS_SPLIT_RANK
+#define DMR_RS_SPLIT_RANK 1   // form the peer masks of all rounds before the serial running-offset updates (more ILP, 8 more registers)
+#endif
+#define RS_TILE_KEYS (DMR_RS_THREADS * DMR_RS_KPT)
 #define RS_MIN_TILE 2048   // smallest tile of any configuration (sizes the descriptor array)
+static_assert(DMR_RS_THREADS >= 256 && DMR_RS_THREADS % 32 == 0 && RS_TILE_KEYS >= RS_MIN_TILE, "onesweep tile shape");
 #define RS_LB 16         // look-back descriptors fetched per step (see the stability note at the look-back)
 
 #define RS_FLAG_AGG  (1u << 30)
@@ -44,7 +59,7 @@ struct SortTempLayout {   // zeroed part first, so that a caller can merge the m
         return L;
     }
     // bytes from the start of the buffer that must be zero before a sort of npass passes
-    size_t zero_bytes(size_t n, int npass) const { return desc + 4 * 256 * ((n + 4095) / 4096) * (size_t)npass; }
+    size_t zero_bytes(size_t n, int npass) const { return desc + 4 * 256 * ((n + RS_TILE_KEYS - 1) / RS_TILE_KEYS) * (size_t)npass; }
 };
 
 size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n, 8).total; }
@@ -251,6 +266,7 @@ __device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, siz
     //      other: 306 vs 282 us per pass at C5; the extra shared-memory traffic costs more than the chain.
     //      A single match.any.sync per key instead of the ballots: 9 % slower, its issue rate is far lower.)
     const uint32_t lt_mask = (1u << lane) - 1u;
+#if DMR_RS_SPLIT_RANK
     unsigned peers[RS_KPT];
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
@@ -263,14 +279,22 @@ __device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, siz
             peers[i] = digit_peers<NBITS>(dig[i], pm);
         }
     }
+#endif
 #pragma unroll
     for (int i = 0; i < RS_KPT; i++) {
         const bool ok = FULL || wbase + i * 32 + lane < nvalid;
         const uint32_t d = dig[i];
-        const int leader = __ffs(peers[i]) - 1;
-        const uint32_t before = __popc(peers[i] & lt_mask);
+#if DMR_RS_SPLIT_RANK
+        const unsigned pr = peers[i];
+#else
+        unsigned pr = 0xffffffffu;
+        if (!FULL) { pr = __ballot_sync(0xffffffffu, ok); if (!ok) pr = ~pr; }
+        pr = digit_peers<NBITS>(d, pr);
+#endif
+        const int leader = __ffs(pr) - 1;
+        const uint32_t before = __popc(pr & lt_mask);
         uint32_t old = 0;
-        if (ok && lane == leader) { old = wh[d]; wh[d] = old + __popc(peers[i]); }
+        if (ok && lane == leader) { old = wh[d]; wh[d] = old + __popc(pr); }
         old = __shfl_sync(0xffffffffu, old, leader);
         if (ok) {
             uint32_t pos = s_dbase[d] + old + before;
@@ -432,7 +456,7 @@ static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* k
     buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
     buf.ktmp = reinterpret_cast<KeyT*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
-    return launch_onesweep<KeyT, 512, 8, 2>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
+    return launch_onesweep<KeyT, DMR_RS_THREADS, DMR_RS_KPT, DMR_RS_MINB>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
 }
 
 int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
