@@ -231,7 +231,7 @@ def run_ours(args, ws, rank, local):
     copy_stream = torch.cuda.Stream(device=dev)
     nslot = 2
     stage = [{"mv": torch.empty_like(mvs[0]), "proj": torch.empty_like(pjs[0]), "tc": torch.empty_like(tgt_c[0]),
-              "td": torch.empty_like(tgt_d[0]), "ready": None, "free": None} for _ in range(nslot)]
+              "td": torch.empty_like(tgt_d[0]), "cams": None, "ready": None, "free": None} for _ in range(nslot)]
     loss_acc = torch.zeros(1, device=dev)
     loss_host = torch.zeros(1).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in wl.host.values())
@@ -245,6 +245,9 @@ def run_ours(args, ws, rank, local):
         with torch.cuda.stream(copy_stream):
             st["mv"][:n].copy_(wl.host["mv"][a:b], non_blocking=True)
             st["proj"][:n].copy_(wl.host["proj"][a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            st["cams"] = ev                         # the forward pass needs only the cameras; the targets follow
             st["tc"][:n].copy_(wl.host["target_color"][a:b], non_blocking=True)
             st["td"][:n].copy_(wl.host["target_depth"][a:b], non_blocking=True)
             ev = torch.cuda.Event()
@@ -264,10 +267,11 @@ def run_ours(args, ws, rank, local):
                 if i + 1 < len(wl.calls):
                     enqueue_copy(i + 1)
                 st, n = stage[i % nslot], b - a
-                main.wait_event(st["ready"])
+                main.wait_event(st["cams"])
                 vdep[i].grad = None
                 fint[i].grad = None
                 color, depth = renderer(verts, s.faces, vcol, fopa, st["mv"][:n], st["proj"][:n], vdep[i], fint[i])
+                main.wait_event(st["ready"])        # target images: they travelled while the forward pass ran
                 dc, dd = color.detach() - st["tc"][:n], depth.detach() - st["td"][:n]
                 torch.autograd.backward([color, depth], [dc, dd])
                 loss_acc.add_(0.5 * (dc.square().sum() + dd.square().sum()))
@@ -406,7 +410,7 @@ def run_ours(args, ws, rank, local):
         with open(tp) as f:
             tj = json.load(f)
         ent = tj.get(args.workload, {}).get(dom)
-        if ent:
+        if isinstance(ent, dict):
             # per launch of the captured configuration, scaled to this launch's views where the capture had fewer
             scale = vpc / float(ent.get("views", vpc))
             traffic = int(ent["dram_bytes"] * scale)

@@ -106,12 +106,12 @@ def _arm(pinned):
 
 def _speculative_binning(lib, key, u8):
     """Binning buffer sized from the previous call with the same shapes (+25%), allocated while the GPU is still
-    busy with phase 1 so that nothing but the launch itself sits between the arrival of num_rendered and phase 2.
-    None on the first call."""
+    busy with phase 1.  Returns (buffer, capacity in instances) or (None, 0) on the first call."""
     prev = _last_R.get(key)
     if not prev:
-        return None
-    return torch.empty(lib.dmr_binning_bytes(prev + prev // 4 + 1024), **u8)
+        return None, 0
+    cap = min(prev + prev // 4 + 1024, _MAX_R)
+    return torch.empty(lib.dmr_binning_bytes(cap), **u8), cap
 
 
 _MAX_R = (1 << 30) - 1          # the sort's descriptors carry 30-bit prefixes (csrc/radix_sort.cu)
@@ -131,6 +131,18 @@ def _wait_R(lib, pinned, key, spec, u8):
     if spec is not None and spec.numel() >= need:
         return R, spec
     return R, torch.empty(need, **u8)
+
+
+def _read_R(lib, pinned, key):
+    """Wait for num_rendered (see _wait_R) without touching buffers."""
+    _lib.check(lib.dmr_wait_i32(pinned[2], _SENTINEL, _stream()))
+    R = int(pinned[1][0])
+    if R < 0 or R > _MAX_R:
+        raise RuntimeError("dmesh_renderer_b200: %s tile instances exceed the supported maximum of 2^30 - 1 "
+                           "(the reference's int limit is 2^31 - 1); render fewer views per call" %
+                           ("more than 2^31" if R < 0 else str(R)))
+    _last_R[key] = R
+    return R
 
 
 class _Inverses:
@@ -273,9 +285,15 @@ def tri_forward_begin(background, verts, faces, verts_color, faces_opacity, mv_m
     return st
 
 
-def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
+def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None, speculative=False):
     """Phase 2 of a forward call started by tri_forward_begin: the one host sync (R), binning buffer, sort, render.
-    `inverses`: the _Inverses object the matrices came from, whose deferred singularity check runs after the sync."""
+    `inverses`: the _Inverses object the matrices came from, whose deferred singularity check runs after the sync.
+    `speculative`: launch phase 2 BEFORE num_rendered has reached the host, on a binning buffer sized from the
+    previous call with the same shapes (+25 %): the phase-2 kernels read the instance count on the device, so the GPU
+    goes straight from the scan into the binning kernels while the host is still waiting for the 4-byte read-back
+    (the reference drains the pipeline there, rasterizer_impl.cu:287-299).  If the scene grew past the buffer, the
+    kernels emit nothing and phase 2 is simply run again with an exact buffer.  In this mode element 0 of the result is
+    the CAPACITY the binning buffer was laid out for (>= num_rendered); pass it to render_tris_backward as `R`."""
     for t, n in ((inv_mv_mats, "inv_mv_mats"), (inv_proj_mats, "inv_proj_mats")):
         if t.dim() != 3 or t.size(1) != 4 or t.size(2) != 4:
             _err("%s must have dimensions (B, 4, 4)" % n)
@@ -297,7 +315,7 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
         _require_cuda(inv_mv_mats, inv_proj_mats)
         imv, ipj = _f32(inv_mv_mats, "inv_mv_mats"), _f32(inv_proj_mats, "inv_proj_mats")
         key = ("tri", B, P, F, 0, W, H)
-        spec = _speculative_binning(lib, key, u8)
+        spec, cap = _speculative_binning(lib, key, u8)
         point_buf, face_buf, img_buf = st.bufs
         out_color, out_depth = st.outs
         # everything that does not depend on R is prepared before the wait
@@ -305,14 +323,26 @@ def tri_forward_finish(st, inv_mv_mats, inv_proj_mats, inverses=None):
         b2 = (_ptr(img_buf), _ptr(out_color), _ptr(out_depth), _stream())
         if inverses is not None:
             inverses.join()
-        # (Measured and rejected: one native call that waits for R and launches phase 2 without returning to Python
-        # in between -- 1163 vs 1159 views/s at C2: the bubble is the D2H + launch latency, not the interpreter.)
         try:
-            R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
+            if speculative and spec is not None:
+                # phase 2 goes out first; the wait below overlaps with it
+                _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, cap, *a, _ptr(spec), *b2))
+                R = _read_R(lib, st.pinned, key)
+                bin_buf = spec
+                if R > cap:     # the scene outgrew the speculative buffer: nothing was emitted, run phase 2 again
+                    cap = R
+                    bin_buf = torch.empty(lib.dmr_binning_bytes(cap), **u8)
+                    _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, cap, *a, _ptr(bin_buf), *b2))
+                R = cap         # the layout count of the binning buffer (see the docstring)
+            else:
+                # (Measured and rejected: one native call that waits for R and launches phase 2 without returning to
+                # Python in between -- 1163 vs 1159 views/s at C2: the bubble is the D2H + launch latency, not the
+                # interpreter.)
+                R, bin_buf = _wait_R(lib, st.pinned, key, spec, u8)   # the one sync: R sizes the binning buffer
+                _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, *a, _ptr(bin_buf), *b2))
         finally:
             _Pinned.release(st.pinned)
             st.pinned = None
-        _lib.check(lib.dmr_tri_forward_render(B, P, F, W, H, R, *a, _ptr(bin_buf), *b2))
         if inverses is not None:
             inverses.check()
     return R, out_color, out_depth, point_buf, face_buf, bin_buf, img_buf
@@ -511,7 +541,7 @@ def render_tets(background, verts, faces, verts_color, faces_opacity, mv_mats, p
                                                _ptr(mv), _ptr(pj), _ptr(tets_c), _ptr(ft_c), _ptr(tf_c), _ptr(point_buf),
                                                _ptr(face_buf), _ptr(tet_rec), rec_valid, pinned[2], stream))
             key = ("tet", B, P, F, T, W, H)
-            spec = _speculative_binning(lib, key, u8)
+            spec, _cap = _speculative_binning(lib, key, u8)
             if inverses is not None:
                 inverses.join()
             R, bin_buf = _wait_R(lib, pinned, key, spec, u8)

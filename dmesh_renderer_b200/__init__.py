@@ -30,6 +30,10 @@ class TriRenderSettings(NamedTuple):      # reference __init__.py:13-16
 
 
 _deterministic_default = False
+# TriRenderer launches phase 2 of a forward call before num_rendered has reached the host (see
+# _C.tri_forward_finish); DMESH_B200_NO_SPECULATIVE=1 restores wait-then-launch (debugging / A-B timing)
+import os as _os
+_speculative_phase2 = _os.environ.get("DMESH_B200_NO_SPECULATIVE") != "1"
 
 
 def set_deterministic(flag: bool) -> bool:
@@ -67,8 +71,10 @@ class _RenderTri(th.autograd.Function):
             pending = _C.tri_forward_begin(render_settings.bg, verts, faces, verts_color, faces_opacity, mv_mats,
                                            proj_mats, verts_depth, faces_intense, render_settings.image_height,
                                            render_settings.image_width)
+            # speculative: phase 2 is enqueued before num_rendered reaches the host; `num_rendered` is then the count
+            # the binning buffer was laid out for (>= the real one), which is what backward needs
             num_rendered, color, depth, pointBuffer, faceBuffer, binningBuffer, imgBuffer = \
-                _C.tri_forward_finish(pending, inv_mv_mats, inv_proj_mats, inv)
+                _C.tri_forward_finish(pending, inv_mv_mats, inv_proj_mats, inv, speculative=_speculative_phase2)
         except Exception as ex:
             print("\nAn error occured in forward.")
             print(ex)

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(DMR_SCAN_THREADS) inclusive_scan_kernel(
     const uint32_t* __restrict__ in, const uint32_t* __restrict__ index, uint32_t* __restrict__ out, size_t n,
     uint32_t* __restrict__ state, int32_t* __restrict__ total_mapped)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint32_t s_warp[DMR_SCAN_THREADS / 32];
     __shared__ unsigned long long s_warp64[DMR_SCAN_THREADS / 32];
     __shared__ uint32_t s_tile;
@@ -162,7 +163,7 @@ int inclusive_scan_u32(const uint32_t* in, const uint32_t* index, uint32_t* out,
     size_t ntile = (n + DMR_SCAN_TILE - 1) / DMR_SCAN_TILE;
     {
     ProfScope prof(ST_SCAN, stream);
-    inclusive_scan_kernel<<<(unsigned)ntile, DMR_SCAN_THREADS, 0, stream>>>(in, index, out, n, state, nullptr);
+    DMR_CUDA(dmr_launch(inclusive_scan_kernel, dim3((unsigned)ntile), dim3(DMR_SCAN_THREADS), 0, stream, in, index, out, n, state, nullptr));
     DMR_LAUNCH_CHECK("inclusive_scan_kernel");
     }
     if (total_host)
@@ -210,13 +211,16 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, SortPre sp, uint2* __restrict__ ranges, size_t n_ranges,
     const uint32_t* __restrict__ total_dev, uint32_t total_host)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     // tiles without instances keep the empty range (0,0): zero the table here (tile_ranges_kernel runs after the
     // sort) instead of with one more memset between the num_rendered read-back and this launch
     for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n_ranges; t += (size_t)gridDim.x * 256)
         ranges[t] = make_uint2(0u, 0u);
-    // The host sized keys / vals from ITS copy of num_rendered.  If that is not the total the scan produced on the
-    // device (a caller mixing up the counts of two calls in flight), emit nothing rather than write out of bounds.
-    if (*total_dev != total_host) return;
+    // The host sized keys / vals for `total_host` instances -- its copy of num_rendered, or, when phase 2 is launched
+    // before num_rendered has reached the host, the capacity of a speculatively sized buffer.  If the scan produced
+    // more than that, emit nothing rather than write out of bounds (the host sees the real total and runs phase 2
+    // again with a buffer that fits).
+    if (*total_dev > total_host) return;
     __shared__ uint32_t s_incl[256];
     __shared__ uint2 s_rect[256];
     __shared__ uint32_t s_tile0[256];   // tiles_per_view * view of the face (per-instance divisions hoisted)
@@ -307,9 +311,15 @@ __global__ void __launch_bounds__(256) duplicate_kernel(
 // rasterizer_impl.cu:330).
 // ---------------------------------------------------------------------------
 #define TR_KPT 8
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ keys, size_t L,
-                                                          uint2* __restrict__ ranges)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ keys, size_t L_cap,
+                                                          uint2* __restrict__ ranges, const uint32_t* __restrict__ total_dev)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
+    // L_cap: capacity the grid was sized for; the number of instances is read on the device.  More instances than
+    // capacity: nothing was emitted (duplicate_kernel), every range stays empty.
+    const uint32_t total = *total_dev;
+    if (total > L_cap) return;
+    const size_t L = total;
     // 8 consecutive keys per thread (2 x 16-byte loads) plus the one before them
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * TR_KPT;
     if (i0 >= L) return;
@@ -396,25 +406,29 @@ int bin_instances(int B, int F, int W, int H, size_t R, const void* fb, const Fa
     int rc;
     SortPre sp;
     const bool fused = R <= DMR_FUSED_TILE_HIST_MAX;
+    const uint32_t* total_dev = at<uint32_t>(fb, L.scan_state) + 1;   // the scan's grand total, on the device
     if ((rc = sort_pre_begin(at<void>(binning_buffer, BL.sort_temp), R, 4, tile_bits, &sp, stream))) return rc;
+    sp.n_dev = total_dev;
     {
         ProfScope prof(ST_DUPLICATE, stream);
         const unsigned nblk = (unsigned)((BF + 255) / 256);
         if (fused)
-            duplicate_kernel<true><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
+            DMR_CUDA(dmr_launch(duplicate_kernel<true>, dim3(nblk), dim3(256), 0, stream, BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
                                                             at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp,
-                                                            ranges, tiles, at<uint32_t>(fb, L.scan_state) + 1, (uint32_t)R);
+                                                            ranges, tiles, total_dev, (uint32_t)R));
         else
-            duplicate_kernel<false><<<nblk, 256, 0, stream>>>(BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
+            DMR_CUDA(dmr_launch(duplicate_kernel<false>, dim3(nblk), dim3(256), 0, stream, BF, F, tx, tx * ty, at<uint32_t>(fb, L.order),
                                                              at<uint32_t>(fb, L.offsets), at<uint2>(fb, L.rect), ku, vu, sp,
-                                                             ranges, tiles, at<uint32_t>(fb, L.scan_state) + 1, (uint32_t)R);
+                                                             ranges, tiles, total_dev, (uint32_t)R));
         DMR_LAUNCH_CHECK("duplicate_kernel");
     }
-    if ((rc = sort_pairs_u32_pre(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, fused, stream))) return rc;
+    if ((rc = sort_pairs_u32_pre(ku, vu, ks, vs, R, tile_bits, at<void>(binning_buffer, BL.sort_temp), true, fused, stream,
+                                 total_dev)))
+        return rc;
     {
         ProfScope prof(ST_RANGES, stream);
         const size_t nthreads = (R + TR_KPT - 1) / TR_KPT;
-        tile_ranges_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(ks, R, ranges);
+        DMR_CUDA(dmr_launch(tile_ranges_kernel, dim3((unsigned)((nthreads + 255) / 256)), dim3(256), 0, stream, ks, R, ranges, total_dev));
         DMR_LAUNCH_CHECK("tile_ranges_kernel");
     }
     return 0;

@@ -8,6 +8,7 @@
 #include "../../include/dmesh_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <sched.h>
 
 namespace dmr {
@@ -25,6 +26,13 @@ int cuda_fail(cudaError_t e, const char* what)
 {
     set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
     return DMR_ECUDA;
+}
+
+bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DMESH_B200_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
 }
 
 // ---- stage timing ------------------------------------------------------------

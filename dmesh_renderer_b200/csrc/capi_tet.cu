@@ -104,7 +104,7 @@ static void fill_params(TetParams& p, int B, int P, int F, int T, int W, int H, 
     p.prev_log_T = at<float>(ib, IL.prev_log_T);
     p.n_contrib = at<uint32_t>(ib, IL.n_contrib);
     p.active = at<uint8_t>(ib, IL.active);
-    p.trail = at<int>(ib, IL.trail);
+    p.trail = at<int4>(ib, IL.trail);
     p.trail_cap = (int)IL.trail_cap;
     p.fi_key = at<unsigned long long>(ib, IL.fi_key);
     p.fi_close = reinterpret_cast<uint32_t*>(p.fi_key + (size_t)B * W * H);

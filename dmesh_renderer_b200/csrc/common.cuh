@@ -53,6 +53,33 @@ struct ProfScope {
 };
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A forward call is a chain of 10-15 short kernels on one stream (6-40 us
+// each at C1 / C2): with ordinary launches every kernel boundary costs the full launch + drain latency.  Kernels
+// launched through dmr_launch carry cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel of the
+// chain is set up and its CTAs become resident while the previous one is still draining.  EVERY kernel launched
+// this way begins with griddep_wait() -- it blocks until the preceding kernel has completed and its writes are
+// visible -- so the data flow is exactly that of ordinary stream order; only the launch latency overlaps.
+// DMESH_B200_NO_PDL=1 in the environment restores ordinary launches (A/B timing).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t dmr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // small vector helpers.  dot/cross/transform keep the expression shape of the
 // reference (cuda_rasterizer/cuda_math.h:1524-1527, 1696-1699 and
 // auxiliary.h:71-90) so that nvcc contracts them into the same FMA chains.

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256) preprocess_points_kernel(
     int depth_mode,                          // 4th lane when verts_depth is null: 0 = clip-space w (tet), 1 = NDC z
     float4* __restrict__ vimg)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int b = blockIdx.y;
     if (idx >= (size_t)P) return;
@@ -57,7 +58,7 @@ int preprocess_points(int B, int P, int W, int H, const float* verts, const floa
     if (B <= 0 || P <= 0) return 0;
     dim3 grid((P + 255) / 256, B);
     ProfScope prof(ST_POINTS, stream);
-    preprocess_points_kernel<<<grid, 256, 0, stream>>>(B, P, W, H, verts, mv, proj, verts_depth, depth_mode, vimg);
+    DMR_CUDA(dmr_launch(preprocess_points_kernel, dim3(grid), dim3(256), 0, stream, B, P, W, H, verts, mv, proj, verts_depth, depth_mode, vimg));
     DMR_LAUNCH_CHECK("preprocess_points_kernel");
     return 0;
 }
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) depth_chain_kernel(int B, int P, const fl
                                                           const float* __restrict__ mv_mats, const float* __restrict__ proj_mats,
                                                           const float* __restrict__ dL_dvdepth, float* __restrict__ dL_dverts)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)P) return;
     const float3 p = f3(verts[3 * idx + 0], verts[3 * idx + 1], verts[3 * idx + 2]);
@@ -109,7 +111,7 @@ int depth_chain(int B, int P, const float* verts, const float* mv, const float* 
 {
     if (B <= 0 || P <= 0) return 0;
     count_launch(1);
-    depth_chain_kernel<<<(P + 255) / 256, 256, 0, stream>>>(B, P, verts, mv, proj, dL_dvdepth, dL_dverts);
+    DMR_CUDA(dmr_launch(depth_chain_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, B, P, verts, mv, proj, dL_dvdepth, dL_dverts));
     DMR_LAUNCH_CHECK("depth_chain_kernel");
     return 0;
 }
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
     uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
     TriRecord* __restrict__ records, SortPre sp)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint4 s_rec[256 * 9];
     __shared__ uint32_t s_hist[HIST ? 4 * 256 : 1];   // digit histograms of the depth keys for the face sort (radix_sort.cuh)
     const int tid = threadIdx.x;
@@ -307,13 +310,13 @@ int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
     dim3 grid((F + 255) / 256, B);
     ProfScope prof(ST_FACES, stream);
     if (sp.npass > 0)
-        tri_preprocess_faces_kernel<true><<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
+        DMR_CUDA(dmr_launch(tri_preprocess_faces_kernel<true>, dim3(grid), dim3(256), 0, stream, B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
                                                                    faces_opacity, faces_intense, tiles_touched, depth_key,
-                                                                   rect, records, sp);
+                                                                   rect, records, sp));
     else
-        tri_preprocess_faces_kernel<false><<<grid, 256, 0, stream>>>(B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
+        DMR_CUDA(dmr_launch(tri_preprocess_faces_kernel<false>, dim3(grid), dim3(256), 0, stream, B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
                                                                     faces_opacity, faces_intense, tiles_touched, depth_key,
-                                                                    rect, records, sp);
+                                                                    rect, records, sp));
     DMR_LAUNCH_CHECK("tri_preprocess_faces_kernel");
     return 0;
 }
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(256) tet_preprocess_faces_kernel(
     uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ depth_key, uint2* __restrict__ rect,
     TetFaceRec* __restrict__ records, SortPre sp)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint4 s_rec[256 * 4];
     __shared__ uint32_t s_hist[HIST ? 4 * 256 : 1];   // digit histograms of the depth keys for the face sort (radix_sort.cuh)
     const int tid = threadIdx.x;
@@ -413,11 +417,11 @@ int tet_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
     dim3 grid((F + 255) / 256, B);
     ProfScope prof(ST_FACES, stream);
     if (sp.npass > 0)
-        tet_preprocess_faces_kernel<true><<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched,
-                                                                   depth_key, rect, rec, sp);
+        DMR_CUDA(dmr_launch(tet_preprocess_faces_kernel<true>, dim3(grid), dim3(256), 0, stream, B, P, F, gx, gy, faces, vimg, verts, tiles_touched,
+                                                                   depth_key, rect, rec, sp));
     else
-        tet_preprocess_faces_kernel<false><<<grid, 256, 0, stream>>>(B, P, F, gx, gy, faces, vimg, verts, tiles_touched,
-                                                                    depth_key, rect, rec, sp);
+        DMR_CUDA(dmr_launch(tet_preprocess_faces_kernel<false>, dim3(grid), dim3(256), 0, stream, B, P, F, gx, gy, faces, vimg, verts, tiles_touched,
+                                                                    depth_key, rect, rec, sp));
     DMR_LAUNCH_CHECK("tet_preprocess_faces_kernel");
     return 0;
 }

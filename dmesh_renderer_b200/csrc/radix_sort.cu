@@ -20,17 +20,26 @@
 namespace dmr {
 
 // Tile shape of a onesweep pass: threads per CTA, keys per thread, resident CTAs per SM (register cap).
+// Measured on B200 after the ranking loop was tightened (one pass over the 32.1 M (u32, u32) pairs of C5, 514 MB;
+// CUB's SM100 onesweep on the same pairs, same box: 279 us, tools/sort_vs_cub.cu):
+//     512 x  8, 2 CTAs/SM (round 1)  250 us        256 x 16, 3 CTAs (80 regs)   205 us
+//     256 x  8, 4 or 6 CTAs          287 us        256 x 16, 4 CTAs (64 regs)   193 us   <- default
+//     384 x  8, 3 CTAs               248 us        256 x 20, 3 CTAs             187 us
+//     512 x  8, 3 CTAs (40 regs)     232 us        512 x 16, 2 CTAs             187 us
+//     512 x 16, 1 CTA (124 regs)     246 us        256 x 24 / 32, 2 CTAs        205 / 207 us (spills)
+// More keys per thread amortise the per-tile work (256-digit scan, look-back, three barriers); the 4096-key tile is
+// kept because the 5120 / 8192-key shapes cost 20 % on the small face sorts (C1: 30 -> 36 us).
 #ifndef DMR_RS_THREADS
-#define DMR_RS_THREADS 512
+#define DMR_RS_THREADS 256
 #endif
 #ifndef DMR_RS_KPT
-#define DMR_RS_KPT 8
+#define DMR_RS_KPT 16
 #endif
 #ifndef DMR_RS_MINB
-#define DMR_RS_MINB 2
+#define DMR_RS_MINB 4
 #endif
 #ifndef DMR_RS_SPLIT_RANK
-#define DMR_RS_SPLIT_RANK 1   // form the peer masks of all rounds before the serial running-offset updates (more ILP, 8 more registers)
+#define DMR_RS_SPLIT_RANK 0   // 1: form the peer masks of all rounds before the serial running-offset updates (more ILP, KPT more registers)
 #endif
 #define RS_TILE_KEYS (DMR_RS_THREADS * DMR_RS_KPT)
 #define RS_MIN_TILE 2048   // smallest tile of any configuration (sizes the descriptor array)
@@ -73,9 +82,11 @@ size_t sort_temp_bytes_u32(size_t n) { return SortTempLayout::make(n, 4).total; 
 // ---------------------------------------------------------------------------
 #define RSH_KPT 8
 template <typename KeyT>
-__global__ void __launch_bounds__(256) rs_hist_kernel(const KeyT* __restrict__ keys, size_t n, int npass, int end_bit,
-                                                      uint32_t* __restrict__ hist)
+__global__ void __launch_bounds__(256) rs_hist_kernel(const KeyT* __restrict__ keys, size_t n_cap, int npass, int end_bit,
+                                                      uint32_t* __restrict__ hist, const uint32_t* __restrict__ n_dev)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
+    const size_t n = rs_count((uint32_t)n_cap, n_dev);
     __shared__ uint32_t s_hist[RS_MAX_PASS * 256];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < npass * 256; i += 256) s_hist[i] = 0;
@@ -121,11 +132,12 @@ __global__ void __launch_bounds__(256) rs_hist_kernel(const KeyT* __restrict__ k
 // 2. plan: exclusive scans + pass skipping + buffer assignment (1 block)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rs_plan_kernel(uint32_t* __restrict__ hist, SortCtl* __restrict__ ctl, size_t n,
-                                                      int npass)
+                                                      int npass, const uint32_t* __restrict__ n_dev)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint32_t s_scan[256];
     __shared__ uint32_t s_skip[RS_MAX_PASS];
-    rs_plan_block(hist, ctl, (uint32_t)n, npass, s_scan, s_skip);
+    rs_plan_block(hist, ctl, rs_count((uint32_t)n, n_dev), npass, s_scan, s_skip);
 }
 
 // ---------------------------------------------------------------------------
@@ -156,7 +168,7 @@ __device__ __forceinline__ unsigned digit_peers(uint32_t d, unsigned peers)
     return peers;
 }
 
-// Phase order per tile (4096 keys, 512 threads x 8 keys):
+// Phase order per tile (4096 keys, 256 threads x 16 keys):
 //   load -> per-warp digit COUNTS (shared atomics) -> publish the tile aggregate EARLY -> stable
 //   ranking (ballot multi-split) -> scatter into shared memory -> look-back -> coalesced write-out.
 // Publishing the aggregate before the long, variable-latency ranking phase means that by the time a
@@ -354,13 +366,18 @@ __device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, siz
 }
 
 template <typename KeyT, int RS_THREADS, int RS_KPT, int RS_MINB, int NBITS>
-__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n, int pass,
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuffers<KeyT> buf, size_t n_cap, int pass,
                                                                           const uint32_t* __restrict__ hist_excl,
-                                                                          SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc)
+                                                                          SortCtl* __restrict__ ctl, uint32_t* __restrict__ desc,
+                                                                          const uint32_t* __restrict__ n_dev)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     constexpr int RS_TILE = RS_THREADS * RS_KPT;
     constexpr int RS_WARPS = RS_THREADS / 32;
     if (!ctl->exec[pass]) return;
+    // the grid is sized for the buffers' capacity; with the count on the device the CTAs beyond it leave at once
+    // (tickets are handed out in launch order, so the tiles that do exist are 0 .. ceil(n / RS_TILE) - 1)
+    const size_t n = rs_count((uint32_t)n_cap, n_dev);
     extern __shared__ __align__(16) unsigned char rs_smem[];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_wsum[8];
@@ -370,6 +387,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
     for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) s_whist[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    if ((size_t)tile * RS_TILE >= n) return;
     if ((size_t)(tile + 1) * RS_TILE <= n)
         rs_onesweep_tile<KeyT, RS_THREADS, RS_KPT, NBITS, true>(buf, n, pass, hist_excl, ctl, desc, rs_smem, tile, s_wsum);
     else
@@ -378,11 +396,11 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_onesweep_kernel(RsBuff
 
 template <typename KeyT, int THREADS, int KPT, int MINB>
 static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int end_bit, const uint32_t* hist, SortCtl* ctl,
-                           uint32_t* desc, bool profile, cudaStream_t stream)
+                           uint32_t* desc, bool profile, cudaStream_t stream, const uint32_t* n_dev)
 {
     constexpr size_t tile = (size_t)THREADS * KPT;
     constexpr size_t smem = sizeof(KeyT) * tile + 4 * tile + 4 * (THREADS / 32) * 256 + 4 * 256 + 4 * 256;
-    typedef void (*Kern)(RsBuffers<KeyT>, size_t, int, const uint32_t*, SortCtl*, uint32_t*);
+    typedef void (*Kern)(RsBuffers<KeyT>, size_t, int, const uint32_t*, SortCtl*, uint32_t*, const uint32_t*);
     static const Kern kern[8] = {
         rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 1>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 2>,
         rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 3>, rs_onesweep_kernel<KeyT, THREADS, KPT, MINB, 4>,
@@ -400,7 +418,7 @@ static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int 
     for (int p = 0; p < npass; p++) {
         const int nbits = (end_bit - 8 * p >= 8) ? 8 : (end_bit - 8 * p);
         if (profile) prof_begin(ST_SORT_PASS0 + p, stream); else count_launch(1);
-        kern[nbits - 1]<<<ntile, THREADS, smem, stream>>>(buf, n, p, hist, ctl, desc);
+        DMR_CUDA(dmr_launch(kern[nbits - 1], dim3(ntile), dim3(THREADS), smem, stream, buf, n, p, hist, ctl, desc, n_dev));
         if (profile) prof_end(ST_SORT_PASS0 + p, stream);
         DMR_LAUNCH_CHECK("rs_onesweep_kernel");
     }
@@ -413,7 +431,8 @@ static int launch_onesweep(const RsBuffers<KeyT>& buf, size_t n, int npass, int 
 // the histograms and computed the plan (radix_sort.cuh); only the passes run here.
 template <typename KeyT>
 static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out, size_t n,
-                           int end_bit, void* temp, bool profile, int prehist /* 0 no, 1 yes, 2 zeroed only */, cudaStream_t stream)
+                           int end_bit, void* temp, bool profile, int prehist /* 0 no, 1 yes, 2 zeroed only */, cudaStream_t stream,
+                           const uint32_t* n_dev = nullptr)
 {
     if (n == 0) return 0;
     if (end_bit < 1 || end_bit > (int)(8 * sizeof(KeyT))) { set_error("sort_pairs: end_bit %d out of range", end_bit); return 1; }
@@ -432,8 +451,6 @@ static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* k
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (sm_count <= 0) sm_count = 148;
     }
-    // 512 threads x 8 keys, 2 CTAs/SM.  Measured alternatives (tools/bench_sort.py, 32 M 64-bit keys): 256x16,
-    // 256x8, 512x16 and 384x16 tiles all land within 3% of this one.
     if (prehist != 1) {
         if (prehist == 0) DMR_CUDA(cudaMemsetAsync(t, 0, L.zero_bytes(n, npass), stream));
         size_t hblocks = (n + 256 * RSH_KPT - 1) / (256 * RSH_KPT);
@@ -441,13 +458,13 @@ static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* k
         if (hblocks > hmax) hblocks = hmax;
         {
             if (profile) prof_begin(ST_SORT_HIST, stream); else count_launch(1);
-            rs_hist_kernel<KeyT><<<(unsigned)hblocks, 256, 0, stream>>>(keys_in, n, npass, end_bit, hist);
+            DMR_CUDA(dmr_launch(rs_hist_kernel<KeyT>, dim3((unsigned)hblocks), dim3(256), 0, stream, keys_in, n, npass, end_bit, hist, n_dev));
             if (profile) prof_end(ST_SORT_HIST, stream);
             DMR_LAUNCH_CHECK("rs_hist_kernel");
         }
         {
             if (profile) prof_begin(ST_SORT_PLAN, stream); else count_launch(1);
-            rs_plan_kernel<<<1, 256, 0, stream>>>(hist, ctl, n, npass);
+            DMR_CUDA(dmr_launch(rs_plan_kernel, dim3(1), dim3(256), 0, stream, hist, ctl, n, npass, n_dev));
             if (profile) prof_end(ST_SORT_PLAN, stream);
             DMR_LAUNCH_CHECK("rs_plan_kernel");
         }
@@ -456,7 +473,7 @@ static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* k
     buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
     buf.ktmp = reinterpret_cast<KeyT*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
-    return launch_onesweep<KeyT, DMR_RS_THREADS, DMR_RS_KPT, DMR_RS_MINB>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream);
+    return launch_onesweep<KeyT, DMR_RS_THREADS, DMR_RS_KPT, DMR_RS_MINB>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream, n_dev);
 }
 
 int sort_pairs(const uint64_t* keys_in, const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n,
@@ -474,9 +491,9 @@ int sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* k
 // have_hist == false: the control region is already zero (the caller's memset) but nobody has built the
 // histograms: run the histogram + plan kernels here
 int sort_pairs_u32_pre(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
-                       int end_bit, void* temp, bool profile, bool have_hist, cudaStream_t stream)
+                       int end_bit, void* temp, bool profile, bool have_hist, cudaStream_t stream, const uint32_t* n_dev)
 {
-    return sort_pairs_impl<uint32_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, profile, have_hist ? 1 : 2, stream);
+    return sort_pairs_impl<uint32_t>(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, profile, have_hist ? 1 : 2, stream, n_dev);
 }
 
 size_t sort_zero_bytes(size_t n, size_t key_bytes, int end_bit)
@@ -493,6 +510,7 @@ int sort_pre_handle(void* temp, size_t n, size_t key_bytes, int end_bit, SortPre
     out->hist = reinterpret_cast<uint32_t*>(t + L.hist);
     out->ctl = reinterpret_cast<SortCtl*>(t + L.ctl);
     out->n = (uint32_t)n;
+    out->n_dev = nullptr;
     out->npass = (end_bit + 7) / 8;
     out->end_bit = end_bit;
     return 0;

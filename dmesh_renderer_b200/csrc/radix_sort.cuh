@@ -27,9 +27,18 @@ struct SortCtl {
 struct SortPre {
     uint32_t* hist;   // [npass][256], zeroed
     SortCtl* ctl;     // zeroed
-    uint32_t n;       // number of keys the producer emits in total
+    uint32_t n;       // number of keys the producer emits in total (n_dev == nullptr) / capacity of the buffers
+    const uint32_t* n_dev;   // when non-null: the number of keys lives in device memory (min(*n_dev, n) are sorted)
     int npass, end_bit;
 };
+
+// number of keys of a sort whose count may live on the device
+__device__ __forceinline__ uint32_t rs_count(uint32_t n_cap, const uint32_t* n_dev)
+{
+    if (!n_dev) return n_cap;
+    const uint32_t v = *n_dev;
+    return v < n_cap ? v : n_cap;
+}
 
 // exclusive scans + pass skipping + buffer assignment; blockDim.x == 256, all threads of ONE block
 __device__ inline void rs_plan_block(uint32_t* __restrict__ hist, SortCtl* __restrict__ ctl, uint32_t n, int npass,
@@ -119,7 +128,7 @@ __device__ __forceinline__ void rs_pre_finish(uint32_t* s_hist, const SortPre& s
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    rs_plan_block(sp.hist, sp.ctl, sp.n, sp.npass, s_scan, s_skip);
+    rs_plan_block(sp.hist, sp.ctl, rs_count(sp.n, sp.n_dev), sp.npass, s_scan, s_skip);
 }
 
 // host side (radix_sort.cu)
@@ -127,6 +136,7 @@ size_t sort_zero_bytes(size_t n, size_t key_bytes, int end_bit);   // leading by
 int sort_pre_handle(void* temp, size_t n, size_t key_bytes, int end_bit, SortPre* out);                       // no memset
 int sort_pre_begin(void* temp, size_t n, size_t key_bytes, int end_bit, SortPre* out, cudaStream_t stream);   // zeroes
 int sort_pairs_u32_pre(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out, size_t n,
-                       int end_bit, void* temp, bool profile, bool have_hist, cudaStream_t stream);   // no memset
+                       int end_bit, void* temp, bool profile, bool have_hist, cudaStream_t stream,
+                       const uint32_t* n_dev = nullptr);   // no memset; n_dev: see SortPre
 
 }  // namespace dmr

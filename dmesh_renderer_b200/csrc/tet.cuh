@@ -73,18 +73,20 @@ struct TetFaceLayout {
     }
 };
 
-// Face trail: the forward march records the id of every face it composites, step-major
-// (trail[k * BI + pixel], coalesced across a warp), so that the backward pass walks the SAME faces in
-// reverse with independent, prefetchable loads instead of re-marching through the adjacency with one
-// dependent load chain per step (cuda_renderer/backward.cu:382-477).  Only the first `cap` steps of a ray
-// are recorded; rays that composite more faces re-march the part beyond the cap exactly as before.
-// cap: 512 steps while the trail stays below 512 MiB, never less than 32 (debug override for tests).
+// Face trail: the forward march records, for every face it composites, the face id AND the hit parameters
+// (t, u, v) it composited with -- one 16-byte entry, step-major (trail[k * BI + pixel], coalesced across a warp) --
+// so that the backward pass walks the SAME faces in reverse with independent, prefetchable loads instead of
+// re-marching through the adjacency with one dependent load chain per step (cuda_renderer/backward.cu:382-477),
+// and needs neither the face's vertices (48 B per step through L1, which bounds the march) nor a second
+// ray/triangle test per step: the values ARE the forward pass's bits.  Only the first `cap` steps of a ray are
+// recorded; rays that composite more faces re-march the part beyond the cap exactly as before.
+// cap: 512 steps while the trail stays below 2 GiB, never less than 32 (debug override for tests).
 extern int g_tet_trail_cap_override;
 __host__ inline size_t tet_trail_cap(size_t BI)
 {
     if (g_tet_trail_cap_override > 0) return (size_t)g_tet_trail_cap_override;
     if (BI == 0) return 32;
-    size_t cap = ((size_t)512 << 20) / (4 * BI);
+    size_t cap = ((size_t)2048 << 20) / (16 * BI);
     return cap > 512 ? 512 : (cap < 32 ? 32 : cap);
 }
 
@@ -110,7 +112,7 @@ struct TetImageLayout {
         // u32 max-depth bits per pixel (one memset)
         L.fi_key = o;      o = align_up(o + 12 * BI, 256);
         L.trail_cap = tet_trail_cap(BI);
-        L.trail = o;       o = align_up(o + 4 * BI * L.trail_cap, 256);
+        L.trail = o;       o = align_up(o + 16 * BI * L.trail_cap, 256);
         L.total = o + 256;
         return L;
     }
@@ -131,7 +133,7 @@ struct TetParams {
     const float2* jitter;         // null when ray_random_seed <= 0
     int* first_face; int* first_tet; int* last_face; int* last_tet;
     float* final_log_T; float* prev_log_T; uint32_t* n_contrib; uint8_t* active;
-    int* trail; int trail_cap;    // [trail_cap][B*W*H] face ids in march order
+    int4* trail; int trail_cap;   // [trail_cap][B*W*H] { face id | flag, t, u, v (float bits) } in march order
     unsigned long long* fi_key;   // [B*W*H] split first-intersect: per-pixel atomicMin slot
     uint32_t* fi_close;           // [B*W*H] smallest max depth (float bits) of any hit found so far
     int fi_split;                 // CTAs per tile in tet_first_intersect_kernel

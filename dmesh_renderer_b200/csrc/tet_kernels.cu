@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(128) tet_build_tetrec_kernel(
     int T, const float* __restrict__ verts, const int* __restrict__ faces, const int* __restrict__ tets,
     const int* __restrict__ face_tets, const int* __restrict__ tet_faces, TetRec* __restrict__ out)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint4 s_rec[128 * 8];   // 128 B per tet; written per thread, read back coalesced
     const int t0 = blockIdx.x * 128;
     const int t = t0 + threadIdx.x;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) tet_build_shade_kernel(
     int F, const int* __restrict__ faces, const float* __restrict__ verts_color, const float* __restrict__ faces_opacity,
     const int* __restrict__ face_tets, TetShade* __restrict__ out)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const int a = faces[3 * (size_t)f], b = faces[3 * (size_t)f + 1], c = faces[3 * (size_t)f + 2];
@@ -190,11 +192,11 @@ int tet_build_records(int P, int F, int T, const float* verts, const int* faces,
     ProfScope prof(ST_TET_RECORDS, stream);
     if (T > 0 && F > 0 && tet_rec && shade) count_launch(1);   // two kernels under one scope
     if (T > 0 && tet_rec) {
-        tet_build_tetrec_kernel<<<(T + 127) / 128, 128, 0, stream>>>(T, verts, faces, tets, face_tets, tet_faces, tet_rec);
+        DMR_CUDA(dmr_launch(tet_build_tetrec_kernel, dim3((T + 127) / 128), dim3(128), 0, stream, T, verts, faces, tets, face_tets, tet_faces, tet_rec));
         DMR_LAUNCH_CHECK("tet_build_tetrec_kernel");
     }
     if (F > 0 && shade) {
-        tet_build_shade_kernel<<<(F + 255) / 256, 256, 0, stream>>>(F, faces, verts_color, faces_opacity, face_tets, shade);
+        DMR_CUDA(dmr_launch(tet_build_shade_kernel, dim3((F + 255) / 256), dim3(256), 0, stream, F, faces, verts_color, faces_opacity, face_tets, shade));
         DMR_LAUNCH_CHECK("tet_build_shade_kernel");
     }
     return 0;
@@ -207,6 +209,7 @@ int tet_build_records(int P, int F, int T, const float* verts, const int* faces,
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tet_jitter_kernel(int BI, int W, int H, int seed, float2* __restrict__ jitter)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= BI) return;
     curandState st;
@@ -224,7 +227,7 @@ int tet_jitter(int B, int W, int H, int seed, float2* jitter, cudaStream_t strea
     int BI = B * W * H;
     if (BI <= 0) return 0;
     ProfScope prof(ST_TET_JITTER, stream);
-    tet_jitter_kernel<<<(BI + 255) / 256, 256, 0, stream>>>(BI, W, H, seed, jitter);
+    DMR_CUDA(dmr_launch(tet_jitter_kernel, dim3((BI + 255) / 256), dim3(256), 0, stream, BI, W, H, seed, jitter));
     DMR_LAUNCH_CHECK("tet_jitter_kernel");
     return 0;
 }
@@ -266,6 +269,7 @@ __device__ __forceinline__ void tet_first_finish(const TetParams& p, int b, size
 // discarded like the reference does.
 __global__ void __launch_bounds__(FI_THREADS) tet_first_intersect_kernel(TetParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint4 s_rec[FI_THREADS * 3];          // p0 p1 p2 | min_depth max_depth bbox_x
     __shared__ uint32_t s_bby[FI_THREADS];
     __shared__ int s_face[FI_THREADS];
@@ -423,6 +427,7 @@ __device__ __forceinline__ void tet_first_finish(const TetParams& p, int b, size
 // split mode: winner of the pixel's partial results -> first_face, first_tet
 __global__ void __launch_bounds__(256) tet_first_resolve_kernel(TetParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     const int b = blockIdx.z;
     const uint32_t px = blockIdx.x * 16 + (threadIdx.x & 15), py = blockIdx.y * 16 + (threadIdx.x >> 4);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
@@ -446,10 +451,10 @@ int tet_first_intersect(const TetParams& p, cudaStream_t stream)
         count_launch(1);   // two kernels under one scope
         DMR_CUDA(cudaMemsetAsync(p.fi_key, 0xff, 12 * (size_t)p.B * p.W * p.H, stream));   // fi_key + fi_close
     }
-    tet_first_intersect_kernel<<<dim3(tx, ty, p.B * p.fi_split), FI_THREADS, 0, stream>>>(p);
+    DMR_CUDA(dmr_launch(tet_first_intersect_kernel, dim3(tx, ty, p.B * p.fi_split), dim3(FI_THREADS), 0, stream, p));
     DMR_LAUNCH_CHECK("tet_first_intersect_kernel");
     if (p.fi_split > 1) {
-        tet_first_resolve_kernel<<<dim3(tx, ty, p.B), 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tet_first_resolve_kernel, dim3(tx, ty, p.B), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tet_first_resolve_kernel");
     }
     return 0;
@@ -543,6 +548,7 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
 // order (forward.cu:645-648, 667-670, 687-759).
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd_kernel(TetParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const uint32_t px = blockIdx.x * 8 + (lane & 7);
@@ -576,7 +582,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
     bool active = false;
     uint32_t n_contrib = 0;
     int curr_face = first_face, curr_tet = first_tet;
-    int* trail = p.trail + bpix;
+    int4* trail = p.trail + bpix;
     const uint32_t trail_cap = (uint32_t)p.trail_cap;
 
     while (!done) {
@@ -592,7 +598,9 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
         // up on the ray (its error case 3), leaving this and all earlier faces without gradient; the
         // replay reproduces that.  (The side we entered through always qualifies as the first candidate:
         // it passed the same hit test one step earlier and its normal sign is checked by tet_step.)
-        if (n_contrib < trail_cap) __stcs(trail + (size_t)n_contrib * BI, curr_face | (s.opposite ? (int)0x80000000u : 0));   // streaming: read once, by the backward pass
+        if (n_contrib < trail_cap)   // streaming: read once, by the backward pass
+            __stcs(trail + (size_t)n_contrib * BI, make_int4(curr_face | (s.opposite ? (int)0x80000000u : 0), __float_as_int(rt),
+                                                             __float_as_int(iu), __float_as_int(iv)));
 
         // 1. composite the current face (forward.cu:600-653)
         const float3 c0 = f3(s0.x, s0.y, s0.z), c1 = f3(s0.w, s1.x, s1.y), c2 = f3(s1.z, s1.w, s2.x);
@@ -652,7 +660,7 @@ int tet_march_forward(const TetParams& p, cudaStream_t stream)
 {
     dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
     ProfScope prof(ST_TET_FWD, stream);
-    tet_march_fwd_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
+    DMR_CUDA(dmr_launch(tet_march_fwd_kernel, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
     DMR_LAUNCH_CHECK("tet_march_fwd_kernel");
     return 0;
 }
@@ -838,52 +846,49 @@ __device__ __forceinline__ void tet_march_bwd_body(const TetParams& p)
     }
 
     // ---- part 2: replay the trail in reverse, loads one step ahead
-    const int* trail = p.trail + bpix;
-    const float* frec = reinterpret_cast<const float*>(p.face_rec + (size_t)b * p.F);
+    const int4* trail = p.trail + bpix;
     const float* fint = p.faces_intense + (size_t)b * p.F;
 
-    int face = __ldcs(trail + (size_t)k * BI) & 0x7fffffff;
-    int face_next = k > 0 ? __ldcs(trail + (size_t)(k - 1) * BI) : 0;
-    float4 q0, q1, q2, s0, s1, s2, s3;
+    int4 e = __ldcs(trail + (size_t)k * BI);
+    int4 e_next = k > 0 ? __ldcs(trail + (size_t)(k - 1) * BI) : make_int4(0, 0, 0, 0);
+    int face = e.x & 0x7fffffff;
+    float4 s0, s1, s2, s3;
     float intense;
     {
-        const float4* w4 = reinterpret_cast<const float4*>(frec + (size_t)face * 16);
-        q0 = w4[0]; q1 = w4[1]; q2 = w4[2];
         const float4* sh4 = reinterpret_cast<const float4*>(p.shade + face);
         s0 = sh4[0]; s1 = sh4[1]; s2 = sh4[2]; s3 = sh4[3];
         intense = fint[face];
     }
     for (; k >= 0; k--) {
         // issue the loads of step k-1 (face id known since the previous iteration), then work on step k
-        const int nf = face_next & 0x7fffffff;
-        const bool stop_here = face_next < 0;   // the reference's reverse march fails between step k and k-1
-        const float4* w4 = reinterpret_cast<const float4*>(frec + (size_t)nf * 16);
-        const float4 nq0 = w4[0], nq1 = w4[1], nq2 = w4[2];
+        const int nf = e_next.x & 0x7fffffff;
+        const bool stop_here = e_next.x < 0;   // the reference's reverse march fails between step k and k-1
         const float4* sh4 = reinterpret_cast<const float4*>(p.shade + nf);
         const float4 ns0 = sh4[0], ns1 = sh4[1], ns2 = sh4[2], ns3 = sh4[3];
         const float nint = fint[nf];
-        face_next = k > 1 ? __ldcs(trail + (size_t)(k - 2) * BI) : 0;
+        const int4 e_cur = e;
+        e = e_next;
+        e_next = k > 1 ? __ldcs(trail + (size_t)(k - 2) * BI) : make_int4(0, 0, 0, 0);
 
-        float3 tuv = f3(0, 0, 0);
-        ray_tri_hit(ro, rd, f3(q0.x, q0.y, q0.z), f3(q0.w, q1.x, q1.y), f3(q1.z, q1.w, q2.x), tuv);
-        tet_bwd_face<DET>(p, st, face, tuv.x, tuv.y, tuv.z, s0, s1, s2, s3, intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot,
-                     final_T, final_prev_T);
+        // (t, u, v) of the step: the forward march's own values
+        tet_bwd_face<DET>(p, st, face, __int_as_float(e_cur.y), __int_as_float(e_cur.z), __int_as_float(e_cur.w), s0, s1, s2, s3,
+                          intense, ro, rd, mv, pj, dLc, gd, bg_dot, bd_dot, final_T, final_prev_T);
 
         if (stop_here) break;
         face = nf;
-        q0 = nq0; q1 = nq1; q2 = nq2;
         s0 = ns0; s1 = ns1; s2 = ns2; s3 = ns3;
         intense = nint;
     }
 }
 
 // Once per vertex: float4 accumulator -> dL_dverts_color[P,3].
-__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams p) { tet_march_bwd_body<false>(p); }
-__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_det_kernel(TetParams p) { tet_march_bwd_body<true>(p); }
+__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_kernel(TetParams p) { griddep_wait(); tet_march_bwd_body<false>(p); }
+__global__ void __launch_bounds__(MARCH_THREADS) tet_march_bwd_det_kernel(TetParams p) { griddep_wait(); tet_march_bwd_body<true>(p); }
 
 // Deterministic mode, last step: fixed-point accumulators -> += into dL_dverts_color[P,3] and dL_dfaces_opacity[F].
 __global__ void __launch_bounds__(256) tet_det_convert_kernel(TetParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     float sv, sg;
     det_scales(*p.det_gmax, sv, sg);
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -913,6 +918,7 @@ __global__ void __launch_bounds__(256) tet_det_convert_kernel(TetParams p)
 
 __global__ void __launch_bounds__(256) tet_grad_vertex_kernel(TetParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= p.P) return;
     const float4 a = p.grad_vacc[v];
@@ -929,12 +935,12 @@ int tet_march_backward_deterministic(const TetParams& p, cudaStream_t stream)
         count_launch(1);   // two kernels under one scope
         int rc = det_gmax(p.dL_dcolor, 3 * p.B * HW, p.dL_ddepth, p.B * HW, const_cast<uint32_t*>(p.det_gmax), stream);
         if (rc) return rc;
-        tet_march_bwd_det_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tet_march_bwd_det_kernel, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
         DMR_LAUNCH_CHECK("tet_march_bwd_det_kernel");
     }
     {
         ProfScope prof(ST_TET_BWD_FINISH, stream);
-        tet_det_convert_kernel<<<(unsigned)(((size_t)p.P + p.F + 255) / 256), 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tet_det_convert_kernel, dim3((unsigned)(((size_t)p.P + p.F + 255) / 256)), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tet_det_convert_kernel");
     }
     return 0;
@@ -945,12 +951,12 @@ int tet_march_backward(const TetParams& p, cudaStream_t stream)
     dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
     {
         ProfScope prof(ST_TET_BWD, stream);
-        tet_march_bwd_kernel<<<grid, MARCH_THREADS, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tet_march_bwd_kernel, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
         DMR_LAUNCH_CHECK("tet_march_bwd_kernel");
     }
     {
         ProfScope prof(ST_TET_BWD_FINISH, stream);
-        tet_grad_vertex_kernel<<<(p.P + 255) / 256, 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tet_grad_vertex_kernel, dim3((p.P + 255) / 256), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tet_grad_vertex_kernel");
     }
     return 0;

@@ -174,6 +174,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 #endif
 __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(TriRenderParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     __shared__ uint4 s_rec[RB * 9];
     __shared__ unsigned char s_bmask[RB];         // [staged instance]: warp blocks of the tile it can touch (tile_block_mask)
     __shared__ unsigned char s_cidx[8 * HB];      // [warp][compacted position] -> position in the staged round
@@ -642,11 +643,13 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 
 __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_kernel(TriRenderParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     tri_render_bwd_body<false>(p);
 }
 
 __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_det_kernel(TriRenderParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     tri_render_bwd_body<true>(p);
 }
 
@@ -655,6 +658,7 @@ __global__ void __launch_bounds__(256, DMR_TRI_BWD_MINB) tri_render_bwd_det_kern
 __global__ void __launch_bounds__(256) det_gmax_kernel(const float* __restrict__ a, size_t na, const float* __restrict__ b,
                                                            size_t nb, uint32_t* __restrict__ gmax)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     uint32_t m = 0;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < na + nb; i += (size_t)gridDim.x * 256) {
         const float x = i < na ? a[i] : b[i - na];
@@ -754,13 +758,14 @@ __device__ __forceinline__ void tri_grad_finish_body(const TriRenderParams& p)
     p.dL_dfintense[idx] = st[8];
 }
 
-__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p) { tri_grad_finish_body<false>(p); }
-__global__ void __launch_bounds__(256) tri_grad_finish_det_kernel(TriRenderParams p) { tri_grad_finish_body<true>(p); }
+__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p) { griddep_wait(); tri_grad_finish_body<false>(p); }
+__global__ void __launch_bounds__(256) tri_grad_finish_det_kernel(TriRenderParams p) { griddep_wait(); tri_grad_finish_body<true>(p); }
 
 // Deterministic mode, last step: fixed-point accumulators -> += into the caller's fp32 gradient tensors.
 // One thread per vertex, then per (view, vertex), then per face.
 __global__ void __launch_bounds__(256) tri_det_convert_kernel(TriRenderParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     float sv, sg;
     det_scales(*p.det_gmax, sv, sg);
     const size_t P = (size_t)p.P, BP = (size_t)p.B * p.P, F = (size_t)p.F;
@@ -800,6 +805,7 @@ __global__ void __launch_bounds__(256) tri_det_convert_kernel(TriRenderParams p)
 // Once per vertex: float4 accumulators -> dL_dverts[P,3], dL_dvcolor[P,3].
 __global__ void __launch_bounds__(256) tri_grad_vertex_kernel(TriRenderParams p)
 {
+    griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= p.P) return;
     const float4 a = p.grad_vacc[v], c = p.grad_vacc[(size_t)p.P + v];
@@ -814,7 +820,7 @@ int tri_render_forward(const TriRenderParams& p, cudaStream_t stream)
     if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
     ProfScope prof(ST_TRI_FWD, stream);
-    tri_render_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+    DMR_CUDA(dmr_launch(tri_render_fwd_kernel, dim3(grid), dim3(256), 0, stream, p));
     DMR_LAUNCH_CHECK("tri_render_fwd_kernel");
     return 0;
 }
@@ -825,17 +831,17 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
     {
         ProfScope prof(ST_TRI_BWD, stream);
-        tri_render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tri_render_bwd_kernel, dim3(grid), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_render_bwd_kernel");
     }
     {
         ProfScope prof(ST_TRI_BWD_FINISH, stream);
         const size_t BF = (size_t)p.B * p.F;
-        tri_grad_finish_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tri_grad_finish_kernel, dim3((unsigned)((BF + 255) / 256)), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_grad_finish_kernel");
         if (p.grad_vacc) {
             count_launch(1);   // two kernels under one scope
-            tri_grad_vertex_kernel<<<(unsigned)((p.P + 255) / 256), 256, 0, stream>>>(p);
+            DMR_CUDA(dmr_launch(tri_grad_vertex_kernel, dim3((unsigned)((p.P + 255) / 256)), dim3(256), 0, stream, p));
             DMR_LAUNCH_CHECK("tri_grad_vertex_kernel");
         }
     }
@@ -844,7 +850,7 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
 
 int det_gmax(const float* a, size_t na, const float* b, size_t nb, uint32_t* gmax, cudaStream_t stream)
 {
-    det_gmax_kernel<<<592, 256, 0, stream>>>(a, na, b, nb, gmax);
+    DMR_CUDA(dmr_launch(det_gmax_kernel, dim3(592), dim3(256), 0, stream, a, na, b, nb, gmax));
     DMR_LAUNCH_CHECK("det_gmax_kernel");
     return 0;
 }
@@ -859,16 +865,16 @@ int tri_render_backward_deterministic(const TriRenderParams& p, cudaStream_t str
         count_launch(1);   // two kernels under one scope
         int rc = det_gmax(p.dL_dcolor, 3 * p.B * HW, p.dL_ddepth, p.B * HW, const_cast<uint32_t*>(p.det_gmax), stream);
         if (rc) return rc;
-        tri_render_bwd_det_kernel<<<grid, 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tri_render_bwd_det_kernel, dim3(grid), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_render_bwd_det_kernel");
     }
     {
         ProfScope prof(ST_TRI_BWD_FINISH, stream);
         count_launch(1);
-        tri_grad_finish_det_kernel<<<(unsigned)((BF + 255) / 256), 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tri_grad_finish_det_kernel, dim3((unsigned)((BF + 255) / 256)), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_grad_finish_det_kernel");
         const size_t n = (size_t)p.P + (size_t)p.B * p.P + (size_t)p.F;
-        tri_det_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+        DMR_CUDA(dmr_launch(tri_det_convert_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_det_convert_kernel");
     }
     return 0;

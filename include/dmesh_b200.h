@@ -128,6 +128,13 @@ int dmr_tri_depth_chain(int B, int P, const float* verts, const float* mv_mats, 
 /* the ranges memset + identifyTileRanges (102-124, 330-337),                */
 /* generateRaysCUDA (forward.cu:184-231) and renderCUDA (forward.cu:257-489).*/
 /* out_color [B,3,H,W], out_depth [B,1,H,W] are fully written.               */
+/* `R` = the number of instances `binning_buffer` was sized and is laid out  */
+/* for (dmr_binning_bytes(R)): num_rendered itself, or any larger capacity.  */
+/* The kernels read the real instance count on the device (the scan's total  */
+/* in `face_buffer`), so this call may be enqueued BEFORE num_rendered has   */
+/* reached the host.  If the real count exceeds R nothing is emitted (all    */
+/* tile ranges empty, background image): call again with a buffer that fits. */
+/* Pass the same R to dmr_tri_backward.                                      */
 /* ------------------------------------------------------------------------ */
 int dmr_tri_forward_render(
     int B, int P, int F, int W, int H, int R,
