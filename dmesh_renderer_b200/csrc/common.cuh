@@ -193,6 +193,10 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
 // bit-identical, including the reference's overflow behaviour.  A degenerate
 // triangle (area == 0) is encoded as ea=eb=ec=0 (never covered).
 // ---------------------------------------------------------------------------
+// (Measured and rejected, round 2: splitting the record in HBM into a 64-byte per-(view, face) part and a 96-byte
+// per-face part shared by the views of a call, L2-resident at C4.  The face-preprocess kernel got 27 % faster at 8
+// views (383 -> 279 us) and tri_grad_finish 7 %, but staging an instance from two arrays cost the render kernels
+// more than that: forward 1842 -> 2033 us, backward 3684 -> 3792 us at C4, forward 420 -> 467 us at C5.)
 struct __align__(16) TriRecord {
     // q0..q2: hot part (coverage test)
     uint32_t ea0, eb0, ec0; float opacity;
