@@ -152,7 +152,12 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 // products and four dots.  -4 % forward, -3 % backward at C4, but it is the same real number with DIFFERENT roundings:
 // for triangles seen edge-on (det tiny against |E1||E2|) the reference's own (u, v) carry a large relative error, and
 // only the reference's exact operation order reproduces it.  C1, C2 and C4 stayed within 1e-5; C5 (4 M triangles,
-// thousands of slivers per image) differed by up to 7e-4 in colour.  Parity wins: ray_tri_tuv stays.)
+// thousands of slivers per image) differed by up to 7e-4 in colour.  Parity wins: ray_tri_tuv stays.
+// Second attempt, also rejected: hoisting only the pixel-independent HALF of ray_tri_tuv (T = ro - p0, E1, E2, T x E1
+// are per (view, face)) into the staging code, same operations on the same operands.  The compiler fuses a*b - c*d
+// either way round depending on context, so the hoisted cross product first differed from the reference by an ulp
+// (C5 failed again); with every dot / cross pinned to explicit fma forms parity held at all configs -- but the 15
+// instructions saved per hit bought nothing: forward 1840 -> 1886 us, backward 3677 -> 3689 us at C4.)
 
 // Forward.  Per round of RB staged instances every warp works through its 8x4 pixel block in passes of HB
 // instances:

@@ -37,15 +37,20 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
+# ncu picks a unit per column and report (us / ms, Mbyte / Gbyte ...): normalise to microseconds and megabytes
+SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}
+NORM = {"duration_us": "us", "dram_read": "Mbyte", "dram_write": "Mbyte"}
 with open(out, "w", newline="") as f:
     w = csv.writer(f)
-    w.writerow([n for _, n in WANT] + ["units: " + "; ".join("%s=%s" % (n, units[idx[m]]) for m, n in WANT if m in idx and units[idx[m]])])
+    w.writerow([n for _, n in WANT] + ["units: duration_us=us; dram_read=Mbyte; dram_write=Mbyte; percentages in %; stall_* = warps per issue-active cycle"])
     for r in rows[2:]:
         vals = []
         for m, n in WANT:
             v = r[idx[m]] if m in idx else ""
             if n == "kernel":
                 v = v.split("(")[0].replace("dmr::", "")
+            elif n in NORM and v:
+                v = "%.6g" % (float(v.replace(",", "")) * SCALE.get(units[idx[m]], 1.0))
             vals.append(v)
         w.writerow(vals)
 print("wrote", out, len(rows) - 2, "launches")
