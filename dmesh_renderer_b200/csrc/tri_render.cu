@@ -369,8 +369,11 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 // 8 lanes 537 / 1172 / 7808, 4 lanes 476 / 1079 / 6752, 2 lanes 459 / 1057 / 6532.  One lane per group would need
 // no shuffles at all but 6 vector reductions per covered pixel, which the LSU/L2 cannot sustain
 // (tools/ubench_red.cu).
+// Resident CTAs per SM.  3 (80 registers, no spills) against 4 (64 registers, 80 bytes of spill): the kernel issues
+// on only ~64 % of the cycles with 5.6 warps per scheduler and its stalls spread evenly over memory, barrier and
+// dependency waits, so two more warps per scheduler win slightly -- C4 3677 -> 3640 us, C5 788 -> 766 us, C2 291 -> 289 us.
 #ifndef DMR_TRI_BWD_MINB
-#define DMR_TRI_BWD_MINB 3
+#define DMR_TRI_BWD_MINB 4
 #endif
 // 1 = form 1/(1-alpha) once per staged instance and multiply, instead of the reference's two divisions per covered
 // pixel (backward.cu:244-252, 299-308).  Changes T and the background term by an ulp per step.

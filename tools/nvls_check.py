@@ -16,7 +16,8 @@ rank, local, ws = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-P, F = 600_000, 200_000    # C2
+# scene size: C2 by default, `nvls_check.py C4` for the 76 MB buffer of the multi-view configuration
+P, F = (3_000_000, 1_000_000) if len(sys.argv) > 1 and sys.argv[1] == "C4" else (600_000, 200_000)
 g = PackedSceneGrads(torch.zeros(P, 3, device=dev), torch.zeros(P, 3, device=dev), torch.zeros(F, device=dev))
 if rank == 0:
     print("NVLS path:", g._nvls is not None, "| collective:", g.collective, "| floats", g.flat.numel(), "padded", g._full.numel(), flush=True)
