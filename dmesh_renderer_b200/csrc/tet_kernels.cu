@@ -24,9 +24,10 @@ namespace dmr {
 // dot / cross with the contraction nvcc applies to cuda_math.h:1524-1527, 1696-1699 written out
 // (fma(z,z', fma(x,x', y*y')) and fma(a,b,-(c*d)), the same forms oracle/oracle.cpp pins): every call
 // site then yields the SAME bits for the same inputs, whatever the surrounding code.  The backward
-// pass depends on that: it recomputes (t,u,v) of a face from the trail with the hit test below and
-// must get what the forward march got (the depth term (pd - accum_recd) of the opacity gradient
-// amplifies a one-ulp change of t by 1e3..1e4).
+// pass depends on that wherever it recomputes (t,u,v) of a face with the hit test below (the last face of a
+// ray, and the re-march beyond the trail): it must get what the forward march got -- the depth term
+// (pd - accum_recd) of the opacity gradient amplifies a one-ulp change of t by 1e3..1e4.  (The recorded part of
+// a ray replays the forward pass's own (t,u,v) from the trail.)
 __device__ __forceinline__ float dot3p(float3 a, float3 b)
 {
     return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
@@ -466,7 +467,10 @@ int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 // The march is independent per pixel (no shared memory, no tile lists) and its cost per ray has a
 // long tail (rays along the cube diagonal cross several times more faces than the mean), so it is
 // launched as many small CTAs: 64 threads = 8x8 pixels = two 8x4 warps.
+#ifndef MARCH_THREADS
 #define MARCH_THREADS 64
+#endif
+#define MARCH_ROWS (MARCH_THREADS / 8)   // pixel rows of a CTA: 8 columns x 4 rows per warp
 // 12 CTAs/SM = 80 registers (measured at C3: uncapped 103 regs 875 us, 80 regs 838 us, 64 regs + spills 947 us)
 #ifndef MARCH_MIN_BLOCKS
 #define MARCH_MIN_BLOCKS 12
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const uint32_t px = blockIdx.x * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * 8 + warp * 4 + (lane >> 3);
+    const uint32_t py = blockIdx.y * MARCH_ROWS + warp * 4 + (lane >> 3);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
     const size_t HW = (size_t)p.W * p.H;
     const size_t BI = (size_t)p.B * HW;
@@ -658,7 +662,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
 
 int tet_march_forward(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
+    dim3 grid((p.W + 7) / 8, (p.H + MARCH_ROWS - 1) / MARCH_ROWS, p.B);
     ProfScope prof(ST_TET_FWD, stream);
     DMR_CUDA(dmr_launch(tet_march_fwd_kernel, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
     DMR_LAUNCH_CHECK("tet_march_fwd_kernel");
@@ -756,9 +760,8 @@ __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st
 }
 
 // Backward march.  Steps recorded in the face trail (all of them unless a ray composited more than
-// trail_cap faces) are replayed in reverse: face id from the trail (coalesced), (t,u,v) from the same
-// hit test on the same vertices the forward pass used, all loads independent of the previous step and
-// issued one step ahead.  Steps beyond the cap are re-marched through the adjacency records exactly like
+// trail_cap faces) are replayed in reverse: face id and the forward pass's own (t,u,v) from the trail
+// (one coalesced 16-byte load), all loads independent of the previous step and issued one step ahead.  Steps beyond the cap are re-marched through the adjacency records exactly like
 // the reference (backward.cu:382-477) until the recorded part is reached.
 template <bool DET>
 __device__ __forceinline__ void tet_march_bwd_body(const TetParams& p)
@@ -766,7 +769,7 @@ __device__ __forceinline__ void tet_march_bwd_body(const TetParams& p)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const uint32_t px = blockIdx.x * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * 8 + warp * 4 + (lane >> 3);
+    const uint32_t py = blockIdx.y * MARCH_ROWS + warp * 4 + (lane >> 3);
     if (!(px < (uint32_t)p.W && py < (uint32_t)p.H)) return;
     const size_t HW = (size_t)p.W * p.H;
     const size_t BI = (size_t)p.B * HW;
@@ -928,7 +931,7 @@ __global__ void __launch_bounds__(256) tet_grad_vertex_kernel(TetParams p)
 
 int tet_march_backward_deterministic(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
+    dim3 grid((p.W + 7) / 8, (p.H + MARCH_ROWS - 1) / MARCH_ROWS, p.B);
     const size_t HW = (size_t)p.W * p.H;
     {
         ProfScope prof(ST_TET_BWD, stream);
@@ -948,7 +951,7 @@ int tet_march_backward_deterministic(const TetParams& p, cudaStream_t stream)
 
 int tet_march_backward(const TetParams& p, cudaStream_t stream)
 {
-    dim3 grid((p.W + 7) / 8, (p.H + 7) / 8, p.B);
+    dim3 grid((p.W + 7) / 8, (p.H + MARCH_ROWS - 1) / MARCH_ROWS, p.B);
     {
         ProfScope prof(ST_TET_BWD, stream);
         DMR_CUDA(dmr_launch(tet_march_bwd_kernel, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));

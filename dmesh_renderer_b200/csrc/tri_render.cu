@@ -9,15 +9,14 @@
 // block.  Instances of the tile are staged in shared memory as 144-byte
 // TriRecords (one contiguous copy per instance).
 //
-// Hierarchical coverage: for every group of 32 staged instances each lane
-// first tests ONE instance against the warp's whole 8x4 block (minimum of each
-// edge function over the block, exact because the record is flagged overflow-
-// free); the ballot of survivors is then walked in list order and only those
-// instances are tested per pixel.  The per-pixel test is the affine edge form
-// documented at TriRecord (bit-identical to in_tri); the shading arithmetic
-// keeps the reference's expression order so that T, the early-termination
-// decision and n_contrib are reproduced exactly.  Rays are recomputed per
-// pixel (the reference stores 24 B/px and reads them back twice).
+// Coverage, in both kernels: the thread that stages an instance decides once which of the tile's eight warp
+// blocks it can touch (tile_block_mask: block bbox of the record + minimum of each edge function over a block,
+// exact because the record is flagged overflow-free); every warp compacts its survivors in list order; ONE LANE
+// PER SURVIVOR then evaluates the exact coverage of all 32 pixels of the block (block_coverage, the affine edge
+// form documented at TriRecord, bit-identical to in_tri) and a 32x32 bit transpose across the warp turns the
+// instance rows into one mask per pixel.  The shading arithmetic keeps the reference's expression order so that
+// T, the early-termination decision and n_contrib are reproduced exactly.  Rays are recomputed per pixel (the
+// reference stores 24 B/px and reads them back twice).
 //
 // Backward: see the design note above tri_render_bwd_kernel (sub-warp groups,
 // sufficient statistics for the vertex-position gradient, transpose-reduction,
