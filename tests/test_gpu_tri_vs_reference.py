@@ -344,3 +344,43 @@ def test_deterministic_mode_default_switch_and_gradient_sink():
             assert torch.equal(a, leaf.grad)          # 0 + x == x
     finally:
         pkg.set_deterministic(old)
+
+
+def test_speculative_phase2_when_the_scene_vanishes_and_two_calls_in_flight():
+    """Round-2 host logic on the GPU: (1) a call whose instance count drops to ZERO while phase 2 was launched
+    speculatively on a buffer sized from the previous call must give the background image and zero gradients;
+    (2) two forward calls between their two phases own separate pinned num_rendered words: finishing
+    them in the opposite order must give each its own result."""
+    dev = "cuda"
+    a = scenes.to_device(scenes.random_tri_scene("inflight_a", 51, 3000, 0.08, 128, 160, B=2), dev)
+    b = scenes.to_device(scenes.random_tri_scene("inflight_b", 52, 3000, 0.03, 128, 160, B=2), dev)   # same shapes, fewer instances
+    renderer = TriRenderer(TriRenderSettings(a.H, a.W, a.bg))
+    # (1)
+    leaves = [a.verts.clone().requires_grad_(), a.verts_color.clone().requires_grad_(), a.faces_opacity.clone().requires_grad_()]
+    c0, d0 = renderer(leaves[0], a.faces, leaves[1], leaves[2], a.mv_mats, a.proj_mats, a.verts_depth, a.faces_intense)
+    far = (a.verts * 0.01 + torch.tensor([3.0, 2.0, 10.0], device=dev) * 3).requires_grad_()      # behind the camera
+    c1, d1 = renderer(far, a.faces, leaves[1], leaves[2], a.mv_mats, a.proj_mats, a.verts_depth, a.faces_intense)
+    assert torch.equal(c1, torch.ones_like(c1)) and torch.equal(d1, torch.ones_like(d1))
+    torch.autograd.backward([c1, d1], [torch.ones_like(c1), torch.ones_like(d1)])
+    assert float(far.grad.abs().max()) == 0.0 and float(leaves[1].grad.abs().max()) == 0.0
+    c2, d2 = renderer(leaves[0], a.faces, leaves[1], leaves[2], a.mv_mats, a.proj_mats, a.verts_depth, a.faces_intense)
+    assert torch.equal(c2, c0) and torch.equal(d2, d0)       # and the next call grows back past the zero capacity
+    # (2)
+    def args(s):
+        mv, pj = s.mv_mats.transpose(1, 2), s.proj_mats.transpose(1, 2)
+        return (s.bg, s.verts, s.faces, s.verts_color, s.faces_opacity, mv, pj), (torch.inverse(mv), torch.inverse(pj)), \
+               (s.verts_depth, s.faces_intense, s.H, s.W)
+    outs = {}
+    for name, s in (("a", a), ("b", b)):
+        x, inv, y = args(s)
+        outs[name] = _C.render_tris(*x, *inv, *y)
+    xa, ia, ya = args(a)
+    xb, ib, yb = args(b)
+    pa = _C.tri_forward_begin(*xa, *ya)
+    pb = _C.tri_forward_begin(*xb, *yb)
+    assert pa.pinned is not pb.pinned and pa.pinned[2].value != pb.pinned[2].value
+    rb = _C.tri_forward_finish(pb, *ib)
+    ra = _C.tri_forward_finish(pa, *ia)
+    assert ra[0] == outs["a"][0] and rb[0] == outs["b"][0] and ra[0] != rb[0]
+    assert torch.equal(ra[1], outs["a"][1]) and torch.equal(rb[1], outs["b"][1])
+    assert torch.equal(ra[2], outs["a"][2]) and torch.equal(rb[2], outs["b"][2])
