@@ -204,9 +204,10 @@ struct __align__(16) TriRecord {
     uint32_t ea2, eb2, ec2; uint32_t flags;   // bit 0: edge values cannot overflow on screen; bits 1..27: block bbox (below)
     // q3..q8: shading part
     float v0[3], v1[3], v2[3];                // world positions
+    int   i0, i1, i2;                         // vertex ids (gradient scatter) -- next to the positions: tri_grad_finish_kernel
+                                              // reads exactly these 48 bytes = sectors 1 and 2 of the record
     float c0[3], c1[3], c2[3];                // vertex colours
     float d0, d1, d2;                         // per-view vertex depths
-    int   i0, i1, i2;                         // vertex ids (gradient scatter)
 };
 static_assert(sizeof(TriRecord) == 144, "TriRecord must be 9 x 16 bytes");
 #define DMR_REC_WORDS 36

@@ -278,10 +278,10 @@ __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
         float w[24];
         w[0] = q0[0]; w[1] = q0[1]; w[2] = q0[2]; w[3] = q1[0]; w[4] = q1[1]; w[5] = q1[2];
         w[6] = q2[0]; w[7] = q2[1]; w[8] = q2[2];
-        w[9] = k0[0]; w[10] = k0[1]; w[11] = k0[2]; w[12] = k1[0]; w[13] = k1[1]; w[14] = k1[2];
-        w[15] = k2[0]; w[16] = k2[1]; w[17] = k2[2];
-        w[18] = a0.w; w[19] = a1.w; w[20] = a2.w;
-        w[21] = __int_as_float(i0); w[22] = __int_as_float(i1); w[23] = __int_as_float(i2);
+        w[9] = __int_as_float(i0); w[10] = __int_as_float(i1); w[11] = __int_as_float(i2);
+        w[12] = k0[0]; w[13] = k0[1]; w[14] = k0[2]; w[15] = k1[0]; w[16] = k1[1]; w[17] = k1[2];
+        w[18] = k2[0]; w[19] = k2[1]; w[20] = k2[2];
+        w[21] = a0.w; w[22] = a1.w; w[23] = a2.w;
 #pragma unroll
         for (int q = 0; q < 6; q++)
             r[3 + q] = make_uint4(__float_as_uint(w[4 * q]), __float_as_uint(w[4 * q + 1]), __float_as_uint(w[4 * q + 2]),

@@ -274,10 +274,10 @@ __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(T
                         float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
                         const float intense = __uint_as_float(e1.w);
                         // forward.cu:442-451
-                        float c0_ = i0 * w[9] + i1 * w[12] + i2 * w[15];  c0_ = c0_ * intense;
-                        float c1_ = i0 * w[10] + i1 * w[13] + i2 * w[16]; c1_ = c1_ * intense;
-                        float c2_ = i0 * w[11] + i1 * w[14] + i2 * w[17]; c2_ = c2_ * intense;
-                        float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
+                        float c0_ = i0 * w[12] + i1 * w[15] + i2 * w[18];  c0_ = c0_ * intense;
+                        float c1_ = i0 * w[13] + i1 * w[16] + i2 * w[19]; c1_ = c1_ * intense;
+                        float c2_ = i0 * w[14] + i1 * w[17] + i2 * w[20]; c2_ = c2_ * intense;
+                        float iD = i0 * w[21] + i1 * w[22] + i2 * w[23];
                         const float alpha = __uint_as_float(e0.w);
                         float test_T = T * (1 - alpha);
                         C0 += c0_ * alpha * T;
@@ -456,8 +456,8 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                 uint4 q[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) q[k] = src[k];
-                q[8].y = face;                                                        // w[21]
-                q[8].z = __float_as_uint(1.0f / (1.0f - __uint_as_float(q[0].w)));    // w[22]
+                q[5].y = face;                                                        // w[9]
+                q[5].z = __float_as_uint(1.0f / (1.0f - __uint_as_float(q[0].w)));    // w[10]
 #pragma unroll
                 for (int k = 0; k < 9; k++) dst[k] = q[k];
                 bm = tile_block_mask(q[0], q[1], q[2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
@@ -545,15 +545,15 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         const float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
                         const float intense = __uint_as_float(e1.w);
                         const float alpha = __uint_as_float(e0.w);
-                        const float raw0 = i0 * w[9] + i1 * w[12] + i2 * w[15];
-                        const float raw1 = i0 * w[10] + i1 * w[13] + i2 * w[16];
-                        const float raw2 = i0 * w[11] + i1 * w[14] + i2 * w[17];
+                        const float raw0 = i0 * w[12] + i1 * w[15] + i2 * w[18];
+                        const float raw1 = i0 * w[13] + i1 * w[16] + i2 * w[19];
+                        const float raw2 = i0 * w[14] + i1 * w[17] + i2 * w[20];
                         const float iC0 = raw0 * intense, iC1 = raw1 * intense, iC2 = raw2 * intense;
-                        const float iD = i0 * w[18] + i1 * w[19] + i2 * w[20];
+                        const float iD = i0 * w[21] + i1 * w[22] + i2 * w[23];
 
                         // backward.cu:244-252
 #if DMR_TRI_BWD_RCP_ALPHA
-                        const float rcpa = w[22];
+                        const float rcpa = w[10];
                         if (!T_first) T = T * rcpa;
 #else
                         if (!T_first) T = T / (1.f - alpha);
@@ -592,9 +592,9 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         // dic*intense is formed once (the reference multiplies (x*dic)*intense per term: one
                         // rounding apart, far inside the 1e-4 gradient tolerance).
                         const float dI0 = dic0 * intense, dI1 = dic1 * intense, dI2 = dic2 * intense;
-                        const float dL_di0 = w[9] * dI0 + w[10] * dI1 + w[11] * dI2 + w[18] * did;
-                        const float dL_di1 = w[12] * dI0 + w[13] * dI1 + w[14] * dI2 + w[19] * did;
-                        const float dL_di2 = w[15] * dI0 + w[16] * dI1 + w[17] * dI2 + w[20] * did;
+                        const float dL_di0 = w[12] * dI0 + w[13] * dI1 + w[14] * dI2 + w[21] * did;
+                        const float dL_di1 = w[15] * dI0 + w[16] * dI1 + w[17] * dI2 + w[22] * did;
+                        const float dL_di2 = w[18] * dI0 + w[19] * dI1 + w[20] * dI2 + w[23] * did;
                         v[12] = i0 * dI0; v[13] = i0 * dI1; v[14] = i0 * dI2;
                         v[15] = i1 * dI0; v[16] = i1 * dI1; v[17] = i1 * dI2;
                         v[18] = i2 * dI0; v[19] = i2 * dI1; v[20] = i2 * dI2;
@@ -627,7 +627,7 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                     if (have) {
                         // fixed-point record in LOGICAL order: this lane holds sums 12*cls .. 12*cls+11
                         const int cls = lane & 1;
-                        long long* rec = p.det_stats + ((size_t)b * p.F + s_rec[j * 9 + 8].y) * 24 + 12 * cls;
+                        long long* rec = p.det_stats + ((size_t)b * p.F + s_rec[j * 9 + 5].y) * 24 + 12 * cls;
 #pragma unroll
                         for (int k = 0; k < 12; k++) {
                             if (cls == 1 && k >= 9) break;                       // logical 21..23: padding
@@ -635,7 +635,7 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         }
                     }
                 } else if (have) {
-                    float* rec = stats + ((size_t)b * p.F + s_rec[j * 9 + 8].y) * 24;
+                    float* rec = stats + ((size_t)b * p.F + s_rec[j * 9 + 5].y) * 24;
                     const int cls = lane & 1;
                     // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
                     red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
@@ -716,7 +716,7 @@ __device__ __forceinline__ void tri_grad_finish_body(const TriRenderParams& p)
     const size_t f = idx - (size_t)b * p.F;
     const float* w = reinterpret_cast<const float*>(p.records + idx) + 12;
     const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
-    const int vi[3] = { __float_as_int(w[21]), __float_as_int(w[22]), __float_as_int(w[23]) };
+    const int vi[3] = { __float_as_int(w[9]), __float_as_int(w[10]), __float_as_int(w[11]) };   // next to the positions: 2 sectors per record
     const float* imv = p.inv_mv + 16 * b;
     const float3 ro = f3(imv[12], imv[13], imv[14]);
     const float3 T = ro - v0, E1 = v1 - v0, E2 = v2 - v0;
