@@ -301,8 +301,10 @@ static int tri_backward_impl(int B, int P, int F, int W, int H, int R, const flo
         return DMR_EINVAL;
     }
     p.grad_stats = at<float>(workspace, WL.grad_stats);
-    // per-vertex vector accumulators only when there are at least two (view, face) records per vertex
-    const bool use_vacc = (size_t)B * F >= 2 * (size_t)P;
+    // per-vertex vector accumulators only when the vertices are shared (the finish kernel scatters once per FACE, the
+    // views already summed: 3F vertex references; from ~4 references per vertex two vector reductions + the fold
+    // kernel beat six scalar atomics per reference)
+    const bool use_vacc = 3 * (size_t)F >= 4 * (size_t)P;
     p.grad_vacc = use_vacc ? at<float4>(workspace, WL.grad_vacc) : nullptr;
     DMR_CUDA(cudaMemsetAsync(workspace, 0, use_vacc ? WL.total - 256 : WL.stats_end, stream));
     return tri_render_backward(p, stream);

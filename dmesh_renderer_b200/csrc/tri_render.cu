@@ -146,6 +146,14 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 #endif
 #define HS (HB / 32)     // 32-entry slices of the compacted list of such a pass
 
+// (Measured and rejected, round 2: L2 prefetch -- prefetch.global.L2, SASS CCTL.E.PF2, one per 32-byte sector -- of the
+// record each thread stages in the NEXT round and of the first round of the tile two waves of CTAs later in the grid.
+// ncu had 24 % of the forward kernel's warp samples at the staging loads and the barrier behind them (a dependent
+// chain range -> face id -> scattered 144-byte gather that misses L2 half of the time), but the prefetches cost more
+// than the latency they hide: C4 forward 1833 -> 1903 us, backward 3602 -> 3766 us; C5 forward 443 -> 822 us.  The
+// bulk form cp.async.bulk.prefetch.L2 is a uniform-datapath instruction -- per-lane addresses compile to a
+// 32-iteration loop around it.)
+
 // (Measured and rejected, round 2: per-(view, face) constants of the ray-triangle system -- E2 x E1, E2 x T, T x E1 formed
 // once per staged instance, so that a covered pixel needs three dot products instead of Moeller-Trumbore's two cross
 // products and four dots.  -4 % forward, -3 % backward at C4, but it is the same real number with DIFFERENT roundings:
@@ -676,97 +684,125 @@ __global__ void __launch_bounds__(256) det_gmax_kernel(const float* __restrict__
     if ((threadIdx.x & 31) == 0 && m != 0) atomicMax(gmax, m);
 }
 
-// Once per (view, face): statistics -> gradients of the five inputs (see tri_render_bwd_kernel).
-template <bool DET>
+// Once per FACE: statistics of all views -> gradients of the five inputs (see tri_render_bwd_kernel).
+// One thread owns face f and walks its B statistics records (view-major, 96 B each, independent loads): the
+// vertex-position and colour gradients of the views are summed in registers and scattered to the three vertices
+// ONCE, the world-space triangle (48 B of the record; identical in every view's record) is read once, from view 0.
+// The first version ran one thread per (view, face): at C4 (8 views per call) it re-read the triangle and
+// re-scattered to the same vertices eight times -- 2.46 GB read + 0.73 GB written, HBM-bound at 520 us.
+template <bool DET, bool MULTI>   // MULTI = false: B == 1 (no view loop, no accumulators: 54 instead of 74 registers)
 __device__ __forceinline__ void tri_grad_finish_body(const TriRenderParams& p)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t BF = (size_t)p.B * p.F;
-    if (idx >= BF) return;
-    float st[24];
-    bool any = false;
+    const int nviews = MULTI ? p.B : 1;
+    const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= (size_t)p.F) return;
     float det_sv = 0.0f, det_sg = 0.0f;
+    double iv = 0.0, ig = 0.0;
     if (DET) {
         det_scales(*p.det_gmax, det_sv, det_sg);
-        if (det_nonfinite(*p.det_gmax)) { p.dL_dfintense[idx] = __int_as_float(0x7fc00000); return; }
+        if (det_nonfinite(*p.det_gmax)) {
+            for (int b = 0; b < nviews; b++) p.dL_dfintense[(size_t)b * p.F + f] = __int_as_float(0x7fc00000);
+            return;
+        }
         if (det_sv == 0.0f) return;
-        const double iv = 1.0 / (double)det_sv, ig = 1.0 / (double)det_sg;
-        const long long* r = p.det_stats + idx * 24;
-#pragma unroll
-        for (int i = 0; i < 21; i++) {
-            const long long q = r[i];
-            any = any || q != 0;
-            st[i] = (float)((double)q * (i < 7 ? ig : iv));
-        }
-        st[21] = st[22] = st[23] = 0.0f;
-    } else {
-        const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + idx * 24);
-        float sm[24];
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-            float4 t = st4[q];
-            sm[4 * q] = t.x; sm[4 * q + 1] = t.y; sm[4 * q + 2] = t.z; sm[4 * q + 3] = t.w;
-            any = any || t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < 24; i++) st[i] = sm[stat_slot(i)];
+        iv = 1.0 / (double)det_sv; ig = 1.0 / (double)det_sg;
     }
-    if (!any) return;
-    const int b = (int)(idx / (size_t)p.F);
-    const size_t f = idx - (size_t)b * p.F;
-    const float* w = reinterpret_cast<const float*>(p.records + idx) + 12;
-    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
-    const int vi[3] = { __float_as_int(w[9]), __float_as_int(w[10]), __float_as_int(w[11]) };   // next to the positions: 2 sectors per record
-    const float* imv = p.inv_mv + 16 * b;
-    const float3 ro = f3(imv[12], imv[13], imv[14]);
-    const float3 T = ro - v0, E1 = v1 - v0, E2 = v2 - v0;
-    const float3 S1 = f3(st[0], st[1], st[2]), S24 = f3(st[3], st[4], st[5]);
-    const float S3 = st[6];
-    const float3 gE1 = S3 * cross3(E2, T) - cross3(S24, E2);
-    const float3 gE2 = cross3(T, S1) - cross3(E1, S24) + S3 * cross3(T, E1);
-    const float3 gT = cross3(S1, E2) + S3 * cross3(E1, E2);
-    const float3 dp[3] = { -gE1 - gE2 - gT, gE1, gE2 };
-    // The reference scatters 6 scalar atomics per vertex here (backward.cu:389-407); two 16-byte vector
-    // reductions into float4-per-vertex accumulators cost a third of the lane-operations
-    // (tri_grad_vertex_kernel folds them into dL_dverts / dL_dvcolor [P,3]).
-    // Used when there are many (view, face) records per vertex (multi-view batches, shared vertices): the
-    // accumulators cost 56 B of extra streaming per VERTEX (C4, 8 views: finish 705 -> 536 us; C5 with one
-    // view of 12 M unshared vertices: 92 -> 175 us, hence the switch in tri_render_backward).
-    if (DET) {
+    bool have_tri = false;
+    float3 v0 = f3(0, 0, 0), E1 = f3(0, 0, 0), E2 = f3(0, 0, 0);
+    int vi[3] = { 0, 0, 0 };
+    float3 dps[3] = { f3(0, 0, 0), f3(0, 0, 0), f3(0, 0, 0) };   // sum over views of dL_dp0..2
+    float cs[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };                  // ... of dL_dcolor[3][3]
+    float opa = 0.0f;                                             // ... of dL_dopacity
+    for (int b = 0; b < nviews; b++) {
+        const size_t idx = (size_t)b * p.F + f;
+        float st[24];
+        bool any = false;
+        if (DET) {
+            const long long* r = p.det_stats + idx * 24;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            long long* a = p.det_vert + 8 * (size_t)vi[k];
-            det_add(a + 0, dp[k].x, det_sg); det_add(a + 1, dp[k].y, det_sg); det_add(a + 2, dp[k].z, det_sg);
-            det_add(a + 4, st[12 + 3 * k], det_sv); det_add(a + 5, st[13 + 3 * k], det_sv); det_add(a + 6, st[14 + 3 * k], det_sv);
-            det_add(p.det_vdepth + (size_t)b * p.P + vi[k], st[9 + k], det_sv);
+            for (int i = 0; i < 21; i++) {
+                const long long q = r[i];
+                any = any || q != 0;
+                st[i] = (float)((double)q * (i < 7 ? ig : iv));
+            }
+            st[21] = st[22] = st[23] = 0.0f;
+        } else {
+            const float4* st4 = reinterpret_cast<const float4*>(p.grad_stats + idx * 24);
+            float sm[24];
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                float4 t = st4[q];
+                sm[4 * q] = t.x; sm[4 * q + 1] = t.y; sm[4 * q + 2] = t.z; sm[4 * q + 3] = t.w;
+                any = any || t.x != 0.0f || t.y != 0.0f || t.z != 0.0f || t.w != 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 24; i++) st[i] = sm[stat_slot(i)];
         }
-        det_add(p.det_fopa + f, st[7], det_sv);
+        if (!any) continue;
+        if (!have_tri) {
+            const float* w = reinterpret_cast<const float*>(p.records + f) + 12;   // view 0's record: 2 sectors
+            v0 = f3(w[0], w[1], w[2]);
+            E1 = f3(w[3], w[4], w[5]) - v0; E2 = f3(w[6], w[7], w[8]) - v0;
+            vi[0] = __float_as_int(w[9]); vi[1] = __float_as_int(w[10]); vi[2] = __float_as_int(w[11]);
+            have_tri = true;
+        }
+        const float* imv = p.inv_mv + 16 * b;
+        const float3 T = f3(imv[12], imv[13], imv[14]) - v0;
+        const float3 S1 = f3(st[0], st[1], st[2]), S24 = f3(st[3], st[4], st[5]);
+        const float S3 = st[6];
+        const float3 gE1 = S3 * cross3(E2, T) - cross3(S24, E2);
+        const float3 gE2 = cross3(T, S1) - cross3(E1, S24) + S3 * cross3(T, E1);
+        const float3 gT = cross3(S1, E2) + S3 * cross3(E1, E2);
+        const float3 dp[3] = { -gE1 - gE2 - gT, gE1, gE2 };
         p.dL_dfintense[idx] = st[8];
-        return;
+        if constexpr (DET) {
+            // fixed-point accumulators: every view's terms are added as before (integer adds commute)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                long long* a = p.det_vert + 8 * (size_t)vi[k];
+                det_add(a + 0, dp[k].x, det_sg); det_add(a + 1, dp[k].y, det_sg); det_add(a + 2, dp[k].z, det_sg);
+                det_add(a + 4, st[12 + 3 * k], det_sv); det_add(a + 5, st[13 + 3 * k], det_sv); det_add(a + 6, st[14 + 3 * k], det_sv);
+                det_add(p.det_vdepth + (size_t)b * p.P + vi[k], st[9 + k], det_sv);
+            }
+            det_add(p.det_fopa + f, st[7], det_sv);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                dps[k] = dps[k] + dp[k];
+                cs[3 * k] += st[12 + 3 * k]; cs[3 * k + 1] += st[13 + 3 * k]; cs[3 * k + 2] += st[14 + 3 * k];
+                atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+            }
+            opa += st[7];
+        }
     }
+    if constexpr (DET) return;
+    if (!have_tri) return;
+    // The reference scatters 6 scalar atomics per vertex and covered pixel here (backward.cu:389-407).  With many
+    // faces per vertex two 16-byte vector reductions into float4-per-vertex accumulators cost a third of the
+    // lane-operations (tri_grad_vertex_kernel folds them into dL_dverts / dL_dvcolor [P,3]), but the accumulators
+    // are 56 B of extra streaming per VERTEX (C5, 12 M unshared vertices: 92 -> 175 us), hence the switch in
+    // tri_render_backward.
     if (p.grad_vacc) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi[k]), dp[k].x, dp[k].y, dp[k].z, 0.0f);
-            red_add_v4(reinterpret_cast<float*>(p.grad_vacc + (size_t)p.P + vi[k]), st[12 + 3 * k], st[13 + 3 * k], st[14 + 3 * k], 0.0f);
-            atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+            red_add_v4(reinterpret_cast<float*>(p.grad_vacc + vi[k]), dps[k].x, dps[k].y, dps[k].z, 0.0f);
+            red_add_v4(reinterpret_cast<float*>(p.grad_vacc + (size_t)p.P + vi[k]), cs[3 * k], cs[3 * k + 1], cs[3 * k + 2], 0.0f);
         }
     } else {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             float* dv = p.dL_dverts + 3 * (size_t)vi[k];
-            atomicAdd(dv + 0, dp[k].x); atomicAdd(dv + 1, dp[k].y); atomicAdd(dv + 2, dp[k].z);
+            atomicAdd(dv + 0, dps[k].x); atomicAdd(dv + 1, dps[k].y); atomicAdd(dv + 2, dps[k].z);
             float* dc = p.dL_dvcolor + 3 * (size_t)vi[k];
-            atomicAdd(dc + 0, st[12 + 3 * k]); atomicAdd(dc + 1, st[13 + 3 * k]); atomicAdd(dc + 2, st[14 + 3 * k]);
-            atomicAdd(p.dL_dvdepth + (size_t)b * p.P + vi[k], st[9 + k]);
+            atomicAdd(dc + 0, cs[3 * k]); atomicAdd(dc + 1, cs[3 * k + 1]); atomicAdd(dc + 2, cs[3 * k + 2]);
         }
     }
-    atomicAdd(p.dL_dfopacity + f, st[7]);
-    p.dL_dfintense[idx] = st[8];
+    atomicAdd(p.dL_dfopacity + f, opa);
 }
 
-__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p) { griddep_wait(); tri_grad_finish_body<false>(p); }
-__global__ void __launch_bounds__(256) tri_grad_finish_det_kernel(TriRenderParams p) { griddep_wait(); tri_grad_finish_body<true>(p); }
+template <bool MULTI>
+__global__ void __launch_bounds__(256) tri_grad_finish_kernel(TriRenderParams p) { griddep_wait(); tri_grad_finish_body<false, MULTI>(p); }
+__global__ void __launch_bounds__(256) tri_grad_finish_det_kernel(TriRenderParams p) { griddep_wait(); tri_grad_finish_body<true, true>(p); }
 
 // Deterministic mode, last step: fixed-point accumulators -> += into the caller's fp32 gradient tensors.
 // One thread per vertex, then per (view, vertex), then per face.
@@ -843,8 +879,8 @@ int tri_render_backward(const TriRenderParams& p, cudaStream_t stream)
     }
     {
         ProfScope prof(ST_TRI_BWD_FINISH, stream);
-        const size_t BF = (size_t)p.B * p.F;
-        DMR_CUDA(dmr_launch(tri_grad_finish_kernel, dim3((unsigned)((BF + 255) / 256)), dim3(256), 0, stream, p));
+        if (p.B > 1) DMR_CUDA(dmr_launch(tri_grad_finish_kernel<true>, dim3((unsigned)((p.F + 255) / 256)), dim3(256), 0, stream, p));
+        else DMR_CUDA(dmr_launch(tri_grad_finish_kernel<false>, dim3((unsigned)((p.F + 255) / 256)), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_grad_finish_kernel");
         if (p.grad_vacc) {
             count_launch(1);   // two kernels under one scope
@@ -866,7 +902,7 @@ int tri_render_backward_deterministic(const TriRenderParams& p, cudaStream_t str
 {
     if (p.B <= 0 || p.W <= 0 || p.H <= 0) return 0;
     dim3 grid((p.W + DMR_TILE - 1) / DMR_TILE, (p.H + DMR_TILE - 1) / DMR_TILE, p.B);
-    const size_t HW = (size_t)p.W * p.H, BF = (size_t)p.B * p.F;
+    const size_t HW = (size_t)p.W * p.H;
     {
         ProfScope prof(ST_TRI_BWD, stream);
         count_launch(1);   // two kernels under one scope
@@ -878,7 +914,7 @@ int tri_render_backward_deterministic(const TriRenderParams& p, cudaStream_t str
     {
         ProfScope prof(ST_TRI_BWD_FINISH, stream);
         count_launch(1);
-        DMR_CUDA(dmr_launch(tri_grad_finish_det_kernel, dim3((unsigned)((BF + 255) / 256)), dim3(256), 0, stream, p));
+        DMR_CUDA(dmr_launch(tri_grad_finish_det_kernel, dim3((unsigned)((p.F + 255) / 256)), dim3(256), 0, stream, p));
         DMR_LAUNCH_CHECK("tri_grad_finish_det_kernel");
         const size_t n = (size_t)p.P + (size_t)p.B * p.P + (size_t)p.F;
         DMR_CUDA(dmr_launch(tri_det_convert_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, p));
