@@ -44,7 +44,9 @@ namespace dmr {
 #define RS_TILE_KEYS (DMR_RS_THREADS * DMR_RS_KPT)
 #define RS_MIN_TILE 2048   // smallest tile of any configuration (sizes the descriptor array)
 static_assert(DMR_RS_THREADS >= 256 && DMR_RS_THREADS % 32 == 0 && RS_TILE_KEYS >= RS_MIN_TILE, "onesweep tile shape");
-#define RS_LB 16         // look-back descriptors fetched per step (see the stability note at the look-back)
+#ifndef RS_LB
+#define RS_LB 8          // look-back descriptors fetched per step (C5 pass: 8 -> 180 us, 16 -> 185 us, 32 -> 186 us)
+#endif
 
 #define RS_FLAG_AGG  (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
@@ -316,26 +318,43 @@ __device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, siz
         __syncwarp();
     }
 
-    // ---- decoupled look-back for digit `tid`
+    // ---- decoupled look-back for digit `tid`: sum the aggregates of the predecessors back to the nearest
+    //      inclusive prefix.  RS_LB descriptors are fetched per step (one L2 round trip) and consumed WITHOUT
+    //      branches: "all ready" is one unsigned minimum over the words (a flag of 0 makes the word < RS_FLAG_AGG),
+    //      the running predicate `open` (no inclusive prefix seen yet) masks the additions.  ~5 instructions per
+    //      descriptor; the first form (a bounds test, a spin loop and two branches per descriptor, 64-bit address
+    //      arithmetic per load) cost ~25 and the look-back was 29 % of the instructions of a pass at C5 (46
+    //      descriptors walked per tile and digit on average).
     if (tid < 256) {
         uint32_t excl = 0;
         if (tile > 0) {
-            const uint32_t* base = desc + (size_t)pass * gridDim.x * 256 + tid;
-            long long t = (long long)tile - 1;
-            bool found = false;
-            while (!found && t >= 0) {
-                uint32_t v[RS_LB];
+            const uint32_t* bp = desc + ((size_t)pass * gridDim.x + (tile - 1)) * 256 + tid;   // tile - 1, then backwards
+            uint32_t left = tile;              // predecessors not yet consumed (tile 0 always holds an inclusive prefix)
+            bool open = true;
+            while (open) {
+                if (left >= RS_LB) {
+                    uint32_t v[RS_LB];
 #pragma unroll
-                for (int i = 0; i < RS_LB; i++) v[i] = (t - i >= 0) ? ld_volatile_u32(base + (size_t)(t - i) * 256) : RS_FLAG_INCL;
+                    for (int i = 0; i < RS_LB; i++) v[i] = ld_volatile_u32(bp - i * 256);
+                    uint32_t mn = v[0];
 #pragma unroll
-                for (int i = 0; i < RS_LB; i++) {
-                    if (!found) {
-                        while ((v[i] >> 30) == 0) v[i] = ld_volatile_u32(base + (size_t)(t - i) * 256);
-                        excl += v[i] & RS_VAL_MASK;
-                        if ((v[i] >> 30) == 2u) found = true;
+                    for (int i = 1; i < RS_LB; i++) mn = min(mn, v[i]);
+                    if (mn < RS_FLAG_AGG) continue;              // a predecessor has not published yet: fetch again
+#pragma unroll
+                    for (int i = 0; i < RS_LB; i++) {
+                        excl += open ? (v[i] & RS_VAL_MASK) : 0u;
+                        open = open && v[i] < RS_FLAG_INCL;
                     }
+                    bp -= RS_LB * 256;
+                    left -= RS_LB;
+                } else {                                         // the first few tiles of a pass: one at a time
+                    uint32_t v;
+                    do { v = ld_volatile_u32(bp); } while (v < RS_FLAG_AGG);
+                    excl += v & RS_VAL_MASK;
+                    open = v < RS_FLAG_INCL;
+                    bp -= 256;
+                    left--;
                 }
-                t -= RS_LB;
             }
             st_volatile_u32(my_desc, RS_FLAG_INCL | (excl + count));
         }
