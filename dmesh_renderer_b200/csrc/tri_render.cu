@@ -152,7 +152,9 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
 // chain range -> face id -> scattered 144-byte gather that misses L2 half of the time), but the prefetches cost more
 // than the latency they hide: C4 forward 1833 -> 1903 us, backward 3602 -> 3766 us; C5 forward 443 -> 822 us.  The
 // bulk form cp.async.bulk.prefetch.L2 is a uniform-datapath instruction -- per-lane addresses compile to a
-// 32-iteration loop around it.)
+// 32-iteration loop around it.  Also rejected: fetching the face id of the instance a thread stages in the NEXT round
+// one round ahead (one register; staging becomes a single dependent gather): C4 forward 1831 -> 1889 us.  The
+// staging latency is already covered by the other three CTAs of the SM.)
 
 // (Measured and rejected, round 2: per-(view, face) constants of the ray-triangle system -- E2 x E1, E2 x T, T x E1 formed
 // once per staged instance, so that a covered pixel needs three dot products instead of Moeller-Trumbore's two cross
