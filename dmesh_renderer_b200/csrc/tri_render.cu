@@ -141,6 +141,31 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane)
     return x;
 }
 
+
+// Staging of a round: every warp copies the 32 records of ITS 32 instances (288 chunks of 16 B) cooperatively --
+// chunk g = it * 32 + lane of the warp belongs to instance g / 9, whose face id comes from lane g / 9 by shuffle --
+// so that nine consecutive lanes read one record's 144 contiguous bytes and a warp-wide LDG.128 touches ~7 cache
+// lines.  The first version let thread t copy record t: every lane of a load instruction hit a different line,
+// 32 L1 wavefronts per instruction, and ncu showed the L1 data pipe (l1tex__data_pipe_lsu_wavefronts), not the
+// issue slots, as the busiest unit of both render kernels (70 % / 67 % of peak at C4, a quarter of it this
+// gather).  `nvw` = instances of the round that fall to this warp (<= 0: none), `face` = this lane's face id.
+__device__ __forceinline__ void stage_records_warp(uint4* __restrict__ dstw, const TriRecord* __restrict__ recs, uint32_t face,
+                                                   int nvw, int lane)
+{
+    // asynchronous copies (cp.async, SASS LDGSTS): global -> shared without a round trip through 36 registers
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(dstw);
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+        const unsigned g = it * 32 + lane, rr = g / 9u, part = g - rr * 9u;
+        const uint32_t fr = __shfl_sync(0xffffffffu, face, rr);
+        if ((int)rr < nvw)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst0 + g * 16u),
+                         "l"(reinterpret_cast<const uint4*>(recs + fr) + part) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
+
 #ifndef HB
 #define HB 256           // staged instances a warp compacts / rasterises / shades in one go (measured: 128 -> 256 = -5 % at C4, -3 % at C2, +-0 at C5)
 #endif
@@ -218,21 +243,14 @@ __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(T
 
     for (int r = 0; r < rounds; r++) {
         if (__syncthreads_count(done) == 256) break;
-        {   // stage: thread t copies instance t of the round (9 x 16 B, contiguous in global) and finds the warp
-            // blocks of the tile the instance can touch
-            uint32_t pos = range.x + (uint32_t)r * RB + tid;
+        {   // stage (stage_records_warp), then thread t finds the warp blocks of the tile that instance t can touch
+            const int nvw = min(32, total - r * RB - warp * 32);
+            uint32_t face = 0u;
+            if (lane < nvw) face = p.face_list[range.x + (uint32_t)r * RB + tid];
+            stage_records_warp(s_rec + warp * 32 * 9, p.records + (size_t)b * p.F, face, nvw, lane);
             uint32_t bm = 0;
-            if (pos < range.y) {
-                uint32_t face = p.face_list[pos];
-                const uint4* src = reinterpret_cast<const uint4*>(p.records + (size_t)b * p.F + face);
-                uint4* dst = s_rec + tid * 9;
-                uint4 q[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) q[k] = src[k];
-#pragma unroll
-                for (int k = 0; k < 9; k++) dst[k] = q[k];
-                bm = tile_block_mask(q[0], q[1], q[2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
-            }
+            if (lane < nvw)
+                bm = tile_block_mask(s_rec[tid * 9 + 0], s_rec[tid * 9 + 1], s_rec[tid * 9 + 2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
             s_bmask[tid] = (unsigned char)bm;
         }
         __syncthreads();
@@ -456,21 +474,19 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 
     for (int c = nchunk - 1; c >= 0; c--) {
         __syncthreads();
-        {
-            const int idx = c * RB + tid;
+        {   // stage (stage_records_warp); the owner of an instance then adds the face id and 1 / (1 - alpha) to the
+            // staged copy and finds the warp blocks of the tile the instance can touch
+            const int nvw = min(32, tile_last - c * RB - warp * 32);
+            uint32_t face = 0u;
+            if (lane < nvw) face = p.face_list[range.x + c * RB + tid];
+            stage_records_warp(s_rec + warp * 32 * 9, p.records + (size_t)b * p.F, face, nvw, lane);
             uint32_t bm = 0;
-            if (idx < tile_last) {
-                uint32_t face = p.face_list[range.x + idx];
-                const uint4* src = reinterpret_cast<const uint4*>(p.records + (size_t)b * p.F + face);
-                uint4* dst = s_rec + tid * 9;
-                uint4 q[9];
-#pragma unroll
-                for (int k = 0; k < 9; k++) q[k] = src[k];
-                q[5].y = face;                                                        // w[9]
-                q[5].z = __float_as_uint(1.0f / (1.0f - __uint_as_float(q[0].w)));    // w[10]
-#pragma unroll
-                for (int k = 0; k < 9; k++) dst[k] = q[k];
-                bm = tile_block_mask(q[0], q[1], q[2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
+            if (lane < nvw) {
+                const uint4 q0 = s_rec[tid * 9 + 0];
+                uint32_t* w9 = reinterpret_cast<uint32_t*>(s_rec + tid * 9 + 5) + 1;
+                w9[0] = face;                                                          // w[9]
+                w9[1] = __float_as_uint(1.0f / (1.0f - __uint_as_float(q0.w)));       // w[10]
+                bm = tile_block_mask(q0, s_rec[tid * 9 + 1], s_rec[tid * 9 + 2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
             }
             s_bmask[tid] = (unsigned char)bm;
         }
