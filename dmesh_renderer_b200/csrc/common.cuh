@@ -198,16 +198,19 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
 // views (383 -> 279 us) and tri_grad_finish 7 %, but staging an instance from two arrays cost the render kernels
 // more than that: forward 1842 -> 2033 us, backward 3684 -> 3792 us at C4, forward 420 -> 467 us at C5.)
 struct __align__(16) TriRecord {
-    // q0..q2: hot part (coverage test)
-    uint32_t ea0, eb0, ec0; float opacity;
-    uint32_t ea1, eb1, ec1; float intense;
-    uint32_t ea2, eb2, ec2; uint32_t flags;   // bit 0: edge values cannot overflow on screen; bits 1..27: block bbox (below)
-    // q3..q8: shading part
-    float v0[3], v1[3], v2[3];                // world positions
-    int   i0, i1, i2;                         // vertex ids (gradient scatter) -- next to the positions: tri_grad_finish_kernel
-                                              // reads exactly these 48 bytes = sectors 1 and 2 of the record
-    float c0[3], c1[3], c2[3];                // vertex colours
-    float d0, d1, d2;                         // per-view vertex depths
+    // q0..q2: coverage part -- three edge functions; the fourth words carry what no pixel needs
+    uint32_t ea0, eb0, ec0; uint32_t flags;   // bit 0: edge values cannot overflow on screen; bits 1..27: block bbox (below)
+    uint32_t ea1, eb1, ec1; int i0;           // vertex ids (gradient scatter, tri_grad_finish_kernel); the backward kernel's
+    uint32_t ea2, eb2, ec2; int i1;           //   STAGED copy carries the face id in place of i0
+    // q3..q8: shading part -- everything a covered pixel reads is exactly these six 16-byte chunks (six LDS.128 per
+    // hit; with opacity / intensity in q0 / q1 a hit cost three more scalar loads, and the L1 data pipe is the
+    // busiest unit of the render kernels)
+    float v0[3]; float opacity;               // world positions
+    float v1[3]; float intense;
+    float v2[3]; int i2;                      //   the backward kernel's staged copy carries 1 / (1 - opacity) in place of i2
+    float c0[3]; float d0;                    // vertex colours, per-view vertex depths
+    float c1[3]; float d1;
+    float c2[3]; float d2;
 };
 static_assert(sizeof(TriRecord) == 144, "TriRecord must be 9 x 16 bytes");
 #define DMR_REC_WORDS 36

@@ -23,6 +23,9 @@ namespace dmr {
 // algorithmic bytes per (b,p): 12 (xyz) + 4 (depth) read, 16 written.
 // The reference also stores ndc.xy (never read downstream).
 // ---------------------------------------------------------------------------
+#ifndef DMR_POINTS_PER_THREAD
+#define DMR_POINTS_PER_THREAD 4
+#endif
 __global__ void __launch_bounds__(256) preprocess_points_kernel(
     int B, int P, int W, int H,
     const float* __restrict__ verts, const float* __restrict__ mv_mats, const float* __restrict__ proj_mats,
@@ -31,32 +34,38 @@ __global__ void __launch_bounds__(256) preprocess_points_kernel(
     float4* __restrict__ vimg)
 {
     griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int b = blockIdx.y;
-    if (idx >= (size_t)P) return;
-    const float* mv = mv_mats + 16 * b;
-    const float* pj = proj_mats + 16 * b;
+    const int b = blockIdx.y;
+    // the two matrices of the view: 28 uniform loads, once per thread and DMR_POINTS_PER_THREAD vertices (with one
+    // vertex per thread they were two thirds of the kernel's load instructions and the L1 data pipe, not HBM, was
+    // its busiest unit: 65 % against 50 % DRAM utilisation at C5)
+    float mv[16], pj[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { mv[i] = mv_mats[16 * b + i]; pj[i] = proj_mats[16 * b + i]; }
+#pragma unroll
+    for (int it = 0; it < DMR_POINTS_PER_THREAD; it++) {
+        const size_t idx = ((size_t)blockIdx.x * DMR_POINTS_PER_THREAD + it) * 256 + threadIdx.x;
+        if (idx >= (size_t)P) return;
+        float3 p = f3(verts[3 * idx + 0], verts[3 * idx + 1], verts[3 * idx + 2]);
+        float3 pv = xform43(p, mv);
+        float4 pp = xform44(pv, pj);
+        float pw = 1.0 / clamp_w(pp.w);                 // forward.cu:38 (double literal, float result)
+        float3 ndc = f3(pp.x * pw, pp.y * pw, pp.z * pw);
 
-    float3 p = f3(verts[3 * idx + 0], verts[3 * idx + 1], verts[3 * idx + 2]);
-    float3 pv = xform43(p, mv);
-    float4 pp = xform44(pv, pj);
-    float pw = 1.0 / clamp_w(pp.w);                 // forward.cu:38 (double literal, float result)
-    float3 ndc = f3(pp.x * pw, pp.y * pw, pp.z * pw);
-
-    float4 o;
-    o.x = ndc2pix(ndc.x, W);
-    o.y = ndc2pix(ndc.y, H);
-    o.z = ndc.z;
-    // tet path: clip-space w (bbox validity); tri path without a verts_depth tensor: the vertex's own NDC z
-    o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : (depth_mode == 1 ? ndc.z : pp.w);
-    vimg[(size_t)b * P + idx] = o;
+        float4 o;
+        o.x = ndc2pix(ndc.x, W);
+        o.y = ndc2pix(ndc.y, H);
+        o.z = ndc.z;
+        // tet path: clip-space w (bbox validity); tri path without a verts_depth tensor: the vertex's own NDC z
+        o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : (depth_mode == 1 ? ndc.z : pp.w);
+        vimg[(size_t)b * P + idx] = o;
+    }
 }
 
 int preprocess_points(int B, int P, int W, int H, const float* verts, const float* mv, const float* proj,
                       const float* verts_depth, int depth_mode, float4* vimg, cudaStream_t stream)
 {
     if (B <= 0 || P <= 0) return 0;
-    dim3 grid((P + 255) / 256, B);
+    dim3 grid((P + 256 * DMR_POINTS_PER_THREAD - 1) / (256 * DMR_POINTS_PER_THREAD), B);
     ProfScope prof(ST_POINTS, stream);
     DMR_CUDA(dmr_launch(preprocess_points_kernel, dim3(grid), dim3(256), 0, stream, B, P, W, H, verts, mv, proj, verts_depth, depth_mode, vimg));
     DMR_LAUNCH_CHECK("preprocess_points_kernel");
@@ -270,22 +279,18 @@ __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
         edge_setup(p0, p1, p2, W, H, ea, eb, ec, flags);
 
         uint4* r = s_rec + tid * 9;
-        r[0] = make_uint4(ea[0], eb[0], ec[0], __float_as_uint(faces_opacity[f]));
-        r[1] = make_uint4(ea[1], eb[1], ec[1], __float_as_uint(faces_intense[bf]));
-        r[2] = make_uint4(ea[2], eb[2], ec[2], flags);
         const float* q0 = verts + 3 * (size_t)i0; const float* q1 = verts + 3 * (size_t)i1; const float* q2 = verts + 3 * (size_t)i2;
         const float* k0 = verts_color + 3 * (size_t)i0; const float* k1 = verts_color + 3 * (size_t)i1; const float* k2 = verts_color + 3 * (size_t)i2;
-        float w[24];
-        w[0] = q0[0]; w[1] = q0[1]; w[2] = q0[2]; w[3] = q1[0]; w[4] = q1[1]; w[5] = q1[2];
-        w[6] = q2[0]; w[7] = q2[1]; w[8] = q2[2];
-        w[9] = __int_as_float(i0); w[10] = __int_as_float(i1); w[11] = __int_as_float(i2);
-        w[12] = k0[0]; w[13] = k0[1]; w[14] = k0[2]; w[15] = k1[0]; w[16] = k1[1]; w[17] = k1[2];
-        w[18] = k2[0]; w[19] = k2[1]; w[20] = k2[2];
-        w[21] = a0.w; w[22] = a1.w; w[23] = a2.w;
-#pragma unroll
-        for (int q = 0; q < 6; q++)
-            r[3 + q] = make_uint4(__float_as_uint(w[4 * q]), __float_as_uint(w[4 * q + 1]), __float_as_uint(w[4 * q + 2]),
-                                  __float_as_uint(w[4 * q + 3]));
+        auto fu = [](float x) { return __float_as_uint(x); };
+        r[0] = make_uint4(ea[0], eb[0], ec[0], flags);
+        r[1] = make_uint4(ea[1], eb[1], ec[1], (uint32_t)i0);
+        r[2] = make_uint4(ea[2], eb[2], ec[2], (uint32_t)i1);
+        r[3] = make_uint4(fu(q0[0]), fu(q0[1]), fu(q0[2]), fu(faces_opacity[f]));
+        r[4] = make_uint4(fu(q1[0]), fu(q1[1]), fu(q1[2]), fu(faces_intense[bf]));
+        r[5] = make_uint4(fu(q2[0]), fu(q2[1]), fu(q2[2]), (uint32_t)i2);
+        r[6] = make_uint4(fu(k0[0]), fu(k0[1]), fu(k0[2]), fu(a0.w));
+        r[7] = make_uint4(fu(k1[0]), fu(k1[1]), fu(k1[2]), fu(a1.w));
+        r[8] = make_uint4(fu(k2[0]), fu(k2[1]), fu(k2[2]), fu(a2.w));
     }
     __syncthreads();
     // coalesced write-out of the block's records

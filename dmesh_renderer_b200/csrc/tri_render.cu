@@ -74,7 +74,7 @@ __device__ __forceinline__ bool ray_tri_tuv(float3 ro, float3 rd, float3 p0, flo
 //     on screen): a block where some edge function is non-negative everywhere.
 __device__ __forceinline__ uint32_t tile_block_mask(const uint4 e0, const uint4 e1, const uint4 e2, int tx0, int ty0)
 {
-    const uint32_t fl = e2.w;
+    const uint32_t fl = e0.w;
     // bbox: block columns tx0/8 + {0,1}, block rows ty0/4 + {0..3}
     const uint32_t nbx = (fl >> DMR_REC_NBX_SHIFT) & 15u, nby = (fl >> DMR_REC_NBY_SHIFT) & 15u;
     const uint32_t dx = (uint32_t)(tx0 >> 3) - ((fl >> DMR_REC_BX0_SHIFT) & 0x1ffu);
@@ -290,23 +290,23 @@ __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(T
                     const int bit = __ffs(mine) - 1;
                     mine &= mine - 1;
                     const int j = cidx[(sl << 5) + bit];
-                    const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
-                    const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
+                    const float4* sh = reinterpret_cast<const float4*>(s_rec + j * 9 + 3);   // the six shading chunks
+                    const float4 a0 = sh[0], a1 = sh[1], a2 = sh[2];                         // (v_k, opacity | intensity | -)
                     float3 tuv = f3(0, 0, 0);
-                    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
-                    const bool hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv);
+                    const bool hit = ray_tri_tuv(ro, rd, f3(a0.x, a0.y, a0.z), f3(a1.x, a1.y, a1.z), f3(a2.x, a2.y, a2.z), tuv);
                     if (hit) {
                         float uc, vc;
                         int code;
                         clamp_bary(tuv.y, tuv.z, uc, vc, code);
                         float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
-                        const float intense = __uint_as_float(e1.w);
+                        const float4 k0 = sh[3], k1 = sh[4], k2 = sh[5];                     // (colour_k, depth_k)
+                        const float intense = a1.w;
                         // forward.cu:442-451
-                        float c0_ = i0 * w[12] + i1 * w[15] + i2 * w[18];  c0_ = c0_ * intense;
-                        float c1_ = i0 * w[13] + i1 * w[16] + i2 * w[19]; c1_ = c1_ * intense;
-                        float c2_ = i0 * w[14] + i1 * w[17] + i2 * w[20]; c2_ = c2_ * intense;
-                        float iD = i0 * w[21] + i1 * w[22] + i2 * w[23];
-                        const float alpha = __uint_as_float(e0.w);
+                        float c0_ = i0 * k0.x + i1 * k1.x + i2 * k2.x; c0_ = c0_ * intense;
+                        float c1_ = i0 * k0.y + i1 * k1.y + i2 * k2.y; c1_ = c1_ * intense;
+                        float c2_ = i0 * k0.z + i1 * k1.z + i2 * k2.z; c2_ = c2_ * intense;
+                        float iD = i0 * k0.w + i1 * k1.w + i2 * k2.w;
+                        const float alpha = a0.w;
                         float test_T = T * (1 - alpha);
                         C0 += c0_ * alpha * T;
                         C1 += c1_ * alpha * T;
@@ -340,6 +340,14 @@ __global__ void __launch_bounds__(256, DMR_TRI_FWD_MINB) tri_render_fwd_kernel(T
 // ---------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------
+
+// 32-bit shared-memory load the compiler cannot merge into a neighbouring vector load
+__device__ __forceinline__ float lds_f32(const float* p)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
 
 // auxiliary.h:374-400
 __device__ __forceinline__ void clamp_bary_grad(int code, float& duc_du, float& duc_dv, float& dvc_du, float& dvc_dv)
@@ -410,8 +418,8 @@ __host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i
 template <bool DET>
 __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 {
-    __shared__ uint4 s_rec[RB * 9];      // staged records; the vertex-id slots (unused here: tri_grad_finish_kernel reads the
-                                         // global record) carry the face id and 1 / (1 - alpha) of the instance
+    __shared__ uint4 s_rec[RB * 9];      // staged records; two vertex-id slots (unused here: tri_grad_finish_kernel reads the
+                                         // global record) carry the face id and 1 / (1 - opacity) of the instance
     __shared__ int s_max[8];
     __shared__ unsigned char s_bmask[RB];         // [staged instance]: warp blocks of the tile it can touch (tile_block_mask)
     __shared__ unsigned char s_cidx[8 * HB];      // [warp][compacted position] -> position in the chunk
@@ -452,6 +460,7 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
     // backward.cu:293-298
     float bg_dot = 0; bg_dot += bg0 * dLc0; bg_dot += bg1 * dLc1; bg_dot += bg2 * dLc2;
     float bd_dot = 0; bd_dot += 1.0 * dLd;
+    const float bgk = -T_final * (bg_dot + bd_dot), bgk1 = -prev_T_final * (bg_dot + bd_dot);
 
     float acc0 = 0, acc1 = 0, acc2 = 0, accd = 0;
     float last_alpha = 0, lc0 = 0, lc1 = 0, lc2 = 0, ld = 0;
@@ -482,11 +491,10 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
             stage_records_warp(s_rec + warp * 32 * 9, p.records + (size_t)b * p.F, face, nvw, lane);
             uint32_t bm = 0;
             if (lane < nvw) {
-                const uint4 q0 = s_rec[tid * 9 + 0];
-                uint32_t* w9 = reinterpret_cast<uint32_t*>(s_rec + tid * 9 + 5) + 1;
-                w9[0] = face;                                                          // w[9]
-                w9[1] = __float_as_uint(1.0f / (1.0f - __uint_as_float(q0.w)));       // w[10]
-                bm = tile_block_mask(q0, s_rec[tid * 9 + 1], s_rec[tid * 9 + 2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
+                uint32_t* rw = reinterpret_cast<uint32_t*>(s_rec + tid * 9);
+                rw[7] = face;                                                                   // q1.w: i0 -> face id
+                rw[23] = __float_as_uint(1.0f / (1.0f - __uint_as_float(rw[15])));             // q5.w: i2 -> 1 / (1 - opacity)
+                bm = tile_block_mask(s_rec[tid * 9 + 0], s_rec[tid * 9 + 1], s_rec[tid * 9 + 2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
             }
             s_bmask[tid] = (unsigned char)bm;
         }
@@ -558,28 +566,30 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 #pragma unroll
                 for (int k = 0; k < 24; k++) v[k] = 0.0f;
                 if (cov) {
-                    const uint4 e0 = s_rec[j * 9 + 0], e1 = s_rec[j * 9 + 1];
-                    const float* w = reinterpret_cast<const float*>(s_rec + j * 9 + 3);
+                    const float4* sh = reinterpret_cast<const float4*>(s_rec + j * 9 + 3);   // the six shading chunks
+                    const float4 a0 = sh[0], a1 = sh[1], a2 = sh[2];                         // (v_k, opacity | intensity | 1 / (1 - opacity))
                     float3 tuv = f3(0, 0, 0);
                     float inv_denom = 0.0f;
-                    const float3 v0 = f3(w[0], w[1], w[2]), v1 = f3(w[3], w[4], w[5]), v2 = f3(w[6], w[7], w[8]);
-                    const bool hit = ray_tri_tuv(ro, rd, v0, v1, v2, tuv, inv_denom);
+                    const bool hit = ray_tri_tuv(ro, rd, f3(a0.x, a0.y, a0.z), f3(a1.x, a1.y, a1.z), f3(a2.x, a2.y, a2.z), tuv, inv_denom);
                     if (hit) {
                         float uc, vc;
                         int code;
                         clamp_bary(tuv.y, tuv.z, uc, vc, code);
                         const float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
-                        const float intense = __uint_as_float(e1.w);
-                        const float alpha = __uint_as_float(e0.w);
-                        const float raw0 = i0 * w[12] + i1 * w[15] + i2 * w[18];
-                        const float raw1 = i0 * w[13] + i1 * w[16] + i2 * w[19];
-                        const float raw2 = i0 * w[14] + i1 * w[17] + i2 * w[20];
+                        const float4 q6 = sh[3], q7 = sh[4], q8 = sh[5];                     // (colour_k, depth_k)
+                        // (scalar loads on purpose: taking these three from the .w lanes of a0..a2 keeps them live across the
+                        // hit test and costs the 64-register kernel three spill accesses per pass: C4 3316 -> 3408 us)
+                        const float intense = lds_f32(&sh[1].w);
+                        const float alpha = lds_f32(&sh[0].w);
+                        const float raw0 = i0 * q6.x + i1 * q7.x + i2 * q8.x;
+                        const float raw1 = i0 * q6.y + i1 * q7.y + i2 * q8.y;
+                        const float raw2 = i0 * q6.z + i1 * q7.z + i2 * q8.z;
                         const float iC0 = raw0 * intense, iC1 = raw1 * intense, iC2 = raw2 * intense;
-                        const float iD = i0 * w[21] + i1 * w[22] + i2 * w[23];
+                        const float iD = i0 * q6.w + i1 * q7.w + i2 * q8.w;
 
                         // backward.cu:244-252
 #if DMR_TRI_BWD_RCP_ALPHA
-                        const float rcpa = w[10];
+                        const float rcpa = lds_f32(&sh[2].w);
                         if (!T_first) T = T * rcpa;
 #else
                         if (!T_first) T = T / (1.f - alpha);
@@ -600,27 +610,23 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
 
                         dL_dalpha *= T;
                         last_alpha = alpha;
-                        // background term, backward.cu:299-308
-                        if (alpha == 1.0f) {
-                            dL_dalpha += (-prev_T_final) * bg_dot;
-                            dL_dalpha += (-prev_T_final) * bd_dot;
-                        } else {
+                        // background term, backward.cu:299-308: (-T_final / (1 - alpha)) * (bg . dL_dC) and the same factor
+                        // times dL_dD.  The pixel constants -T_final * (bg . dL_dC + dL_dD) and its alpha == 1 counterpart
+                        // are formed once (two live registers instead of four; one rounding apart from the reference's
+                        // two separate products, far inside the gradient tolerance)
 #if DMR_TRI_BWD_RCP_ALPHA
-                            const float k = -T_final * rcpa;
+                        dL_dalpha += (alpha == 1.0f) ? bgk1 : bgk * rcpa;
 #else
-                            const float k = -T_final / (1.f - alpha);
+                        dL_dalpha += (alpha == 1.0f) ? bgk1 : bgk / (1.f - alpha);
 #endif
-                            dL_dalpha += k * bg_dot;
-                            dL_dalpha += k * bd_dot;
-                        }
 
                         // backward.cu:327-349.  The per-term products are the reference's; the common factor
                         // dic*intense is formed once (the reference multiplies (x*dic)*intense per term: one
                         // rounding apart, far inside the 1e-4 gradient tolerance).
                         const float dI0 = dic0 * intense, dI1 = dic1 * intense, dI2 = dic2 * intense;
-                        const float dL_di0 = w[12] * dI0 + w[13] * dI1 + w[14] * dI2 + w[21] * did;
-                        const float dL_di1 = w[15] * dI0 + w[16] * dI1 + w[17] * dI2 + w[22] * did;
-                        const float dL_di2 = w[18] * dI0 + w[19] * dI1 + w[20] * dI2 + w[23] * did;
+                        const float dL_di0 = q6.x * dI0 + q6.y * dI1 + q6.z * dI2 + q6.w * did;
+                        const float dL_di1 = q7.x * dI0 + q7.y * dI1 + q7.z * dI2 + q7.w * did;
+                        const float dL_di2 = q8.x * dI0 + q8.y * dI1 + q8.z * dI2 + q8.w * did;
                         v[12] = i0 * dI0; v[13] = i0 * dI1; v[14] = i0 * dI2;
                         v[15] = i1 * dI0; v[16] = i1 * dI1; v[17] = i1 * dI2;
                         v[18] = i2 * dI0; v[19] = i2 * dI1; v[20] = i2 * dI2;
@@ -653,7 +659,7 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                     if (have) {
                         // fixed-point record in LOGICAL order: this lane holds sums 12*cls .. 12*cls+11
                         const int cls = lane & 1;
-                        long long* rec = p.det_stats + ((size_t)b * p.F + s_rec[j * 9 + 5].y) * 24 + 12 * cls;
+                        long long* rec = p.det_stats + ((size_t)b * p.F + s_rec[j * 9 + 1].w) * 24 + 12 * cls;
 #pragma unroll
                         for (int k = 0; k < 12; k++) {
                             if (cls == 1 && k >= 9) break;                       // logical 21..23: padding
@@ -661,7 +667,7 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         }
                     }
                 } else if (have) {
-                    float* rec = stats + ((size_t)b * p.F + s_rec[j * 9 + 5].y) * 24;
+                    float* rec = stats + ((size_t)b * p.F + s_rec[j * 9 + 1].w) * 24;
                     const int cls = lane & 1;
                     // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
                     red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
@@ -758,10 +764,10 @@ __device__ __forceinline__ void tri_grad_finish_body(const TriRenderParams& p)
         }
         if (!any) continue;
         if (!have_tri) {
-            const float* w = reinterpret_cast<const float*>(p.records + f) + 12;   // view 0's record: 2 sectors
-            v0 = f3(w[0], w[1], w[2]);
-            E1 = f3(w[3], w[4], w[5]) - v0; E2 = f3(w[6], w[7], w[8]) - v0;
-            vi[0] = __float_as_int(w[9]); vi[1] = __float_as_int(w[10]); vi[2] = __float_as_int(w[11]);
+            const TriRecord* rec = p.records + f;                                   // view 0's record: bytes 28..95
+            v0 = f3(rec->v0[0], rec->v0[1], rec->v0[2]);
+            E1 = f3(rec->v1[0], rec->v1[1], rec->v1[2]) - v0; E2 = f3(rec->v2[0], rec->v2[1], rec->v2[2]) - v0;
+            vi[0] = rec->i0; vi[1] = rec->i1; vi[2] = rec->i2;
             have_tri = true;
         }
         const float* imv = p.inv_mv + 16 * b;
