@@ -471,9 +471,10 @@ int tet_first_intersect(const TetParams& p, cudaStream_t stream)
 #define MARCH_THREADS 64
 #endif
 #define MARCH_ROWS (MARCH_THREADS / 8)   // pixel rows of a CTA: 8 columns x 4 rows per warp
-// 12 CTAs/SM = 80 registers (measured at C3: uncapped 103 regs 875 us, 80 regs 838 us, 64 regs + spills 947 us)
+// 10 CTAs/SM = 96 registers (forward march at C3 after the depth computation left the loop: 8 CTAs / 112 registers
+// 820 us, 10 / 96 (2 spill slots) 772 us, 12 / 80 (14 spill accesses per step) 783 us; round 1: 64 registers 947 us)
 #ifndef MARCH_MIN_BLOCKS
-#define MARCH_MIN_BLOCKS 12
+#define MARCH_MIN_BLOCKS 10
 #endif
 
 struct TetStep {   // result of looking for the exit (or entry) face of a tet
