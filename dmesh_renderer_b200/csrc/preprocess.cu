@@ -20,7 +20,7 @@ namespace dmr {
 
 // ---------------------------------------------------------------------------
 // points: out[b*P+p] = { pix.x, pix.y, ndc.z, verts_depth[b,p] }  (tet: 4th lane = clip w)
-// algorithmic bytes per (b,p): 12 (xyz) + 4 (depth) read, 16 written.
+// algorithmic bytes per (b,p): 4 (depth) read, 16 written; + 12 (xyz) per vertex and call.
 // The reference also stores ndc.xy (never read downstream).
 // ---------------------------------------------------------------------------
 #ifndef DMR_POINTS_PER_THREAD
@@ -34,30 +34,39 @@ __global__ void __launch_bounds__(256) preprocess_points_kernel(
     float4* __restrict__ vimg)
 {
     griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
-    const int b = blockIdx.y;
-    // the two matrices of the view: 28 uniform loads, once per thread and DMR_POINTS_PER_THREAD vertices (with one
-    // vertex per thread they were two thirds of the kernel's load instructions and the L1 data pipe, not HBM, was
-    // its busiest unit: 65 % against 50 % DRAM utilisation at C5)
-    float mv[16], pj[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { mv[i] = mv_mats[16 * b + i]; pj[i] = proj_mats[16 * b + i]; }
+    // A thread owns DMR_POINTS_PER_THREAD vertices (block-strided, so every access stays coalesced) and walks the
+    // views: the positions are read once per call instead of once per view (12 of the 32 bytes per (view, vertex)),
+    // and the two matrices of a view -- 28 uniform loads -- once per thread and view (with one (view, vertex) per
+    // thread they were two thirds of the kernel's load instructions; the L1 data pipe, not HBM, was its busiest
+    // unit: 65 % against 50 % DRAM utilisation at C5).
+    float3 pos[DMR_POINTS_PER_THREAD];
+    size_t idx[DMR_POINTS_PER_THREAD];
 #pragma unroll
     for (int it = 0; it < DMR_POINTS_PER_THREAD; it++) {
-        const size_t idx = ((size_t)blockIdx.x * DMR_POINTS_PER_THREAD + it) * 256 + threadIdx.x;
-        if (idx >= (size_t)P) return;
-        float3 p = f3(verts[3 * idx + 0], verts[3 * idx + 1], verts[3 * idx + 2]);
-        float3 pv = xform43(p, mv);
-        float4 pp = xform44(pv, pj);
-        float pw = 1.0 / clamp_w(pp.w);                 // forward.cu:38 (double literal, float result)
-        float3 ndc = f3(pp.x * pw, pp.y * pw, pp.z * pw);
+        idx[it] = ((size_t)blockIdx.x * DMR_POINTS_PER_THREAD + it) * 256 + threadIdx.x;
+        pos[it] = idx[it] < (size_t)P ? f3(verts[3 * idx[it] + 0], verts[3 * idx[it] + 1], verts[3 * idx[it] + 2]) : f3(0, 0, 0);
+    }
+    for (int b = 0; b < B; b++) {
+        float mv[16], pj[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { mv[i] = mv_mats[16 * b + i]; pj[i] = proj_mats[16 * b + i]; }
+#pragma unroll
+        for (int it = 0; it < DMR_POINTS_PER_THREAD; it++) {
+            if (idx[it] >= (size_t)P) break;
+            float3 p = pos[it];
+            float3 pv = xform43(p, mv);
+            float4 pp = xform44(pv, pj);
+            float pw = 1.0 / clamp_w(pp.w);                 // forward.cu:38 (double literal, float result)
+            float3 ndc = f3(pp.x * pw, pp.y * pw, pp.z * pw);
 
-        float4 o;
-        o.x = ndc2pix(ndc.x, W);
-        o.y = ndc2pix(ndc.y, H);
-        o.z = ndc.z;
-        // tet path: clip-space w (bbox validity); tri path without a verts_depth tensor: the vertex's own NDC z
-        o.w = verts_depth ? verts_depth[(size_t)b * P + idx] : (depth_mode == 1 ? ndc.z : pp.w);
-        vimg[(size_t)b * P + idx] = o;
+            float4 o;
+            o.x = ndc2pix(ndc.x, W);
+            o.y = ndc2pix(ndc.y, H);
+            o.z = ndc.z;
+            // tet path: clip-space w (bbox validity); tri path without a verts_depth tensor: the vertex's own NDC z
+            o.w = verts_depth ? verts_depth[(size_t)b * P + idx[it]] : (depth_mode == 1 ? ndc.z : pp.w);
+            vimg[(size_t)b * P + idx[it]] = o;
+        }
     }
 }
 
@@ -65,7 +74,7 @@ int preprocess_points(int B, int P, int W, int H, const float* verts, const floa
                       const float* verts_depth, int depth_mode, float4* vimg, cudaStream_t stream)
 {
     if (B <= 0 || P <= 0) return 0;
-    dim3 grid((P + 256 * DMR_POINTS_PER_THREAD - 1) / (256 * DMR_POINTS_PER_THREAD), B);
+    dim3 grid((P + 256 * DMR_POINTS_PER_THREAD - 1) / (256 * DMR_POINTS_PER_THREAD));
     ProfScope prof(ST_POINTS, stream);
     DMR_CUDA(dmr_launch(preprocess_points_kernel, dim3(grid), dim3(256), 0, stream, B, P, W, H, verts, mv, proj, verts_depth, depth_mode, vimg));
     DMR_LAUNCH_CHECK("preprocess_points_kernel");
@@ -219,11 +228,15 @@ __device__ __forceinline__ void edge_setup(float2 p1, float2 p2, float2 p3, int 
 
 // ---------------------------------------------------------------------------
 // faces (tri): tiles_touched, tile rect, depth key, 144-byte record.
-// algorithmic bytes per (b,f): read 12 (idx) + 3*16 (vimg) + 3*12 (pos) +
-// 3*12 (colour) + 4 + 4, write 4 + 4 + 8 + 144.
+// algorithmic bytes per (b,f): read 3*16 (vimg) + 4 (intensity), write 4 + 4 + 8 + 144; per face and call: read
+// 12 (idx) + 3*12 (pos) + 3*12 (colour) + 4 (opacity).
 // ---------------------------------------------------------------------------
-template <bool HIST>   // HIST: accumulate the face sort's histograms as a by-product (small inputs only)
-__global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
+#ifndef DMR_FACES_MINB
+#define DMR_FACES_MINB 4
+#endif
+template <bool HIST, bool MULTI>   // HIST: accumulate the face sort's histograms as a by-product (small inputs only);
+                                   // MULTI = false: B == 1 (no view loop: 58 instead of 64 registers + spills)
+__global__ void __launch_bounds__(256, DMR_FACES_MINB) tri_preprocess_faces_kernel(
     int B, int P, int F, int W, int H, int gx, int gy,
     const int* __restrict__ faces, const float4* __restrict__ vimg,
     const float* __restrict__ verts, const float* __restrict__ verts_color,
@@ -239,70 +252,87 @@ __global__ void __launch_bounds__(256) tri_preprocess_faces_kernel(
         for (int i = tid; i < 4 * 256; i += 256) s_hist[i] = 0;
         __syncthreads();
     }
+    // A thread owns face f and walks the views: the face's indices, world positions, colours and opacity (88 of the
+    // 300 bytes moved per (view, face)) are read once per call instead of once per view.
     const size_t f0 = (size_t)blockIdx.x * 256;
-    const int b = blockIdx.y;
     const size_t f = f0 + tid;
     const bool valid = f < (size_t)F;
-    uint32_t sort_key[1] = { 0u };
-
+    const size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
+    int i0 = 0, i1 = 0, i2 = 0;
+    uint32_t pos[9], col[9], opa = 0u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { pos[k] = 0u; col[k] = 0u; }
     if (valid) {
-        int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-        const float4* vb = vimg + (size_t)b * P;
-        float4 a0 = vb[i0], a1 = vb[i1], a2 = vb[i2];
-
-        // forward.cu:101-121
-        float max_z = a0.z, min_z = a0.z, depth = 0;
-        depth += a0.z;
-        max_z = fmaxf(max_z, a1.z); min_z = fminf(min_z, a1.z); depth += a1.z;
-        max_z = fmaxf(max_z, a2.z); min_z = fminf(min_z, a2.z); depth += a2.z;
-        depth = depth / 3.0f;
-
-        uint32_t touched = 0;
-        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-        float2 p0 = make_float2(a0.x, a0.y), p1 = make_float2(a1.x, a1.y), p2 = make_float2(a2.x, a2.y);
-        if (!(max_z < -1.0f || min_z > 1.0f)) {    // forward.cu:124
-            tile_rect(p0, p1, p2, gx, gy, x0, y0, x1, y1);
-            if (x1 > x0 && y1 > y0) touched = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
+        i0 = faces[3 * f + 0]; i1 = faces[3 * f + 1]; i2 = faces[3 * f + 2];
+        const int vi[3] = { i0, i1, i2 };
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float* q = verts + 3 * (size_t)vi[k];
+            const float* c = verts_color + 3 * (size_t)vi[k];
+            pos[3 * k] = __float_as_uint(q[0]); pos[3 * k + 1] = __float_as_uint(q[1]); pos[3 * k + 2] = __float_as_uint(q[2]);
+            col[3 * k] = __float_as_uint(c[0]); col[3 * k + 1] = __float_as_uint(c[1]); col[3 * k + 2] = __float_as_uint(c[2]);
         }
-        // forward.cu:146-148
-        float dk = (depth + 1.0f) * 0.5f;
-        if (dk < 0.0f) dk = 0.0f;
-        if (dk > 1.0f) dk = 1.0f;
-
-        size_t bf = (size_t)b * F + f;
-        tiles_touched[bf] = touched;
-        depth_key[bf] = __float_as_uint(dk);
-        sort_key[0] = __float_as_uint(dk);
-        rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
-
-        uint32_t ea[3], eb[3], ec[3], flags;
-        edge_setup(p0, p1, p2, W, H, ea, eb, ec, flags);
-
-        uint4* r = s_rec + tid * 9;
-        const float* q0 = verts + 3 * (size_t)i0; const float* q1 = verts + 3 * (size_t)i1; const float* q2 = verts + 3 * (size_t)i2;
-        const float* k0 = verts_color + 3 * (size_t)i0; const float* k1 = verts_color + 3 * (size_t)i1; const float* k2 = verts_color + 3 * (size_t)i2;
-        auto fu = [](float x) { return __float_as_uint(x); };
-        r[0] = make_uint4(ea[0], eb[0], ec[0], flags);
-        r[1] = make_uint4(ea[1], eb[1], ec[1], (uint32_t)i0);
-        r[2] = make_uint4(ea[2], eb[2], ec[2], (uint32_t)i1);
-        r[3] = make_uint4(fu(q0[0]), fu(q0[1]), fu(q0[2]), fu(faces_opacity[f]));
-        r[4] = make_uint4(fu(q1[0]), fu(q1[1]), fu(q1[2]), fu(faces_intense[bf]));
-        r[5] = make_uint4(fu(q2[0]), fu(q2[1]), fu(q2[2]), (uint32_t)i2);
-        r[6] = make_uint4(fu(k0[0]), fu(k0[1]), fu(k0[2]), fu(a0.w));
-        r[7] = make_uint4(fu(k1[0]), fu(k1[1]), fu(k1[2]), fu(a1.w));
-        r[8] = make_uint4(fu(k2[0]), fu(k2[1]), fu(k2[2]), fu(a2.w));
+        opa = __float_as_uint(faces_opacity[f]);
     }
-    __syncthreads();
-    // coalesced write-out of the block's records
-    size_t nvalid = (f0 + 256 <= (size_t)F) ? 256 : ((size_t)F > f0 ? (size_t)F - f0 : 0);
-    uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
-    for (size_t i = tid; i < nvalid * 9; i += 256) dst[i] = s_rec[i];
-    // by-product: digit histograms of the depth keys + (last block) the plan of the face sort
-    if (HIST) {
-        const bool sort_valid[1] = { valid };
-        rs_pre_add<1>(s_hist, sort_key, sort_valid, sp);
-        rs_pre_finish(s_hist, sp, gridDim.x * gridDim.y);
+
+    const int nviews = MULTI ? B : 1;
+    for (int b = 0; b < nviews; b++) {
+        uint32_t sort_key[1] = { 0u };
+        if (valid) {
+            const float4* vb = vimg + (size_t)b * P;
+            float4 a0 = vb[i0], a1 = vb[i1], a2 = vb[i2];
+
+            // forward.cu:101-121
+            float max_z = a0.z, min_z = a0.z, depth = 0;
+            depth += a0.z;
+            max_z = fmaxf(max_z, a1.z); min_z = fminf(min_z, a1.z); depth += a1.z;
+            max_z = fmaxf(max_z, a2.z); min_z = fminf(min_z, a2.z); depth += a2.z;
+            depth = depth / 3.0f;
+
+            uint32_t touched = 0;
+            int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+            float2 p0 = make_float2(a0.x, a0.y), p1 = make_float2(a1.x, a1.y), p2 = make_float2(a2.x, a2.y);
+            if (!(max_z < -1.0f || min_z > 1.0f)) {    // forward.cu:124
+                tile_rect(p0, p1, p2, gx, gy, x0, y0, x1, y1);
+                if (x1 > x0 && y1 > y0) touched = (uint32_t)(y1 - y0) * (uint32_t)(x1 - x0);
+            }
+            // forward.cu:146-148
+            float dk = (depth + 1.0f) * 0.5f;
+            if (dk < 0.0f) dk = 0.0f;
+            if (dk > 1.0f) dk = 1.0f;
+
+            size_t bf = (size_t)b * F + f;
+            tiles_touched[bf] = touched;
+            depth_key[bf] = __float_as_uint(dk);
+            sort_key[0] = __float_as_uint(dk);
+            rect[bf] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+
+            uint32_t ea[3], eb[3], ec[3], flags;
+            edge_setup(p0, p1, p2, W, H, ea, eb, ec, flags);
+
+            uint4* r = s_rec + tid * 9;
+            r[0] = make_uint4(ea[0], eb[0], ec[0], flags);
+            r[1] = make_uint4(ea[1], eb[1], ec[1], (uint32_t)i0);
+            r[2] = make_uint4(ea[2], eb[2], ec[2], (uint32_t)i1);
+            r[3] = make_uint4(pos[0], pos[1], pos[2], opa);
+            r[4] = make_uint4(pos[3], pos[4], pos[5], __float_as_uint(faces_intense[bf]));
+            r[5] = make_uint4(pos[6], pos[7], pos[8], (uint32_t)i2);
+            r[6] = make_uint4(col[0], col[1], col[2], __float_as_uint(a0.w));
+            r[7] = make_uint4(col[3], col[4], col[5], __float_as_uint(a1.w));
+            r[8] = make_uint4(col[6], col[7], col[8], __float_as_uint(a2.w));
+        }
+        __syncthreads();
+        // coalesced write-out of the block's records of this view
+        uint4* dst = reinterpret_cast<uint4*>(records + (size_t)b * F + f0);
+        for (size_t i = tid; i < nvalid * 9; i += 256) dst[i] = s_rec[i];
+        // by-product: digit histograms of the depth keys
+        if (HIST) {
+            const bool sort_valid[1] = { valid };
+            rs_pre_add<1>(s_hist, sort_key, sort_valid, sp);
+        }
+        if (MULTI) __syncthreads();   // the next view overwrites s_rec
     }
+    if (HIST) rs_pre_finish(s_hist, sp, gridDim.x);   // (last block) the plan of the face sort
 }
 
 int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, const float4* vimg, const float* verts,
@@ -312,16 +342,14 @@ int tri_preprocess_faces(int B, int P, int F, int W, int H, const int* faces, co
 {
     if (B <= 0 || F <= 0) return 0;
     int gx = (W + DMR_TILE - 1) / DMR_TILE, gy = (H + DMR_TILE - 1) / DMR_TILE;
-    dim3 grid((F + 255) / 256, B);
+    dim3 grid((F + 255) / 256);
     ProfScope prof(ST_FACES, stream);
-    if (sp.npass > 0)
-        DMR_CUDA(dmr_launch(tri_preprocess_faces_kernel<true>, dim3(grid), dim3(256), 0, stream, B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
-                                                                   faces_opacity, faces_intense, tiles_touched, depth_key,
-                                                                   rect, records, sp));
-    else
-        DMR_CUDA(dmr_launch(tri_preprocess_faces_kernel<false>, dim3(grid), dim3(256), 0, stream, B, P, F, W, H, gx, gy, faces, vimg, verts, verts_color,
-                                                                    faces_opacity, faces_intense, tiles_touched, depth_key,
-                                                                    rect, records, sp));
+#define DMR_FACES_LAUNCH(HIST_, MULTI_)                                                                                         \
+    DMR_CUDA(dmr_launch(tri_preprocess_faces_kernel<HIST_, MULTI_>, dim3(grid), dim3(256), 0, stream, B, P, F, W, H, gx, gy, faces,   \
+                        vimg, verts, verts_color, faces_opacity, faces_intense, tiles_touched, depth_key, rect, records, sp))
+    if (sp.npass > 0) { if (B > 1) DMR_FACES_LAUNCH(true, true); else DMR_FACES_LAUNCH(true, false); }
+    else              { if (B > 1) DMR_FACES_LAUNCH(false, true); else DMR_FACES_LAUNCH(false, false); }
+#undef DMR_FACES_LAUNCH
     DMR_LAUNCH_CHECK("tri_preprocess_faces_kernel");
     return 0;
 }
