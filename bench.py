@@ -419,7 +419,8 @@ def run_ours(args, ws, rank, local):
     npass = (bit_length(tiles) + 7) // 8          # instance sort: tile bits only (two-level binning)
     BF = F * vpc
     alg = {
-        "preprocess_points": 32 * P * vpc, "preprocess_faces": (12 + 48 + 72 + 8 + 16 + 144) * BF,
+        # positions / indices / colours / opacity are read once per call (the kernels walk the views inside a thread)
+        "preprocess_points": 12 * P + 20 * P * vpc, "preprocess_faces": (12 + 72 + 4) * F + (48 + 4 + 16 + 144) * BF,
         "face_depth_sort": (4 + 4 * 16) * BF,      # histogram read + 4 eight-bit passes over (u32 key, u32 index) pairs
         "scan": 12 * BF,                           # order + gathered tiles_touched read, offsets written
         "duplicate_with_keys": 16 * BF + 8 * R,    # order, offsets, rect read; (u32 tile, u32 face) written
@@ -427,7 +428,8 @@ def run_ours(args, ws, rank, local):
         "tile_ranges": 4 * R + 8 * tiles,
         "tri_render_forward": 132 * R + 28 * px * vpc,
         "tri_render_backward": 132 * R + 28 * px * vpc + 4 * (6 * P + F) + 4 * (P + F) * vpc,
-        "tri_grad_finish": (96 + 144) * BF + 4 * (6 * P + F) + 4 * (P + F) * vpc,
+        # statistics of every (view, face); the triangle (96 B of the record) and the vertex scatter once per face
+        "tri_grad_finish": 96 * BF + 96 * F + 4 * (6 * P + F) + 4 * (P + F) * vpc,
     }
     for i in range(8):
         alg["sort_pass%d" % i] = 16 * R

@@ -23,6 +23,10 @@ WANT = [
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
     ("lts__t_sectors_op_red.sum", "l2_red_sectors"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1_data_pipe_lsu_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1_data_pipe_shared_pct"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared_bank_conflicts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared_wavefronts"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_scoreboard"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_scoreboard"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall_barrier"),
