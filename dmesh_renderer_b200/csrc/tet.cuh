@@ -30,8 +30,9 @@ static_assert(sizeof(TetFaceRec) == 64, "TetFaceRec must be 4 x 16 bytes");
 // version: 224 B): vert[k] is the tet vertex OPPOSITE side k, side k's triangle is made of the other
 // three, and a 4-bit order code says in which order faces[] lists them -- the hit test must see
 // (p0,p1,p2) in the reference's order to reproduce its (t,u,v) bits.  A tet whose sides are not made
-// of its own four vertices (inconsistent input tables) cannot be represented: it is flagged and the
-// march treats entering it as a numerical failure (pixel inactive).
+// of its own four vertices (inconsistent input tables, or two coincident vertices) cannot be represented:
+// it is flagged (code 0xF) and the march tests its sides with the vertices of the per-(view, face) records --
+// the triangle the reference gathers through faces[] -- on an out-of-line path (tet_side_hit_irregular).
 struct __align__(16) TetRec {
     int face[4];          // tet_faces[4*t + k]
     uint32_t next[4];     // bits 0..27: 1 + first entry of face_tets[face[k]] that is neither t nor -1 (0 = none)

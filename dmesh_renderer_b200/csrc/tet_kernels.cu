@@ -527,6 +527,20 @@ __device__ __forceinline__ float tet_depth_at(const TetDepth& d, float t)
     return (d.az + t * d.bz) * pw;
 }
 
+// Hit test of one side of an IRREGULAR tet (TetRec code 0xF: the side is not made of the tet's own four vertices --
+// inconsistent input tables, or two vertices of the tet coincide -- so the compact record cannot present its
+// vertices).  The reference gathers the side's vertices through faces[] / verts[] whatever the tet looks like
+// (forward.cu:700-722); the per-(view, face) record holds exactly that triangle, in faces[] order.  Rare and
+// deliberately out of line: the march kernels are register-bound and must not carry this path's live ranges.
+__device__ __noinline__ bool tet_side_hit_irregular(const TetFaceRec* __restrict__ face_rec, float3 ro, float3 rd, float3* tuv)
+{
+    const float* w = reinterpret_cast<const float*>(face_rec);
+    float3 r = f3(0, 0, 0);
+    const bool hit = ray_tri_hit(ro, rd, f3(w[0], w[1], w[2]), f3(w[3], w[4], w[5]), f3(w[6], w[7], w[8]), r);
+    *tuv = r;
+    return hit;
+}
+
 template <bool EXIT>
 __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const TetRec* __restrict__ tr, int curr_face,
                                             float3 ro, float3 rd)
@@ -557,11 +571,15 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
         }
         cnt++;
         const int code = (int)(nx[k] >> 28);
-        if (code == 0xF) { s.ok = false; continue; }   // irregular tet (see TetRec)
-        const int ia = code & 3, ib = code >> 2, ic = 3 - ia - ib;
-        const float3 A = v[(k + 1) & 3], B = v[(k + 2) & 3], C = v[(k + 3) & 3];
         float3 tuv;
-        bool hit = ray_tri_hit(ro, rd, sel3(ia, A, B, C), sel3(ib, A, B, C), sel3(ic, A, B, C), tuv);
+        bool hit;
+        if (code == 0xF) {   // irregular tet (see TetRec): the side's own vertices, as the reference gathers them
+            hit = tet_side_hit_irregular(p.face_rec + (size_t)b * p.F + f[k], ro, rd, &tuv);
+        } else {
+            const int ia = code & 3, ib = code >> 2, ic = 3 - ia - ib;
+            const float3 A = v[(k + 1) & 3], B = v[(k + 2) & 3], C = v[(k + 3) & 3];
+            hit = ray_tri_hit(ro, rd, sel3(ia, A, B, C), sel3(ib, A, B, C), sel3(ic, A, B, C), tuv);
+        }
         if (hit && (EXIT ? (dn > 0.0f) : (dn < 0.0f))) {
             s.face = f[k]; s.tet = (int)(nx[k] & 0x0fffffffu) - 1;
             s.rt = tuv.x; s.iu = tuv.y; s.iv = tuv.z;

@@ -184,3 +184,53 @@ def test_tet_deterministic_backward_is_reproducible_and_matches(name, seed, cap)
         assert float(z[0].abs().max()) == 0.0 and float(z[1].abs().max()) == 0.0
     finally:
         lib.dmr_debug_set_tet_trail_cap(0)
+
+
+def _with_irregular_tets(s, nfaces=40, shift=2e-3, seed=5):
+    """A copy of scene `s` (on the CPU) whose tables are INCONSISTENT for `nfaces` interior faces: the face's first
+    vertex is replaced by a slightly shifted copy of it, so both tets next to the face have a side that is not made of
+    their own four vertices.  The reference marches through such tets with the vertices it gathers through faces[];
+    the compact adjacency records cannot present them (TetRec code 0xF) and take the out-of-line path."""
+    g = torch.Generator().manual_seed(seed)
+    interior = ((s.face_tets[:, 0] >= 0) & (s.face_tets[:, 1] >= 0)).nonzero().flatten()
+    pick = interior[torch.randperm(interior.numel(), generator=g)[:nfaces]]
+    faces = s.faces.clone()
+    old = faces[pick, 0].long()
+    P = s.verts.shape[0]
+    new_ids = torch.arange(P, P + pick.numel(), dtype=faces.dtype)
+    faces[pick, 0] = new_ids
+    verts = torch.cat([s.verts, s.verts[old] + shift * (torch.rand(pick.numel(), 3, generator=g) - 0.5)])
+    verts_color = torch.cat([s.verts_color, torch.rand(pick.numel(), 3, generator=g)])
+    verts_depth = torch.cat([s.verts_depth, s.verts_depth[:, old]], dim=1)
+    return s._replace(verts=verts.contiguous(), faces=faces.contiguous(), verts_color=verts_color.contiguous(),
+                      verts_depth=verts_depth.contiguous())
+
+
+def test_tet_irregular_tets_follow_the_reference():
+    """Tets whose sides are not made of their own vertices: same march decisions, images and gradients as the
+    reference (which gathers every side through faces[] / verts[])."""
+    need_ref()
+    s = scenes.to_device(_with_irregular_tets(scenes.config("small_tet")), "cuda")
+    B, P, F, T = s.mv_mats.shape[0], s.verts.shape[0], s.faces.shape[0], s.tets.shape[0]
+    ref = ref_harness.ref_tet_forward(s, 0)
+    ri = ref_harness.ref_tet_intermediates(s, ref)
+    color, depth, active, pb, fb, bb, ib = ours_forward(s, 0)
+    dims = dict(B=B, P=P, F=F, W=s.W, H=s.H, R=ri["R"], T=T)
+    np.testing.assert_array_equal(debug.view("tet", "first_face", ib, **dims), ri["first_face"])
+    np.testing.assert_array_equal(debug.view("tet", "n_contrib", ib, **dims), ri["n_contrib"])
+    assert torch.equal(active > 0.5, ref["active"] > 0.5)
+    assert (color - ref["color"]).abs().max().item() <= IMG_TOL
+    assert (depth - ref["depth"]).abs().max().item() <= IMG_TOL
+    assert (active > 0.5).float().mean().item() > 0.3      # rays still get through the perturbed tets
+
+    gc, gd = [t.cuda() for t in scenes.cotangents(s)]
+    rg = ref_harness.ref_tet_backward(s, ref, gc, gd)
+    vc = s.verts_color.clone().requires_grad_()
+    fo = s.faces_opacity.clone().requires_grad_()
+    renderer = TetRenderer(TetRenderSettings(s.H, s.W, s.bg, 0))
+    c2, d2, _ = renderer(s.verts, s.faces, vc, fo, s.mv_mats, s.proj_mats, s.verts_depth, s.faces_intense, s.tets,
+                         s.face_tets, s.tet_faces)
+    torch.autograd.backward([c2, d2], [gc, gd])
+    for n, g, r in (("verts_color", vc.grad, rg[0]), ("faces_opacity", fo.grad, rg[1])):
+        e = rel_l2(g, r)
+        assert e <= GRAD_TOL, "%s: rel L2 %.3e" % (n, e)
