@@ -482,6 +482,7 @@ struct TetStep {   // result of looking for the exit (or entry) face of a tet
     float rt, iu, iv;
     bool ok;
     bool opposite;   // some other side is hit with the OPPOSITE normal sign (see the face trail)
+    bool irregular;  // IRR = false only: a side of an irregular tet was met (ok is false; the caller re-marches the ray)
 };
 
 // Among the sides of `tet` other than `curr_face`, the unique one hit by the ray whose
@@ -531,7 +532,10 @@ __device__ __forceinline__ float tet_depth_at(const TetDepth& d, float t)
 // inconsistent input tables, or two vertices of the tet coincide -- so the compact record cannot present its
 // vertices).  The reference gathers the side's vertices through faces[] / verts[] whatever the tet looks like
 // (forward.cu:700-722); the per-(view, face) record holds exactly that triangle, in faces[] order.  Rare and
-// deliberately out of line: the march kernels are register-bound and must not carry this path's live ranges.
+// deliberately out of line -- and even so the call costs the forward march 10 % (844 against 768 us at C3: the
+// kernel is register-bound), so the forward march runs in two passes: tet_step<EXIT, false> only REPORTS an
+// irregular side, the ray is given up and marked, and a second launch of the kernel, instantiated with the slow
+// path, re-marches the marked rays from their first face (no rays: the launch costs ~3 us).
 __device__ __noinline__ bool tet_side_hit_irregular(const TetFaceRec* __restrict__ face_rec, float3 ro, float3 rd, float3* tuv)
 {
     const float* w = reinterpret_cast<const float*>(face_rec);
@@ -541,12 +545,13 @@ __device__ __noinline__ bool tet_side_hit_irregular(const TetFaceRec* __restrict
     return hit;
 }
 
-template <bool EXIT>
+template <bool EXIT, bool IRR>
 __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const TetRec* __restrict__ tr, int curr_face,
                                             float3 ro, float3 rd)
 {
     TetStep s;
     s.ok = true;
+    s.irregular = false;
     s.face = -1; s.tet = -1; s.rt = 0; s.iu = 0; s.iv = 0;
     const uint4* r4 = reinterpret_cast<const uint4*>(tr);
     const uint4 fid = r4[0], nxt = r4[1];
@@ -574,6 +579,7 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
         float3 tuv;
         bool hit;
         if (code == 0xF) {   // irregular tet (see TetRec): the side's own vertices, as the reference gathers them
+            if (!IRR) { s.ok = false; s.irregular = true; continue; }
             hit = tet_side_hit_irregular(p.face_rec + (size_t)b * p.F + f[k], ro, rd, &tuv);
         } else {
             const int ia = code & 3, ib = code >> 2, ic = 3 - ia - ib;
@@ -599,6 +605,8 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
 // compositing arithmetic -- two independent dependency chains in one basic block.  Its result is
 // simply discarded when the ray terminates in this step; the decisions are taken in the reference's
 // order (forward.cu:645-648, 667-670, 687-759).
+#define DMR_TET_REDO 2   // value of active[] between the two passes of the forward march: ray met an irregular tet
+template <bool IRR>      // IRR = true: second pass, only the rays the first pass marked (see tet_side_hit_irregular)
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd_kernel(TetParams p)
 {
     griddep_wait();   // programmatic dependent launch: see dmr_launch (common.cuh)
@@ -611,6 +619,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
     const size_t BI = (size_t)p.B * HW;
     const size_t pix = (size_t)py * p.W + px;
     const size_t bpix = (size_t)b * HW + pix;
+    if (IRR && p.active[bpix] != DMR_TET_REDO) return;
+    bool redo = false;
 
     float3 ro, rd;
     tet_pixel_ray(p, b, px, py, bpix, ro, rd);
@@ -644,7 +654,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
         const float4 s0 = sh4[0], s1 = sh4[1], s2 = sh4[2];
         const float log1m = s2.z;
         const float intense = p.faces_intense[(size_t)b * p.F + curr_face];
-        const TetStep s = tet_step<true>(p, b, p.tet_rec + (curr_tet >= 0 ? curr_tet : 0), curr_face, ro, rd);
+        const TetStep s = tet_step<true, IRR>(p, b, p.tet_rec + (curr_tet >= 0 ? curr_tet : 0), curr_face, ro, rd);
         // Trail entry: face id; bit 31 flags a tet in which a second side is hit with an inward normal.
         // The reference's reverse march (backward.cu:382-477) finds two entry candidates there and gives
         // up on the ray (its error case 3), leaving this and all earlier faces without gradient; the
@@ -677,12 +687,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd
         // 2. next face (forward.cu:662-775)
         if (curr_tet == -1) { active = true; done = true; }
         if (!done) {
-            if (!s.ok) { done = true; }   // numerical failure: pixel stays inactive
+            if (!s.ok) { done = true; if (!IRR) redo = s.irregular; }   // numerical failure: pixel stays inactive
             curr_face = s.face; curr_tet = s.tet;
             rt = s.rt; iu = s.iu; iv = s.iv;
         }
     }
 
+    if (!IRR && redo) { p.active[bpix] = DMR_TET_REDO; return; }   // the second pass writes this pixel
     p.final_log_T[bpix] = log_T;
     p.prev_log_T[bpix] = prev_log_T;
     p.last_face[bpix] = last_face;
@@ -709,8 +720,11 @@ int tet_march_forward(const TetParams& p, cudaStream_t stream)
 {
     dim3 grid((p.W + 7) / 8, (p.H + MARCH_ROWS - 1) / MARCH_ROWS, p.B);
     ProfScope prof(ST_TET_FWD, stream);
-    DMR_CUDA(dmr_launch(tet_march_fwd_kernel, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
+    DMR_CUDA(dmr_launch(tet_march_fwd_kernel<false>, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
     DMR_LAUNCH_CHECK("tet_march_fwd_kernel");
+    count_launch(1);   // two kernels under one scope
+    DMR_CUDA(dmr_launch(tet_march_fwd_kernel<true>, dim3(grid), dim3(MARCH_THREADS), 0, stream, p));
+    DMR_LAUNCH_CHECK("tet_march_fwd_kernel<irregular>");
     return 0;
 }
 
@@ -882,7 +896,7 @@ __device__ __forceinline__ void tet_march_bwd_body(const TetParams& p)
             k--;
             if (curr_face == first_face) return;         // backward.cu:363-366
             if (curr_tet == -1) return;                  // backward.cu:373-376
-            TetStep s = tet_step<false>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
+            TetStep s = tet_step<false, true>(p, b, p.tet_rec + curr_tet, curr_face, ro, rd);
             if (!s.ok) return;
             curr_face = s.face; curr_tet = s.tet;
             rt = s.rt; iu = s.iu; iv = s.iv;
