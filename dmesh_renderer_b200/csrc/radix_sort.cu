@@ -42,7 +42,21 @@ namespace dmr {
 #define DMR_RS_SPLIT_RANK 0   // 1: form the peer masks of all rounds before the serial running-offset updates (more ILP, KPT more registers)
 #endif
 #define RS_TILE_KEYS (DMR_RS_THREADS * DMR_RS_KPT)
-#define RS_MIN_TILE 2048   // smallest tile of any configuration (sizes the descriptor array)
+#define RS_MIN_TILE 2048   // smallest tile of any configuration of the large shape (sizes the descriptor array)
+// Small sorts (the face / tile sorts of C1, C2) are a handful of tiles on an otherwise idle GPU: a pass lasts as long as
+// ONE tile takes (16 serial ranking rounds, ~6 us), not as long as the data takes to move.  Up to RS_SMALL_N keys the
+// tiles are 256 x RS_SMALL_KPT keys: four times as many CTAs, a quarter of the serial rounds each.
+// (Measured and rejected for these sizes: 32 instead of 8 descriptors per look-back step -- the walk over the
+// predecessors is not what a small pass waits for.  And for the large shape: key and value through shared memory as
+// one 64-bit word, one STS.64 / LDS.64 per pair: C5 pass 182.7 -> 186.8 us.)
+#ifndef RS_SMALL_N
+#define RS_SMALL_N (1u << 20)
+#endif
+#ifndef RS_SMALL_KPT
+#define RS_SMALL_KPT 8
+#endif
+#define RS_SMALL_TILE (256 * RS_SMALL_KPT)
+__host__ __device__ constexpr size_t rs_tile_keys(size_t n) { return n <= RS_SMALL_N ? (size_t)RS_SMALL_TILE : (size_t)RS_TILE_KEYS; }
 static_assert(DMR_RS_THREADS >= 256 && DMR_RS_THREADS % 32 == 0 && RS_TILE_KEYS >= RS_MIN_TILE, "onesweep tile shape");
 #ifndef RS_LB
 #define RS_LB 8          // look-back descriptors fetched per step (C5 pass: 8 -> 180 us, 16 -> 185 us, 32 -> 186 us)
@@ -58,7 +72,7 @@ struct SortTempLayout {   // zeroed part first, so that a caller can merge the m
     __host__ static SortTempLayout make(size_t n, size_t key_bytes)
     {
         SortTempLayout L;
-        L.ntile = (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
+        L.ntile = n <= RS_SMALL_N ? (n + RS_SMALL_TILE - 1) / RS_SMALL_TILE : (n + RS_MIN_TILE - 1) / RS_MIN_TILE;
         size_t o = 0;
         L.hist = o;     o = align_up(o + 4 * 256 * RS_MAX_PASS, 256);
         L.ctl = o;      o = align_up(o + sizeof(SortCtl), 256);
@@ -70,7 +84,7 @@ struct SortTempLayout {   // zeroed part first, so that a caller can merge the m
         return L;
     }
     // bytes from the start of the buffer that must be zero before a sort of npass passes
-    size_t zero_bytes(size_t n, int npass) const { return desc + 4 * 256 * ((n + RS_TILE_KEYS - 1) / RS_TILE_KEYS) * (size_t)npass; }
+    size_t zero_bytes(size_t n, int npass) const { return desc + 4 * 256 * ((n + rs_tile_keys(n) - 1) / rs_tile_keys(n)) * (size_t)npass; }
 };
 
 size_t sort_temp_bytes(size_t n) { return SortTempLayout::make(n, 8).total; }
@@ -347,13 +361,20 @@ __device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, siz
                     }
                     bp -= RS_LB * 256;
                     left -= RS_LB;
-                } else {                                         // the first few tiles of a pass: one at a time
-                    uint32_t v;
-                    do { v = ld_volatile_u32(bp); } while (v < RS_FLAG_AGG);
-                    excl += v & RS_VAL_MASK;
-                    open = v < RS_FLAG_INCL;
-                    bp -= 256;
-                    left--;
+                } else {                                         // the first RS_LB tiles of a pass: one predicated batch
+                    uint32_t v[RS_LB];                           // (slots beyond tile 0 read as an empty inclusive prefix)
+#pragma unroll
+                    for (int i = 0; i < RS_LB; i++) v[i] = (uint32_t)i < left ? ld_volatile_u32(bp - i * 256) : RS_FLAG_INCL;
+                    uint32_t mn = v[0];
+#pragma unroll
+                    for (int i = 1; i < RS_LB; i++) mn = min(mn, v[i]);
+                    if (mn < RS_FLAG_AGG) continue;
+#pragma unroll
+                    for (int i = 0; i < RS_LB; i++) {
+                        excl += open ? (v[i] & RS_VAL_MASK) : 0u;
+                        open = open && v[i] < RS_FLAG_INCL;
+                    }
+                    // tile 0 holds an inclusive prefix, so the walk has ended (open == false)
                 }
             }
             st_volatile_u32(my_desc, RS_FLAG_INCL | (excl + count));
@@ -492,6 +513,8 @@ static int sort_pairs_impl(const KeyT* keys_in, const uint32_t* vals_in, KeyT* k
     buf.kin = keys_in; buf.vin = vals_in; buf.kout = keys_out; buf.vout = vals_out;
     buf.ktmp = reinterpret_cast<KeyT*>(t + L.keys_tmp);
     buf.vtmp = reinterpret_cast<uint32_t*>(t + L.vals_tmp);
+    if (n <= RS_SMALL_N)
+        return launch_onesweep<KeyT, 256, RS_SMALL_KPT, 4>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream, n_dev);
     return launch_onesweep<KeyT, DMR_RS_THREADS, DMR_RS_KPT, DMR_RS_MINB>(buf, n, npass, end_bit, hist, ctl, desc, profile, stream, n_dev);
 }
 
