@@ -819,6 +819,10 @@ __device__ __forceinline__ void tet_bwd_face(const TetParams& p, TetBwdState& st
 // trail_cap faces) are replayed in reverse: face id and the forward pass's own (t,u,v) from the trail
 // (one coalesced 16-byte load), all loads independent of the previous step and issued one step ahead.  Steps beyond the cap are re-marched through the adjacency records exactly like
 // the reference (backward.cu:382-477) until the recorded part is reached.
+// (Measured and rejected: the replay alone in its own kernel -- rays beyond the cap left to a second launch -- so that
+// it fits 80 / 72 / 64 registers and 12 / 14 / 16 CTAs per SM instead of 10: C3 588.6 / 601 / 652 us against 587.8 us.
+// More resident warps do not help: the kernel is bound by the wavefronts its per-lane gathers and reductions push
+// through the L1 data pipe, not by the latency of a single chain.)
 template <bool DET>
 __device__ __forceinline__ void tet_march_bwd_body(const TetParams& p)
 {

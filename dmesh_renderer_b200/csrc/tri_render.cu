@@ -382,17 +382,7 @@ __device__ __forceinline__ void xreduce_step(float* v, bool hi)
 // three sector operations per group and pass at the L2 (round 1's layout -- quads 2c, 2c + 1 and the pair 2c, 2c + 1 of
 // the last 32 bytes -- cost five, a class-major layout six: C5, whose 4 M statistics records do not stay in L2, ran
 // its backward kernel 12 % slower with the latter), and the three addresses of a lane are one base + immediates.
-#ifndef DMR_TRI_BWD_CLAMP_REGROUP
-#define DMR_TRI_BWD_CLAMP_REGROUP 1
-#endif
-#ifndef DMR_TRI_BWD_SECTOR_STATS
-#define DMR_TRI_BWD_SECTOR_STATS 1
-#endif
-#if DMR_TRI_BWD_SECTOR_STATS
 __host__ __device__ constexpr int stat_slot(int i) { return 8 * ((i % 12) / 4) + 4 * (i / 12) + (i % 4); }
-#else
-__host__ __device__ constexpr int stat_slot(int i) { return (i % 6) < 4 ? 4 * (i / 6) + (i % 6) : 16 + 2 * (i / 6) + (i % 6) - 4; }
-#endif
 
 // Backward design
 // ---------------
@@ -507,11 +497,7 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
             uint32_t bm = 0;
             if (lane < nvw) {
                 uint32_t* rw = reinterpret_cast<uint32_t*>(s_rec + tid * 9);
-#if DMR_TRI_BWD_SECTOR_STATS
                 rw[7] = (uint32_t)b * (uint32_t)p.F + face;                                     // q1.w: i0 -> index of the (view, face) statistics record
-#else
-                rw[7] = face;                                                                   // q1.w: i0 -> face id
-#endif
                 rw[23] = __float_as_uint(1.0f / (1.0f - __uint_as_float(rw[15])));             // q5.w: i2 -> 1 / (1 - opacity)
                 bm = tile_block_mask(s_rec[tid * 9 + 0], s_rec[tid * 9 + 1], s_rec[tid * 9 + 2], blockIdx.x * DMR_TILE, blockIdx.y * DMR_TILE);
             }
@@ -656,19 +642,11 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         // backward.cu:354-369: chain through the clamp
                         float duc_du, duc_dv, dvc_du, dvc_dv;
                         clamp_bary_grad(code, duc_du, duc_dv, dvc_du, dvc_dv);
-#if DMR_TRI_BWD_CLAMP_REGROUP
                         // i0 = 1 - uc - vc, i1 = uc, i2 = vc: dL/duc = dL_di1 - dL_di0, dL/dvc = dL_di2 - dL_di0 (the reference
                         // expands the same sum over the three weights with the +-1 / 0 factors written out)
                         const float dL_duc = dL_di1 - dL_di0, dL_dvc = dL_di2 - dL_di0;
                         const float dL_du = dL_duc * duc_du + dL_dvc * dvc_du;
                         const float dL_dv = dL_duc * duc_dv + dL_dvc * dvc_dv;
-#else
-                        const float di0_du = -1 * duc_du + -1 * dvc_du, di0_dv = -1 * duc_dv + -1 * dvc_dv;
-                        const float di1_du = 1 * duc_du + 0 * dvc_du, di1_dv = 1 * duc_dv + 0 * dvc_dv;
-                        const float di2_du = 0 * duc_du + 1 * dvc_du, di2_dv = 0 * duc_dv + 1 * dvc_dv;
-                        const float dL_du = dL_di0 * di0_du + dL_di1 * di1_du + dL_di2 * di2_du;
-                        const float dL_dv = dL_di0 * di0_dv + dL_di1 * di1_dv + dL_di2 * di2_dv;
-#endif
                         // sufficient statistics of the vertex-position gradient (see header comment)
                         const float k1 = dL_du * inv_denom;
                         const float k24 = (dL_du * tuv.y + dL_dv * tuv.x) * inv_denom;
@@ -679,18 +657,14 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                 }
 
                 // ---- reduce over the two lanes of each group: 24 -> 12 values per lane; lane class c = lane & 1
-                //      owns logical 12c..12c+11 = quads 2c, 2c+1 and the two adjacent pairs 2c, 2c+1 (one more
-                //      16-byte vector)
+                //      owns logical 12c..12c+11 = three 16-byte vectors, the c-th half of each 32-byte sector of the
+                //      record (stat_slot)
                 xreduce_step<12, 1>(v, h1);
                 if (DET) {
                     if (have) {
                         // fixed-point record in LOGICAL order: this lane holds sums 12*cls .. 12*cls+11
                         const int cls = lane & 1;
-#if DMR_TRI_BWD_SECTOR_STATS
                         long long* rec = p.det_stats + (size_t)s_rec[j * 9 + 1].w * 24 + 12 * cls;
-#else
-                        long long* rec = p.det_stats + ((size_t)b * p.F + s_rec[j * 9 + 1].w) * 24 + 12 * cls;
-#endif
 #pragma unroll
                         for (int k = 0; k < 12; k++) {
                             if (cls == 1 && k >= 9) break;                       // logical 21..23: padding
@@ -698,20 +672,11 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         }
                     }
                 } else if (have) {
-#if DMR_TRI_BWD_SECTOR_STATS
                     // index of the (view, face) record (staged next to the positions) and the lane class in one address
                     float* rec = stats + ((size_t)s_rec[j * 9 + 1].w * 6 + (size_t)h1) * 4;
                     red_add_v4(rec, v[0], v[1], v[2], v[3]);
                     red_add_v4(rec + 8, v[4], v[5], v[6], v[7]);
                     red_add_v4(rec + 16, v[8], v[9], v[10], v[11]);
-#else
-                    float* rec = stats + ((size_t)b * p.F + s_rec[j * 9 + 1].w) * 24;
-                    const int cls = lane & 1;
-                    // (no zero tests: a group that has a covered pixel has non-zero sums in every vector)
-                    red_add_v4(rec + 8 * cls, v[0], v[1], v[2], v[3]);
-                    red_add_v4(rec + 8 * cls + 4, v[6], v[7], v[8], v[9]);
-                    red_add_v4(rec + 16 + 4 * cls, v[4], v[5], v[10], v[11]);
-#endif
                 }
             }
             __syncwarp();   // the next pass overwrites the index list and the masks
