@@ -292,7 +292,11 @@ __device__ __forceinline__ void rs_onesweep_tile(const RsBuffers<KeyT>& buf, siz
     //      (Measured and rejected: packed per-round counters -- 8 x 8-bit counts per (warp, digit) filled by the
     //      leader of every digit run, ranks from byte prefixes -- which make the 8 rounds independent of each
     //      other: 306 vs 282 us per pass at C5; the extra shared-memory traffic costs more than the chain.
-    //      A single match.any.sync per key instead of the ballots: 9 % slower, its issue rate is far lower.)
+    //      A single match.any.sync per key instead of the ballots: 9 % slower, its issue rate is far lower.
+    //      Ranking BEFORE the scan, so that the per-warp counts fall out of the ballots and the 16 counting atomics per
+    //      thread disappear (ranks parked in registers as 16-bit pairs, values loaded after the ranking): C5 pass
+    //      182.7 -> 182.7 us, C4 105 / 99 -> 107 / 103 us, face sorts +2..6 % -- the aggregate is published a ranking
+    //      phase later and the successors' look-back waits for it; the atomics were not what the pass waits for.)
     const uint32_t lt_mask = (1u << lane) - 1u;
 #if DMR_RS_SPLIT_RANK
     unsigned peers[RS_KPT];
