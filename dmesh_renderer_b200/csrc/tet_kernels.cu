@@ -605,6 +605,13 @@ __device__ __forceinline__ TetStep tet_step(const TetParams& p, int b, const Tet
 // compositing arithmetic -- two independent dependency chains in one basic block.  Its result is
 // simply discarded when the ray terminates in this step; the decisions are taken in the reference's
 // order (forward.cu:645-648, 667-670, 687-759).
+// (Measured and rejected at the end of round 2: warp-cooperative staging of the adjacency records.  ncu shows no sharing
+// between the lanes of a warp -- 128 sectors per warp and step: every lane is in its own tet -- so the eight LDG.128 of
+// a lane cost one L1 wavefront per lane each, ~190 of the ~200 wavefronts of a step.  Copying the warp's 32 records to
+// shared memory with eight cp.async rounds in which eight consecutive lanes fetch ONE record's line, then eight
+// conflict-free LDS.128 per lane (144-byte stride), halves the wavefronts -- and makes the march 4.5 % SLOWER, C3
+// 780 -> 815 us: the loop becomes warp-uniform with a copy / wait / read-back round trip in every step's dependent
+// chain, and the L1 data pipe at 56 % was not what the step waits for.)
 #define DMR_TET_REDO 2   // value of active[] between the two passes of the forward march: ray met an irregular tet
 template <bool IRR>      // IRR = true: second pass, only the rays the first pass marked (see tet_side_hit_irregular)
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_MIN_BLOCKS) tet_march_fwd_kernel(TetParams p)
