@@ -383,6 +383,13 @@ __device__ __forceinline__ void xreduce_step(float* v, bool hi)
 // the last 32 bytes -- cost five, a class-major layout six: C5, whose 4 M statistics records do not stay in L2, ran
 // its backward kernel 12 % slower with the latter), and the three addresses of a lane are one base + immediates.
 __host__ __device__ constexpr int stat_slot(int i) { return 8 * ((i % 12) / 4) + 4 * (i / 12) + (i % 4); }
+constexpr bool stat_slot_is_permutation()
+{
+    unsigned seen = 0;
+    for (int i = 0; i < 24; i++) seen |= 1u << stat_slot(i);
+    return seen == 0xffffffu;
+}
+static_assert(stat_slot_is_permutation(), "stat_slot must map the 24 statistics onto the 24 floats of a record");
 
 // Backward design
 // ---------------
