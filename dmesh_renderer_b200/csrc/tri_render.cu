@@ -590,7 +590,9 @@ __device__ __forceinline__ void tri_render_bwd_body(const TriRenderParams& p)
                         const float i0 = 1 - uc - vc, i1 = uc, i2 = vc;
                         const float4 q6 = sh[3], q7 = sh[4], q8 = sh[5];                     // (colour_k, depth_k)
                         // (scalar loads on purpose: taking these three from the .w lanes of a0..a2 keeps them live across the
-                        // hit test and costs the 64-register kernel three spill accesses per pass: C4 3316 -> 3408 us)
+                        // hit test and costs the 64-register kernel three spill accesses per pass: C4 3316 -> 3408 us;
+                        // re-measured after the statistics addressing freed registers -- one extra spill load per pass
+                        // instead of three: C4 3133 -> 3173 us, C5 699 -> 707 us)
                         const float intense = lds_f32(&sh[1].w);
                         const float alpha = lds_f32(&sh[0].w);
                         const float raw0 = i0 * q6.x + i1 * q7.x + i2 * q8.x;
