@@ -32,7 +32,7 @@ def cpu_sort(keys, vals, end_bit):
     return keys[order], vals[order]
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 257, 4096, 4097, 100_003, 1_000_000, 5_000_011])
+@pytest.mark.parametrize("n", [1, 2, 31, 257, 2048, 2049, 4096, 4097, 100_003, 1_000_000, 1_048_576, 1_048_577, 5_000_011])
 @pytest.mark.parametrize("end_bit", [45, 64, 33])
 def test_sort_random(n, end_bit):
     rng = np.random.default_rng(n * 131 + end_bit)
@@ -72,3 +72,36 @@ def test_sort_all_equal_and_sorted_inputs():
         ck, cv = cpu_sort(keys, vals, 45)
         np.testing.assert_array_equal(gk, ck)
         np.testing.assert_array_equal(gv, cv)
+
+
+def gpu_sort_u32(keys, vals, end_bit):
+    """dmr_sort_pairs_u32: the (u32 key, u32 value) form the renderers use; vals=None stands for the identity."""
+    lib = _lib.load()
+    n = keys.size
+    dk = torch.from_numpy(keys.view(np.int32)).cuda()
+    dv = torch.from_numpy(vals.view(np.int32)).cuda() if vals is not None else None
+    ok = torch.empty_like(dk)
+    ov = torch.empty_like(dk)
+    temp = torch.empty(lib.dmr_sort_temp_bytes(n), dtype=torch.uint8, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+    _lib.check(lib.dmr_sort_pairs_u32(p(dk), p(dv), p(ok), p(ov), n, end_bit, p(temp),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return ok.cpu().numpy().view(np.uint32), ov.cpu().numpy().view(np.uint32)
+
+
+# 2^20 keys is where the onesweep passes switch from 2048-key to 4096-key tiles (csrc/radix_sort.cu: RS_SMALL_N);
+# 2047 / 2048 / 2049 and 4095 / 4096 / 4097 straddle one tile of either shape
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 4095, 4097, 1_048_575, 1_048_576, 1_048_577, 3_000_001])
+@pytest.mark.parametrize("end_bit,identity", [(32, True), (13, False), (17, False)])
+def test_sort_u32_both_tile_shapes(n, end_bit, identity):
+    rng = np.random.default_rng(n * 7 + end_bit)
+    keys = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+    if end_bit < 32:
+        keys &= np.uint32((1 << end_bit) - 1)
+    keys[::5] = keys[0]   # ties: stability
+    vals = None if identity else rng.integers(0, 2 ** 31, size=n, dtype=np.uint64).astype(np.uint32)
+    gk, gv = gpu_sort_u32(keys, vals, end_bit)
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(gk, keys[order])
+    np.testing.assert_array_equal(gv, order.astype(np.uint32) if identity else vals[order])
