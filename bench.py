@@ -197,9 +197,8 @@ class Workload:
                                     "working set >> L2" if self.name == "C4" else "; one timed region per step, L2 flushed in between") +
                                    "); verts_depth / faces_intense are scene-derived device tensors (DMesh computes them from "
                                    "the scene on the GPU), the scene is resident",
-                "e2e_result_read": "the scalar image loss of every step is copied D2H into pinned memory at the end of the "
-                                   "step; the host reads step k's value after it has enqueued step k+1 (one-step-lagged "
-                                   "logging), the last step's before the timed region ends"}
+                "e2e_result_read": "the scalar image loss of every step is copied D2H into pinned memory and read by the "
+                                   "host (stream synchronisation) before the next step is enqueued"}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -238,19 +237,8 @@ def run_ours(args, ws, rank, local):
     nslot = 2
     stage = [{"mv": torch.empty_like(mvs[0]), "proj": torch.empty_like(pjs[0]), "tc": torch.empty_like(tgt_c[0]),
               "td": torch.empty_like(tgt_d[0]), "cams": None, "ready": None, "free": None} for _ in range(nslot)]
-    # the step's result (image loss) is copied D2H every step; the host reads step k's value while step k + 1 is
-    # already enqueued (one-step-lagged logging, two alternating slots), the last step's before the region ends
-    loss_accs = [torch.zeros(1, device=dev) for _ in range(2)]
-    loss_hosts = [torch.zeros(1).pin_memory() for _ in range(2)]
-    loss_events = [None, None]
-    losses_read = []
-
-    def read_loss(slot):
-        ev = loss_events[slot]
-        if ev is not None:
-            ev.synchronize()
-            losses_read.append(float(loss_hosts[slot][0]))
-            loss_events[slot] = None
+    loss_acc = torch.zeros(1, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in wl.host.values())
 
     ncalls = len(wl.calls)
@@ -286,8 +274,6 @@ def run_ours(args, ws, rank, local):
         across step boundaries too (a data loader that prefetches the next batch): every step's inputs are copied
         inside the region, once per step."""
         main = torch.cuda.current_stream()
-        slot = k & 1
-        loss_acc = loss_accs[slot]
         leaves.zero_()
         loss_acc.zero_()
         with leaves.direct():
@@ -309,13 +295,9 @@ def run_ours(args, ws, rank, local):
                 ev.record(main)
                 st["free"] = ev
         leaves.all_reduce()
-        loss_hosts[slot].copy_(loss_acc, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        loss_events[slot] = ev
-        read_loss(slot ^ 1)                         # the previous step's result: read while this step runs
-        if last_step:
-            read_loss(slot)                         # nothing follows: wait for this step's result
+        loss_host.copy_(loss_acc, non_blocking=True)
+        main.synchronize()                          # the step's result is read on the host every step
+        return float(loss_host[0])
 
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
